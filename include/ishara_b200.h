@@ -1,0 +1,155 @@
+/* ishara_b200 — C ABI of the B200-native (sm_100a) Ishara encoder hot path.
+ *
+ * Drop-in boundary for the reference's model call. The reference has no FFI of its
+ * own — its boundary is the Keras model call inside the notebooks — so every entry point below names
+ * the reference call site it replaces:
+ *
+ *   ishara_model_create / set_param / finalize   <- get_model(...)            nb:conv-hybrid-model c7:1-72
+ *                                                   model.load_weights / save_weights           c9:10
+ *   ishara_model_forward[_host]                  <- model(x) / model(x, training=False)   c7:82, c9:15, c13:17
+ *   ishara_ctc_loss                              <- CTCLoss(labels, logits)                     c6:1-13
+ *   ishara_greedy_decode                         <- decode_phrase / decode_batch_predictions    c8:4-20
+ *   ishara_op_*                                  <- operator-level building blocks (tests, P-rows of §8a)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensors are dense, row-major, C order.
+ *   - every function returns an ishara_status_t (0 = ok); ishara_last_error() gives a thread-local
+ *     message for the last failure on the calling thread. Nothing aborts.
+ *   - "dev" pointers are device memory on the model's device; "host" pointers are host memory
+ *     (pinned or pageable). The caller owns every buffer; the library only owns its handle
+ *     (packed weights, workspace, TMA descriptors) and never retains caller pointers past a call.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it without a host sync unless
+ *     the function name ends in _host.
+ *   - a handle is bound to one device and is not re-entrant; distinct handles may be driven from
+ *     distinct threads. There is no CPU fallback: without a Blackwell GPU every compute call fails
+ *     with ISHARA_ERR_CUDA.
+ */
+#ifndef ISHARA_B200_H_
+#define ISHARA_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ISHARA_API __attribute__((visibility("default")))
+#else
+#define ISHARA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ISHARA_OK = 0,
+  ISHARA_ERR_INVALID = 1,   /* null handle / bad enum / unknown parameter name */
+  ISHARA_ERR_SHAPE = 2,     /* shape, alignment or size mismatch */
+  ISHARA_ERR_CUDA = 3,      /* CUDA runtime / driver error (message has the details) */
+  ISHARA_ERR_STATE = 4      /* call order (e.g. forward before finalize, missing parameters) */
+} ishara_status_t;
+
+typedef struct ishara_model ishara_model_t;
+
+/* get_model(...) keyword arguments (c7:1-11) plus the two module-level globals it closes over
+ * (INPUT_SHAPE c1:27 and len(char_to_num) c1:4-7). */
+typedef struct {
+  int32_t dim;                      /* 256 */
+  int32_t num_conv_squeeze_blocks;  /* 2 */
+  int32_t num_conv_conform_blocks;  /* 2 */
+  int32_t num_conv_per_block;       /* 3 */
+  int32_t kernel_sizes[8];          /* {11,5,3} */
+  int32_t num_kernel_sizes;         /* 3 */
+  int32_t num_heads;                /* 8 */
+  int32_t expansion_factor;         /* 2 */
+  int32_t transformer_kernel_size;  /* 15 */
+  int32_t frames;                   /* T = INPUT_SHAPE[0] (384) */
+  int32_t features;                 /* INPUT_SHAPE[1] (276) */
+  int32_t num_classes;              /* 60 */
+} ishara_config_t;
+
+ISHARA_API const char* ishara_version(void);
+ISHARA_API const char* ishara_last_error(void);
+/* number of CUDA devices visible, or 0 (never fails) */
+ISHARA_API int32_t ishara_device_count(void);
+
+/* ---- model lifetime ------------------------------------------------------------------------- */
+ISHARA_API ishara_status_t ishara_model_create(const ishara_config_t* cfg, int32_t device, ishara_model_t** out);
+ISHARA_API ishara_status_t ishara_model_destroy(ishara_model_t* m);
+
+/* Parameter enumeration in canonical order (Keras layer names). */
+ISHARA_API int32_t ishara_model_num_params(const ishara_model_t* m);
+ISHARA_API ishara_status_t ishara_model_param_info(const ishara_model_t* m, int32_t index, const char** name,
+                                        int64_t* numel, int32_t* ndim, int64_t shape[4]);
+/* Upload one parameter in Keras layout (Dense [in,out]; Conv1D [k,in/groups,out]; depthwise [k,C,1]),
+ * fp32, from host memory. */
+ISHARA_API ishara_status_t ishara_model_set_param(ishara_model_t* m, const char* name, const float* host_data, int64_t numel);
+/* Read back the fp32 master copy. */
+ISHARA_API ishara_status_t ishara_model_get_param(const ishara_model_t* m, const char* name, float* host_out, int64_t numel);
+/* Pack weights for the kernels (bf16, K-major, BatchNorm folded). Must follow set_param of every
+ * parameter and precede forward. May be called again after parameters change. */
+ISHARA_API ishara_status_t ishara_model_finalize(ishara_model_t* m);
+
+/* ---- hot path -------------------------------------------------------------------------------- */
+/* logits[B,T,num_classes] fp32 = model(x[B,T,features] fp32), inference mode (BatchNorm moving
+ * statistics, dropout off). Device pointers. */
+ISHARA_API ishara_status_t ishara_model_forward(ishara_model_t* m, const float* x_dev, int32_t batch, float* logits_dev,
+                                     void* stream);
+/* Same through host buffers: H2D copy, forward, D2H copy, stream sync (the reference-facing call). */
+ISHARA_API ishara_status_t ishara_model_forward_host(ishara_model_t* m, const float* x_host, int32_t batch, float* logits_host);
+/* Whole inference step through host buffers: forward + greedy decode (+ CTC loss when labels != NULL).
+ * ids_host int32 [B,T], lens_host int32 [B], nll_host fp32 [B] (or NULL), logits_host optional (or NULL). */
+ISHARA_API ishara_status_t ishara_model_infer_host(ishara_model_t* m, const float* x_host, int32_t batch,
+                                        const int32_t* labels_host, int32_t max_label_len, float* logits_host,
+                                        int32_t* ids_host, int32_t* lens_host, float* nll_host);
+
+/* CTCLoss (c6:1-13): per-sequence negative log-likelihood nll[B] (the reference returns their mean) and,
+ * when grad_dev != NULL, d nll_b / d logits [B,T,V]. labels int32 [B,L] padded with `blank`. */
+ISHARA_API ishara_status_t ishara_ctc_loss(const float* logits_dev, const int32_t* labels_dev, int32_t batch, int32_t frames,
+                                int32_t num_classes, int32_t max_label_len, int32_t blank, float* nll_dev,
+                                float* grad_dev, void* stream);
+/* decode_phrase (c8:4-12) for a batch: ids_dev int32 [B,T] (first lens[b] entries valid, rest -1). */
+ISHARA_API ishara_status_t ishara_greedy_decode(const float* logits_dev, int32_t batch, int32_t frames, int32_t num_classes,
+                                     int32_t blank, int32_t* ids_dev, int32_t* lens_dev, void* stream);
+
+/* ---- operator-level entry points (device pointers; bf16 tensors are raw uint16 bit patterns) --- */
+typedef struct {
+  const void* a;        /* bf16 [M,K], row pitch lda */
+  const void* wt;       /* bf16 [N,K] (weight transposed, K contiguous) */
+  void* out0;           /* bf16 or fp32 [M,Nout] */
+  void* out1;           /* bf16 [M,Nout] or NULL (LayerNorm'd copy) */
+  const float* bias;    /* [N] or NULL */
+  const float* gate;    /* [M/rows_per_seq, N] or NULL */
+  const float* rowtab;  /* [rows_per_seq, N] or NULL */
+  const void* resid;    /* bf16 [M,Nout] or NULL */
+  const float* ln0_g; const float* ln0_b; float ln0_eps;
+  const float* ln1_g; const float* ln1_b; float ln1_eps;
+  int32_t M, N, K, lda;
+  int32_t nout;         /* logical output columns (<= N, or <= N/2 for GLU); 0 = all */
+  int32_t rows_per_seq;
+  int32_t act;          /* 0 none, 1 swish, 2 relu, 3 GLU (Nout = N/2) */
+  int32_t block_n;      /* 64, 128, 256 */
+  int32_t out_f32;      /* 0 | 1 */
+  int32_t row_mode;     /* 1: full-row epilogue (residual + LayerNorm fusion), needs N == block_n */
+} ishara_gemm_args_t;
+ISHARA_API ishara_status_t ishara_op_gemm(const ishara_gemm_args_t* args, void* stream);
+
+/* depthwise temporal conv; post: 0 none, 1 swish, 2 ECA (needs eca_w[5]); see csrc/kernels.h DwConvArgs */
+ISHARA_API ishara_status_t ishara_op_dwconv(const void* in_bf16, void* out_bf16, const float* w, const float* bias,
+                                 const float* eca_w, float* colsum, int32_t B, int32_t T, int32_t C, int32_t k,
+                                 int32_t pad_left, int32_t post, void* stream);
+/* attention core on per-head-interleaved qkv bf16 [B*T, 3*H*dh] -> out bf16 [B*T, H*dh] */
+ISHARA_API ishara_status_t ishara_op_attention(const void* qkv_bf16, void* out_bf16, const uint8_t* key_mask, int32_t B, int32_t T,
+                                    int32_t H, int32_t dh, float scale, void* stream);
+ISHARA_API ishara_status_t ishara_op_layernorm(const void* x_bf16, void* out_bf16, const float* gamma, const float* beta,
+                                    float eps, int64_t M, int32_t D, void* stream);
+ISHARA_API ishara_status_t ishara_op_cast_pad(const float* x, void* out_bf16, int64_t M, int32_t F, int32_t Fpad, void* stream);
+
+/* ---- debugging aid: copy an internal activation of the last forward (bf16 -> fp32) to the host ---
+ * Enable with ishara_model_set_debug(m, 1) before the forward. Names: "stem", a Conv1DBlock name
+ * ("convsqueeze_0_1", ...), "squeezeformer_<i>", "conformer_<i>": the residual stream after that module. */
+ISHARA_API ishara_status_t ishara_model_set_debug(ishara_model_t* m, int32_t on);
+ISHARA_API ishara_status_t ishara_model_debug_fetch(ishara_model_t* m, const char* name, float* host_out, int64_t numel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISHARA_B200_H_ */

@@ -1,0 +1,286 @@
+// ishara_b200 — extern "C" surface (include/ishara_b200.h). Thin: argument checks + calls into model.cu
+// and the kernel launchers. No torch, no Python types.
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ishara_b200.h"
+#include "kernels.h"
+
+// model.cu
+struct ishara_model;
+namespace ishara {
+int model_create(const ishara_config_t* cfg, int device, ishara_model** out);
+int model_destroy(ishara_model* m);
+int model_finalize(ishara_model* m);
+int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_dev, cudaStream_t stream);
+}  // namespace ishara
+
+// model.cu keeps the struct definition private; the accessors below are implemented there too.
+namespace ishara {
+struct ModelView {
+  const ishara_config_t* cfg;
+  int device;
+  cudaStream_t stream;
+  float* x_dev;
+  float* logits_own;
+  int32_t* ids_dev;
+  int32_t* lens_dev;
+  float* nll_dev;
+};
+int model_view(ishara_model* m, int batch, ModelView* v);                       // ensures workspace
+int model_labels_buffer(ishara_model* m, size_t count, int32_t** out);
+int model_num_params(const ishara_model* m);
+int model_param_info(const ishara_model* m, int idx, const char** name, int64_t* numel, int32_t* ndim, int64_t shape[4]);
+int model_set_param(ishara_model* m, const char* name, const float* data, int64_t numel);
+int model_get_param(const ishara_model* m, const char* name, float* out, int64_t numel);
+int model_set_debug(ishara_model* m, int on);
+int model_debug_fetch(ishara_model* m, const char* name, float* host_out, int64_t numel);
+}  // namespace ishara
+
+using namespace ishara;
+
+#define CAPI_CUDA_OK(expr)                                                                          \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+      return ISHARA_ERR_CUDA;                                                                       \
+    }                                                                                               \
+  } while (0)
+
+#define CHECK_HANDLE(m)                      \
+  if ((m) == nullptr) {                      \
+    set_last_error("null model handle");     \
+    return ISHARA_ERR_INVALID;               \
+  }
+
+extern "C" {
+
+const char* ishara_version(void) { return "ishara_b200 0.1.0 (sm_100a)"; }
+const char* ishara_last_error(void) { return get_last_error(); }
+int32_t ishara_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+ishara_status_t ishara_model_create(const ishara_config_t* cfg, int32_t device, ishara_model_t** out) {
+  return static_cast<ishara_status_t>(model_create(cfg, device, reinterpret_cast<ishara_model**>(out)));
+}
+ishara_status_t ishara_model_destroy(ishara_model_t* m) {
+  return static_cast<ishara_status_t>(model_destroy(reinterpret_cast<ishara_model*>(m)));
+}
+int32_t ishara_model_num_params(const ishara_model_t* m) {
+  if (m == nullptr) return 0;
+  return model_num_params(reinterpret_cast<const ishara_model*>(m));
+}
+ishara_status_t ishara_model_param_info(const ishara_model_t* m, int32_t index, const char** name, int64_t* numel,
+                                        int32_t* ndim, int64_t shape[4]) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(
+      model_param_info(reinterpret_cast<const ishara_model*>(m), index, name, numel, ndim, shape));
+}
+ishara_status_t ishara_model_set_param(ishara_model_t* m, const char* name, const float* host_data, int64_t numel) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_set_param(reinterpret_cast<ishara_model*>(m), name, host_data, numel));
+}
+ishara_status_t ishara_model_get_param(const ishara_model_t* m, const char* name, float* host_out, int64_t numel) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_get_param(reinterpret_cast<const ishara_model*>(m), name, host_out, numel));
+}
+ishara_status_t ishara_model_finalize(ishara_model_t* m) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_finalize(reinterpret_cast<ishara_model*>(m)));
+}
+ishara_status_t ishara_model_set_debug(ishara_model_t* m, int32_t on) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_set_debug(reinterpret_cast<ishara_model*>(m), on));
+}
+ishara_status_t ishara_model_debug_fetch(ishara_model_t* m, const char* name, float* host_out, int64_t numel) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_debug_fetch(reinterpret_cast<ishara_model*>(m), name, host_out, numel));
+}
+
+ishara_status_t ishara_model_forward(ishara_model_t* m, const float* x_dev, int32_t batch, float* logits_dev,
+                                     void* stream) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(
+      model_forward(reinterpret_cast<ishara_model*>(m), x_dev, batch, logits_dev, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_model_forward_host(ishara_model_t* mh, const float* x_host, int32_t batch, float* logits_host) {
+  CHECK_HANDLE(mh);
+  if (x_host == nullptr || logits_host == nullptr || batch <= 0) {
+    set_last_error("forward_host: bad arguments");
+    return ISHARA_ERR_INVALID;
+  }
+  ishara_model* m = reinterpret_cast<ishara_model*>(mh);
+  ModelView v;
+  int rc = model_view(m, batch, &v);
+  if (rc) return static_cast<ishara_status_t>(rc);
+  const size_t M = static_cast<size_t>(batch) * v.cfg->frames;
+  CAPI_CUDA_OK(cudaMemcpyAsync(v.x_dev, x_host, M * v.cfg->features * sizeof(float), cudaMemcpyHostToDevice, v.stream));
+  if ((rc = model_forward(m, v.x_dev, batch, v.logits_own, v.stream))) return static_cast<ishara_status_t>(rc);
+  CAPI_CUDA_OK(cudaMemcpyAsync(logits_host, v.logits_own, M * v.cfg->num_classes * sizeof(float), cudaMemcpyDeviceToHost,
+                                 v.stream));
+  CAPI_CUDA_OK(cudaStreamSynchronize(v.stream));
+  return ISHARA_OK;
+}
+
+ishara_status_t ishara_model_infer_host(ishara_model_t* mh, const float* x_host, int32_t batch,
+                                        const int32_t* labels_host, int32_t max_label_len, float* logits_host,
+                                        int32_t* ids_host, int32_t* lens_host, float* nll_host) {
+  CHECK_HANDLE(mh);
+  if (x_host == nullptr || batch <= 0 || ids_host == nullptr || lens_host == nullptr) {
+    set_last_error("infer_host: bad arguments");
+    return ISHARA_ERR_INVALID;
+  }
+  if (labels_host != nullptr && (nll_host == nullptr || max_label_len <= 0)) {
+    set_last_error("infer_host: labels need nll_host and max_label_len > 0");
+    return ISHARA_ERR_INVALID;
+  }
+  ishara_model* m = reinterpret_cast<ishara_model*>(mh);
+  ModelView v;
+  int rc = model_view(m, batch, &v);
+  if (rc) return static_cast<ishara_status_t>(rc);
+  const ishara_config_t& c = *v.cfg;
+  const size_t M = static_cast<size_t>(batch) * c.frames;
+  const int blank = c.num_classes - 1;  // pad_token_idx = 59 (c1:4-7)
+  CAPI_CUDA_OK(cudaMemcpyAsync(v.x_dev, x_host, M * c.features * sizeof(float), cudaMemcpyHostToDevice, v.stream));
+  int32_t* labels_dev = nullptr;
+  if (labels_host != nullptr) {
+    if ((rc = model_labels_buffer(m, static_cast<size_t>(batch) * max_label_len, &labels_dev)))
+      return static_cast<ishara_status_t>(rc);
+    CAPI_CUDA_OK(cudaMemcpyAsync(labels_dev, labels_host, static_cast<size_t>(batch) * max_label_len * sizeof(int32_t),
+                                   cudaMemcpyHostToDevice, v.stream));
+  }
+  if ((rc = model_forward(m, v.x_dev, batch, v.logits_own, v.stream))) return static_cast<ishara_status_t>(rc);
+  if ((rc = greedy_decode_launch(v.logits_own, batch, c.frames, c.num_classes, blank, v.ids_dev, v.lens_dev, v.stream)))
+    return static_cast<ishara_status_t>(rc);
+  if (labels_host != nullptr) {
+    if ((rc = ctc_loss_launch(v.logits_own, labels_dev, batch, c.frames, c.num_classes, max_label_len, blank, v.nll_dev,
+                              nullptr, v.stream)))
+      return static_cast<ishara_status_t>(rc);
+    CAPI_CUDA_OK(cudaMemcpyAsync(nll_host, v.nll_dev, batch * sizeof(float), cudaMemcpyDeviceToHost, v.stream));
+  }
+  CAPI_CUDA_OK(cudaMemcpyAsync(ids_host, v.ids_dev, M * sizeof(int32_t), cudaMemcpyDeviceToHost, v.stream));
+  CAPI_CUDA_OK(cudaMemcpyAsync(lens_host, v.lens_dev, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, v.stream));
+  if (logits_host != nullptr)
+    CAPI_CUDA_OK(cudaMemcpyAsync(logits_host, v.logits_own, M * c.num_classes * sizeof(float), cudaMemcpyDeviceToHost,
+                                   v.stream));
+  CAPI_CUDA_OK(cudaStreamSynchronize(v.stream));
+  return ISHARA_OK;
+}
+
+ishara_status_t ishara_ctc_loss(const float* logits_dev, const int32_t* labels_dev, int32_t batch, int32_t frames,
+                                int32_t num_classes, int32_t max_label_len, int32_t blank, float* nll_dev,
+                                float* grad_dev, void* stream) {
+  if (logits_dev == nullptr || labels_dev == nullptr || nll_dev == nullptr) {
+    set_last_error("ctc_loss: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  return static_cast<ishara_status_t>(ctc_loss_launch(logits_dev, labels_dev, batch, frames, num_classes, max_label_len,
+                                                      blank, nll_dev, grad_dev, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_greedy_decode(const float* logits_dev, int32_t batch, int32_t frames, int32_t num_classes,
+                                     int32_t blank, int32_t* ids_dev, int32_t* lens_dev, void* stream) {
+  if (logits_dev == nullptr || ids_dev == nullptr || lens_dev == nullptr) {
+    set_last_error("greedy_decode: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  return static_cast<ishara_status_t>(greedy_decode_launch(logits_dev, batch, frames, num_classes, blank, ids_dev,
+                                                           lens_dev, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_gemm(const ishara_gemm_args_t* a, void* stream) {
+  if (a == nullptr || a->a == nullptr || a->wt == nullptr || a->out0 == nullptr) {
+    set_last_error("op_gemm: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  GemmPlan p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.block_n = a->block_n;
+  p.out_f32 = a->out_f32 != 0;
+  p.row_mode = a->row_mode != 0;
+  p.epi.bias = a->bias;
+  p.epi.gate = a->gate;
+  p.epi.rowtab = a->rowtab;
+  p.epi.resid = static_cast<const bf16*>(a->resid);
+  p.epi.ln0_g = a->ln0_g; p.epi.ln0_b = a->ln0_b; p.epi.ln0_eps = a->ln0_eps;
+  p.epi.ln1_g = a->ln1_g; p.epi.ln1_b = a->ln1_b; p.epi.ln1_eps = a->ln1_eps;
+  p.epi.rows_per_seq = a->rows_per_seq > 0 ? a->rows_per_seq : 1;
+  p.epi.act = a->act;
+  const int nfull = a->act == ACT_GLU ? a->N / 2 : a->N;
+  const int nout = (a->nout > 0 && a->nout <= nfull) ? a->nout : nfull;
+  p.epi.ld_resid = nout;
+  if ((a->ln0_g != nullptr || a->ln1_g != nullptr) && !p.row_mode) {
+    set_last_error("op_gemm: LayerNorm fusion needs row_mode");
+    return ISHARA_ERR_SHAPE;
+  }
+  if (a->ln1_g != nullptr && a->out1 == nullptr) {
+    set_last_error("op_gemm: ln1 needs out1");
+    return ISHARA_ERR_INVALID;
+  }
+  int rc = gemm_plan_init(&p, static_cast<const bf16*>(a->a), a->lda, static_cast<const bf16*>(a->wt), a->out0, nout, nout,
+                          static_cast<bf16*>(a->out1), nout);
+  if (rc) return static_cast<ishara_status_t>(rc);
+  int dev = 0, sms = 148;
+  CAPI_CUDA_OK(cudaGetDevice(&dev));
+  CAPI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return static_cast<ishara_status_t>(gemm_launch(p, sms, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_dwconv(const void* in_bf16, void* out_bf16, const float* w, const float* bias,
+                                 const float* eca_w, float* colsum, int32_t B, int32_t T, int32_t C, int32_t k,
+                                 int32_t pad_left, int32_t post, void* stream) {
+  if (in_bf16 == nullptr || out_bf16 == nullptr || w == nullptr) {
+    set_last_error("op_dwconv: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  DwConvArgs a;
+  a.in = static_cast<const bf16*>(in_bf16);
+  a.out = static_cast<bf16*>(out_bf16);
+  a.w = w; a.bias = bias; a.eca_w = eca_w; a.colsum = colsum;
+  a.B = B; a.T = T; a.C = C; a.k = k; a.pad_left = pad_left; a.post = post;
+  return static_cast<ishara_status_t>(dwconv_launch(a, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_attention(const void* qkv_bf16, void* out_bf16, const uint8_t* key_mask, int32_t B, int32_t T,
+                                    int32_t H, int32_t dh, float scale, void* stream) {
+  if (qkv_bf16 == nullptr || out_bf16 == nullptr) {
+    set_last_error("op_attention: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  AttnArgs a;
+  a.qkv = static_cast<const bf16*>(qkv_bf16);
+  a.out = static_cast<bf16*>(out_bf16);
+  a.key_mask = key_mask;
+  a.B = B; a.T = T; a.H = H; a.dh = dh; a.scale = scale;
+  return static_cast<ishara_status_t>(attention_launch(a, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_layernorm(const void* x_bf16, void* out_bf16, const float* gamma, const float* beta, float eps,
+                                    int64_t M, int32_t D, void* stream) {
+  if (x_bf16 == nullptr || out_bf16 == nullptr || gamma == nullptr || beta == nullptr) {
+    set_last_error("op_layernorm: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  return static_cast<ishara_status_t>(layernorm_launch(static_cast<const bf16*>(x_bf16), static_cast<bf16*>(out_bf16),
+                                                       gamma, beta, eps, M, D, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_cast_pad(const float* x, void* out_bf16, int64_t M, int32_t F, int32_t Fpad, void* stream) {
+  if (x == nullptr || out_bf16 == nullptr) {
+    set_last_error("op_cast_pad: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  return static_cast<ishara_status_t>(
+      cast_pad_launch(x, static_cast<bf16*>(out_bf16), M, F, Fpad, static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,323 @@
+// ishara_b200 — warp-level CTC loss (forward + gradient) and greedy CTC decode (sm_100a).
+//
+// CTC: CTCLoss (nb:conv-hybrid-model c6:1-13) = tf.nn.ctc_loss(labels, logits, label_length =
+// #(labels != blank), logit_length = T, blank_index = 59, logits_time_major=False); per-sequence
+// negative log-likelihood, log-softmax inside, no zero_infinity (infeasible => +inf). SURVEY.md §8a T13.
+// One warp per sequence; the S = 2L+1 extended states are blocked SPL-per-lane in registers, the
+// alpha/beta recursions run in fp32 log space, neighbours are exchanged with two shuffles per step.
+// The gradient (d nll / d logits = softmax - state occupancy) is produced in the beta sweep from
+// alphas parked in a global workspace.
+//
+// Decode: decode_phrase (c8:4-12): argmax over classes (first index on ties) -> keep position t only
+// if t < T-1 and ids[t] != ids[t+1] -> drop blanks. NOTE the reference quirk, reproduced on purpose:
+// the last run is never emitted because index T-1 is never selected.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ishara {
+namespace {
+
+constexpr float kLogZero = -1.0e30f;
+constexpr int kCtcWarps = 4;
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m <= 0.5f * kLogZero) return kLogZero;
+  return m + __logf(__expf(a - m) + __expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m <= 0.5f * kLogZero) return kLogZero;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+// dynamic smem per warp: lse[T] floats + occ[Vpad] floats
+template <int SPL>
+__global__ void __launch_bounds__(kCtcWarps * 32)
+ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
+           float* __restrict__ nll, float* __restrict__ grad, float* __restrict__ alpha_ws) {
+  extern __shared__ float smem_ctc[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kCtcWarps + warp;
+  if (b >= B) return;
+  const int Vpad = (V + 31) & ~31;
+  float* lse = smem_ctc + warp * (T + Vpad);
+  float* occ = lse + T;
+  const float* lg = logits + static_cast<size_t>(b) * T * V;
+  const int32_t* lab = labels + static_cast<size_t>(b) * L;
+
+  // label length = number of non-blank entries (reference: reduce_sum(labels != pad))
+  int cnt = 0;
+  for (int i = lane; i < L; i += 32) cnt += (lab[i] != blank) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const int Lb = cnt;
+  const int S = 2 * Lb + 1;
+
+  // per-lane extended states s = lane*SPL + i
+  int ext[SPL];
+  bool skip_fwd[SPL];  // alpha: transition from s-2 allowed
+  bool skip_bwd[SPL];  // beta: transition to s+2 allowed
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    int e = blank;
+    if (s < S && (s & 1)) e = lab[s >> 1];
+    ext[i] = e;
+    skip_fwd[i] = (s < S) && (s & 1) && (s >= 3) && (lab[s >> 1] != lab[(s >> 1) - 1]);
+    skip_bwd[i] = (s + 2 < S) && (s & 1) && (lab[(s >> 1) + 1] != lab[s >> 1]);
+  }
+
+  // log-sum-exp of every frame (parallel over t)
+  for (int t = lane; t < T; t += 32) {
+    const float* row = lg + static_cast<size_t>(t) * V;
+    float m = -INFINITY;
+    for (int v = 0; v < V; ++v) m = fmaxf(m, row[v]);
+    float z = 0.f;
+    for (int v = 0; v < V; ++v) z += __expf(row[v] - m);
+    lse[t] = m + __logf(z);
+  }
+  __syncwarp();
+
+  float* aw = alpha_ws != nullptr ? alpha_ws + static_cast<size_t>(b) * T * (32 * SPL) : nullptr;
+
+  // ---------------- alpha sweep ----------------
+  float a[SPL];
+  {
+    const float l0 = lse[0];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      const int s = lane * SPL + i;
+      a[i] = (s < 2 && s < S) ? lg[ext[i]] - l0 : kLogZero;
+    }
+    if (aw != nullptr) {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) aw[lane * SPL + i] = a[i];
+    }
+  }
+  float em_next[SPL];
+  if (T > 1) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) em_next[i] = lg[static_cast<size_t>(1) * V + ext[i]];
+  }
+  for (int t = 1; t < T; ++t) {
+    float em[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) em[i] = em_next[i];
+    if (t + 1 < T) {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) em_next[i] = lg[static_cast<size_t>(t + 1) * V + ext[i]];
+    }
+    const float lt = lse[t];
+    float up1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+    float up2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
+    if (lane == 0) { up1 = kLogZero; up2 = kLogZero; }
+    float na[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      const float p1 = (i >= 1) ? a[i - 1] : up1;
+      const float p2 = (i >= 2) ? a[i - 2] : (i == 1 ? up1 : up2);
+      // i == 0: (s-1, s-2) = (up1, up2); i == 1: (a[0], up1)
+      const float q1 = (i == 0) ? up1 : p1;
+      const float q2 = (i == 0) ? up2 : p2;
+      const float acc = skip_fwd[i] ? lse3(a[i], q1, q2) : lse2(a[i], q1);
+      const int s = lane * SPL + i;
+      na[i] = (s < S) ? acc + (em[i] - lt) : kLogZero;
+    }
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) a[i] = na[i];
+    if (aw != nullptr) {
+      float* dst = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) dst[i] = a[i];
+    }
+  }
+  // log p(l|x) = lse(alpha_T-1(S-1), alpha_T-1(S-2))
+  float fin = kLogZero;
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    if (s == S - 1 || (s == S - 2 && S >= 2)) fin = lse2(fin, a[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fin = lse2(fin, __shfl_xor_sync(0xffffffffu, fin, o));
+  const float logp = fin;
+  const bool feasible = logp > 0.5f * kLogZero;
+  if (lane == 0) nll[b] = feasible ? -logp : INFINITY;
+  if (grad == nullptr) return;
+
+  // ---------------- beta sweep + gradient ----------------
+  float* gr = grad + static_cast<size_t>(b) * T * V;
+  float bt[SPL];
+  for (int t = T - 1; t >= 0; --t) {
+    const float lt = lse[t];
+    float em[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) em[i] = lg[static_cast<size_t>(t) * V + ext[i]] - lt;
+    if (t == T - 1) {
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        const int s = lane * SPL + i;
+        bt[i] = (s == S - 1 || (s == S - 2 && S >= 2)) ? em[i] : kLogZero;
+      }
+    } else {
+      float dn1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+      float dn2 = __shfl_down_sync(0xffffffffu, bt[SPL > 1 ? 1 : 0], 1);
+      if (lane == 31) { dn1 = kLogZero; dn2 = kLogZero; }
+      float nb[SPL];
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        const float q1 = (i + 1 < SPL) ? bt[i + 1] : dn1;
+        const float q2 = (i + 2 < SPL) ? bt[i + 2] : (i + 1 < SPL ? dn1 : dn2);
+        const float acc = skip_bwd[i] ? lse3(bt[i], q1, q2) : lse2(bt[i], q1);
+        const int s = lane * SPL + i;
+        nb[i] = (s < S) ? acc + em[i] : kLogZero;
+      }
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) bt[i] = nb[i];
+    }
+    // occupancy: exp(alpha_t(s) + beta_t(s) - logy_t(ext s) - logp), scattered by class
+    for (int v = lane; v < Vpad; v += 32) occ[v] = 0.f;
+    __syncwarp();
+    if (feasible) {
+      const float* asrc = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        const int s = lane * SPL + i;
+        if (s < S) {
+          const float e = asrc[i] + bt[i] - em[i] - logp;
+          if (e > -80.f) atomicAdd(&occ[ext[i]], __expf(e));
+        }
+      }
+    }
+    __syncwarp();
+    for (int v = lane; v < V; v += 32) {
+      const float y = __expf(lg[static_cast<size_t>(t) * V + v] - lt);
+      gr[static_cast<size_t>(t) * V + v] = feasible ? (y - occ[v]) : __int_as_float(0x7fc00000);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy decode: one warp per sequence
+// ------------------------------------------------------------------------------------------------
+constexpr int kDecWarps = 4;
+__global__ void __launch_bounds__(kDecWarps * 32)
+greedy_decode_kernel(const float* __restrict__ logits, int B, int T, int V, int blank, int32_t* __restrict__ ids_out,
+                     int32_t* __restrict__ lens) {
+  extern __shared__ int32_t smem_dec[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kDecWarps + warp;
+  if (b >= B) return;
+  int32_t* ids = smem_dec + warp * (T + 1);
+  const float* lg = logits + static_cast<size_t>(b) * T * V;
+  for (int t = lane; t < T; t += 32) {
+    const float* row = lg + static_cast<size_t>(t) * V;
+    float best = row[0];
+    int bi = 0;
+    if ((V & 3) == 0) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      for (int v4 = 0; v4 < V / 4; ++v4) {
+        const float4 x = __ldg(r4 + v4);
+        if (x.x > best) { best = x.x; bi = 4 * v4; }
+        if (x.y > best) { best = x.y; bi = 4 * v4 + 1; }
+        if (x.z > best) { best = x.z; bi = 4 * v4 + 2; }
+        if (x.w > best) { best = x.w; bi = 4 * v4 + 3; }
+      }
+    } else {
+      for (int v = 1; v < V; ++v) {
+        const float x = __ldg(row + v);
+        if (x > best) { best = x; bi = v; }
+      }
+    }
+    ids[t] = bi;
+  }
+  __syncwarp();
+  int32_t* dst = ids_out + static_cast<size_t>(b) * T;
+  int total = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    bool keep = false;
+    int id = 0;
+    if (t < T - 1) {
+      id = ids[t];
+      keep = (id != ids[t + 1]) && (id != blank);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) dst[total + __popc(m & ((1u << lane) - 1u))] = id;
+    total += __popc(m);
+  }
+  // pad the tail with -1 so the buffer is deterministic
+  for (int i = total + lane; i < T; i += 32) dst[i] = -1;
+  if (lane == 0) lens[b] = total;
+}
+
+float* g_alpha_ws = nullptr;
+size_t g_alpha_ws_bytes = 0;
+
+}  // namespace
+
+int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, int V, int L, int blank, float* nll,
+                    float* grad, cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || V <= 0 || L < 0 || blank < 0 || blank >= V) {
+    set_last_error("ctc_loss: bad shape");
+    return 2;
+  }
+  const int spl = (2 * L + 1 + 31) / 32;
+  const int Vpad = (V + 31) & ~31;
+  const size_t smem = static_cast<size_t>(kCtcWarps) * (T + Vpad) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_last_error("ctc_loss: T too large for the per-warp frame table");
+    return 2;
+  }
+  const int SPL = spl <= 5 ? 5 : 9;
+  if (spl > 9) {
+    set_last_error("ctc_loss: label length above 143 is not supported");
+    return 2;
+  }
+  float* ws = nullptr;
+  if (grad != nullptr) {
+    const size_t need = static_cast<size_t>(B) * T * 32 * SPL * sizeof(float);
+    if (need > g_alpha_ws_bytes) {
+      if (g_alpha_ws != nullptr) ISHARA_CUDA_OK(cudaFree(g_alpha_ws));
+      g_alpha_ws = nullptr;
+      g_alpha_ws_bytes = 0;
+      ISHARA_CUDA_OK(cudaMalloc(&g_alpha_ws, need));
+      g_alpha_ws_bytes = need;
+    }
+    ws = g_alpha_ws;
+  }
+  const int grid = (B + kCtcWarps - 1) / kCtcWarps;
+  if (SPL == 5) {
+    auto kern = ctc_kernel<5>;
+    if (smem > 48 * 1024)
+      ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kCtcWarps * 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
+  } else {
+    auto kern = ctc_kernel<9>;
+    if (smem > 48 * 1024)
+      ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kCtcWarps * 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
+  }
+  ISHARA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int greedy_decode_launch(const float* logits, int B, int T, int V, int blank, int32_t* ids_out, int32_t* lens,
+                         cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || V <= 0) {
+    set_last_error("greedy_decode: bad shape");
+    return 2;
+  }
+  const size_t smem = static_cast<size_t>(kDecWarps) * (T + 1) * sizeof(int32_t);
+  const int grid = (B + kDecWarps - 1) / kDecWarps;
+  if (smem > 48 * 1024)
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(greedy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+  greedy_decode_kernel<<<grid, kDecWarps * 32, smem, stream>>>(logits, B, T, V, blank, ids_out, lens);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ishara

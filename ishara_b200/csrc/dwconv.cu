@@ -1,0 +1,235 @@
+// ishara_b200 — depthwise temporal Conv1D over a whole sequence per CTA (memory-bound, sm_100a).
+//
+// Covers the three depthwise convolutions of the get_model path (SURVEY.md §8a T4,T5,T8,T11):
+//   * Conv1DBlock:   CausalDWConv1D(k=11/5/3) -> BatchNorm -> ECA      (nb:conv-hybrid-model c5:17-39,73,1-15)
+//   * Squeezeformer: CausalDWConv1D(k=15) -> swish, + column sums for SqueezeExcite (c5:141,149-150,120-133)
+//   * Conformer:     Conv1D(k=15,'same',groups=D,+bias) -> BatchNorm   (c5:265-271,298-301)
+// BatchNorm (inference) is folded into the taps/bias by the caller.
+//
+// Layout: activations are [B, T, C] bf16 channels-last. One CTA owns (sequence b, 64-channel slab):
+// the T x 64 tile (128 B per row) is staged once in shared memory with its zero halo rows, every
+// lane owns one bf16x2 channel pair (conflict-free 4-byte smem reads, 128-byte coalesced stores) and
+// slides a register window down its time range. Because the whole T axis of the slab lives in the
+// CTA, the global-average-pool that ECA needs is a CTA-local reduction; the 5-tap conv across the
+// CHANNEL axis needs two channels from each neighbouring slab, which are exchanged through
+// distributed shared memory: the C/64 CTAs of one sequence form one thread-block cluster.
+#include <cooperative_groups.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ishara {
+namespace {
+
+constexpr int kSlab = 64;    // channels per CTA
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTB = 8;       // outputs per register block
+
+__device__ __forceinline__ float exact_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <int K, int POST>
+__global__ void __launch_bounds__(kThreads)
+dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ w,
+              const float* __restrict__ bias, const float* __restrict__ eca_w, float* __restrict__ colsum, int T,
+              int C, int pad_left, int rows_alloc) {
+  extern __shared__ __align__(16) uint8_t smem_dw[];
+  uint32_t* tile = reinterpret_cast<uint32_t*>(smem_dw);           // [rows_alloc][32] bf16x2
+  float* red = reinterpret_cast<float*>(tile + rows_alloc * 32);   // [kWarps][64]
+  float* mean_s = red + kWarps * kSlab;                            // [64] (+ scale reuse)
+
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * kSlab;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- stage the slab: smem row r holds input row (r - pad_left); zero outside [0, T) ----
+  const bf16* src = in + (static_cast<size_t>(b) * T) * C + c0;
+  for (int i = tid; i < rows_alloc * 8; i += kThreads) {
+    const int r = i >> 3, ch = i & 7;
+    const int t = r - pad_left;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(t) * C) + ch);
+    reinterpret_cast<uint4*>(tile)[i] = v;
+  }
+
+  // taps for this lane's channel pair
+  float2 wt[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wt[j] = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(j) * C + c0) + lane);
+  float2 bs = make_float2(0.f, 0.f);
+  if (bias != nullptr) bs = __ldg(reinterpret_cast<const float2*>(bias + c0) + lane);
+  __syncthreads();
+
+  const int rows_per_warp = ((T + kWarps - 1) / kWarps + kTB - 1) / kTB * kTB;
+  const int t_begin = warp * rows_per_warp;
+  const int t_end = min(T, t_begin + rows_per_warp);
+
+  float2 scale = make_float2(1.f, 1.f);
+  if constexpr (POST == 2) {
+    // ---- ECA: mean over T of y = conv + bias, then 5-tap conv over channels, sigmoid ----
+    float2 s = make_float2(0.f, 0.f);
+    for (int t0 = t_begin; t0 < t_end; t0 += kTB) {
+      float2 x[kTB + K - 1];
+#pragma unroll
+      for (int i = 0; i < kTB + K - 1; ++i) {
+        const uint32_t u = tile[(t0 + i) * 32 + lane];
+        x[i] = make_float2(bf16_lo(u), bf16_hi(u));
+      }
+#pragma unroll
+      for (int i = 0; i < kTB; ++i) {
+        if (t0 + i < t_end) {
+          float2 a = bs;
+#pragma unroll
+          for (int j = 0; j < K; ++j) { a.x = fmaf(wt[j].x, x[i + j].x, a.x); a.y = fmaf(wt[j].y, x[i + j].y, a.y); }
+          s.x += a.x; s.y += a.y;
+        }
+      }
+    }
+    red[warp * kSlab + 2 * lane] = s.x;
+    red[warp * kSlab + 2 * lane + 1] = s.y;
+    __syncthreads();
+    if (tid < kSlab) {
+      float m = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kWarps; ++wv) m += red[wv * kSlab + tid];
+      mean_s[tid] = m / static_cast<float>(T);
+    }
+    // exchange slab-edge means with the neighbouring slabs of the same sequence (DSMEM)
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (tid < kSlab) {
+      const int rank = static_cast<int>(cluster.block_rank());
+      const int nrank = static_cast<int>(cluster.num_blocks());
+      float acc = 0.f;
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int c = tid + d;  // channel within this slab, may spill into a neighbour
+        float mv = 0.f;
+        if (c >= 0 && c < kSlab) {
+          mv = mean_s[c];
+        } else if (c < 0 && rank > 0) {
+          mv = cluster.map_shared_rank(mean_s, rank - 1)[c + kSlab];
+        } else if (c >= kSlab && rank + 1 < nrank) {
+          mv = cluster.map_shared_rank(mean_s, rank + 1)[c - kSlab];
+        }
+        acc = fmaf(__ldg(eca_w + d + 2), mv, acc);
+      }
+      red[tid] = exact_sigmoid(acc);  // red[0..63] reused for the per-channel scale
+    }
+    cluster.sync();  // neighbours finished reading mean_s; red[] visible to the CTA
+    scale = make_float2(red[2 * lane], red[2 * lane + 1]);
+  }
+
+  // ---- main pass ----
+  bf16* dst = out + (static_cast<size_t>(b) * T) * C + c0;
+  float2 cs = make_float2(0.f, 0.f);
+  for (int t0 = t_begin; t0 < t_end; t0 += kTB) {
+    float2 x[kTB + K - 1];
+#pragma unroll
+    for (int i = 0; i < kTB + K - 1; ++i) {
+      const uint32_t u = tile[(t0 + i) * 32 + lane];
+      x[i] = make_float2(bf16_lo(u), bf16_hi(u));
+    }
+#pragma unroll
+    for (int i = 0; i < kTB; ++i) {
+      if (t0 + i < t_end) {
+        float2 a = bs;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { a.x = fmaf(wt[j].x, x[i + j].x, a.x); a.y = fmaf(wt[j].y, x[i + j].y, a.y); }
+        if constexpr (POST == 1) { a.x = a.x * exact_sigmoid(a.x); a.y = a.y * exact_sigmoid(a.y); }
+        if constexpr (POST == 2) { a.x *= scale.x; a.y *= scale.y; }
+        const uint32_t packed = pack_bf16x2(a.x, a.y);
+        reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(t0 + i) * C)[lane] = packed;
+        cs.x += bf16_lo(packed); cs.y += bf16_hi(packed);
+      }
+    }
+  }
+  if (colsum != nullptr) {
+    __syncthreads();  // red[] free again (POST==2 consumers are done: scale already in registers)
+    red[warp * kSlab + 2 * lane] = cs.x;
+    red[warp * kSlab + 2 * lane + 1] = cs.y;
+    __syncthreads();
+    if (tid < kSlab) {
+      float m = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kWarps; ++wv) m += red[wv * kSlab + tid];
+      colsum[static_cast<size_t>(b) * C + c0 + tid] = m;
+    }
+  }
+}
+
+template <int K, int POST>
+int launch_inst(const DwConvArgs& a, cudaStream_t stream) {
+  const int rows_per_warp = ((a.T + kWarps - 1) / kWarps + kTB - 1) / kTB * kTB;
+  const int rows_alloc = rows_per_warp * kWarps + K - 1;
+  const size_t smem = static_cast<size_t>(rows_alloc) * 128 + (kWarps * kSlab + kSlab) * sizeof(float);
+  auto kern = dwconv_kernel<K, POST>;
+  static size_t smem_attr = 0;
+  if (smem > smem_attr) {
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_attr = smem;
+  }
+  const int slabs = a.C / kSlab;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(slabs, a.B, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int nattr = 0;
+  if (POST == 2) {
+    if (slabs > 16) {
+      set_last_error("dwconv: ECA needs C/64 <= 16 (one cluster per sequence)");
+      return 2;
+    }
+    if (slabs > 8) ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = slabs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    nattr = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  ISHARA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a.in, a.out, a.w, a.bias, a.eca_w, a.colsum, a.T, a.C, a.pad_left,
+                                    rows_alloc));
+  return 0;
+}
+
+template <int K>
+int launch_k(const DwConvArgs& a, cudaStream_t stream) {
+  switch (a.post) {
+    case 0: return launch_inst<K, 0>(a, stream);
+    case 1: return launch_inst<K, 1>(a, stream);
+    case 2: return launch_inst<K, 2>(a, stream);
+  }
+  set_last_error("dwconv: bad post mode");
+  return 2;
+}
+
+}  // namespace
+
+int dwconv_launch(const DwConvArgs& a, cudaStream_t stream) {
+  if (a.C % kSlab != 0 || a.T < a.k || a.B <= 0) {
+    set_last_error("dwconv: C must be a multiple of 64 and T >= k");
+    return 2;
+  }
+  if (a.post == 2 && a.eca_w == nullptr) {
+    set_last_error("dwconv: ECA post-op needs eca_w");
+    return 2;
+  }
+  switch (a.k) {
+    case 3: return launch_k<3>(a, stream);
+    case 5: return launch_k<5>(a, stream);
+    case 7: return launch_k<7>(a, stream);
+    case 9: return launch_k<9>(a, stream);
+    case 11: return launch_k<11>(a, stream);
+    case 15: return launch_k<15>(a, stream);
+  }
+  set_last_error("dwconv: unsupported kernel size (3,5,7,9,11,15)");
+  return 2;
+}
+
+}  // namespace ishara

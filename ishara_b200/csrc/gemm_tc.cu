@@ -1,0 +1,514 @@
+// ishara_b200 — tcgen05/TMEM GEMM with fused epilogues (sm_100a only).
+//
+// Serves every dense contraction on the get_model hot path (SURVEY.md §8a T2,T3,T6-T12): Dense /
+// 1x1-conv layers of the reference (nb:conv-hybrid-model c5:61-65,77-80,97-99,140-142,163-165,
+// 258-278; c7:14,61-63) become  out = epilogue(A[M,K] @ Wt[N,K]^T)  with M = B*T rows.
+//
+// Structure (one persistent CTA per SM, 384 threads):
+//   warp 0      TMA producer   : A tile 128x64 and W tile BNx64 (bf16, 128B swizzle) -> smem ring
+//   warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, fp32 accum in TMEM
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue group 0  (even tiles, TMEM buffer 0)
+//   warps 8-11  epilogue group 1  (odd tiles,  TMEM buffer 1)
+// The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of tile
+// i+1. Each epilogue thread owns one output row (tcgen05.ld 32x32b: lane == row), which makes the
+// LayerNorm statistics of a full 256-wide row thread-local: the residual add and up to two chained
+// LayerNorms are fused here and the normalised copy for the next GEMM is produced in the same
+// pass (values parked in TMEM between passes with tcgen05.st). Output leaves through swizzled
+// staging tiles and TMA stores.
+#include <cstdio>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ishara {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kAStageBytes = kBM * kBK * 2;
+constexpr int kStgBytes = 128 * 128;  // one staging tile: 128 rows x 128 bytes
+constexpr int kNumStg = 4;            // 2 per epilogue group
+
+__host__ __device__ constexpr int gemm_stages(int bn) { return bn >= 256 ? 3 : 4; }
+__host__ __device__ constexpr int gemm_stage_bytes(int bn) { return kAStageBytes + bn * kBK * 2; }
+__host__ __device__ constexpr int gemm_smem_bytes(int bn) {
+  return gemm_stages(bn) * gemm_stage_bytes(bn) + kNumStg * kStgBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+}
+
+struct EpiThread {
+  int row;        // global row
+  int r;          // row within tile (0..127)
+  bool valid;     // row < M
+  int seq;        // row / rows_per_seq
+  int t;          // row % rows_per_seq
+  uint32_t taddr; // TMEM address of (lane quarter, buffer col 0)
+};
+
+// v[j] = epilogue-input for 32 consecutive columns starting at global column `col0`
+__device__ __forceinline__ void epi_affine(float (&v)[32], const GemmEpi& ep, const EpiThread& th, int col0,
+                                           int ldn) {
+  if (ep.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (ep.gate != nullptr && th.valid) {
+    const float4* g4 = reinterpret_cast<const float4*>(ep.gate + static_cast<size_t>(th.seq) * ldn + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 g = __ldg(g4 + j);
+      v[4 * j + 0] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
+    }
+  }
+  if (ep.rowtab != nullptr && th.valid) {
+    const float4* t4 = reinterpret_cast<const float4*>(ep.rowtab + static_cast<size_t>(th.t) * ldn + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 g = __ldg(t4 + j);
+      v[4 * j + 0] += g.x; v[4 * j + 1] += g.y; v[4 * j + 2] += g.z; v[4 * j + 3] += g.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_resid(float (&v)[32], const GemmEpi& ep, const EpiThread& th, int col0) {
+  if (ep.resid != nullptr && th.valid) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(ep.resid + static_cast<size_t>(th.row) * ep.ld_resid + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 q = __ldg(r4 + j);
+      v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
+      v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
+      v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
+      v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_layernorm(float (&v)[32], const float* g, const float* b, float mean,
+                                              float rstd, int col0) {
+  const float4* g4 = reinterpret_cast<const float4*>(g + col0);
+  const float4* b4 = reinterpret_cast<const float4*>(b + col0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 gg = __ldg(g4 + j), bb = __ldg(b4 + j);
+    v[4 * j + 0] = fmaf((v[4 * j + 0] - mean) * rstd, gg.x, bb.x);
+    v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, gg.y, bb.y);
+    v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, gg.z, bb.z);
+    v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, gg.w, bb.w);
+  }
+}
+
+// write 32 values of this thread's row into the swizzled staging tile (128-byte rows, 16-byte chunks
+// XOR-ed with row%8 — identical to CU_TENSOR_MAP_SWIZZLE_128B, so the TMA store un-swizzles it).
+template <bool F32>
+__device__ __forceinline__ void stage_write(uint32_t stg, int r, int sub, const float (&v)[32]) {
+  const uint32_t rowbase = stg + static_cast<uint32_t>(r) * 128u;
+  const uint32_t x = static_cast<uint32_t>(r & 7);
+  if constexpr (F32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(rowbase + ((static_cast<uint32_t>(j) ^ x) << 4), __float_as_uint(v[4 * j + 0]),
+                   __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st_shared_v4(rowbase + ((static_cast<uint32_t>(sub * 4 + j) ^ x) << 4), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
+                   pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                   pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+// Staging/TMA-store protocol for one epilogue group (128 threads, named barrier `bar_id`).
+struct StoreRing {
+  uint32_t stg_base;  // smem address of this group's two staging tiles
+  uint32_t iter;      // running chunk counter (selects the buffer)
+  uint32_t bar_id;
+  bool leader;
+  __device__ __forceinline__ uint32_t acquire() {
+    if (leader) tma_store_wait_read<1>();  // the store that last used this buffer has drained
+    named_bar_sync(bar_id, 128);
+    return stg_base + (iter & 1u) * kStgBytes;
+  }
+  __device__ __forceinline__ void release(const CUtensorMap* tm, uint32_t buf, int c0, int c1) {
+    fence_proxy_async_smem();
+    named_bar_sync(bar_id, 128);
+    if (leader) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                       reinterpret_cast<uint64_t>(tm)),
+                   "r"(buf), "r"(c0), "r"(c1)
+                   : "memory");
+      tma_store_commit();
+    }
+    ++iter;
+  }
+};
+
+template <int BN, bool ROW, bool OUT_F32>
+__global__ void __launch_bounds__(384, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+               const GemmEpi ep, int M, int N, int K, int num_m_tiles, int num_n_tiles) {
+  constexpr int STAGES = gemm_stages(BN);
+  constexpr int STAGE_BYTES = gemm_stage_bytes(BN);
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr uint32_t IDESC = umma_idesc(kBM, BN, /*bf16*/ 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  uint8_t* stage_ptr = smem;
+  uint8_t* stg_ptr = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_ptr + kNumStg * kStgBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_kb = K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO0);
+    if (ep.ln1_g != nullptr) tma_prefetch_desc(&tmO1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 128);
+    mbar_init(&tempty[1], 128);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* sa = stage_ptr + stage * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_tile * kBM);
+          tma_load_2d(sa + kAStageBytes, &tmB, &full[stage], kb * kBK, n_tile * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + kAStageBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
+            umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull[buf]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue groups =====================
+    const int g = (warp - 4) >> 2;  // 0 | 1
+    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    StoreRing ring;
+    ring.stg_base = smem_u32(stg_ptr) + g * 2 * kStgBytes;
+    ring.iter = 0;
+    ring.bar_id = 1 + g;
+    ring.leader = ((threadIdx.x - 128) & 127) == 0;
+
+    constexpr int OC = BN;               // tile output columns before GLU halving
+    constexpr int CH = OUT_F32 ? 32 : 64;  // output columns per staging tile
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != g) continue;
+      const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+      EpiThread th;
+      th.r = q * 32 + lane;
+      th.row = m_tile * kBM + th.r;
+      th.valid = th.row < M;
+      th.seq = th.valid ? th.row / ep.rows_per_seq : 0;
+      th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
+      th.taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+      mbar_wait(&tfull[g], (it >> 1) & 1);
+      tc_fence_after();
+
+      float v[32];
+      uint32_t raw[32];
+
+      if constexpr (!ROW) {
+        // ---- single pass: bias / gate / rowtab / act / resid -> out0 ----
+        const bool glu = ep.act == ACT_GLU;
+        const int oc = glu ? OC / 2 : OC;
+        for (int c0 = 0; c0 < oc; c0 += CH) {
+          const uint32_t buf = ring.acquire();
+#pragma unroll 1
+          for (int sub = 0; sub < CH / 32; ++sub) {
+            const int tc = c0 + sub * 32;  // tmem column (a-half for GLU)
+            tmem_ld32(th.taddr + tc, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            epi_affine(v, ep, th, n_tile * BN + tc, N);
+            if (glu) {
+              float u[32];
+              tmem_ld32(th.taddr + oc + tc, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(raw[j]);
+              epi_affine(u, ep, th, n_tile * BN + oc + tc, N);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(u[j]);
+            } else if (ep.act == ACT_SWISH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fast_swish(v[j]);
+            } else if (ep.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            epi_resid(v, ep, th, n_tile * oc + tc);
+            stage_write<OUT_F32>(buf, th.r, sub, v);
+          }
+          ring.release(&tmO0, buf, n_tile * oc + c0, m_tile * kBM);
+        }
+      } else {
+        // ---- full-row epilogue: (resid add) -> [LN0] -> out0 -> [LN1 -> out1] ----
+        const bool ln0 = ep.ln0_g != nullptr, ln1 = ep.ln1_g != nullptr;
+        float sum = 0.f, sq = 0.f;
+        // pass A: v = epi(acc); stats; park in TMEM if a later pass needs it; emit out0 unless LN0 pending
+        for (int c0 = 0; c0 < OC; c0 += CH) {
+          uint32_t buf = 0;
+          if (!ln0) buf = ring.acquire();
+#pragma unroll 1
+          for (int sub = 0; sub < CH / 32; ++sub) {
+            const int tc = c0 + sub * 32;
+            tmem_ld32(th.taddr + tc, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            epi_affine(v, ep, th, tc, N);
+            if (ep.act == ACT_SWISH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fast_swish(v[j]);
+            }
+            epi_resid(v, ep, th, tc);
+            if (ln0 || ln1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { sum += v[j]; sq = fmaf(v[j], v[j], sq); }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(v[j]);
+              tmem_st32(th.taddr + tc, raw);
+            }
+            if (!ln0) stage_write<OUT_F32>(buf, th.r, sub, v);
+          }
+          if (!ln0) ring.release(&tmO0, buf, c0, m_tile * kBM);
+        }
+        if (ln0 || ln1) tmem_st_wait();
+        if (ln0) {
+          // pass B: u = LN0(v) -> out0; stats of u for LN1
+          const float mean = sum * (1.f / OC);
+          const float var = fmaxf(sq * (1.f / OC) - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + ep.ln0_eps);
+          sum = 0.f; sq = 0.f;
+          for (int c0 = 0; c0 < OC; c0 += CH) {
+            const uint32_t buf = ring.acquire();
+#pragma unroll 1
+            for (int sub = 0; sub < CH / 32; ++sub) {
+              const int tc = c0 + sub * 32;
+              tmem_ld32(th.taddr + tc, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+              epi_layernorm(v, ep.ln0_g, ep.ln0_b, mean, rstd, tc);
+              if (ln1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { sum += v[j]; sq = fmaf(v[j], v[j], sq); }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(v[j]);
+                tmem_st32(th.taddr + tc, raw);
+              }
+              stage_write<OUT_F32>(buf, th.r, sub, v);
+            }
+            ring.release(&tmO0, buf, c0, m_tile * kBM);
+          }
+          if (ln1) tmem_st_wait();
+        }
+        if (ln1) {
+          // pass C: out1 = bf16(LN1(stream))
+          const float mean = sum * (1.f / OC);
+          const float var = fmaxf(sq * (1.f / OC) - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + ep.ln1_eps);
+          for (int c0 = 0; c0 < OC; c0 += 64) {
+            const uint32_t buf = ring.acquire();
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+              const int tc = c0 + sub * 32;
+              tmem_ld32(th.taddr + tc, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+              epi_layernorm(v, ep.ln1_g, ep.ln1_b, mean, rstd, tc);
+              stage_write<false>(buf, th.r, sub, v);
+            }
+            ring.release(&tmO1, buf, c0, m_tile * kBM);
+          }
+        }
+      }
+      // this tile's accumulator buffer may be overwritten by the MMA warp now
+      tc_fence_before();
+      mbar_arrive(&tempty[g]);
+    }
+    if (ring.leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <int BN, bool ROW, bool OUT_F32>
+int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
+  auto kern = gemm_tc_kernel<BN, ROW, OUT_F32>;
+  static bool attr_set = false;
+  const int smem = gemm_smem_bytes(BN);
+  if (!attr_set) {
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int mt = (p.M + kBM - 1) / kBM;
+  const int nt = p.N / BN;
+  int grid = mt * nt;
+  if (grid > num_sms) grid = num_sms;
+  kern<<<grid, 384, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.epi, p.M, p.N, p.K, mt, nt);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return 3;
+  }
+  const uint32_t es = dt == TM_BF16 ? 2 : 4;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld_elems * es};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const uint32_t inner = box_cols * es;
+  CUtensorMapSwizzle sw = inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (gstr[0] & 15) != 0) {
+    set_last_error("make_tmap_2d: base/pitch not 16-byte aligned");
+    return 2;
+  }
+  CUresult r = fn(out, dt == TM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed, CUresult " + std::to_string(static_cast<int>(r)) + " rows " +
+                   std::to_string(rows) + " cols " + std::to_string(cols) + " ld " + std::to_string(ld_elems) +
+                   " box " + std::to_string(box_rows) + "x" + std::to_string(box_cols));
+    return 3;
+  }
+  return 0;
+}
+
+int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* out0, int ldo0, int nout, bf16* out1,
+                   int ldo1) {
+  if (p->K % kBK != 0 || p->N % p->block_n != 0) {
+    set_last_error("gemm_plan_init: K must be a multiple of 64 and N a multiple of block_n");
+    return 2;
+  }
+  if (p->row_mode && p->N != p->block_n) {
+    set_last_error("gemm_plan_init: row_mode needs N == block_n");
+    return 2;
+  }
+  int rc;
+  if ((rc = make_tmap_2d(&p->tmA, A, TM_BF16, p->M, p->K, lda, kBM, kBK))) return rc;
+  if ((rc = make_tmap_2d(&p->tmB, Wt, TM_BF16, p->N, p->K, p->K, p->block_n, kBK))) return rc;
+  if (p->out_f32) {
+    if ((rc = make_tmap_2d(&p->tmO0, out0, TM_F32, p->M, nout, ldo0, kBM, 32))) return rc;
+  } else {
+    if ((rc = make_tmap_2d(&p->tmO0, out0, TM_BF16, p->M, nout, ldo0, kBM, 64))) return rc;
+  }
+  if (out1 != nullptr) {
+    if ((rc = make_tmap_2d(&p->tmO1, out1, TM_BF16, p->M, nout, ldo1, kBM, 64))) return rc;
+  } else {
+    p->tmO1 = p->tmO0;
+  }
+  return 0;
+}
+
+int gemm_launch(const GemmPlan& p, int num_sms, cudaStream_t stream) {
+  if (p.row_mode) {
+    if (p.block_n == 256 && !p.out_f32) return launch_inst<256, true, false>(p, num_sms, stream);
+    if (p.block_n == 128 && !p.out_f32) return launch_inst<128, true, false>(p, num_sms, stream);
+  } else {
+    if (p.block_n == 256 && !p.out_f32) return launch_inst<256, false, false>(p, num_sms, stream);
+    if (p.block_n == 128 && !p.out_f32) return launch_inst<128, false, false>(p, num_sms, stream);
+    if (p.block_n == 64 && !p.out_f32) return launch_inst<64, false, false>(p, num_sms, stream);
+    if (p.block_n == 64 && p.out_f32) return launch_inst<64, false, true>(p, num_sms, stream);
+  }
+  set_last_error("gemm_launch: unsupported (block_n, row_mode, out_f32) combination");
+  return 2;
+}
+
+}  // namespace ishara

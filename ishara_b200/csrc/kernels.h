@@ -1,0 +1,132 @@
+// ishara_b200 — internal launcher interface between the model runtime (model.cu / capi.cu) and the
+// sm_100a kernels. Not part of the public C ABI (that is include/ishara_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+namespace ishara {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+#define ISHARA_CUDA_OK(expr)                                                                           \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      ::ishara::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +  \
+                               ":" + std::to_string(__LINE__) + ")");                                  \
+      return 3; /* ISHARA_ERR_CUDA */                                                                  \
+    }                                                                                                  \
+  } while (0)
+
+// ---- TMA tensor maps --------------------------------------------------------------------------
+enum TmapDtype { TM_BF16 = 0, TM_F32 = 1 };
+// 2-D row-major tensor [rows, cols] with row pitch `ld_elems`; box = [box_rows, box_cols];
+// 128-byte swizzle when box_cols*elemsize == 128, 64-byte swizzle when == 64.
+int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t rows, uint64_t cols,
+                 uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+
+// ---- tcgen05 GEMM ------------------------------------------------------------------------------
+enum GemmAct { ACT_NONE = 0, ACT_SWISH = 1, ACT_RELU = 2, ACT_GLU = 3 };
+
+// out0[M, Nout] = f( A[M,K] @ Wt[N,K]^T ), f assembled from the non-null fields, in this order:
+//   v = acc + bias[n]; v *= gate[row / rows_per_seq][n]; v += rowtab[row % rows_per_seq][n];
+//   v = act(v)  (GLU: v = a * sigmoid(b), a/b = the two halves of the N-tile; Nout = N/2);
+//   v += resid[row][n];
+//   if ln0: v = LN(v; ln0_g, ln0_b, ln0_eps)        (needs the full row in one tile: N == block_n)
+//   out0 = v (bf16 or fp32)
+//   if ln1: out1 = bf16( LN(v; ln1_g, ln1_b, ln1_eps) )
+struct GemmEpi {
+  const float* bias = nullptr;
+  const float* gate = nullptr;
+  const float* rowtab = nullptr;
+  const bf16* resid = nullptr;
+  const float* ln0_g = nullptr;
+  const float* ln0_b = nullptr;
+  const float* ln1_g = nullptr;
+  const float* ln1_b = nullptr;
+  float ln0_eps = 0.f, ln1_eps = 0.f;
+  int rows_per_seq = 1;
+  int ld_resid = 0;
+  int act = ACT_NONE;
+};
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB, tmO0, tmO1;
+  GemmEpi epi;
+  int M = 0, N = 0, K = 0;  // N = packed weight rows (MMA N extent), K multiple of 64
+  int block_n = 256;        // 64 | 128 | 256
+  bool out_f32 = false;
+  bool row_mode = false;    // full-row epilogue (LN capable); requires N == block_n
+};
+
+// Fill tensor maps of a plan. A [M,K] bf16 (ld = lda), Wt [N,K] bf16 (ld = K),
+// out0 [M,Nout] (bf16|f32, ld = ldo0), out1 [M,Nout] bf16 (ld = ldo1) or null.
+int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* out0, int ldo0, int nout,
+                   bf16* out1, int ldo1);
+int gemm_launch(const GemmPlan& p, int num_sms, cudaStream_t stream);
+
+// ---- depthwise temporal convolution over a whole sequence per CTA ---------------------------
+// in/out [B, T, C] bf16 channels-last. y[t,c] = post( sum_j w[j,c] * in[t - pad_left + j, c] + bias[c] )
+// (zeros outside [0,T)); BatchNorm is folded into w/bias by the caller.
+//   post: 0 none, 1 swish, 2 ECA: y *= sigmoid( conv1d_k5_same over channels of mean_t(y) )
+// colsum (optional): [B, C] fp32 = sum_t of the post-activated output (bf16-rounded values).
+struct DwConvArgs {
+  const bf16* in = nullptr;
+  bf16* out = nullptr;
+  const float* w = nullptr;     // [k, C] fp32
+  const float* bias = nullptr;  // [C] fp32 or null
+  const float* eca_w = nullptr; // [5] fp32 (post == 2)
+  float* colsum = nullptr;      // [B, C] or null
+  int B = 0, T = 0, C = 0, k = 0, pad_left = 0, post = 0;
+};
+int dwconv_launch(const DwConvArgs& a, cudaStream_t stream);
+
+// ---- attention -------------------------------------------------------------------------------
+// qkv [B*T, 3*D] bf16, per-head interleaved columns [h][q|k|v][dh]; out [B*T, D] bf16 (head-major).
+// softmax(q k^T * scale + maskbias) v ; key_mask [B,T] uint8 (1 = keep) or null.
+struct AttnArgs {
+  const bf16* qkv = nullptr;
+  bf16* out = nullptr;
+  const uint8_t* key_mask = nullptr;
+  int B = 0, T = 0, H = 0, dh = 0;
+  float scale = 1.f;
+};
+int attention_launch(const AttnArgs& a, cudaStream_t stream);
+
+// ---- small memory-bound kernels ---------------------------------------------------------------
+// x fp32 [M, F] -> bf16 [M, Fpad] (zero pad)
+int cast_pad_launch(const float* x, bf16* out, int64_t M, int F, int Fpad, cudaStream_t stream);
+// SE gate from column sums (linearity of the 1x1 conv): gate[b,:] = sigmoid(fc2(swish(fc1(mean @ W3 + b3))))
+struct SeGateArgs {
+  const float* colsum = nullptr;  // [B, C]
+  const bf16* w3t = nullptr;      // [D, C] bf16 (packed, K-major)
+  const float* b3 = nullptr;      // [D]
+  const float* fc1_w = nullptr;   // [D, R] fp32
+  const float* fc1_b = nullptr;   // [R]
+  const float* fc2_w = nullptr;   // [R, D] fp32
+  const float* fc2_b = nullptr;   // [D]
+  float* gate = nullptr;          // [B, D]
+  int B = 0, C = 0, D = 0, R = 0;
+  float inv_T = 1.f;
+};
+int se_gate_launch(const SeGateArgs& a, cudaStream_t stream);
+// standalone LayerNorm (fallback / operator-level use): x bf16 [M, D] -> bf16
+int layernorm_launch(const bf16* x, bf16* out, const float* g, const float* b, float eps, int64_t M, int D,
+                     cudaStream_t stream);
+
+// ---- CTC + greedy decode ----------------------------------------------------------------------
+// logits fp32 [B,T,V]; labels int32 [B,L] padded with `blank`; nll [B]; grad [B,T,V] or null
+// (grad = d nll_b / d logits, unreduced).
+int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, int V, int L, int blank, float* nll,
+                    float* grad, cudaStream_t stream);
+// ids_out int32 [B, T] (first lens[b] valid), lens int32 [B]; reproduces the reference decode_phrase quirk.
+int greedy_decode_launch(const float* logits, int B, int T, int V, int blank, int32_t* ids_out, int32_t* lens,
+                         cudaStream_t stream);
+
+}  // namespace ishara

@@ -1,0 +1,144 @@
+// ishara_b200 — small memory-bound helpers: input cast/pad, SqueezeExcite gate, standalone LayerNorm.
+#include <mutex>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ishara {
+
+// ---- error plumbing (thread-local message, returned by ishara_last_error) ----
+static thread_local std::string tls_error;
+void set_last_error(const std::string& msg) { tls_error = msg; }
+const char* get_last_error() { return tls_error.c_str(); }
+
+namespace {
+
+// x fp32 [M, F] -> bf16 [M, Fpad], zero padded. One warp per row chunk; F*4 bytes per row is 16B aligned
+// for F = 276 (1104 B), so float4 loads are legal when F % 4 == 0.
+__global__ void cast_pad_kernel(const float* __restrict__ x, bf16* __restrict__ out, int64_t M, int F, int Fpad) {
+  const int64_t total = M * (Fpad / 4);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / (Fpad / 4);
+    const int c = static_cast<int>(i - row * (Fpad / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + 3 < F) {
+      v = __ldg(reinterpret_cast<const float4*>(x + row * F + c));
+    } else {
+      if (c + 0 < F) v.x = x[row * F + c + 0];
+      if (c + 1 < F) v.y = x[row * F + c + 1];
+      if (c + 2 < F) v.z = x[row * F + c + 2];
+    }
+    uint2 p;
+    p.x = pack_bf16x2(v.x, v.y);
+    p.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + row * Fpad + c) = p;
+  }
+}
+
+// SqueezeExcite gate (nb:conv-hybrid-model c5:120-133) computed from the column sums of the conv3 INPUT:
+// mean_t(conv3(h)) = mean_t(h) @ W3 + b3 (1x1 conv is linear), so no pass over the [T, D] output is needed.
+__global__ void __launch_bounds__(256)
+se_gate_kernel(SeGateArgs a) {
+  extern __shared__ float sm[];
+  float* mean = sm;            // [C]
+  float* z = mean + a.C;       // [D]
+  float* hid = z + a.D;        // [R]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int c = tid; c < a.C; c += 256) mean[c] = a.colsum[static_cast<size_t>(b) * a.C + c] * a.inv_T;
+  __syncthreads();
+  for (int d = warp; d < a.D; d += 8) {
+    const bf16* wr = a.w3t + static_cast<size_t>(d) * a.C;
+    float acc = 0.f;
+    for (int c = lane * 2; c < a.C; c += 64) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(wr + c);
+      acc = fmaf(bf16_lo(u), mean[c], acc);
+      acc = fmaf(bf16_hi(u), mean[c + 1], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) z[d] = acc + a.b3[d];
+  }
+  __syncthreads();
+  for (int r = tid; r < a.R; r += 256) {
+    float acc = a.fc1_b[r];
+    for (int d = 0; d < a.D; ++d) acc = fmaf(z[d], a.fc1_w[static_cast<size_t>(d) * a.R + r], acc);
+    hid[r] = acc / (1.f + __expf(-acc));  // swish
+  }
+  __syncthreads();
+  for (int d = tid; d < a.D; d += 256) {
+    float acc = a.fc2_b[d];
+    for (int r = 0; r < a.R; ++r) acc = fmaf(hid[r], a.fc2_w[static_cast<size_t>(r) * a.D + d], acc);
+    a.gate[static_cast<size_t>(b) * a.D + d] = 1.f / (1.f + __expf(-acc));
+  }
+}
+
+// LayerNorm over the last axis, one warp per row, D <= 1024, D % 64 == 0 not required (D % 2 == 0).
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, const float* __restrict__ g,
+                 const float* __restrict__ bta, float eps, int64_t M, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * 8ll + warp;
+  if (row >= M) return;
+  const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + row * D);
+  float v[32];  // up to 1024 columns: 16 bf16x2 per lane
+  int n = 0;
+  float s = 0.f;
+  for (int c = lane; c < D / 2; c += 32) {
+    const uint32_t u = xr[c];
+    v[n] = bf16_lo(u); v[n + 1] = bf16_hi(u);
+    s += v[n] + v[n + 1];
+    n += 2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / D;
+  float q = 0.f;
+  for (int i = 0; i < n; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / D + eps);
+  uint32_t* orow = reinterpret_cast<uint32_t*>(out + row * D);
+  n = 0;
+  for (int c = lane; c < D / 2; c += 32) {
+    const float a0 = (v[n] - mean) * rstd * g[2 * c] + bta[2 * c];
+    const float a1 = (v[n + 1] - mean) * rstd * g[2 * c + 1] + bta[2 * c + 1];
+    orow[c] = pack_bf16x2(a0, a1);
+    n += 2;
+  }
+}
+
+}  // namespace
+
+int cast_pad_launch(const float* x, bf16* out, int64_t M, int F, int Fpad, cudaStream_t stream) {
+  if (Fpad % 4 != 0 || F > Fpad || F % 4 != 0) {
+    set_last_error("cast_pad: F and Fpad must be multiples of 4 and F <= Fpad");
+    return 2;
+  }
+  const int64_t total = M * (Fpad / 4);
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  cast_pad_kernel<<<grid, 256, 0, stream>>>(x, out, M, F, Fpad);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int se_gate_launch(const SeGateArgs& a, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(a.C + a.D + a.R) * sizeof(float);
+  se_gate_kernel<<<a.B, 256, smem, stream>>>(a);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int layernorm_launch(const bf16* x, bf16* out, const float* g, const float* b, float eps, int64_t M, int D,
+                     cudaStream_t stream) {
+  if (D > 1024 || D % 2 != 0) {
+    set_last_error("layernorm: D must be even and <= 1024");
+    return 2;
+  }
+  layernorm_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, stream>>>(x, out, g, b, eps, M, D);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ishara

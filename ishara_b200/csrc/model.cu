@@ -1,0 +1,870 @@
+// ishara_b200 — model runtime: parameter registry (Keras names/layouts), weight packing, workspace,
+// and the launch program of get_model's forward (nb:conv-hybrid-model c7:12-65).
+//
+// HBM layout: activations are [B*T, C] bf16 row-major (channels-last, exactly the TF layout), the
+// residual stream S lives in ONE buffer that the stream-producing GEMMs update in place (they read
+// it only as the per-row residual), XN holds LayerNorm(S) for the next GEMM, H1/H2 hold the wide
+// (2D / ef*D / 3D) intermediates. Weights are packed once: transposed to [N, K] (K contiguous, the
+// UMMA "K-major" B operand), bf16, inference BatchNorm folded into the neighbouring linear op.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ishara_b200.h"
+#include "kernels.h"
+
+namespace ishara {
+
+namespace {
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool set = false;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct LnRef {
+  const float* g = nullptr;
+  const float* b = nullptr;
+  float eps = 0.f;
+};
+
+enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP };
+struct Op {
+  OpKind kind;
+  GemmPlan gemm;
+  DwConvArgs dw;
+  AttnArgs at;
+  SeGateArgs se;
+  // OP_LN
+  const bf16* ln_in = nullptr;
+  bf16* ln_out = nullptr;
+  LnRef ln;
+  int tap = -1;
+  const char* label = "";
+};
+
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);                      // round to nearest even
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace
+}  // namespace ishara
+
+using namespace ishara;
+
+struct ishara_model {
+  ishara_config_t cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::vector<Param> params;
+  std::unordered_map<std::string, int> index;
+  bool finalized = false;
+  bool debug_taps = false;
+
+  std::vector<void*> wallocs;  // packed weights
+  std::unordered_map<std::string, void*> packed;
+
+  // workspace
+  int cap_batch = 0;
+  std::vector<void*> wsallocs;
+  bf16 *XIN = nullptr, *S = nullptr, *XN = nullptr, *H1 = nullptr, *H2 = nullptr, *O = nullptr, *HEAD = nullptr;
+  float *colsum = nullptr, *gate = nullptr;
+  float* logits_own = nullptr;
+  int32_t *ids_dev = nullptr, *lens_dev = nullptr, *labels_dev = nullptr;
+  float* nll_dev = nullptr;
+  int labels_cap = 0;
+  float* x_dev = nullptr;
+  std::vector<bf16*> taps;
+  std::vector<std::string> tap_names;
+
+  std::vector<Op> program;
+  int program_batch = 0;
+  float* program_logits = nullptr;
+  cudaStream_t stream = nullptr;
+
+  int fpad() const { return (cfg.features + 63) / 64 * 64; }
+  int vpad() const { return (cfg.num_classes + 63) / 64 * 64; }
+};
+
+namespace ishara {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// parameter table
+// ------------------------------------------------------------------------------------------------
+void add_param(ishara_model* m, const std::string& name, std::vector<int64_t> shape) {
+  Param p;
+  p.name = name;
+  p.shape = std::move(shape);
+  m->index[name] = static_cast<int>(m->params.size());
+  m->params.push_back(std::move(p));
+}
+void add_norm(ishara_model* m, const std::string& base, int64_t d, bool bn) {
+  add_param(m, base + ".gamma", {d});
+  add_param(m, base + ".beta", {d});
+  if (bn) {
+    add_param(m, base + ".moving_mean", {d});
+    add_param(m, base + ".moving_variance", {d});
+  }
+}
+void add_dense(ishara_model* m, const std::string& base, int64_t in, int64_t out, bool bias, bool conv1x1 = false) {
+  if (conv1x1) add_param(m, base + ".kernel", {1, in, out});
+  else add_param(m, base + ".kernel", {in, out});
+  if (bias) add_param(m, base + ".bias", {out});
+}
+
+int conv_kernel_size(const ishara_config_t& c, int j) { return c.kernel_sizes[j % c.num_kernel_sizes]; }
+
+void add_conv_blocks(ishara_model* m, const std::string& tag, int i) {
+  const ishara_config_t& c = m->cfg;
+  const int64_t D = c.dim;
+  for (int j = 0; j < c.num_conv_per_block; ++j) {
+    const std::string n = "conv" + tag + "_" + std::to_string(i) + "_" + std::to_string(j + 1);
+    add_dense(m, n + "_expand_conv", D, 2 * D, true);
+    add_param(m, n + "_dwconv.depthwise_kernel", {conv_kernel_size(c, j), 2 * D, 1});
+    add_norm(m, n + "_bn", 2 * D, true);
+    add_param(m, n + "_eca.kernel", {5, 1, 1});
+    add_dense(m, n + "_project_conv", 2 * D, D, true);
+  }
+}
+void add_ffn(ishara_model* m, const std::string& base, int64_t D, int64_t E) {
+  add_dense(m, base + ".0", D, E, true);
+  add_dense(m, base + ".2", E, D, true);
+}
+
+void build_param_table(ishara_model* m) {
+  const ishara_config_t& c = m->cfg;
+  const int64_t D = c.dim, E = static_cast<int64_t>(c.expansion_factor) * c.dim, tk = c.transformer_kernel_size;
+  add_dense(m, "stem_conv", c.features, D, false);
+  add_norm(m, "stem_bn", D, true);
+  for (int i = 0; i < c.num_conv_squeeze_blocks; ++i) {
+    add_conv_blocks(m, "squeeze", i);
+    const std::string n = "squeezeformer_" + std::to_string(i);
+    add_norm(m, n + ".norm1", D, false);
+    add_ffn(m, n + ".ffn1", D, E);
+    add_norm(m, n + ".norm2", D, false);
+    add_dense(m, n + ".mha.qkv", D, 3 * D, false);
+    add_dense(m, n + ".mha.proj", D, D, false);
+    add_norm(m, n + ".conv.norm", D, false);
+    add_dense(m, n + ".conv.conv1", D, E, true, true);
+    add_param(m, n + ".conv.conv2.depthwise_kernel", {tk, E, 1});
+    add_dense(m, n + ".conv.conv3", E, D, true, true);
+    const int64_t R = std::max<int64_t>(1, D / 8);
+    add_dense(m, n + ".conv.se.fc1", D, R, true);
+    add_dense(m, n + ".conv.se.fc2", R, D, true);
+    add_norm(m, n + ".norm3", D, false);
+    add_ffn(m, n + ".ffn2", D, E);
+  }
+  for (int i = 0; i < c.num_conv_conform_blocks; ++i) {
+    add_conv_blocks(m, "conform", i);
+    const std::string n = "conformer_" + std::to_string(i);
+    add_norm(m, n + ".layer_norm1", D, false);
+    add_norm(m, n + ".layer_norm2", D, false);
+    add_ffn(m, n + ".ffn1", D, E);
+    add_dense(m, n + ".mha.qkv", D, 3 * D, false);
+    add_dense(m, n + ".mha.proj", D, D, false);
+    add_dense(m, n + ".conv.pointwise_conv1", D, 2 * D, true, true);
+    add_param(m, n + ".conv.depthwise_conv.kernel", {tk, 1, D});
+    add_param(m, n + ".conv.depthwise_conv.bias", {D});
+    add_norm(m, n + ".conv.batch_norm", D, true);
+    add_dense(m, n + ".conv.pointwise_conv2", D, D, true, true);
+    add_norm(m, n + ".conv.layer_norm", D, false);
+    add_ffn(m, n + ".ffn2", D, E);
+  }
+  add_dense(m, "top_conv", D, 2 * D, true);
+  add_dense(m, "classifier", 2 * D, c.num_classes, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing helpers
+// ------------------------------------------------------------------------------------------------
+const std::vector<float>& P(const ishara_model* m, const std::string& name) {
+  return m->params[m->index.at(name)].data;
+}
+
+int upload(ishara_model* m, const std::string& key, const void* host, size_t bytes, void** out) {
+  void* d = nullptr;
+  ISHARA_CUDA_OK(cudaMalloc(&d, bytes < 256 ? 256 : bytes));
+  ISHARA_CUDA_OK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  m->wallocs.push_back(d);
+  m->packed[key] = d;
+  *out = d;
+  return 0;
+}
+
+// kernel [K, N] fp32 (Keras Dense) -> bf16 [Npad, Kpad], row n = column perm[n] of the kernel scaled
+// by col_scale[perm[n]]; zero padding.
+int pack_linear(ishara_model* m, const std::string& key, const std::vector<float>& kernel, int K, int N, int Kpad,
+                int Npad, const std::vector<float>* col_scale, const std::vector<int>* perm, bf16** out) {
+  std::vector<uint16_t> h(static_cast<size_t>(Npad) * Kpad, 0);
+  for (int n = 0; n < Npad; ++n) {
+    const int src = perm ? (*perm)[n] : n;
+    if (src < 0 || src >= N) continue;
+    const float s = col_scale ? (*col_scale)[src] : 1.f;
+    for (int k = 0; k < K; ++k) h[static_cast<size_t>(n) * Kpad + k] = f2bf(kernel[static_cast<size_t>(k) * N + src] * s);
+  }
+  void* d;
+  int rc = upload(m, key, h.data(), h.size() * 2, &d);
+  *out = static_cast<bf16*>(d);
+  return rc;
+}
+int pack_f32(ishara_model* m, const std::string& key, const std::vector<float>& v, float** out) {
+  void* d;
+  int rc = upload(m, key, v.data(), v.size() * 4, &d);
+  *out = static_cast<float*>(d);
+  return rc;
+}
+// inference BatchNorm as y = x*s + o  (Keras default epsilon 1e-3; c5:73, c7:17, c5:281)
+void bn_fold(const ishara_model* m, const std::string& base, std::vector<float>* s, std::vector<float>* o) {
+  const auto &g = P(m, base + ".gamma"), &b = P(m, base + ".beta"), &mu = P(m, base + ".moving_mean"),
+             &var = P(m, base + ".moving_variance");
+  s->resize(g.size());
+  o->resize(g.size());
+  for (size_t i = 0; i < g.size(); ++i) {
+    const double sc = static_cast<double>(g[i]) / std::sqrt(static_cast<double>(var[i]) + 1e-3);
+    (*s)[i] = static_cast<float>(sc);
+    (*o)[i] = static_cast<float>(static_cast<double>(b[i]) - static_cast<double>(mu[i]) * sc);
+  }
+}
+
+int wide_block_n(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+
+struct Packed {
+  // lazily looked up packed device pointers by key
+  ishara_model* m;
+  template <typename T>
+  T* get(const std::string& key) const {
+    auto it = m->packed.find(key);
+    return it == m->packed.end() ? nullptr : static_cast<T*>(it->second);
+  }
+};
+
+int pack_ln(ishara_model* m, const std::string& base) {
+  float* d;
+  int rc;
+  if ((rc = pack_f32(m, base + ".gamma", P(m, base + ".gamma"), &d))) return rc;
+  return pack_f32(m, base + ".beta", P(m, base + ".beta"), &d);
+}
+int pack_dense(ishara_model* m, const std::string& base, int K, int N, bool bias) {
+  bf16* w;
+  int rc;
+  if ((rc = pack_linear(m, base + ".w", P(m, base + ".kernel"), K, N, K, N, nullptr, nullptr, &w))) return rc;
+  if (bias) {
+    float* b;
+    if ((rc = pack_f32(m, base + ".b", P(m, base + ".bias"), &b))) return rc;
+  }
+  return 0;
+}
+
+int pack_conv_blocks(ishara_model* m, const std::string& tag, int i) {
+  const ishara_config_t& c = m->cfg;
+  const int D = c.dim;
+  int rc;
+  for (int j = 0; j < c.num_conv_per_block; ++j) {
+    const std::string n = "conv" + tag + "_" + std::to_string(i) + "_" + std::to_string(j + 1);
+    if ((rc = pack_dense(m, n + "_expand_conv", D, 2 * D, true))) return rc;
+    std::vector<float> s, o;
+    bn_fold(m, n + "_bn", &s, &o);
+    const int k = conv_kernel_size(c, j);
+    std::vector<float> w = P(m, n + "_dwconv.depthwise_kernel");  // [k, 2D, 1]
+    for (int t = 0; t < k; ++t)
+      for (int ch = 0; ch < 2 * D; ++ch) w[static_cast<size_t>(t) * 2 * D + ch] *= s[ch];
+    float* d;
+    if ((rc = pack_f32(m, n + "_dw.w", w, &d))) return rc;
+    if ((rc = pack_f32(m, n + "_dw.b", o, &d))) return rc;
+    if ((rc = pack_f32(m, n + "_eca.w", P(m, n + "_eca.kernel"), &d))) return rc;
+    if ((rc = pack_dense(m, n + "_project_conv", 2 * D, D, true))) return rc;
+  }
+  return 0;
+}
+
+int pack_all(ishara_model* m) {
+  for (void* p : m->wallocs) cudaFree(p);
+  m->wallocs.clear();
+  m->packed.clear();
+  const ishara_config_t& c = m->cfg;
+  const int D = c.dim, E = c.expansion_factor * c.dim, tk = c.transformer_kernel_size, T = c.frames;
+  int rc;
+  {
+    // stem: BN(x@W + PE) = x@(W*s) + (PE*s + o)      (c7:14-17, positional_encoding c5:226-235)
+    std::vector<float> s, o;
+    bn_fold(m, "stem_bn", &s, &o);
+    bf16* w;
+    if ((rc = pack_linear(m, "stem.w", P(m, "stem_conv.kernel"), c.features, D, m->fpad(), D, &s, nullptr, &w))) return rc;
+    std::vector<float> tab(static_cast<size_t>(T) * D);
+    const int half = D / 2;
+    const float depth = static_cast<float>(D) / 2.f;
+    for (int t = 0; t < T; ++t) {
+      for (int i = 0; i < half; ++i) {
+        const float rate = 1.f / powf(10000.f, static_cast<float>(i) / depth);
+        const float ang = static_cast<float>(t) * rate;
+        tab[static_cast<size_t>(t) * D + i] = sinf(ang) * s[i] + o[i];
+        tab[static_cast<size_t>(t) * D + half + i] = cosf(ang) * s[half + i] + o[half + i];
+      }
+    }
+    float* d;
+    if ((rc = pack_f32(m, "stem.tab", tab, &d))) return rc;
+  }
+  auto pack_ffn = [&](const std::string& base) -> int {
+    int r;
+    if ((r = pack_dense(m, base + ".0", D, E, true))) return r;
+    return pack_dense(m, base + ".2", E, D, true);
+  };
+  for (int i = 0; i < c.num_conv_squeeze_blocks; ++i) {
+    if ((rc = pack_conv_blocks(m, "squeeze", i))) return rc;
+    const std::string n = "squeezeformer_" + std::to_string(i);
+    for (const char* ln : {".norm1", ".norm2", ".norm3", ".conv.norm"})
+      if ((rc = pack_ln(m, n + ln))) return rc;
+    if ((rc = pack_ffn(n + ".ffn1"))) return rc;
+    if ((rc = pack_ffn(n + ".ffn2"))) return rc;
+    if ((rc = pack_dense(m, n + ".mha.qkv", D, 3 * D, false))) return rc;
+    if ((rc = pack_dense(m, n + ".mha.proj", D, D, false))) return rc;
+    if ((rc = pack_dense(m, n + ".conv.conv1", D, E, true))) return rc;
+    float* d;
+    if ((rc = pack_f32(m, n + ".conv.dw.w", P(m, n + ".conv.conv2.depthwise_kernel"), &d))) return rc;
+    if ((rc = pack_dense(m, n + ".conv.conv3", E, D, true))) return rc;
+    if ((rc = pack_f32(m, n + ".se.fc1.w", P(m, n + ".conv.se.fc1.kernel"), &d))) return rc;
+    if ((rc = pack_f32(m, n + ".se.fc1.b", P(m, n + ".conv.se.fc1.bias"), &d))) return rc;
+    if ((rc = pack_f32(m, n + ".se.fc2.w", P(m, n + ".conv.se.fc2.kernel"), &d))) return rc;
+    if ((rc = pack_f32(m, n + ".se.fc2.b", P(m, n + ".conv.se.fc2.bias"), &d))) return rc;
+  }
+  for (int i = 0; i < c.num_conv_conform_blocks; ++i) {
+    if ((rc = pack_conv_blocks(m, "conform", i))) return rc;
+    const std::string n = "conformer_" + std::to_string(i);
+    for (const char* ln : {".layer_norm1", ".layer_norm2", ".conv.layer_norm"})
+      if ((rc = pack_ln(m, n + ln))) return rc;
+    if ((rc = pack_ffn(n + ".ffn1"))) return rc;
+    if ((rc = pack_ffn(n + ".ffn2"))) return rc;
+    if ((rc = pack_dense(m, n + ".mha.qkv", D, 3 * D, false))) return rc;
+    if ((rc = pack_dense(m, n + ".mha.proj", D, D, false))) return rc;
+    {
+      // pointwise_conv1 + GLU (c5:293-295): out = a * sigmoid(b), a = first D channels, b = last D.
+      // Packed so that every BN-wide N tile holds [a-slice | matching b-slice].
+      const int bn = wide_block_n(2 * D);
+      std::vector<int> perm(2 * D);
+      const int halfw = bn / 2;
+      for (int tile = 0; tile < 2 * D / bn; ++tile)
+        for (int j = 0; j < halfw; ++j) {
+          perm[tile * bn + j] = tile * halfw + j;
+          perm[tile * bn + halfw + j] = D + tile * halfw + j;
+        }
+      bf16* w;
+      if ((rc = pack_linear(m, n + ".conv.pw1.w", P(m, n + ".conv.pointwise_conv1.kernel"), D, 2 * D, D, 2 * D, nullptr,
+                            &perm, &w)))
+        return rc;
+      const auto& b = P(m, n + ".conv.pointwise_conv1.bias");
+      std::vector<float> bp(2 * D);
+      for (int j = 0; j < 2 * D; ++j) bp[j] = b[perm[j]];
+      float* d;
+      if ((rc = pack_f32(m, n + ".conv.pw1.b", bp, &d))) return rc;
+    }
+    {
+      // grouped Conv1D 'same' + bias, then BN (momentum .99, eps 1e-3): y = (conv + b)*s + o
+      std::vector<float> s, o;
+      bn_fold(m, n + ".conv.batch_norm", &s, &o);
+      std::vector<float> w = P(m, n + ".conv.depthwise_conv.kernel");  // [tk, 1, D]
+      const auto& b = P(m, n + ".conv.depthwise_conv.bias");
+      std::vector<float> bb(D);
+      for (int t = 0; t < tk; ++t)
+        for (int ch = 0; ch < D; ++ch) w[static_cast<size_t>(t) * D + ch] *= s[ch];
+      for (int ch = 0; ch < D; ++ch) bb[ch] = b[ch] * s[ch] + o[ch];
+      float* d;
+      if ((rc = pack_f32(m, n + ".conv.dw.w", w, &d))) return rc;
+      if ((rc = pack_f32(m, n + ".conv.dw.b", bb, &d))) return rc;
+    }
+    if ((rc = pack_dense(m, n + ".conv.pointwise_conv2", D, D, true))) return rc;
+  }
+  if ((rc = pack_dense(m, "top_conv", D, 2 * D, true))) return rc;
+  {
+    bf16* w;
+    if ((rc = pack_linear(m, "classifier.w", P(m, "classifier.kernel"), 2 * D, c.num_classes, 2 * D, m->vpad(), nullptr,
+                          nullptr, &w)))
+      return rc;
+    std::vector<float> b(m->vpad(), 0.f);
+    const auto& src = P(m, "classifier.bias");
+    for (int i = 0; i < c.num_classes; ++i) b[i] = src[i];
+    float* d;
+    if ((rc = pack_f32(m, "classifier.b", b, &d))) return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace + program
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int ws_alloc(ishara_model* m, T** p, size_t count) {
+  void* d = nullptr;
+  ISHARA_CUDA_OK(cudaMalloc(&d, count * sizeof(T) + 256));
+  m->wsallocs.push_back(d);
+  *p = static_cast<T*>(d);
+  return 0;
+}
+
+int ensure_workspace(ishara_model* m, int batch) {
+  if (batch <= m->cap_batch) return 0;
+  for (void* p : m->wsallocs) cudaFree(p);
+  m->wsallocs.clear();
+  m->taps.clear();
+  m->program.clear();
+  m->program_batch = 0;
+  const ishara_config_t& c = m->cfg;
+  const size_t M = static_cast<size_t>(batch) * c.frames;
+  const size_t D = c.dim, E = static_cast<size_t>(c.expansion_factor) * c.dim;
+  const size_t W1 = std::max<size_t>(std::max<size_t>(2 * D, E), 3 * D), W2 = std::max<size_t>(2 * D, E);
+  int rc;
+  if ((rc = ws_alloc(m, &m->x_dev, M * c.features))) return rc;
+  if ((rc = ws_alloc(m, &m->XIN, M * m->fpad()))) return rc;
+  if ((rc = ws_alloc(m, &m->S, M * D))) return rc;
+  if ((rc = ws_alloc(m, &m->XN, M * D))) return rc;
+  if ((rc = ws_alloc(m, &m->H1, M * W1))) return rc;
+  if ((rc = ws_alloc(m, &m->H2, M * W2))) return rc;
+  if ((rc = ws_alloc(m, &m->O, M * D))) return rc;
+  if ((rc = ws_alloc(m, &m->HEAD, M * 2 * D))) return rc;
+  if ((rc = ws_alloc(m, &m->colsum, static_cast<size_t>(batch) * E))) return rc;
+  if ((rc = ws_alloc(m, &m->gate, static_cast<size_t>(batch) * D))) return rc;
+  if ((rc = ws_alloc(m, &m->logits_own, M * c.num_classes))) return rc;
+  if ((rc = ws_alloc(m, &m->ids_dev, M))) return rc;
+  if ((rc = ws_alloc(m, &m->lens_dev, static_cast<size_t>(batch)))) return rc;
+  if ((rc = ws_alloc(m, &m->nll_dev, static_cast<size_t>(batch)))) return rc;
+  m->labels_dev = nullptr;
+  m->labels_cap = 0;
+  m->cap_batch = batch;
+  return 0;
+}
+
+struct Builder {
+  ishara_model* m;
+  int B, M, D, E, T;
+  std::vector<Op>& ops;
+  Packed pk;
+  int rc = 0;
+
+  void wide_gemm(const char* label, const bf16* A, int K, const std::string& wkey, const std::string& bkey, int N,
+                 int act, bf16* out) {
+    if (rc) return;
+    Op op;
+    op.kind = OP_GEMM;
+    op.label = label;
+    GemmPlan& p = op.gemm;
+    p.M = M; p.N = N; p.K = K;
+    p.block_n = wide_block_n(N);
+    p.row_mode = false;
+    p.out_f32 = false;
+    p.epi.bias = bkey.empty() ? nullptr : pk.get<float>(bkey);
+    p.epi.act = act;
+    p.epi.rows_per_seq = T;
+    const int nout = act == ACT_GLU ? N / 2 : N;
+    rc = gemm_plan_init(&p, A, K, pk.get<bf16>(wkey), out, nout, nout, nullptr, 0);
+    ops.push_back(op);
+  }
+
+  // S = [LN0]( A@W + bias [*gate] [+rowtab] [+S] ) ; XN = LN1(S)
+  void stream_gemm(const char* label, const bf16* A, int K, const std::string& wkey, const std::string& bkey,
+                   const float* gate, const float* rowtab, bool resid, LnRef ln0, LnRef ln1) {
+    if (rc) return;
+    Op op;
+    op.kind = OP_GEMM;
+    op.label = label;
+    GemmPlan& p = op.gemm;
+    p.M = M; p.N = D; p.K = K;
+    p.out_f32 = false;
+    p.epi.bias = bkey.empty() ? nullptr : pk.get<float>(bkey);
+    p.epi.gate = gate;
+    p.epi.rowtab = rowtab;
+    p.epi.resid = resid ? m->S : nullptr;
+    p.epi.ld_resid = D;
+    p.epi.rows_per_seq = T;
+    const bool fused = (D == 256 || D == 128);
+    if (fused) {
+      p.block_n = D;
+      p.row_mode = true;
+      p.epi.ln0_g = ln0.g; p.epi.ln0_b = ln0.b; p.epi.ln0_eps = ln0.eps;
+      p.epi.ln1_g = ln1.g; p.epi.ln1_b = ln1.b; p.epi.ln1_eps = ln1.eps;
+      rc = gemm_plan_init(&p, A, K, pk.get<bf16>(wkey), m->S, D, D, ln1.g ? m->XN : nullptr, D);
+      ops.push_back(op);
+    } else {
+      p.block_n = wide_block_n(D);
+      p.row_mode = false;
+      rc = gemm_plan_init(&p, A, K, pk.get<bf16>(wkey), m->S, D, D, nullptr, 0);
+      ops.push_back(op);
+      if (ln0.g) layernorm(m->S, m->S, ln0);
+      if (ln1.g) layernorm(m->S, m->XN, ln1);
+    }
+  }
+  void layernorm(const bf16* in, bf16* out, LnRef ln) {
+    Op op;
+    op.kind = OP_LN;
+    op.label = "layernorm";
+    op.ln_in = in; op.ln_out = out; op.ln = ln;
+    ops.push_back(op);
+  }
+  void dwconv(const char* label, const bf16* in, bf16* out, int C, int k, int pad_left, const std::string& wkey,
+              const std::string& bkey, const std::string& ecakey, int post, float* colsum) {
+    if (rc) return;
+    Op op;
+    op.kind = OP_DW;
+    op.label = label;
+    op.dw.in = in; op.dw.out = out;
+    op.dw.w = pk.get<float>(wkey);
+    op.dw.bias = bkey.empty() ? nullptr : pk.get<float>(bkey);
+    op.dw.eca_w = ecakey.empty() ? nullptr : pk.get<float>(ecakey);
+    op.dw.colsum = colsum;
+    op.dw.B = B; op.dw.T = T; op.dw.C = C; op.dw.k = k; op.dw.pad_left = pad_left; op.dw.post = post;
+    ops.push_back(op);
+  }
+  void attention(const bf16* qkv, bf16* out) {
+    if (rc) return;
+    Op op;
+    op.kind = OP_ATTN;
+    op.label = "attention";
+    op.at.qkv = qkv; op.at.out = out; op.at.key_mask = nullptr;
+    op.at.B = B; op.at.T = T; op.at.H = m->cfg.num_heads; op.at.dh = D / m->cfg.num_heads;
+    op.at.scale = 1.f / std::sqrt(static_cast<float>(D));  // self.scale = dim ** -0.5 (c5:95), NOT dh ** -0.5
+    ops.push_back(op);
+  }
+  void tap(const std::string& name) {
+    if (!m->debug_taps) return;
+    Op op;
+    op.kind = OP_TAP;
+    op.label = "tap";
+    op.tap = static_cast<int>(m->taps.size());
+    bf16* buf = nullptr;
+    if (ws_alloc(m, &buf, static_cast<size_t>(M) * D)) { rc = 3; return; }
+    m->taps.push_back(buf);
+    m->tap_names.push_back(name);
+    ops.push_back(op);
+  }
+  LnRef ln(const std::string& base, float eps) {
+    LnRef r;
+    r.g = pk.get<float>(base + ".gamma");
+    r.b = pk.get<float>(base + ".beta");
+    r.eps = eps;
+    return r;
+  }
+
+  void conv_blocks(const std::string& tag, int i, LnRef next_ln) {
+    const ishara_config_t& c = m->cfg;
+    for (int j = 0; j < c.num_conv_per_block; ++j) {
+      const std::string n = "conv" + tag + "_" + std::to_string(i) + "_" + std::to_string(j + 1);
+      const int k = conv_kernel_size(c, j);
+      wide_gemm("conv1d.expand", m->S, D, n + "_expand_conv.w", n + "_expand_conv.b", 2 * D, ACT_SWISH, m->H1);
+      dwconv("conv1d.dw_bn_eca", m->H1, m->H2, 2 * D, k, k - 1, n + "_dw.w", n + "_dw.b", n + "_eca.w", 2, nullptr);
+      const bool last = j == c.num_conv_per_block - 1;
+      stream_gemm("conv1d.project", m->H2, 2 * D, n + "_project_conv.w", n + "_project_conv.b", nullptr, nullptr, true,
+                  LnRef(), last ? next_ln : LnRef());
+      tap(n);
+    }
+  }
+  void ffn(const std::string& base, LnRef next_ln) {
+    wide_gemm("ffn.up", m->XN, D, base + ".0.w", base + ".0.b", E, ACT_SWISH, m->H1);
+    stream_gemm("ffn.down", m->H1, E, base + ".2.w", base + ".2.b", nullptr, nullptr, true, LnRef(), next_ln);
+  }
+  void mhsa(const std::string& base, LnRef next_ln) {
+    wide_gemm("mhsa.qkv", m->XN, D, base + ".qkv.w", "", 3 * D, ACT_NONE, m->H1);
+    attention(m->H1, m->O);
+    stream_gemm("mhsa.proj", m->O, D, base + ".proj.w", "", nullptr, nullptr, true, LnRef(), next_ln);
+  }
+};
+
+int build_program(ishara_model* m, int batch, float* logits) {
+  const ishara_config_t& c = m->cfg;
+  m->program.clear();
+  m->tap_names.clear();
+  m->taps.clear();
+  Builder b{m, batch, batch * c.frames, c.dim, c.expansion_factor * c.dim, c.frames, m->program, Packed{m}};
+  const int D = c.dim, E = b.E, tk = c.transformer_kernel_size;
+
+  // what the first module after the stem wants as its normalised input
+  auto first_ln_of = [&](int sq_i, int cf_i) -> LnRef {
+    if (sq_i < c.num_conv_squeeze_blocks) return b.ln("squeezeformer_" + std::to_string(sq_i) + ".norm1", 1e-6f);
+    if (cf_i < c.num_conv_conform_blocks) return b.ln("conformer_" + std::to_string(cf_i) + ".layer_norm1", 1e-6f);
+    return LnRef();
+  };
+  const bool has_conv = c.num_conv_per_block > 0;
+
+  {
+    // stem
+    LnRef nl = has_conv ? LnRef() : first_ln_of(0, 0);
+    b.stream_gemm("stem", m->XIN, m->fpad(), "stem.w", "", nullptr, b.pk.get<float>("stem.tab"), false, LnRef(), nl);
+    b.tap("stem");
+  }
+  for (int i = 0; i < c.num_conv_squeeze_blocks; ++i) {
+    const std::string n = "squeezeformer_" + std::to_string(i);
+    b.conv_blocks("squeeze", i, b.ln(n + ".norm1", 1e-6f));
+    // next module's LN (only when there are no conv blocks in between)
+    LnRef after = has_conv ? LnRef() : first_ln_of(i + 1, 0);
+    b.ffn(n + ".ffn1", b.ln(n + ".norm2", 1e-6f));
+    b.mhsa(n + ".mha", b.ln(n + ".conv.norm", 1e-6f));
+    // ConvModule (c5:145-153): LN -> 1x1 -> swish -> causal DW -> swish -> 1x1 -> SE -> + x
+    b.wide_gemm("sqz.conv1", m->XN, D, n + ".conv.conv1.w", n + ".conv.conv1.b", E, ACT_SWISH, m->H1);
+    b.dwconv("sqz.dw_swish", m->H1, m->H2, E, tk, tk - 1, n + ".conv.dw.w", "", "", 1, m->colsum);
+    {
+      Op op;
+      op.kind = OP_SEGATE;
+      op.label = "sqz.se_gate";
+      op.se.colsum = m->colsum;
+      op.se.w3t = b.pk.get<bf16>(n + ".conv.conv3.w");
+      op.se.b3 = b.pk.get<float>(n + ".conv.conv3.b");
+      op.se.fc1_w = b.pk.get<float>(n + ".se.fc1.w");
+      op.se.fc1_b = b.pk.get<float>(n + ".se.fc1.b");
+      op.se.fc2_w = b.pk.get<float>(n + ".se.fc2.w");
+      op.se.fc2_b = b.pk.get<float>(n + ".se.fc2.b");
+      op.se.gate = m->gate;
+      op.se.B = batch; op.se.C = E; op.se.D = D; op.se.R = std::max(1, D / 8);
+      op.se.inv_T = 1.f / static_cast<float>(c.frames);
+      m->program.push_back(op);
+    }
+    b.stream_gemm("sqz.conv3_se", m->H2, E, n + ".conv.conv3.w", n + ".conv.conv3.b", m->gate, nullptr, true, LnRef(),
+                  b.ln(n + ".norm3", 1e-6f));
+    b.ffn(n + ".ffn2", after);
+    b.tap(n);
+  }
+  for (int i = 0; i < c.num_conv_conform_blocks; ++i) {
+    const std::string n = "conformer_" + std::to_string(i);
+    const LnRef ln1 = b.ln(n + ".layer_norm1", 1e-6f);
+    b.conv_blocks("conform", i, ln1);
+    LnRef after = has_conv ? LnRef() : first_ln_of(c.num_conv_squeeze_blocks, i + 1);
+    b.ffn(n + ".ffn1", ln1);            // layer_norm1 is reused for the MHSA input (c5:324,330)
+    b.mhsa(n + ".mha", LnRef());        // conv module consumes the raw stream
+    // ConvolutionModule (c5:288-309)
+    b.wide_gemm("cf.pw1_glu", m->S, D, n + ".conv.pw1.w", n + ".conv.pw1.b", 2 * D, ACT_GLU, m->H2);
+    b.dwconv("cf.dw_bn", m->H2, m->O, D, tk, (tk - 1) / 2, n + ".conv.dw.w", n + ".conv.dw.b", "", 0, nullptr);
+    b.stream_gemm("cf.pw2_ln", m->O, D, n + ".conv.pointwise_conv2.w", n + ".conv.pointwise_conv2.b", nullptr, nullptr,
+                  true, b.ln(n + ".conv.layer_norm", 1e-3f), b.ln(n + ".layer_norm2", 1e-6f));
+    b.ffn(n + ".ffn2", after);
+    b.tap(n);
+  }
+  // head (c7:61-63)
+  b.wide_gemm("head.top_conv", m->S, D, "top_conv.w", "top_conv.b", 2 * D, ACT_RELU, m->HEAD);
+  if (!b.rc) {
+    Op op;
+    op.kind = OP_GEMM;
+    op.label = "head.classifier";
+    GemmPlan& p = op.gemm;
+    p.M = b.M; p.N = m->vpad(); p.K = 2 * D;
+    p.block_n = 64;
+    p.out_f32 = true;
+    p.epi.bias = b.pk.get<float>("classifier.b");
+    p.epi.rows_per_seq = c.frames;
+    b.rc = gemm_plan_init(&p, m->HEAD, 2 * D, b.pk.get<bf16>("classifier.w"), logits, c.num_classes, c.num_classes,
+                          nullptr, 0);
+    m->program.push_back(op);
+  }
+  if (b.rc) {
+    m->program.clear();
+    return b.rc;
+  }
+  m->program_batch = batch;
+  m->program_logits = logits;
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// entry points used by capi.cu
+// ------------------------------------------------------------------------------------------------
+int model_create(const ishara_config_t* cfg, int device, ishara_model** out) {
+  if (cfg == nullptr || out == nullptr) { set_last_error("null argument"); return ISHARA_ERR_INVALID; }
+  const ishara_config_t& c = *cfg;
+  if (c.dim <= 0 || c.dim % 64 != 0) { set_last_error("dim must be a positive multiple of 64"); return ISHARA_ERR_SHAPE; }
+  if (c.num_heads <= 0 || c.dim % c.num_heads != 0) { set_last_error("dim must be divisible by num_heads"); return ISHARA_ERR_SHAPE; }
+  const int dh = c.dim / c.num_heads;
+  if (dh != 16 && dh != 32 && dh != 48 && dh != 64) { set_last_error("head dim must be 16/32/48/64"); return ISHARA_ERR_SHAPE; }
+  if (c.num_kernel_sizes < 0 || c.num_kernel_sizes > 8 || (c.num_conv_per_block > 0 && c.num_kernel_sizes == 0)) {
+    set_last_error("kernel_sizes: need 1..8 entries"); return ISHARA_ERR_SHAPE;
+  }
+  if (c.features % 4 != 0 || c.num_classes % 4 != 0 || c.frames <= 0 || c.expansion_factor <= 0) {
+    set_last_error("features and num_classes must be multiples of 4; frames, expansion_factor > 0"); return ISHARA_ERR_SHAPE;
+  }
+  auto m = std::make_unique<ishara_model>();
+  m->cfg = c;
+  m->device = device;
+  build_param_table(m.get());
+  *out = m.release();
+  return ISHARA_OK;
+}
+
+int model_destroy(ishara_model* m) {
+  if (m == nullptr) return ISHARA_OK;
+  if (m->finalized || !m->wsallocs.empty()) cudaSetDevice(m->device);
+  for (void* p : m->wallocs) cudaFree(p);
+  for (void* p : m->wsallocs) cudaFree(p);
+  if (m->labels_dev) cudaFree(m->labels_dev);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return ISHARA_OK;
+}
+
+int model_finalize(ishara_model* m) {
+  for (const Param& p : m->params)
+    if (!p.set) { set_last_error("parameter not set: " + p.name); return ISHARA_ERR_STATE; }
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  int sms = 0;
+  ISHARA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+  int major = 0;
+  ISHARA_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, m->device));
+  if (major != 10) { set_last_error("ishara_b200 needs a Blackwell (sm_100a) device; no fallback exists"); return ISHARA_ERR_CUDA; }
+  m->num_sms = sms;
+  if (m->stream == nullptr) ISHARA_CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  int rc = pack_all(m);
+  if (rc) return rc;
+  m->finalized = true;
+  m->program.clear();
+  m->program_batch = 0;
+  return ISHARA_OK;
+}
+
+int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_dev, cudaStream_t stream) {
+  if (!m->finalized) { set_last_error("forward before finalize"); return ISHARA_ERR_STATE; }
+  if (batch <= 0 || x_dev == nullptr || logits_dev == nullptr) { set_last_error("forward: bad arguments"); return ISHARA_ERR_INVALID; }
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = ensure_workspace(m, batch))) return rc;
+  if (m->program_batch != batch || m->program_logits != logits_dev || m->program.empty())
+    if ((rc = build_program(m, batch, logits_dev))) return rc;
+  const ishara_config_t& c = m->cfg;
+  const int64_t M = static_cast<int64_t>(batch) * c.frames;
+  if ((rc = cast_pad_launch(x_dev, m->XIN, M, c.features, m->fpad(), stream))) return rc;
+  for (const Op& op : m->program) {
+    switch (op.kind) {
+      case OP_GEMM: rc = gemm_launch(op.gemm, m->num_sms, stream); break;
+      case OP_DW: rc = dwconv_launch(op.dw, stream); break;
+      case OP_ATTN: rc = attention_launch(op.at, stream); break;
+      case OP_SEGATE: rc = se_gate_launch(op.se, stream); break;
+      case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, M, c.dim, stream); break;
+      case OP_TAP:
+        rc = cudaMemcpyAsync(m->taps[op.tap], m->S, M * c.dim * sizeof(bf16), cudaMemcpyDeviceToDevice, stream) == cudaSuccess ? 0 : 3;
+        break;
+    }
+    if (rc) {
+      set_last_error(std::string("forward: op '") + op.label + "' failed: " + get_last_error());
+      return rc;
+    }
+  }
+  return ISHARA_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// accessors used by capi.cu (the struct stays private to this file)
+// ------------------------------------------------------------------------------------------------
+struct ModelView {
+  const ishara_config_t* cfg;
+  int device;
+  cudaStream_t stream;
+  float* x_dev;
+  float* logits_own;
+  int32_t* ids_dev;
+  int32_t* lens_dev;
+  float* nll_dev;
+};
+
+int model_view(ishara_model* m, int batch, ModelView* v) {
+  if (!m->finalized) { set_last_error("model not finalized"); return ISHARA_ERR_STATE; }
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  int rc = ensure_workspace(m, batch);
+  if (rc) return rc;
+  v->cfg = &m->cfg;
+  v->device = m->device;
+  v->stream = m->stream;
+  v->x_dev = m->x_dev;
+  v->logits_own = m->logits_own;
+  v->ids_dev = m->ids_dev;
+  v->lens_dev = m->lens_dev;
+  v->nll_dev = m->nll_dev;
+  return 0;
+}
+
+int model_labels_buffer(ishara_model* m, size_t count, int32_t** out) {
+  if (static_cast<size_t>(m->labels_cap) < count) {
+    if (m->labels_dev) ISHARA_CUDA_OK(cudaFree(m->labels_dev));
+    m->labels_dev = nullptr;
+    m->labels_cap = 0;
+    ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&m->labels_dev), count * sizeof(int32_t)));
+    m->labels_cap = static_cast<int>(count);
+  }
+  *out = m->labels_dev;
+  return 0;
+}
+
+int model_num_params(const ishara_model* m) { return static_cast<int>(m->params.size()); }
+
+int model_param_info(const ishara_model* m, int idx, const char** name, int64_t* numel, int32_t* ndim, int64_t shape[4]) {
+  if (idx < 0 || idx >= static_cast<int>(m->params.size())) { set_last_error("param index out of range"); return ISHARA_ERR_INVALID; }
+  const Param& p = m->params[idx];
+  if (name) *name = p.name.c_str();
+  if (numel) *numel = p.numel();
+  if (ndim) *ndim = static_cast<int32_t>(p.shape.size());
+  if (shape) for (size_t i = 0; i < 4; ++i) shape[i] = i < p.shape.size() ? p.shape[i] : 1;
+  return 0;
+}
+
+int model_set_param(ishara_model* m, const char* name, const float* data, int64_t numel) {
+  if (name == nullptr || data == nullptr) { set_last_error("set_param: null argument"); return ISHARA_ERR_INVALID; }
+  auto it = m->index.find(name);
+  if (it == m->index.end()) { set_last_error(std::string("unknown parameter: ") + name); return ISHARA_ERR_INVALID; }
+  Param& p = m->params[it->second];
+  if (p.numel() != numel) {
+    set_last_error(std::string("set_param ") + name + ": expected " + std::to_string(p.numel()) + " elements, got " + std::to_string(numel));
+    return ISHARA_ERR_SHAPE;
+  }
+  p.data.assign(data, data + numel);
+  p.set = true;
+  m->finalized = false;
+  return 0;
+}
+
+int model_get_param(const ishara_model* m, const char* name, float* out, int64_t numel) {
+  if (name == nullptr || out == nullptr) { set_last_error("get_param: null argument"); return ISHARA_ERR_INVALID; }
+  auto it = m->index.find(name);
+  if (it == m->index.end()) { set_last_error(std::string("unknown parameter: ") + name); return ISHARA_ERR_INVALID; }
+  const Param& p = m->params[it->second];
+  if (!p.set) { set_last_error(std::string("parameter not set: ") + name); return ISHARA_ERR_STATE; }
+  if (p.numel() != numel) { set_last_error("get_param: size mismatch"); return ISHARA_ERR_SHAPE; }
+  std::memcpy(out, p.data.data(), numel * sizeof(float));
+  return 0;
+}
+
+int model_set_debug(ishara_model* m, int on) {
+  m->debug_taps = on != 0;
+  m->program.clear();
+  m->program_batch = 0;
+  return 0;
+}
+
+int model_debug_fetch(ishara_model* m, const char* name, float* host_out, int64_t numel) {
+  if (name == nullptr || host_out == nullptr) { set_last_error("debug_fetch: null argument"); return ISHARA_ERR_INVALID; }
+  for (size_t i = 0; i < m->tap_names.size(); ++i) {
+    if (m->tap_names[i] != name) continue;
+    const int64_t n = static_cast<int64_t>(m->program_batch) * m->cfg.frames * m->cfg.dim;
+    if (numel != n) { set_last_error("debug_fetch: expected " + std::to_string(n) + " elements"); return ISHARA_ERR_SHAPE; }
+    std::vector<uint16_t> tmp(n);
+    ISHARA_CUDA_OK(cudaStreamSynchronize(m->stream));
+    ISHARA_CUDA_OK(cudaDeviceSynchronize());
+    ISHARA_CUDA_OK(cudaMemcpy(tmp.data(), m->taps[i], n * 2, cudaMemcpyDeviceToHost));
+    for (int64_t j = 0; j < n; ++j) {
+      const uint32_t u = static_cast<uint32_t>(tmp[j]) << 16;
+      std::memcpy(&host_out[j], &u, 4);
+    }
+    return 0;
+  }
+  set_last_error(std::string("debug_fetch: no tap named ") + name + " (enable ishara_model_set_debug before forward)");
+  return ISHARA_ERR_INVALID;
+}
+
+}  // namespace ishara
