@@ -143,6 +143,19 @@ ISHARA_API ishara_status_t ishara_op_layernorm(const void* x_bf16, void* out_bf1
                                     float eps, int64_t M, int32_t D, void* stream);
 ISHARA_API ishara_status_t ishara_op_cast_pad(const float* x, void* out_bf16, int64_t M, int32_t F, int32_t Fpad, void* stream);
 
+
+/* ---- raw buffers (so a host without PyTorch can own device / pinned memory; DLPack producers in
+ * ishara_b200/_dlpack.py sit on top of these) ------------------------------------------------- */
+ISHARA_API ishara_status_t ishara_device_malloc(int32_t device, int64_t bytes, void** out_dev);
+ISHARA_API ishara_status_t ishara_device_free(int32_t device, void* dev_ptr);
+ISHARA_API ishara_status_t ishara_host_malloc_pinned(int64_t bytes, void** out_host);
+ISHARA_API ishara_status_t ishara_host_free_pinned(void* host_ptr);
+/* kind: 1 host->device, 2 device->host, 3 device->device. Asynchronous on `stream`. */
+ISHARA_API ishara_status_t ishara_memcpy_async(void* dst, const void* src, int64_t bytes, int32_t kind, void* stream);
+ISHARA_API ishara_status_t ishara_stream_synchronize(int32_t device, void* stream);
+/* the handle's own stream (used by the *_host entry points) */
+ISHARA_API void* ishara_model_stream(ishara_model_t* m);
+
 /* ---- debugging aid: copy an internal activation of the last forward (bf16 -> fp32) to the host ---
  * Enable with ishara_model_set_debug(m, 1) before the forward. Names: "stem", a Conv1DBlock name
  * ("convsqueeze_0_1", ...), "squeezeformer_<i>", "conformer_<i>": the residual stream after that module. */

@@ -94,6 +94,13 @@ SIGNATURES = {
     "ishara_op_attention": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "ishara_op_layernorm": (_i32, [_vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp]),
     "ishara_op_cast_pad": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "ishara_device_malloc": (_i32, [_i32, _i64, C.POINTER(_vp)]),
+    "ishara_device_free": (_i32, [_i32, _vp]),
+    "ishara_host_malloc_pinned": (_i32, [_i64, C.POINTER(_vp)]),
+    "ishara_host_free_pinned": (_i32, [_vp]),
+    "ishara_memcpy_async": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "ishara_stream_synchronize": (_i32, [_i32, _vp]),
+    "ishara_model_stream": (_vp, [_vp]),
     "ishara_model_set_debug": (_i32, [_vp, _i32]),
     "ishara_model_debug_fetch": (_i32, [_vp, C.c_char_p, _vp, _i64]),
 }

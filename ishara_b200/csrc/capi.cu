@@ -283,4 +283,47 @@ ishara_status_t ishara_op_cast_pad(const float* x, void* out_bf16, int64_t M, in
       cast_pad_launch(x, static_cast<bf16*>(out_bf16), M, F, Fpad, static_cast<cudaStream_t>(stream)));
 }
 
+ishara_status_t ishara_device_malloc(int32_t device, int64_t bytes, void** out_dev) {
+  if (out_dev == nullptr || bytes < 0) { set_last_error("device_malloc: bad arguments"); return ISHARA_ERR_INVALID; }
+  CAPI_CUDA_OK(cudaSetDevice(device));
+  CAPI_CUDA_OK(cudaMalloc(out_dev, static_cast<size_t>(bytes > 0 ? bytes : 1)));
+  return ISHARA_OK;
+}
+ishara_status_t ishara_device_free(int32_t device, void* dev_ptr) {
+  if (dev_ptr == nullptr) return ISHARA_OK;
+  CAPI_CUDA_OK(cudaSetDevice(device));
+  CAPI_CUDA_OK(cudaFree(dev_ptr));
+  return ISHARA_OK;
+}
+ishara_status_t ishara_host_malloc_pinned(int64_t bytes, void** out_host) {
+  if (out_host == nullptr || bytes < 0) { set_last_error("host_malloc_pinned: bad arguments"); return ISHARA_ERR_INVALID; }
+  CAPI_CUDA_OK(cudaMallocHost(out_host, static_cast<size_t>(bytes > 0 ? bytes : 1)));
+  return ISHARA_OK;
+}
+ishara_status_t ishara_host_free_pinned(void* host_ptr) {
+  if (host_ptr == nullptr) return ISHARA_OK;
+  CAPI_CUDA_OK(cudaFreeHost(host_ptr));
+  return ISHARA_OK;
+}
+ishara_status_t ishara_memcpy_async(void* dst, const void* src, int64_t bytes, int32_t kind, void* stream) {
+  if (dst == nullptr || src == nullptr || bytes < 0 || kind < 1 || kind > 3) {
+    set_last_error("memcpy_async: bad arguments");
+    return ISHARA_ERR_INVALID;
+  }
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  CAPI_CUDA_OK(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), k, static_cast<cudaStream_t>(stream)));
+  return ISHARA_OK;
+}
+ishara_status_t ishara_stream_synchronize(int32_t device, void* stream) {
+  CAPI_CUDA_OK(cudaSetDevice(device));
+  CAPI_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return ISHARA_OK;
+}
+void* ishara_model_stream(ishara_model_t* m) {
+  if (m == nullptr) return nullptr;
+  ModelView v;
+  if (model_view(reinterpret_cast<ishara_model*>(m), 1, &v)) return nullptr;
+  return v.stream;
+}
+
 }  // extern "C"

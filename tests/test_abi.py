@@ -1,0 +1,153 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/ishara_b200.h
+declares, and its host-side logic (parameter table, argument checks, error reporting) behaves without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ishara_b200 as ib
+from ishara_b200 import _lib
+from oracle import ishara_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ishara_b200.h")).read()
+    return sorted(set(re.findall(r"ISHARA_API[^;(]*?\b(ishara_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ishara_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype in ishara_b200/_lib.py"
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_no_torch_types_in_header():
+    src = open(os.path.join(ROOT, "include", "ishara_b200.h")).read()
+    assert "#include <torch" not in src and "at::" not in src and "torch::" not in src and "#include <cuda" not in src
+
+
+def test_version_and_device_count():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.ishara_version()
+    assert lib.ishara_device_count() >= 0
+
+
+@pytest.mark.parametrize("kw", [
+    {},
+    dict(dim=384, num_conv_squeeze_blocks=4, num_conv_conform_blocks=4, input_shape=(1024, 276)),
+    dict(dim=128, num_conv_squeeze_blocks=1, num_conv_conform_blocks=0, kernel_sizes=(5,), num_conv_per_block=2,
+         num_heads=4, expansion_factor=4, transformer_kernel_size=7, input_shape=(96, 64), num_classes=28),
+])
+def test_param_table_matches_oracle(kw):
+    m = ib.get_model(**kw)
+    okw = dict(kw)
+    if "input_shape" in okw:
+        okw["frames"], okw["features"] = okw.pop("input_shape")
+    if "kernel_sizes" in okw:
+        okw["kernel_sizes"] = tuple(okw["kernel_sizes"])
+    cfg = O.Config(**okw)
+    assert m.param_specs == O.param_specs(cfg)
+    assert m.count_params() == O.count_params(cfg)[0]
+
+
+def test_get_model_signature_matches_reference():
+    import inspect
+
+    sig = inspect.signature(ib.get_model)
+    names = list(sig.parameters)
+    # c7:1-11, in order, with the reference's defaults
+    assert names[:9] == ["dim", "num_conv_squeeze_blocks", "num_conv_conform_blocks", "kernel_sizes",
+                         "num_conv_per_block", "dropout_rate", "num_heads", "expansion_factor",
+                         "transformer_kernel_size"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["dim"], d["num_conv_squeeze_blocks"], d["num_conv_conform_blocks"], tuple(d["kernel_sizes"]),
+            d["num_conv_per_block"], d["dropout_rate"], d["num_heads"], d["expansion_factor"],
+            d["transformer_kernel_size"]) == (256, 2, 2, (11, 5, 3), 3, 0.2, 8, 2, 15)
+
+
+def test_weights_round_trip_and_keras_default_init(tmp_path):
+    m = ib.get_model(dim=64, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, num_heads=4, input_shape=(32, 20),
+                     num_classes=12)
+    w = m.get_weights()
+    assert np.all(w["stem_bn.gamma"] == 1) and np.all(w["stem_bn.moving_variance"] == 1)
+    assert np.all(w["top_conv.bias"] == 0) and np.all(w["stem_bn.moving_mean"] == 0)
+    lim = np.sqrt(6.0 / (20 + 64))
+    assert np.abs(w["stem_conv.kernel"]).max() <= lim and w["stem_conv.kernel"].std() > 0.3 * lim
+    p = O.init_params(O.Config(dim=64, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, num_heads=4, frames=32,
+                               features=20, num_classes=12))
+    m.load_weights(p)
+    path = tmp_path / "w.npz"
+    m.save_weights(path)
+    m2 = ib.get_model(dim=64, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, num_heads=4, input_shape=(32, 20),
+                      num_classes=12).load_weights(str(path))
+    for k, v in m2.get_weights().items():
+        assert np.array_equal(v, p[k]), k
+
+
+def test_error_reporting_without_gpu():
+    lib = _lib.load()
+    m = ib.get_model(dim=64, num_conv_squeeze_blocks=0, num_conv_conform_blocks=1, num_heads=4, input_shape=(32, 20),
+                     num_classes=12)
+    with pytest.raises(KeyError):
+        m.load_weights({"nope.kernel": np.zeros(3, np.float32)})
+    with pytest.raises(ValueError):
+        m.load_weights({"stem_conv.kernel": np.zeros((3, 3), np.float32)})
+    a = np.zeros(5, np.float32)
+    st = lib.ishara_model_set_param(m._h, b"nope", a.ctypes.data_as(C.c_void_p), 5)
+    assert st == _lib.ERR_INVALID and b"unknown parameter" in lib.ishara_last_error()
+    st = lib.ishara_model_set_param(m._h, b"stem_conv.kernel", a.ctypes.data_as(C.c_void_p), 5)
+    assert st == _lib.ERR_SHAPE
+    assert lib.ishara_model_forward(None, None, 1, None, None) == _lib.ERR_INVALID
+    # forward before finalize (finalize itself needs the GPU)
+    st = lib.ishara_model_forward(m._h, C.c_void_p(16), 1, C.c_void_p(16), None)
+    assert st == _lib.ERR_STATE
+    with pytest.raises(ValueError):
+        m(np.zeros((1, 31, 20), np.float32))
+    with pytest.raises(NotImplementedError):
+        ib.get_model(mask_mode="propagated")
+    bad = _lib.Config()
+    h = C.c_void_p()
+    assert lib.ishara_model_create(C.byref(bad), 0, C.byref(h)) == _lib.ERR_SHAPE
+
+
+def test_no_cpu_fallback_compute_fails_loudly_without_gpu():
+    lib = _lib.load()
+    if lib.ishara_device_count() > 0:
+        pytest.skip("GPU present")
+    m = ib.get_model(dim=64, num_conv_squeeze_blocks=0, num_conv_conform_blocks=0, num_heads=4, input_shape=(32, 20),
+                     num_classes=12)
+    with pytest.raises(ib.IsharaError) as e:
+        m(np.zeros((1, 32, 20), np.float32))
+    assert e.value.status == _lib.ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ishara_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+def test_host_char_map_and_postprocess_match_oracle():
+    assert ib.char_to_num == O.CHAR_TO_NUM and ib.num_to_char == O.NUM_TO_CHAR
+    assert "".join(ib.num_to_char_fn(ib.FALLBACK_IDS)) == "2 a-e -aroe"
+    for ids in ([1, 2], list(range(13)), []):
+        assert np.array_equal(ib.tflite_postprocess(ids), O.tflite_postprocess(np.asarray(ids)))
+
+
+def test_dlpack_view_of_numpy_is_rejected_as_device_operand():
+    from ishara_b200 import _dlpack
+
+    v = _dlpack.view(np.zeros((2, 3), np.float32))
+    assert v.shape == (2, 3) and v.dtype == "float32" and not v.on_cuda
+    with pytest.raises(ValueError):
+        _dlpack.view(np.zeros((4, 4), np.float32)[:, ::2])

@@ -1,0 +1,232 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ishara_b200's host mirror) against the CPU oracle
+on the same seeded inputs. Tolerances (stated here):
+
+  logits   bf16 activations / fp32 accumulate vs the fp64 oracle: max |err| <= LOGIT_ATOL + LOGIT_RTOL*|ref|
+           relative to the logit scale, and >= ARGMAX_AGREE of frames with the same argmax
+  CTC      per-sequence NLL within 1e-3 relative (fed identical logits); gradient within 2e-3 absolute
+  decode   bit-exact ids given identical logits
+"""
+import numpy as np
+import pytest
+
+import ishara_b200 as ib
+from oracle import ishara_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL = 3e-2      # of the logits' max magnitude
+ARGMAX_AGREE = 0.97    # untrained random weights give near-tied logits; trained models sit far above this
+
+
+def _model_for(cfg: O.Config, params):
+    m = ib.get_model(cfg.dim, cfg.num_conv_squeeze_blocks, cfg.num_conv_conform_blocks, cfg.kernel_sizes,
+                     cfg.num_conv_per_block, cfg.dropout_rate, cfg.num_heads, cfg.expansion_factor,
+                     cfg.transformer_kernel_size, input_shape=(cfg.frames, cfg.features), num_classes=cfg.num_classes)
+    return m.load_weights(params)
+
+
+def _check_logits(got, ref, what):
+    assert got.shape == ref.shape and np.isfinite(got).all(), what
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref).max()
+    agree = (got.argmax(-1) == ref.argmax(-1)).mean()
+    print(f"{what}: max_abs_err={err:.4g} logit_scale={scale:.4g} rel={err / scale:.4g} argmax_agree={agree:.5f}")
+    assert err <= LOGIT_RTOL * scale, f"{what}: max abs err {err} vs scale {scale}"
+    assert agree >= ARGMAX_AGREE, f"{what}: argmax agreement {agree}"
+    return err / scale, agree
+
+
+@pytest.fixture(scope="module")
+def base():
+    cfg = O.Config()
+    params = O.init_params(cfg, seed=42)
+    return cfg, params, _model_for(cfg, params)
+
+
+def test_cfg1_batch1_forward_and_decode(base):
+    """BASELINE configs[0]: batch 1, T=384, forward + greedy decode."""
+    cfg, params, m = base
+    x = O.make_inputs(cfg, 1, seed=1234)
+    ref = O.forward(params, x, cfg, "float64")
+    got = m(x)
+    _check_logits(got, ref, "cfg1 logits")
+    # decode parity: bit-exact on identical logits
+    assert m.decode(got) == O.decode_batch_predictions(got)
+    assert [list(i) for i in m.decode_ids(ref.astype(np.float32))] == [list(O.decode_phrase(r)) for r in ref.astype(np.float32)]
+
+
+def test_batched_forward_matches_oracle_and_is_batch_invariant(base):
+    cfg, params, m = base
+    x = O.make_inputs(cfg, 5, seed=7, ragged=True)
+    ref = O.forward(params, x, cfg, "float64")
+    got = m(x)
+    _check_logits(got, ref, "B=5 ragged logits")
+    # sequences are independent in inference: row b of a batch == the same sequence alone, bit for bit
+    solo = m(x[2:3])
+    assert np.array_equal(solo[0], got[2])
+
+
+def test_per_module_error_growth(base):
+    cfg, params, m = base
+    x = O.make_inputs(cfg, 2, seed=11)
+    taps = {}
+    O.forward(params, x, cfg, "float64", taps=taps)
+    names = ["stem", "convsqueeze_0_1", "convsqueeze_0_3", "squeezeformer_0", "squeezeformer_1", "convconform_0_3",
+             "conformer_0", "conformer_1"]
+    got = m.debug_activations(x, names)
+    for n in names:
+        r = taps[n]
+        e = np.abs(got[n] - r).max() / np.abs(r).max()
+        print(f"tap {n}: rel err {e:.4g} (scale {np.abs(r).max():.3g})")
+        assert e < 4e-2, n
+
+
+def test_device_path_dlpack_torch(base):
+    torch = pytest.importorskip("torch")
+    cfg, params, m = base
+    x = O.make_inputs(cfg, 3, seed=5)
+    host = m(x)
+    xt = torch.from_numpy(x).cuda()
+    out = m(xt)
+    assert isinstance(out, torch.Tensor) and out.is_cuda and out.shape == (3, cfg.frames, cfg.num_classes)
+    assert np.array_equal(out.cpu().numpy(), host)
+    # DLPack producer without torch on the caller side
+    xd = ib.from_host(x)
+    out2 = m(xd)
+    assert isinstance(out2, ib.DeviceTensor)
+    assert np.array_equal(out2.numpy(), host)
+    assert np.array_equal(torch.from_dlpack(out2).cpu().numpy(), host)
+
+
+def test_infer_host_whole_step(base):
+    cfg, params, m = base
+    x = O.make_inputs(cfg, 4, seed=21)
+    y = O.make_labels(cfg, 4, seed=22)
+    r = m.infer(x, labels=y, return_logits=True)
+    assert np.array_equal(r["logits"], m(x))
+    assert r["text"] == O.decode_batch_predictions(r["logits"])
+    ref_nll = O.ctc_loss(y, r["logits"])
+    assert np.allclose(r["nll"], ref_nll, rtol=1e-3)
+    r2 = m.infer(x)
+    assert r2["nll"] is None and r2["text"] == r["text"]
+
+
+@pytest.mark.parametrize("kw", [
+    dict(dim=128, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, num_heads=4, frames=96, features=64,
+         num_classes=28, kernel_sizes=(5, 3), num_conv_per_block=2, transformer_kernel_size=7),
+    dict(dim=256, num_conv_squeeze_blocks=1, num_conv_conform_blocks=0, frames=200, expansion_factor=4),
+    dict(dim=256, num_conv_squeeze_blocks=0, num_conv_conform_blocks=1, frames=130, num_conv_per_block=0),
+    dict(dim=384, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, frames=256),   # cfg5 width (dh=48)
+])
+def test_other_configurations(kw):
+    cfg = O.Config(**kw)
+    params = O.init_params(cfg, seed=9)
+    m = _model_for(cfg, params)
+    x = O.make_inputs(cfg, 2, seed=3, ragged=True)
+    _check_logits(m(x), O.forward(params, x, cfg, "float64"), f"cfg {kw}")
+
+
+# ------------------------------------------------------------------------------------------------
+# CTC
+# ------------------------------------------------------------------------------------------------
+def _ctc_case(rng, B, T, V, L, lens):
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    labels = np.full((B, L), V - 1, np.int32)
+    for b, n in enumerate(lens):
+        labels[b, :n] = rng.integers(0, V - 1, n)
+        if n > 3:
+            labels[b, 1] = labels[b, 0]
+    return logits, labels
+
+
+@pytest.mark.parametrize("T,V,L,lens", [
+    (384, 60, 64, [64, 0, 1, 33, 8, 64]),
+    (20, 8, 5, [5, 0, 3]),
+    (176, 60, 64, [64, 40]),
+    (384, 60, 100, [100, 77]),          # long labels: the 9-states-per-lane variant
+])
+def test_ctc_loss_and_gradient(T, V, L, lens):
+    rng = np.random.default_rng(T + L)
+    logits, labels = _ctc_case(rng, len(lens), T, V, L, lens)
+    ref_nll, ref_grad = O.ctc_loss(labels, logits, blank=V - 1, with_grad=True)
+    nll, grad = ib.CTCLoss(labels, logits, blank=V - 1, reduction="none", return_grad=True)
+    assert np.allclose(nll, ref_nll, rtol=1e-3, atol=1e-3), (nll, ref_nll)
+    assert np.abs(grad - ref_grad).max() < 2e-3
+    mean = ib.CTCLoss(labels, logits, blank=V - 1)
+    assert abs(mean - ref_nll.mean()) <= 1e-3 * abs(ref_nll.mean())
+
+
+def test_ctc_infeasible_is_inf_like_the_reference():
+    logits = np.zeros((2, 3, 5), np.float32)
+    labels = np.array([[0, 0, 1, 4], [1, 4, 4, 4]], np.int32)   # row 0 needs >= 4 frames
+    nll = ib.CTCLoss(labels, logits, blank=4, reduction="none")
+    assert np.isinf(nll[0]) and nll[0] > 0 and np.isfinite(nll[1])
+    assert abs(nll[1] - O.ctc_loss(labels, logits, blank=4)[1]) < 1e-4
+
+
+def test_ctc_shift_invariance_and_full_size_properties(base):
+    """Size-independent properties at the BASELINE batch: adding a per-frame constant to the logits leaves the
+    loss unchanged (log-softmax), and every gradient row sums to zero."""
+    rng = np.random.default_rng(0)
+    B, T, V, L = 256, 384, 60, 64
+    logits = rng.standard_normal((B, T, V)).astype(np.float32)
+    labels = O.make_labels(O.Config(), B)
+    nll, grad = ib.CTCLoss(labels, logits, reduction="none", return_grad=True)
+    shifted = logits + rng.standard_normal((B, T, 1)).astype(np.float32)
+    nll2 = ib.CTCLoss(labels, shifted, reduction="none")
+    assert np.allclose(nll, nll2, rtol=2e-4)
+    assert np.abs(grad.sum(-1)).max() < 2e-3
+    sub = [0, 17, 255]
+    assert np.allclose(nll[sub], O.ctc_loss(labels[sub], logits[sub]), rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# greedy decode
+# ------------------------------------------------------------------------------------------------
+def test_decode_bit_exact_on_random_runs():
+    rng = np.random.default_rng(4)
+    B, T, V = 9, 384, 60
+    base_l = rng.standard_normal((B, T, V)).astype(np.float32)
+    idx = np.sort(rng.integers(0, T, (B, T)), axis=1)                      # repeated frames => runs
+    logits = np.take_along_axis(base_l, idx[:, :, None], axis=1)
+    logits[:, :, V - 1] += 1.0                                             # plenty of blanks
+    got = ib.decode_ids(logits)
+    for b in range(B):
+        assert list(got[b]) == list(O.decode_phrase(logits[b]))
+    assert ib.decode_batch_predictions(logits) == O.decode_batch_predictions(logits)
+    assert list(ib.decode_phrase(logits[0])) == list(O.decode_phrase(logits[0]))
+
+
+def test_decode_edge_cases_quirk_ties_and_short_sequences():
+    def onehot(ids, V=60):
+        p = np.zeros((len(ids), V), np.float32)
+        p[np.arange(len(ids)), ids] = 1
+        return p
+
+    for ids in ([3, 3, 4, 4], [3, 59, 3, 59], [59, 59, 59], [7], [1, 2, 3, 59], [5, 6], list(range(40)) * 3):
+        p = onehot(ids)
+        assert list(ib.decode_phrase(p)) == list(O.decode_phrase(p)), ids
+    ties = np.zeros((1, 33, 60), np.float32)
+    ties[0, 5, 10] = ties[0, 5, 20] = 2.0                                  # first index wins
+    assert list(ib.decode_ids(ties)[0]) == list(O.decode_phrase(ties[0]))
+    # odd class count (no float4 path)
+    rng = np.random.default_rng(1)
+    lg = rng.standard_normal((3, 50, 13)).astype(np.float32)
+    got = ib.decode_ids(lg, blank=12)
+    assert [list(g) for g in got] == [list(O.decode_phrase(r, blank=12)) for r in lg]
+
+
+def test_decode_full_size_properties():
+    """At BASELINE batch size: output never contains the blank, never exceeds T-1 tokens, has no immediate
+    repeats unless separated in the argmax stream, and is idempotent under frame duplication of the last frame."""
+    rng = np.random.default_rng(8)
+    B, T, V = 256, 384, 60
+    logits = rng.standard_normal((B, T, V)).astype(np.float32)
+    logits[:, :, V - 1] += 1.5
+    ids = ib.decode_ids(logits)
+    am = logits.argmax(-1)
+    for b in range(0, B, 17):
+        assert list(ids[b]) == list(O.decode_phrase(logits[b]))
+    for b in range(B):
+        assert (ids[b] != V - 1).all() and len(ids[b]) <= T - 1
+        assert len(ids[b]) == int(((am[b, :-1] != am[b, 1:]) & (am[b, :-1] != V - 1)).sum())
