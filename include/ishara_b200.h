@@ -156,6 +156,17 @@ ISHARA_API ishara_status_t ishara_stream_synchronize(int32_t device, void* strea
 /* the handle's own stream (used by the *_host entry points) */
 ISHARA_API void* ishara_model_stream(ishara_model_t* m);
 
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------
+ * With profiling on, every forward records one CUDA event per launch on the launch stream; entries are the
+ * launches of the LAST forward in order (entry 0 = the input cast). ms = device time event-to-event; flops /
+ * bytes = the algorithmic cost of that launch. kind: "gemm" | "dwconv" | "attention" | ... */
+ISHARA_API ishara_status_t ishara_model_set_profile(ishara_model_t* m, int32_t on);
+ISHARA_API int32_t ishara_model_profile_count(const ishara_model_t* m);
+ISHARA_API ishara_status_t ishara_model_profile_entry(ishara_model_t* m, int32_t index, const char** label,
+                                           const char** kind, float* ms, double* flops, double* bytes);
+/* kernels launched by this library in this process so far */
+ISHARA_API uint64_t ishara_launch_count(void);
+
 /* ---- debugging aid: copy an internal activation of the last forward (bf16 -> fp32) to the host ---
  * Enable with ishara_model_set_debug(m, 1) before the forward. Names: "stem", a Conv1DBlock name
  * ("convsqueeze_0_1", ...), "squeezeformer_<i>", "conformer_<i>": the residual stream after that module. */

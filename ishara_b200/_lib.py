@@ -101,6 +101,11 @@ SIGNATURES = {
     "ishara_memcpy_async": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "ishara_stream_synchronize": (_i32, [_i32, _vp]),
     "ishara_model_stream": (_vp, [_vp]),
+    "ishara_model_set_profile": (_i32, [_vp, _i32]),
+    "ishara_model_profile_count": (_i32, [_vp]),
+    "ishara_model_profile_entry": (_i32, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(_f32),
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ishara_launch_count": (C.c_uint64, []),
     "ishara_model_set_debug": (_i32, [_vp, _i32]),
     "ishara_model_debug_fetch": (_i32, [_vp, C.c_char_p, _vp, _i64]),
 }

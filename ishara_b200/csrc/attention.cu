@@ -198,6 +198,7 @@ int launch_inst(const AttnArgs& a, cudaStream_t stream) {
   kern<<<dim3(a.H, a.B), kAttnThreads, smem, stream>>>(a.qkv, a.out, a.key_mask, a.T, a.H, Tp,
                                                       a.scale * 1.4426950408889634f);
   ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 

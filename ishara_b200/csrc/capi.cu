@@ -35,6 +35,9 @@ int model_param_info(const ishara_model* m, int idx, const char** name, int64_t*
 int model_set_param(ishara_model* m, const char* name, const float* data, int64_t numel);
 int model_get_param(const ishara_model* m, const char* name, float* out, int64_t numel);
 int model_set_debug(ishara_model* m, int on);
+int model_set_profile(ishara_model* m, int on);
+int model_profile_count(const ishara_model* m);
+int model_profile_entry(ishara_model* m, int i, const char** label, const char** kind, float* ms, double* flops, double* bytes);
 int model_debug_fetch(ishara_model* m, const char* name, float* host_out, int64_t numel);
 }  // namespace ishara
 
@@ -319,6 +322,22 @@ ishara_status_t ishara_stream_synchronize(int32_t device, void* stream) {
   CAPI_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return ISHARA_OK;
 }
+ishara_status_t ishara_model_set_profile(ishara_model_t* m, int32_t on) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_set_profile(reinterpret_cast<ishara_model*>(m), on));
+}
+int32_t ishara_model_profile_count(const ishara_model_t* m) {
+  if (m == nullptr) return 0;
+  return model_profile_count(reinterpret_cast<const ishara_model*>(m));
+}
+ishara_status_t ishara_model_profile_entry(ishara_model_t* m, int32_t index, const char** label, const char** kind,
+                                           float* ms, double* flops, double* bytes) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(
+      model_profile_entry(reinterpret_cast<ishara_model*>(m), index, label, kind, ms, flops, bytes));
+}
+uint64_t ishara_launch_count(void) { return launch_count(); }
+
 void* ishara_model_stream(ishara_model_t* m) {
   if (m == nullptr) return nullptr;
   ModelView v;

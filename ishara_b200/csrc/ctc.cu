@@ -176,19 +176,35 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
 #pragma unroll
       for (int i = 0; i < SPL; ++i) bt[i] = nb[i];
     }
-    // occupancy: exp(alpha_t(s) + beta_t(s) - logy_t(ext s) - logp), scattered by class
+    // occupancy: alpha_t(s) beta_t(s) / y_t(ext s), scattered by class. In exact arithmetic the sum over s is
+    // p(l|x) at every t; normalising by the per-frame sum instead of exp(logp) keeps fp32 drift out of the
+    // gradient (each row of d nll / d logits then sums to zero to rounding).
     for (int v = lane; v < Vpad; v += 32) occ[v] = 0.f;
     __syncwarp();
     if (feasible) {
       const float* asrc = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
+      float e[SPL];
+      float mx = kLogZero;
 #pragma unroll
       for (int i = 0; i < SPL; ++i) {
         const int s = lane * SPL + i;
-        if (s < S) {
-          const float e = asrc[i] + bt[i] - em[i] - logp;
-          if (e > -80.f) atomicAdd(&occ[ext[i]], __expf(e));
-        }
+        e[i] = (s < S) ? asrc[i] + bt[i] - em[i] : kLogZero;
+        mx = fmaxf(mx, e[i]);
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        e[i] = (e[i] - mx > -80.f) ? __expf(e[i] - mx) : 0.f;
+        sum += e[i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int i = 0; i < SPL; ++i)
+        if (e[i] != 0.f) atomicAdd(&occ[ext[i]], e[i] * inv);
     }
     __syncwarp();
     for (int v = lane; v < V; v += 32) {
@@ -301,6 +317,7 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
     kern<<<grid, kCtcWarps * 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
   }
   ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -317,6 +334,7 @@ int greedy_decode_launch(const float* logits, int B, int T, int V, int blank, in
                                         static_cast<int>(smem)));
   greedy_decode_kernel<<<grid, kDecWarps * 32, smem, stream>>>(logits, B, T, V, blank, ids_out, lens);
   ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 

@@ -195,6 +195,7 @@ int launch_inst(const DwConvArgs& a, cudaStream_t stream) {
   cfg.numAttrs = nattr;
   ISHARA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a.in, a.out, a.w, a.bias, a.eca_w, a.colsum, a.T, a.C, a.pad_left,
                                     rows_alloc));
+  note_launch();
   return 0;
 }
 

@@ -434,6 +434,7 @@ int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   if (grid > num_sms) grid = num_sms;
   kern<<<grid, 384, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.epi, p.M, p.N, p.K, mt, nt);
   ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 

@@ -14,6 +14,9 @@ typedef __nv_bfloat16 bf16;
 // ---- error plumbing -------------------------------------------------------------------------
 void set_last_error(const std::string& msg);
 const char* get_last_error();
+// every kernel launcher bumps this process-wide counter (bench.py reports it as gpu_launches)
+void note_launch();
+uint64_t launch_count();
 #define ISHARA_CUDA_OK(expr)                                                                           \
   do {                                                                                                 \
     cudaError_t _e = (expr);                                                                           \

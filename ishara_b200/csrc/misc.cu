@@ -1,4 +1,5 @@
 // ishara_b200 — small memory-bound helpers: input cast/pad, SqueezeExcite gate, standalone LayerNorm.
+#include <atomic>
 #include <mutex>
 
 #include "kernels.h"
@@ -10,6 +11,10 @@ namespace ishara {
 static thread_local std::string tls_error;
 void set_last_error(const std::string& msg) { tls_error = msg; }
 const char* get_last_error() { return tls_error.c_str(); }
+
+static std::atomic<uint64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 namespace {
 
@@ -120,6 +125,7 @@ int cast_pad_launch(const float* x, bf16* out, int64_t M, int F, int Fpad, cudaS
   if (grid > 148 * 16) grid = 148 * 16;
   cast_pad_kernel<<<grid, 256, 0, stream>>>(x, out, M, F, Fpad);
   ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -127,6 +133,7 @@ int se_gate_launch(const SeGateArgs& a, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(a.C + a.D + a.R) * sizeof(float);
   se_gate_kernel<<<a.B, 256, smem, stream>>>(a);
   ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
@@ -138,6 +145,7 @@ int layernorm_launch(const bf16* x, bf16* out, const float* g, const float* b, f
   }
   layernorm_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, stream>>>(x, out, g, b, eps, M, D);
   ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 

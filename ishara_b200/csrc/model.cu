@@ -50,6 +50,9 @@ struct Op {
   LnRef ln;
   int tap = -1;
   const char* label = "";
+  // algorithmic cost of one launch: useful flops and compulsory HBM bytes (operands read once,
+  // results written once; weights counted once per launch)
+  double flops = 0.0, bytes = 0.0;
 };
 
 inline uint16_t f2bf(float f) {
@@ -91,6 +94,8 @@ struct ishara_model {
   std::vector<std::string> tap_names;
 
   std::vector<Op> program;
+  bool profile = false;               // record one CUDA event per op during forward
+  std::vector<cudaEvent_t> events;    // [0] before cast_pad, [1] after it, [2+i] after program[i]
   int program_batch = 0;
   float* program_logits = nullptr;
   cudaStream_t stream = nullptr;
@@ -469,13 +474,16 @@ struct Builder {
     p.epi.rows_per_seq = T;
     const int nout = act == ACT_GLU ? N / 2 : N;
     rc = gemm_plan_init(&p, A, K, pk.get<bf16>(wkey), out, nout, nout, nullptr, 0);
+    op.flops = 2.0 * M * N * K;
+    op.bytes = 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * nout);
     ops.push_back(op);
   }
 
   // S = [LN0]( A@W + bias [*gate] [+rowtab] [+S] ) ; XN = LN1(S)
   void stream_gemm(const char* label, const bf16* A, int K, const std::string& wkey, const std::string& bkey,
-                   const float* gate, const float* rowtab, bool resid, LnRef ln0, LnRef ln1) {
+                   const float* gate, const float* rowtab, bool resid, LnRef ln0, LnRef ln1, int klogical = 0) {
     if (rc) return;
+    if (klogical == 0) klogical = K;
     Op op;
     op.kind = OP_GEMM;
     op.label = label;
@@ -495,11 +503,18 @@ struct Builder {
       p.epi.ln0_g = ln0.g; p.epi.ln0_b = ln0.b; p.epi.ln0_eps = ln0.eps;
       p.epi.ln1_g = ln1.g; p.epi.ln1_b = ln1.b; p.epi.ln1_eps = ln1.eps;
       rc = gemm_plan_init(&p, A, K, pk.get<bf16>(wkey), m->S, D, D, ln1.g ? m->XN : nullptr, D);
+      op.flops = 2.0 * M * D * klogical;
+      op.bytes = 2.0 * (static_cast<double>(M) * K + static_cast<double>(D) * K +
+                        static_cast<double>(M) * D * (1 + (resid ? 1 : 0) + (ln1.g ? 1 : 0))) +
+                 (rowtab ? 4.0 * T * D : 0.0) + (gate ? 4.0 * B * D : 0.0);
       ops.push_back(op);
     } else {
       p.block_n = wide_block_n(D);
       p.row_mode = false;
       rc = gemm_plan_init(&p, A, K, pk.get<bf16>(wkey), m->S, D, D, nullptr, 0);
+      op.flops = 2.0 * M * D * klogical;
+      op.bytes = 2.0 * (static_cast<double>(M) * K + static_cast<double>(D) * K + static_cast<double>(M) * D * (1 + (resid ? 1 : 0))) +
+                 (rowtab ? 4.0 * T * D : 0.0) + (gate ? 4.0 * B * D : 0.0);
       ops.push_back(op);
       if (ln0.g) layernorm(m->S, m->S, ln0);
       if (ln1.g) layernorm(m->S, m->XN, ln1);
@@ -510,6 +525,8 @@ struct Builder {
     op.kind = OP_LN;
     op.label = "layernorm";
     op.ln_in = in; op.ln_out = out; op.ln = ln;
+    op.flops = 8.0 * M * D;
+    op.bytes = 4.0 * M * D;
     ops.push_back(op);
   }
   void dwconv(const char* label, const bf16* in, bf16* out, int C, int k, int pad_left, const std::string& wkey,
@@ -524,6 +541,8 @@ struct Builder {
     op.dw.eca_w = ecakey.empty() ? nullptr : pk.get<float>(ecakey);
     op.dw.colsum = colsum;
     op.dw.B = B; op.dw.T = T; op.dw.C = C; op.dw.k = k; op.dw.pad_left = pad_left; op.dw.post = post;
+    op.flops = 2.0 * M * C * k;
+    op.bytes = 4.0 * M * C;  // bf16 in + bf16 out
     ops.push_back(op);
   }
   void attention(const bf16* qkv, bf16* out) {
@@ -534,6 +553,8 @@ struct Builder {
     op.at.qkv = qkv; op.at.out = out; op.at.key_mask = nullptr;
     op.at.B = B; op.at.T = T; op.at.H = m->cfg.num_heads; op.at.dh = D / m->cfg.num_heads;
     op.at.scale = 1.f / std::sqrt(static_cast<float>(D));  // self.scale = dim ** -0.5 (c5:95), NOT dh ** -0.5
+    op.flops = 4.0 * M * T * D;             // QK^T and PV: 2 * (2 * T * T * D) per sequence
+    op.bytes = 2.0 * M * (3.0 * D + D);     // qkv read + out write
     ops.push_back(op);
   }
   void tap(const std::string& name) {
@@ -599,7 +620,8 @@ int build_program(ishara_model* m, int batch, float* logits) {
   {
     // stem
     LnRef nl = has_conv ? LnRef() : first_ln_of(0, 0);
-    b.stream_gemm("stem", m->XIN, m->fpad(), "stem.w", "", nullptr, b.pk.get<float>("stem.tab"), false, LnRef(), nl);
+    b.stream_gemm("stem", m->XIN, m->fpad(), "stem.w", "", nullptr, b.pk.get<float>("stem.tab"), false, LnRef(), nl,
+                  c.features);
     b.tap("stem");
   }
   for (int i = 0; i < c.num_conv_squeeze_blocks; ++i) {
@@ -626,6 +648,8 @@ int build_program(ishara_model* m, int batch, float* logits) {
       op.se.gate = m->gate;
       op.se.B = batch; op.se.C = E; op.se.D = D; op.se.R = std::max(1, D / 8);
       op.se.inv_T = 1.f / static_cast<float>(c.frames);
+      op.flops = 2.0 * batch * (static_cast<double>(E) * D + 2.0 * D * op.se.R);
+      op.bytes = 4.0 * batch * (E + D) + 2.0 * E * D;
       m->program.push_back(op);
     }
     b.stream_gemm("sqz.conv3_se", m->H2, E, n + ".conv.conv3.w", n + ".conv.conv3.b", m->gate, nullptr, true, LnRef(),
@@ -662,6 +686,8 @@ int build_program(ishara_model* m, int batch, float* logits) {
     p.epi.rows_per_seq = c.frames;
     b.rc = gemm_plan_init(&p, m->HEAD, 2 * D, b.pk.get<bf16>("classifier.w"), logits, c.num_classes, c.num_classes,
                           nullptr, 0);
+    op.flops = 2.0 * b.M * c.num_classes * 2.0 * D;
+    op.bytes = 2.0 * b.M * 2.0 * D + 2.0 * m->vpad() * 2.0 * D + 4.0 * b.M * c.num_classes;
     m->program.push_back(op);
   }
   if (b.rc) {
@@ -704,6 +730,7 @@ int model_destroy(ishara_model* m) {
   if (m->finalized || !m->wsallocs.empty()) cudaSetDevice(m->device);
   for (void* p : m->wallocs) cudaFree(p);
   for (void* p : m->wsallocs) cudaFree(p);
+  for (cudaEvent_t e : m->events) cudaEventDestroy(e);
   if (m->labels_dev) cudaFree(m->labels_dev);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -739,7 +766,18 @@ int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_
     if ((rc = build_program(m, batch, logits_dev))) return rc;
   const ishara_config_t& c = m->cfg;
   const int64_t M = static_cast<int64_t>(batch) * c.frames;
+  const bool prof = m->profile;
+  if (prof) {
+    while (m->events.size() < m->program.size() + 2) {
+      cudaEvent_t e;
+      ISHARA_CUDA_OK(cudaEventCreate(&e));
+      m->events.push_back(e);
+    }
+    ISHARA_CUDA_OK(cudaEventRecord(m->events[0], stream));
+  }
   if ((rc = cast_pad_launch(x_dev, m->XIN, M, c.features, m->fpad(), stream))) return rc;
+  if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[1], stream));
+  size_t op_index = 0;
   for (const Op& op : m->program) {
     switch (op.kind) {
       case OP_GEMM: rc = gemm_launch(op.gemm, m->num_sms, stream); break;
@@ -755,8 +793,44 @@ int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_
       set_last_error(std::string("forward: op '") + op.label + "' failed: " + get_last_error());
       return rc;
     }
+    if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[2 + op_index], stream));
+    ++op_index;
   }
   return ISHARA_OK;
+}
+
+int model_set_profile(ishara_model* m, int on) {
+  m->profile = on != 0;
+  return 0;
+}
+int model_profile_count(const ishara_model* m) { return m->program.empty() ? 0 : static_cast<int>(m->program.size()) + 1; }
+// entry 0 = the fp32->bf16 input cast; entry 1+i = program[i]. ms = device time of that launch in the LAST
+// profiled forward (event to event on the launch stream, so it includes the launch gap before the kernel).
+int model_profile_entry(ishara_model* m, int i, const char** label, const char** kind, float* ms, double* flops,
+                        double* bytes) {
+  const int n = model_profile_count(m);
+  if (i < 0 || i >= n) { set_last_error("profile_entry: index out of range"); return ISHARA_ERR_INVALID; }
+  if (m->events.size() < static_cast<size_t>(n) + 1) { set_last_error("profile_entry: no profiled forward yet"); return ISHARA_ERR_STATE; }
+  ISHARA_CUDA_OK(cudaEventSynchronize(m->events[n]));
+  float t = 0.f;
+  ISHARA_CUDA_OK(cudaEventElapsedTime(&t, m->events[i], m->events[i + 1]));
+  const ishara_config_t& c = m->cfg;
+  const double M = static_cast<double>(m->program_batch) * c.frames;
+  static const char* kinds[] = {"gemm", "dwconv", "attention", "se_gate", "layernorm", "tap"};
+  if (i == 0) {
+    if (label) *label = "input.cast_pad";
+    if (kind) *kind = "cast";
+    if (flops) *flops = 0.0;
+    if (bytes) *bytes = M * (4.0 * c.features + 2.0 * m->fpad());
+  } else {
+    const Op& op = m->program[i - 1];
+    if (label) *label = op.label;
+    if (kind) *kind = kinds[op.kind];
+    if (flops) *flops = op.flops;
+    if (bytes) *bytes = op.bytes;
+  }
+  if (ms) *ms = t;
+  return 0;
 }
 
 

@@ -265,6 +265,36 @@ class IsharaModel:
         id_list = [ids[b, : lens[b]].astype(np.int64) for b in range(B)]
         return {"ids": id_list, "text": ["".join(num_to_char_fn(i)) for i in id_list], "nll": nll, "logits": logits}
 
+    # ---- measurement hook (bench.py) ------------------------------------------------------------
+    def profile_forward(self, x: ArrayLike, logits=None) -> List[dict]:
+        """Run one forward with one CUDA event per launch; returns [{'label','kind','ms','flops','bytes'}] in
+        launch order (device time event-to-event on the launch stream; algorithmic flops/bytes per launch)."""
+        _lib.check(self._lib.ishara_model_set_profile(self._h, 1))
+        try:
+            self(x) if logits is None else self.forward_into(x, logits)
+            out = []
+            for i in range(self._lib.ishara_model_profile_count(self._h)):
+                label, kind, ms = C.c_char_p(), C.c_char_p(), C.c_float()
+                fl, by = C.c_double(), C.c_double()
+                _lib.check(self._lib.ishara_model_profile_entry(self._h, i, C.byref(label), C.byref(kind), C.byref(ms),
+                                                                C.byref(fl), C.byref(by)))
+                out.append({"label": label.value.decode(), "kind": kind.value.decode(), "ms": float(ms.value),
+                            "flops": float(fl.value), "bytes": float(by.value)})
+            return out
+        finally:
+            _lib.check(self._lib.ishara_model_set_profile(self._h, 0))
+
+    def forward_into(self, x: ArrayLike, logits: ArrayLike):
+        """Device-resident forward into a caller-owned logits tensor (no allocation; what a serving loop calls)."""
+        xd = _Dev(x, "float32", self.device)
+        self._check_x(xd.shape)
+        od = _Dev(logits, "float32", self.device)
+        if tuple(od.shape) != (xd.shape[0], self.frames, self.num_classes):
+            raise ValueError("logits must be [B,T,num_classes]")
+        self._ensure_finalized()
+        _lib.check(self._lib.ishara_model_forward(self._h, _vp(xd.ptr), xd.shape[0], _vp(od.ptr), _vp(xd.stream)))
+        return logits
+
     # ---- debugging aid -------------------------------------------------------------------------
     def debug_activations(self, x: np.ndarray, names: Iterable[str]) -> Dict[str, np.ndarray]:
         """Residual stream after the named modules ('stem', 'convsqueeze_0_1', 'squeezeformer_0', …) as fp32."""
