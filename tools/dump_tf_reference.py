@@ -1,0 +1,79 @@
+"""Emit true golden vectors from the REAL reference (needs TensorFlow 2.12-era + tensorflow_addons and a checkout
+of tanmayrainanda/ishara; neither exists in the build image, so this script is the documented upgrade path from
+"parity unpinned" to "pinned" — DESIGN.md §3).
+
+It does not contain reference code: it loads cells c5-c8 of `Test Notebooks/conv-hybrid-model.ipynb` from the
+checkout you point it at, executes them, builds get_model() with the BASELINE kwargs, loads the seeded weights
+that oracle.init_params generates (so both sides share weights), runs seeded inputs and writes
+
+    tests/golden/tf_reference.npz   weights (Keras names), x, labels, logits, per-sequence CTC loss, decoded ids
+
+usage: python tools/dump_tf_reference.py /path/to/ishara [--frames 384] [--batch 4]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("reference_checkout")
+    ap.add_argument("--frames", type=int, default=384)
+    ap.add_argument("--batch", type=int, default=4)
+    args = ap.parse_args()
+
+    import tensorflow as tf
+    import tensorflow_addons as tfa  # noqa: F401  (get_model's optimizer)
+
+    from oracle import ishara_oracle as O
+
+    nb = json.load(open(os.path.join(args.reference_checkout, "Test Notebooks", "conv-hybrid-model.ipynb")))
+    code = [c for c in nb["cells"] if c["cell_type"] == "code"]
+    ns = {"tf": tf, "tfa": tfa, "np": np, "INPUT_SHAPE": [args.frames, 276], "pad_token_idx": O.PAD_TOKEN_IDX,
+          "char_to_num": dict(O.CHAR_TO_NUM), "num_to_char": dict(O.NUM_TO_CHAR)}
+    for idx in (5, 6):
+        exec("".join(code[idx]["source"]), ns)
+    c7 = "".join(code[7]["source"]).split("tf.keras.backend.clear_session()")[0]   # the def only, not the demo call
+    exec(c7, ns)
+    exec("".join(code[8]["source"]), ns)
+
+    cfg = O.Config(frames=args.frames)
+    params = O.init_params(cfg, seed=42)
+    model = ns["get_model"]()
+    x = O.make_inputs(cfg, args.batch, seed=1234)
+    y = O.make_labels(cfg, args.batch)
+    model(x)  # build
+
+    def keras_name_to_ours(layer, var):
+        return f"{layer}.{var}"
+
+    assigned = 0
+    for v in model.variables:
+        path = v.name.split(":")[0]                      # e.g. 'squeezeformer_0/mha/qkv/kernel' (TF 2.12 naming)
+        cand = path.replace("/", ".")
+        for name in params:
+            if cand.endswith(name) or name.replace("_eca.", ".").endswith(cand):
+                v.assign(params[name].reshape(v.shape))
+                assigned += 1
+                break
+        else:
+            raise SystemExit(f"no oracle parameter for Keras variable {v.name} — extend the name map")
+    assert assigned == len(params), (assigned, len(params))
+    logits = model(x, training=False).numpy()
+    nll = tf.nn.ctc_loss(labels=y, logits=logits, label_length=(y != 59).sum(-1).astype(np.int32),
+                         logit_length=np.full(args.batch, args.frames, np.int32), blank_index=59,
+                         logits_time_major=False).numpy()
+    ids = [ns["decode_phrase"](l).numpy() for l in logits]
+    out = os.path.join(ROOT, "tests", "golden", "tf_reference.npz")
+    np.savez(out, x=x, labels=y, logits=logits, nll=nll, ids=np.array(ids, dtype=object), **{"w:" + k: v for k, v in params.items()})
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()
