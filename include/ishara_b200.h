@@ -139,6 +139,24 @@ ISHARA_API ishara_status_t ishara_op_dwconv(const void* in_bf16, void* out_bf16,
 /* attention core on per-head-interleaved qkv bf16 [B*T, 3*H*dh] -> out bf16 [B*T, H*dh] */
 ISHARA_API ishara_status_t ishara_op_attention(const void* qkv_bf16, void* out_bf16, const uint8_t* key_mask, int32_t B, int32_t T,
                                     int32_t H, int32_t dh, float scale, void* stream);
+/* Transformer-XL relative-position attention core (squeezeformer/attention.py:25-110): qkv as above (biases already
+ * added), pos bf16 [2T-1, H*dh] = pos_proj(pos_emb), u_bias / v_bias fp32 [H*dh]; the reference's _relative_shift is
+ * folded into index arithmetic. key_mask uint8 [B,T], 1 = keep (the reference's mask is True = masked). */
+ISHARA_API ishara_status_t ishara_op_relpos_attention(const void* qkv_bf16, const void* pos_bf16, const float* u_bias,
+                                           const float* v_bias, void* out_bf16, const uint8_t* key_mask, int32_t B,
+                                           int32_t T, int32_t H, int32_t dh, float scale, void* stream);
+/* TimeReductionLayer (squeezeformer/convolution.py:241-269): Conv2d(1->1,3,stride 2)+bias+Swish over the [T,D] plane;
+ * x bf16 [B,T,D] -> out bf16 [B,(T-3)/2+1, ldo] (first (D-3)/2+1 columns valid, rest zero). w9 = 3x3 weight (host). */
+ISHARA_API ishara_status_t ishara_op_time_reduce(const void* x_bf16, void* out_bf16, const float* w9_host, float bias, int32_t B,
+                                      int32_t T, int32_t D, int32_t ldo, void* stream);
+/* recover step (squeezeformer/modules.py:137-142 + encoder.py:157-162): out[b,t,:] = y[b,t/2,:] + rec[b,t,:], t < 2*T2 */
+ISHARA_API ishara_status_t ishara_op_upsample_add(const void* y_bf16, const void* rec_bf16, void* out_bf16, int32_t B, int32_t T2,
+                                       int32_t T, int32_t D, void* stream);
+/* DepthwiseConv2dSubsampling (squeezeformer/convolution.py:39-73): x fp32 [B,T,F] -> bf16 [B,T4,ldo], column c*F4+f.
+ * w1/b1: Conv2d(1->C,3,s2) [C,9]/[C]; w2/b2: depthwise Conv2d(C,3,s2) [C,9]/[C]; all device fp32. */
+ISHARA_API ishara_status_t ishara_op_conv2d_subsample(const float* x, void* out_bf16, const float* w1, const float* b1,
+                                           const float* w2, const float* b2, int32_t B, int32_t T, int32_t F, int32_t C,
+                                           int32_t ldo, void* stream);
 ISHARA_API ishara_status_t ishara_op_layernorm(const void* x_bf16, void* out_bf16, const float* gamma, const float* beta,
                                     float eps, int64_t M, int32_t D, void* stream);
 ISHARA_API ishara_status_t ishara_op_cast_pad(const float* x, void* out_bf16, int64_t M, int32_t F, int32_t Fpad, void* stream);

@@ -92,6 +92,10 @@ SIGNATURES = {
     "ishara_op_gemm": (_i32, [C.POINTER(GemmArgs), _vp]),
     "ishara_op_dwconv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ishara_op_attention": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "ishara_op_relpos_attention": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "ishara_op_time_reduce": (_i32, [_vp, _vp, _vp, _f32, _i32, _i32, _i32, _i32, _vp]),
+    "ishara_op_upsample_add": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ishara_op_conv2d_subsample": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ishara_op_layernorm": (_i32, [_vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp]),
     "ishara_op_cast_pad": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "ishara_device_malloc": (_i32, [_i32, _i64, C.POINTER(_vp)]),

@@ -267,6 +267,66 @@ ishara_status_t ishara_op_attention(const void* qkv_bf16, void* out_bf16, const 
   return static_cast<ishara_status_t>(attention_launch(a, static_cast<cudaStream_t>(stream)));
 }
 
+ishara_status_t ishara_op_relpos_attention(const void* qkv_bf16, const void* pos_bf16, const float* u_bias,
+                                           const float* v_bias, void* out_bf16, const uint8_t* key_mask, int32_t B,
+                                           int32_t T, int32_t H, int32_t dh, float scale, void* stream) {
+  if (qkv_bf16 == nullptr || pos_bf16 == nullptr || u_bias == nullptr || v_bias == nullptr || out_bf16 == nullptr) {
+    set_last_error("op_relpos_attention: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  AttnArgs a;
+  a.qkv = static_cast<const bf16*>(qkv_bf16);
+  a.pos = static_cast<const bf16*>(pos_bf16);
+  a.u_bias = u_bias; a.v_bias = v_bias;
+  a.out = static_cast<bf16*>(out_bf16);
+  a.key_mask = key_mask;
+  a.B = B; a.T = T; a.H = H; a.dh = dh; a.scale = scale;
+  return static_cast<ishara_status_t>(attention_launch(a, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_time_reduce(const void* x_bf16, void* out_bf16, const float* w9_host, float bias, int32_t B,
+                                      int32_t T, int32_t D, int32_t ldo, void* stream) {
+  if (x_bf16 == nullptr || out_bf16 == nullptr || w9_host == nullptr) {
+    set_last_error("op_time_reduce: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  TimeReduceArgs a;
+  a.x = static_cast<const bf16*>(x_bf16);
+  a.out = static_cast<bf16*>(out_bf16);
+  for (int i = 0; i < 9; ++i) a.w[i] = w9_host[i];
+  a.bias = bias;
+  a.B = B; a.T = T; a.D = D; a.T2 = (T - 3) / 2 + 1; a.D2 = (D - 3) / 2 + 1; a.ldo = ldo;
+  return static_cast<ishara_status_t>(time_reduce_launch(a, static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_upsample_add(const void* y_bf16, const void* rec_bf16, void* out_bf16, int32_t B, int32_t T2,
+                                       int32_t T, int32_t D, void* stream) {
+  if (y_bf16 == nullptr || rec_bf16 == nullptr || out_bf16 == nullptr) {
+    set_last_error("op_upsample_add: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  return static_cast<ishara_status_t>(upsample_add_launch(static_cast<const bf16*>(y_bf16), static_cast<const bf16*>(rec_bf16),
+                                                          static_cast<bf16*>(out_bf16), B, T2, T, D,
+                                                          static_cast<cudaStream_t>(stream)));
+}
+
+ishara_status_t ishara_op_conv2d_subsample(const float* x, void* out_bf16, const float* w1, const float* b1,
+                                           const float* w2, const float* b2, int32_t B, int32_t T, int32_t F, int32_t C,
+                                           int32_t ldo, void* stream) {
+  if (x == nullptr || out_bf16 == nullptr || w1 == nullptr || b1 == nullptr || w2 == nullptr || b2 == nullptr) {
+    set_last_error("op_conv2d_subsample: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  Conv2dSubsampleArgs a;
+  a.x = x; a.out = static_cast<bf16*>(out_bf16);
+  a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2;
+  a.B = B; a.T = T; a.F = F; a.C = C;
+  a.T4 = (((T - 3) / 2 + 1) - 3) / 2 + 1;
+  a.F4 = (((F - 3) / 2 + 1) - 3) / 2 + 1;
+  a.ldo = ldo;
+  return static_cast<ishara_status_t>(conv2d_subsample_launch(a, static_cast<cudaStream_t>(stream)));
+}
+
 ishara_status_t ishara_op_layernorm(const void* x_bf16, void* out_bf16, const float* gamma, const float* beta, float eps,
                                     int64_t M, int32_t D, void* stream) {
   if (x_bf16 == nullptr || out_bf16 == nullptr || gamma == nullptr || beta == nullptr) {

@@ -228,8 +228,9 @@ int dwconv_launch(const DwConvArgs& a, cudaStream_t stream) {
     case 9: return launch_k<9>(a, stream);
     case 11: return launch_k<11>(a, stream);
     case 15: return launch_k<15>(a, stream);
+    case 31: return launch_k<31>(a, stream);
   }
-  set_last_error("dwconv: unsupported kernel size (3,5,7,9,11,15)");
+  set_last_error("dwconv: unsupported kernel size (3,5,7,9,11,15,31)");
   return 2;
 }
 

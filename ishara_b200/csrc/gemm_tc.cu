@@ -30,6 +30,7 @@ constexpr int kBK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kAStageBytes = kBM * kBK * 2;
 constexpr int kStgBytes = 128 * 128;  // one staging tile: 128 rows x 128 bytes
 constexpr int kNumStg = 4;            // 2 per epilogue group
+constexpr int kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 
 __host__ __device__ constexpr int gemm_stages(int bn) { return bn >= 256 ? 3 : 4; }
 __host__ __device__ constexpr int gemm_stage_bytes(int bn) { return kAStageBytes + bn * kBK * 2; }
@@ -129,10 +130,14 @@ struct StoreRing {
   uint32_t iter;      // running chunk counter (selects the buffer)
   uint32_t bar_id;
   bool leader;
+  bool single;        // one staging tile per group instead of two
   __device__ __forceinline__ uint32_t acquire() {
-    if (leader) tma_store_wait_read<1>();  // the store that last used this buffer has drained
+    if (leader) {     // the store that last used this buffer has drained
+      if (single) tma_store_wait_read<0>();
+      else tma_store_wait_read<1>();
+    }
     named_bar_sync(bar_id, 128);
-    return stg_base + (iter & 1u) * kStgBytes;
+    return stg_base + (single ? 0u : (iter & 1u) * kStgBytes);
   }
   __device__ __forceinline__ void release(const CUtensorMap* tm, uint32_t buf, int c0, int c1) {
     fence_proxy_async_smem();
@@ -148,33 +153,46 @@ struct StoreRing {
   }
 };
 
-template <int BN, bool ROW, bool OUT_F32>
+// RESB ("resident B", weight-stationary): the CTA keeps its whole [BN x K] weight slice in shared memory for the
+// lifetime of the kernel and streams only A tiles through the ring, so the L2->SM traffic per tile drops from
+// A + B to A alone (ncu on the streaming variant: MMA issue waits on the TMA ring, tensor pipe 22 % active). Each CTA
+// is pinned to one n-tile; m-tiles are strided over the CTAs of that n-tile.
+template <int BN, bool ROW, bool OUT_F32, bool RESB>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-               const GemmEpi ep, int M, int N, int K, int num_m_tiles, int num_n_tiles) {
-  constexpr int STAGES = gemm_stages(BN);
-  constexpr int STAGE_BYTES = gemm_stage_bytes(BN);
+               const GemmEpi ep, int M, int N, int K, int num_m_tiles, int num_n_tiles, int num_stages) {
+  constexpr int B_KB_BYTES = BN * kBK * 2;                              // one k-block of the weight slice
+  constexpr int STAGE_BYTES = RESB ? kAStageBytes : gemm_stage_bytes(BN);
+  constexpr int NUM_STG = RESB ? 2 : kNumStg;                           // staging tiles (per group: NUM_STG / 2)
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   constexpr uint32_t IDESC = umma_idesc(kBM, BN, /*bf16*/ 1);
+  const int STAGES = num_stages;
+  const int num_kb = K / kBK;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  uint8_t* stage_ptr = smem;
-  uint8_t* stg_ptr = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_ptr + kNumStg * kStgBytes);
+  const uint32_t resb_bytes = RESB ? static_cast<uint32_t>(num_kb) * B_KB_BYTES : 0u;
+  uint8_t* resb_ptr = smem;                                             // [num_kb][BN x 64] (RESB only)
+  uint8_t* stage_ptr = smem + resb_bytes;
+  uint8_t* stg_ptr = stage_ptr + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_ptr + NUM_STG * kStgBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bfull = bars + 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = num_m_tiles * num_n_tiles;
-  const int num_kb = K / kBK;
+  // tile walk: streaming variant strides over all (m, n) tiles; RESB pins the CTA to n-tile (blockIdx.x % num_n_tiles)
+  // and strides m-tiles by the CTAs sharing that n-tile (gridDim.x is a multiple of num_n_tiles).
+  const int tile_begin = RESB ? (blockIdx.x / num_n_tiles) * num_n_tiles + (blockIdx.x % num_n_tiles) : blockIdx.x;
+  const int tile_step = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -191,6 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], 128);
     mbar_init(&tempty[1], 128);
+    mbar_init(bfull, 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -203,14 +222,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if constexpr (RESB) {
+        if (tile_begin < num_tiles) {
+          const int n_tile = tile_begin % num_n_tiles;
+          mbar_arrive_expect_tx(bfull, resb_bytes);
+          for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(resb_ptr + kb * B_KB_BYTES, &tmB, bfull, kb * kBK, n_tile * BN);
+        }
+      }
+      for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
         const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = stage_ptr + stage * STAGE_BYTES;
           tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_tile * kBM);
-          tma_load_2d(sa + kAStageBytes, &tmB, &full[stage], kb * kBK, n_tile * BN);
+          if constexpr (!RESB) tma_load_2d(sa + kAStageBytes, &tmB, &full[stage], kb * kBK, n_tile * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -220,7 +246,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if constexpr (RESB) {
+        if (tile_begin < num_tiles) mbar_wait(bfull, 0);
+      }
+      for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1u);
         tc_fence_after();
@@ -228,8 +257,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + kAStageBytes;
+          const uint32_t sa = smem_base + resb_bytes + stage * STAGE_BYTES;
+          const uint32_t sb = RESB ? smem_base + kb * B_KB_BYTES : sa + kAStageBytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
@@ -247,7 +276,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int g = (warp - 4) >> 2;  // 0 | 1
     const int q = warp & 3;         // TMEM lane quarter this warp may access
     StoreRing ring;
-    ring.stg_base = smem_u32(stg_ptr) + g * 2 * kStgBytes;
+    ring.stg_base = smem_u32(stg_ptr) + g * (NUM_STG / 2) * kStgBytes;
+    ring.single = NUM_STG == 2;
     ring.iter = 0;
     ring.bar_id = 1 + g;
     ring.leader = ((threadIdx.x - 128) & 127) == 0;
@@ -256,7 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CH = OUT_F32 ? 32 : 64;  // output columns per staging tile
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++it) {
       if ((it & 1) != g) continue;
       const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
       EpiThread th;
@@ -419,23 +449,39 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool ROW, bool OUT_F32>
+template <int BN, bool ROW, bool OUT_F32, bool RESB>
 int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<BN, ROW, OUT_F32>;
-  static bool attr_set = false;
-  const int smem = gemm_smem_bytes(BN);
-  if (!attr_set) {
-    ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  auto kern = gemm_tc_kernel<BN, ROW, OUT_F32, RESB>;
+  static int attr_smem = 0;
   const int mt = (p.M + kBM - 1) / kBM;
   const int nt = p.N / BN;
+  int stages, smem;
+  if (RESB) {
+    const int fixed = (p.K / kBK) * BN * kBK * 2 + 2 * kStgBytes + 256 + 1024;
+    stages = (kMaxSmem - fixed) / kAStageBytes;
+    if (stages > 8) stages = 8;
+    smem = fixed + stages * kAStageBytes;
+  } else {
+    stages = gemm_stages(BN);
+    smem = gemm_smem_bytes(BN);
+  }
+  if (smem > attr_smem) {
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
   int grid = mt * nt;
   if (grid > num_sms) grid = num_sms;
-  kern<<<grid, 384, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.epi, p.M, p.N, p.K, mt, nt);
+  if (RESB) grid = grid / nt * nt;  // every CTA owns exactly one n-tile
+  kern<<<grid, 384, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.epi, p.M, p.N, p.K, mt, nt, stages);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;
+}
+
+// weight-stationary variant is used when the [BN x K] slice plus >= 3 A stages fit in shared memory
+bool resident_fits(int bn, int K) {
+  const int fixed = (K / kBK) * bn * kBK * 2 + 2 * kStgBytes + 256 + 1024;
+  return fixed + 3 * kAStageBytes <= kMaxSmem;
 }
 
 }  // namespace
@@ -499,14 +545,17 @@ int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* ou
 }
 
 int gemm_launch(const GemmPlan& p, int num_sms, cudaStream_t stream) {
+  const bool res = !p.no_resident && resident_fits(p.block_n, p.K) && (p.M + kBM - 1) / kBM * (p.N / p.block_n) >= num_sms;
   if (p.row_mode) {
-    if (p.block_n == 256 && !p.out_f32) return launch_inst<256, true, false>(p, num_sms, stream);
-    if (p.block_n == 128 && !p.out_f32) return launch_inst<128, true, false>(p, num_sms, stream);
+    if (p.block_n == 256 && !p.out_f32)
+      return res ? launch_inst<256, true, false, true>(p, num_sms, stream) : launch_inst<256, true, false, false>(p, num_sms, stream);
+    if (p.block_n == 128 && !p.out_f32) return launch_inst<128, true, false, false>(p, num_sms, stream);
   } else {
-    if (p.block_n == 256 && !p.out_f32) return launch_inst<256, false, false>(p, num_sms, stream);
-    if (p.block_n == 128 && !p.out_f32) return launch_inst<128, false, false>(p, num_sms, stream);
-    if (p.block_n == 64 && !p.out_f32) return launch_inst<64, false, false>(p, num_sms, stream);
-    if (p.block_n == 64 && p.out_f32) return launch_inst<64, false, true>(p, num_sms, stream);
+    if (p.block_n == 256 && !p.out_f32)
+      return res ? launch_inst<256, false, false, true>(p, num_sms, stream) : launch_inst<256, false, false, false>(p, num_sms, stream);
+    if (p.block_n == 128 && !p.out_f32) return launch_inst<128, false, false, false>(p, num_sms, stream);
+    if (p.block_n == 64 && !p.out_f32) return launch_inst<64, false, false, false>(p, num_sms, stream);
+    if (p.block_n == 64 && p.out_f32) return launch_inst<64, false, true, false>(p, num_sms, stream);
   }
   set_last_error("gemm_launch: unsupported (block_n, row_mode, out_f32) combination");
   return 2;

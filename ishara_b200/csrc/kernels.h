@@ -66,6 +66,7 @@ struct GemmPlan {
   int block_n = 256;        // 64 | 128 | 256
   bool out_f32 = false;
   bool row_mode = false;    // full-row epilogue (LN capable); requires N == block_n
+  bool no_resident = false; // force the streaming-B variant (tests / A-B timing)
 };
 
 // Fill tensor maps of a plan. A [M,K] bf16 (ld = lda), Wt [N,K] bf16 (ld = K),
@@ -97,6 +98,11 @@ struct AttnArgs {
   const bf16* qkv = nullptr;
   bf16* out = nullptr;
   const uint8_t* key_mask = nullptr;
+  // Transformer-XL relative-position variant (squeezeformer/attention.py:25-110) when pos != null:
+  // pos [2T-1, H*dh] bf16 = pos_proj(pos_emb) (head-major columns), u_bias / v_bias [H*dh] fp32.
+  const bf16* pos = nullptr;
+  const float* u_bias = nullptr;
+  const float* v_bias = nullptr;
   int B = 0, T = 0, H = 0, dh = 0;
   float scale = 1.f;
 };
@@ -122,6 +128,28 @@ int se_gate_launch(const SeGateArgs& a, cudaStream_t stream);
 // standalone LayerNorm (fallback / operator-level use): x bf16 [M, D] -> bf16
 int layernorm_launch(const bf16* x, bf16* out, const float* g, const float* b, float eps, int64_t M, int D,
                      cudaStream_t stream);
+
+// ---- time down/up-sampling (vendored Squeezeformer, rows P7/P8) -------------------------------
+struct TimeReduceArgs {
+  const bf16* x = nullptr;  // [B, T, D]
+  bf16* out = nullptr;      // [B, T2, ldo], columns >= D2 zero
+  float w[9] = {0};         // Conv2d(1,1,3,3) weight, row-major (time, channel)
+  float bias = 0.f;
+  int B = 0, T = 0, D = 0, T2 = 0, D2 = 0, ldo = 0;
+};
+int time_reduce_launch(const TimeReduceArgs& a, cudaStream_t stream);
+// out[b, t, :] = y[b, t/2, :] + rec[b, t, :] for t < 2*T2  (y [B,T2,D], rec [B,T,D], out [B,2*T2,D])
+int upsample_add_launch(const bf16* y, const bf16* rec, bf16* out, int B, int T2, int T, int D, cudaStream_t stream);
+struct Conv2dSubsampleArgs {
+  const float* x = nullptr;   // [B, T, F] fp32 features
+  bf16* out = nullptr;        // [B, T4, ldo]: column c*F4 + f
+  const float* w1 = nullptr;  // [C, 9]  Conv2d(1->C, 3, stride 2)
+  const float* b1 = nullptr;  // [C]
+  const float* w2 = nullptr;  // [C, 9]  depthwise Conv2d(C, 3, stride 2)
+  const float* b2 = nullptr;  // [C]
+  int B = 0, T = 0, F = 0, C = 0, T4 = 0, F4 = 0, ldo = 0;
+};
+int conv2d_subsample_launch(const Conv2dSubsampleArgs& a, cudaStream_t stream);
 
 // ---- CTC + greedy decode ----------------------------------------------------------------------
 // logits fp32 [B,T,V]; labels int32 [B,L] padded with `blank`; nll [B]; grad [B,T,V] or null

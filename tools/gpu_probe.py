@@ -227,6 +227,9 @@ CASES = {
     "gemm_many_tiles": lambda: gemm_case(148 * 128 * 3 + 77, 256, 768, 256),
     "gemm_big_time": lambda: gemm_case(98304, 256, 512, 256, act=1, bias=True, time_it=True),
     "gemm_big_time_row": lambda: gemm_case(98304, 512, 256, 256, bias=True, resid=True, ln1=True, row_mode=True, time_it=True),
+    "gemm_big_time_row256": lambda: gemm_case(98304, 256, 256, 256, bias=True, resid=True, ln0=True, ln1=True, row_mode=True, time_it=True),
+    "gemm_big_glu": lambda: gemm_case(98304, 256, 512, 256, act=3, bias=True, time_it=True),
+    "gemm_big_qkv": lambda: gemm_case(98304, 256, 768, 256, time_it=True),
     "dw_eca": lambda: dw_case(3, 384, 512, 11, 10, 2),
     "dw_eca_k3": lambda: dw_case(2, 100, 128, 3, 2, 2),
     "dw_swish_colsum": lambda: dw_case(3, 384, 512, 15, 14, 1, bias=False, colsum=True),
