@@ -17,141 +17,23 @@
 // pass (values parked in TMEM between passes with tcgen05.st). Output leaves through swizzled
 // staging tiles and TMA stores.
 #include <cstdio>
+#include <cstdlib>
 
-#include "kernels.h"
-#include "ptx.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace ishara {
 
 namespace {
 
-constexpr int kBM = 128;
-constexpr int kBK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kAStageBytes = kBM * kBK * 2;
-constexpr int kStgBytes = 128 * 128;  // one staging tile: 128 rows x 128 bytes
+#define ISHARA_TRACE(it_, ev_) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[(it_) * 8 + (ev_)] = clock64(); } while (0)
+
 constexpr int kNumStg = 4;            // 2 per epilogue group
-constexpr int kMaxSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 
 __host__ __device__ constexpr int gemm_stages(int bn) { return bn >= 256 ? 3 : 4; }
 __host__ __device__ constexpr int gemm_stage_bytes(int bn) { return kAStageBytes + bn * kBK * 2; }
 __host__ __device__ constexpr int gemm_smem_bytes(int bn) {
   return gemm_stages(bn) * gemm_stage_bytes(bn) + kNumStg * kStgBytes + 256 /*barriers*/ + 1024 /*align slack*/;
 }
-
-struct EpiThread {
-  int row;        // global row
-  int r;          // row within tile (0..127)
-  bool valid;     // row < M
-  int seq;        // row / rows_per_seq
-  int t;          // row % rows_per_seq
-  uint32_t taddr; // TMEM address of (lane quarter, buffer col 0)
-};
-
-// v[j] = epilogue-input for 32 consecutive columns starting at global column `col0`
-__device__ __forceinline__ void epi_affine(float (&v)[32], const GemmEpi& ep, const EpiThread& th, int col0,
-                                           int ldn) {
-  if (ep.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-    }
-  }
-  if (ep.gate != nullptr && th.valid) {
-    const float4* g4 = reinterpret_cast<const float4*>(ep.gate + static_cast<size_t>(th.seq) * ldn + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 g = __ldg(g4 + j);
-      v[4 * j + 0] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
-    }
-  }
-  if (ep.rowtab != nullptr && th.valid) {
-    const float4* t4 = reinterpret_cast<const float4*>(ep.rowtab + static_cast<size_t>(th.t) * ldn + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 g = __ldg(t4 + j);
-      v[4 * j + 0] += g.x; v[4 * j + 1] += g.y; v[4 * j + 2] += g.z; v[4 * j + 3] += g.w;
-    }
-  }
-}
-
-__device__ __forceinline__ void epi_resid(float (&v)[32], const GemmEpi& ep, const EpiThread& th, int col0) {
-  if (ep.resid != nullptr && th.valid) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(ep.resid + static_cast<size_t>(th.row) * ep.ld_resid + col0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 q = __ldg(r4 + j);
-      v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
-      v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
-      v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
-      v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
-    }
-  }
-}
-
-__device__ __forceinline__ void epi_layernorm(float (&v)[32], const float* g, const float* b, float mean,
-                                              float rstd, int col0) {
-  const float4* g4 = reinterpret_cast<const float4*>(g + col0);
-  const float4* b4 = reinterpret_cast<const float4*>(b + col0);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 gg = __ldg(g4 + j), bb = __ldg(b4 + j);
-    v[4 * j + 0] = fmaf((v[4 * j + 0] - mean) * rstd, gg.x, bb.x);
-    v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, gg.y, bb.y);
-    v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, gg.z, bb.z);
-    v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, gg.w, bb.w);
-  }
-}
-
-// write 32 values of this thread's row into the swizzled staging tile (128-byte rows, 16-byte chunks
-// XOR-ed with row%8 — identical to CU_TENSOR_MAP_SWIZZLE_128B, so the TMA store un-swizzles it).
-template <bool F32>
-__device__ __forceinline__ void stage_write(uint32_t stg, int r, int sub, const float (&v)[32]) {
-  const uint32_t rowbase = stg + static_cast<uint32_t>(r) * 128u;
-  const uint32_t x = static_cast<uint32_t>(r & 7);
-  if constexpr (F32) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      st_shared_v4(rowbase + ((static_cast<uint32_t>(j) ^ x) << 4), __float_as_uint(v[4 * j + 0]),
-                   __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      st_shared_v4(rowbase + ((static_cast<uint32_t>(sub * 4 + j) ^ x) << 4), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
-                   pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
-                   pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-  }
-}
-
-// Staging/TMA-store protocol for one epilogue group (128 threads, named barrier `bar_id`).
-struct StoreRing {
-  uint32_t stg_base;  // smem address of this group's two staging tiles
-  uint32_t iter;      // running chunk counter (selects the buffer)
-  uint32_t bar_id;
-  bool leader;
-  bool single;        // one staging tile per group instead of two
-  __device__ __forceinline__ uint32_t acquire() {
-    if (leader) {     // the store that last used this buffer has drained
-      if (single) tma_store_wait_read<0>();
-      else tma_store_wait_read<1>();
-    }
-    named_bar_sync(bar_id, 128);
-    return stg_base + (single ? 0u : (iter & 1u) * kStgBytes);
-  }
-  __device__ __forceinline__ void release(const CUtensorMap* tm, uint32_t buf, int c0, int c1) {
-    fence_proxy_async_smem();
-    named_bar_sync(bar_id, 128);
-    if (leader) {
-      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                       reinterpret_cast<uint64_t>(tm)),
-                   "r"(buf), "r"(c0), "r"(c1)
-                   : "memory");
-      tma_store_commit();
-    }
-    ++iter;
-  }
-};
 
 // RESB ("resident B", weight-stationary): the CTA keeps its whole [BN x K] weight slice in shared memory for the
 // lifetime of the kernel and streams only A tiles through the ring, so the L2->SM traffic per tile drops from
@@ -229,10 +111,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(resb_ptr + kb * B_KB_BYTES, &tmB, bfull, kb * kBK, n_tile * BN);
         }
       }
-      for (int tile = tile_begin; tile < num_tiles; tile += tile_step) {
+      int pit = 0;
+      for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++pit) {
         const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
+          if (kb == 0) ISHARA_TRACE(pit, 0);
+          if (kb == num_kb - 1) ISHARA_TRACE(pit, 1);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* sa = stage_ptr + stage * STAGE_BYTES;
           tma_load_2d(sa, &tmA, &full[stage], kb * kBK, m_tile * kBM);
@@ -253,45 +138,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t buf = it & 1;
         mbar_wait(&tempty[buf], ((it >> 1) & 1) ^ 1u);
         tc_fence_after();
+        ISHARA_TRACE(it, 2);
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (kb == 0) ISHARA_TRACE(it, 3);
+          if (kb == num_kb - 1) ISHARA_TRACE(it, 4);
           const uint32_t sa = smem_base + resb_bytes + stage * STAGE_BYTES;
           const uint32_t sb = RESB ? smem_base + kb * B_KB_BYTES : sa + kAStageBytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
+            if (ep.dbg & 4) break;
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
             umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC,
                       (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull[buf]);
+          if (kb == num_kb - 1) { umma_commit(&tfull[buf]); ISHARA_TRACE(it, 5); }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue groups =====================
-    const int g = (warp - 4) >> 2;  // 0 | 1
+    const int g = (warp - 4) >> 2;  // 0 | 1: even / odd tiles, TMEM buffer g
     const int q = warp & 3;         // TMEM lane quarter this warp may access
-    StoreRing ring;
-    ring.stg_base = smem_u32(stg_ptr) + g * (NUM_STG / 2) * kStgBytes;
-    ring.single = NUM_STG == 2;
-    ring.iter = 0;
-    ring.bar_id = 1 + g;
-    ring.leader = ((threadIdx.x - 128) & 127) == 0;
+    WarpStore st;
+    st.single = NUM_STG == 2;
+    st.base = smem_u32(stg_ptr) + static_cast<uint32_t>((warp - 4) * (st.single ? 1 : 2)) * kWarpStgBytes;
+    st.iter = 0;
+    st.lane = lane;
+    st.skip_store = (ep.dbg & 1) != 0;
+    st.skip_fence = (ep.dbg & 16) != 0;
 
-    constexpr int OC = BN;               // tile output columns before GLU halving
-    constexpr int CH = OUT_F32 ? 32 : 64;  // output columns per staging tile
+    constexpr int OC = BN;                 // tile output columns before GLU halving
+    constexpr int CH = OUT_F32 ? 32 : 64;  // output columns per staging box
 
     int it = 0;
     for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++it) {
       if ((it & 1) != g) continue;
       const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+      const int row0 = m_tile * kBM + q * 32;  // first row of this warp's box
       EpiThread th;
-      th.r = q * 32 + lane;
-      th.row = m_tile * kBM + th.r;
+      th.row = row0 + lane;
       th.valid = th.row < M;
       th.seq = th.valid ? th.row / ep.rows_per_seq : 0;
       th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
@@ -299,133 +189,129 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tfull[g], (it >> 1) & 1);
       tc_fence_after();
+      if (q == 0 && lane == 0) ISHARA_TRACE(it, 6);
 
-      float v[32];
-      uint32_t raw[32];
-
+      if (ep.dbg & 2) {
+        tc_fence_before();
+        mbar_arrive(&tempty[g]);
+        continue;
+      }
       if constexpr (!ROW) {
         // ---- single pass: bias / gate / rowtab / act / resid -> out0 ----
-        const bool glu = ep.act == ACT_GLU;
-        const int oc = glu ? OC / 2 : OC;
-        for (int c0 = 0; c0 < oc; c0 += CH) {
-          const uint32_t buf = ring.acquire();
+        if (ep.act == ACT_GLU) {
+          constexpr int oc = OC / 2;
+          uint32_t buf = 0;
 #pragma unroll 1
-          for (int sub = 0; sub < CH / 32; ++sub) {
-            const int tc = c0 + sub * 32;  // tmem column (a-half for GLU)
+          for (int c = 0; c < oc / 32; ++c) {
+            uint32_t raw[32];
+            float v[32], u[32];
+            const int tc = c * 32;
             tmem_ld32(th.taddr + tc, raw);
             tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            to_float(v, raw);
+            tmem_ld32(th.taddr + oc + tc, raw);
+            tmem_ld_wait();
+            to_float(u, raw);
             epi_affine(v, ep, th, n_tile * BN + tc, N);
-            if (glu) {
-              float u[32];
-              tmem_ld32(th.taddr + oc + tc, raw);
-              tmem_ld_wait();
+            epi_affine(u, ep, th, n_tile * BN + oc + tc, N);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(raw[j]);
-              epi_affine(u, ep, th, n_tile * BN + oc + tc, N);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(u[j]);
-            } else if (ep.act == ACT_SWISH) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fast_swish(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(u[j]);
+            epi_resid(v, ep, th, n_tile * oc + tc);
+            const int sub = OUT_F32 ? 0 : (c & 1);
+            if (sub == 0) buf = st.acquire();
+            stage_write<OUT_F32>(buf, lane, sub, v);
+            if (OUT_F32 || sub == 1) st.release(&tmO0, buf, n_tile * oc + (c * 32 / CH) * CH, row0);
+          }
+        } else {
+          uint32_t buf = 0;
+          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
+            float v[32];
+            to_float(v, raw);
+            const int tc = c * 32;
+            epi_affine(v, ep, th, n_tile * BN + tc, N);
+            if (ep.act == ACT_SWISH) {
+              epi_swish(v);
             } else if (ep.act == ACT_RELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            epi_resid(v, ep, th, n_tile * oc + tc);
-            stage_write<OUT_F32>(buf, th.r, sub, v);
-          }
-          ring.release(&tmO0, buf, n_tile * oc + c0, m_tile * kBM);
+            epi_resid(v, ep, th, n_tile * OC + tc);
+            const int sub = OUT_F32 ? 0 : (c & 1);
+            if (sub == 0) buf = st.acquire();
+            if (!(ep.dbg & 8)) stage_write<OUT_F32>(buf, lane, sub, v);
+            if (OUT_F32 || sub == 1) st.release(&tmO0, buf, n_tile * OC + (c * 32 / CH) * CH, row0);
+          });
         }
       } else {
-        // ---- full-row epilogue: (resid add) -> [LN0] -> out0 -> [LN1 -> out1] ----
+        // ---- full-row epilogue: (resid add) -> [LN0] -> out0 -> [LN1 -> out1]; lane == row, so row statistics
+        //      are thread-local; values are parked in TMEM (tcgen05.st) between passes ----
         const bool ln0 = ep.ln0_g != nullptr, ln1 = ep.ln1_g != nullptr;
-        float sum = 0.f, sq = 0.f;
-        // pass A: v = epi(acc); stats; park in TMEM if a later pass needs it; emit out0 unless LN0 pending
-        for (int c0 = 0; c0 < OC; c0 += CH) {
-          uint32_t buf = 0;
-          if (!ln0) buf = ring.acquire();
-#pragma unroll 1
-          for (int sub = 0; sub < CH / 32; ++sub) {
-            const int tc = c0 + sub * 32;
-            tmem_ld32(th.taddr + tc, raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-            epi_affine(v, ep, th, tc, N);
-            if (ep.act == ACT_SWISH) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fast_swish(v[j]);
-            }
-            epi_resid(v, ep, th, tc);
-            if (ln0 || ln1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { sum += v[j]; sq = fmaf(v[j], v[j], sq); }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(v[j]);
-              tmem_st32(th.taddr + tc, raw);
-            }
-            if (!ln0) stage_write<OUT_F32>(buf, th.r, sub, v);
+        RowStats rs;
+        uint32_t buf = 0;
+        // pass A: v = epi(acc); stats; park if a later pass needs it; emit out0 unless LN0 is pending
+        chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
+          float v[32];
+          to_float(v, raw);
+          const int tc = c * 32;
+          epi_affine(v, ep, th, tc, N);
+          if (ep.act == ACT_SWISH) epi_swish(v);
+          epi_resid(v, ep, th, tc);
+          if (ln0 || ln1) {
+            rs.add(v);
+            to_raw(raw, v);
+            tmem_st32(th.taddr + tc, raw);
           }
-          if (!ln0) ring.release(&tmO0, buf, c0, m_tile * kBM);
-        }
+          if (!ln0) {
+            const int sub = c & 1;
+            if (sub == 0) buf = st.acquire();
+            stage_write<false>(buf, lane, sub, v);
+            if (sub == 1) st.release(&tmO0, buf, (c >> 1) * 64, row0);
+          }
+        });
         if (ln0 || ln1) tmem_st_wait();
         if (ln0) {
           // pass B: u = LN0(v) -> out0; stats of u for LN1
-          const float mean = sum * (1.f / OC);
-          const float var = fmaxf(sq * (1.f / OC) - mean * mean, 0.f);
-          const float rstd = rsqrtf(var + ep.ln0_eps);
-          sum = 0.f; sq = 0.f;
-          for (int c0 = 0; c0 < OC; c0 += CH) {
-            const uint32_t buf = ring.acquire();
-#pragma unroll 1
-            for (int sub = 0; sub < CH / 32; ++sub) {
-              const int tc = c0 + sub * 32;
-              tmem_ld32(th.taddr + tc, raw);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-              epi_layernorm(v, ep.ln0_g, ep.ln0_b, mean, rstd, tc);
-              if (ln1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { sum += v[j]; sq = fmaf(v[j], v[j], sq); }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(v[j]);
-                tmem_st32(th.taddr + tc, raw);
-              }
-              stage_write<OUT_F32>(buf, th.r, sub, v);
+          float mean, rstd;
+          rs.finish(OC, ep.ln0_eps, &mean, &rstd);
+          rs = RowStats();
+          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
+            float v[32];
+            to_float(v, raw);
+            const int tc = c * 32;
+            epi_layernorm(v, ep.ln0_g, ep.ln0_b, mean, rstd, tc);
+            if (ln1) {
+              rs.add(v);
+              to_raw(raw, v);
+              tmem_st32(th.taddr + tc, raw);
             }
-            ring.release(&tmO0, buf, c0, m_tile * kBM);
-          }
+            const int sub = c & 1;
+            if (sub == 0) buf = st.acquire();
+            stage_write<false>(buf, lane, sub, v);
+            if (sub == 1) st.release(&tmO0, buf, (c >> 1) * 64, row0);
+          });
           if (ln1) tmem_st_wait();
         }
         if (ln1) {
           // pass C: out1 = bf16(LN1(stream))
-          const float mean = sum * (1.f / OC);
-          const float var = fmaxf(sq * (1.f / OC) - mean * mean, 0.f);
-          const float rstd = rsqrtf(var + ep.ln1_eps);
-          for (int c0 = 0; c0 < OC; c0 += 64) {
-            const uint32_t buf = ring.acquire();
-#pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-              const int tc = c0 + sub * 32;
-              tmem_ld32(th.taddr + tc, raw);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-              epi_layernorm(v, ep.ln1_g, ep.ln1_b, mean, rstd, tc);
-              stage_write<false>(buf, th.r, sub, v);
-            }
-            ring.release(&tmO1, buf, c0, m_tile * kBM);
-          }
+          float mean, rstd;
+          rs.finish(OC, ep.ln1_eps, &mean, &rstd);
+          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
+            float v[32];
+            to_float(v, raw);
+            epi_layernorm(v, ep.ln1_g, ep.ln1_b, mean, rstd, c * 32);
+            const int sub = c & 1;
+            if (sub == 0) buf = st.acquire();
+            stage_write<false>(buf, lane, sub, v);
+            if (sub == 1) st.release(&tmO1, buf, (c >> 1) * 64, row0);
+          });
         }
       }
       // this tile's accumulator buffer may be overwritten by the MMA warp now
       tc_fence_before();
       mbar_arrive(&tempty[g]);
+      if (q == 0 && lane == 0) ISHARA_TRACE(it, 7);
     }
-    if (ring.leader) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -486,6 +372,10 @@ bool resident_fits(int bn, int K) {
 
 }  // namespace
 
+bool gemm2_applicable(const GemmPlan& p, int num_sms);
+int gemm_launch_inner(const GemmPlan& p, int num_sms, cudaStream_t stream);
+int gemm2_launch(const GemmPlan& p, int num_sms, cudaStream_t stream);
+
 int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                  uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();
@@ -531,20 +421,75 @@ int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* ou
   int rc;
   if ((rc = make_tmap_2d(&p->tmA, A, TM_BF16, p->M, p->K, lda, kBM, kBK))) return rc;
   if ((rc = make_tmap_2d(&p->tmB, Wt, TM_BF16, p->N, p->K, p->K, p->block_n, kBK))) return rc;
+  if (p->block_n == 256)  // CTA-pair variant: each CTA loads its 128-row half of the weight tile
+    if ((rc = make_tmap_2d(&p->tmBh, Wt, TM_BF16, p->N, p->K, p->K, 128, kBK))) return rc;
   if (p->out_f32) {
-    if ((rc = make_tmap_2d(&p->tmO0, out0, TM_F32, p->M, nout, ldo0, kBM, 32))) return rc;
+    if ((rc = make_tmap_2d(&p->tmO0, out0, TM_F32, p->M, nout, ldo0, 32, 32))) return rc;
   } else {
-    if ((rc = make_tmap_2d(&p->tmO0, out0, TM_BF16, p->M, nout, ldo0, kBM, 64))) return rc;
+    if ((rc = make_tmap_2d(&p->tmO0, out0, TM_BF16, p->M, nout, ldo0, 32, 64))) return rc;
   }
   if (out1 != nullptr) {
-    if ((rc = make_tmap_2d(&p->tmO1, out1, TM_BF16, p->M, nout, ldo1, kBM, 64))) return rc;
+    if ((rc = make_tmap_2d(&p->tmO1, out1, TM_BF16, p->M, nout, ldo1, 32, 64))) return rc;
   } else {
     p->tmO1 = p->tmO0;
   }
   return 0;
 }
 
-int gemm_launch(const GemmPlan& p, int num_sms, cudaStream_t stream) {
+int gemm_launch(const GemmPlan& p_in, int num_sms, cudaStream_t stream) {
+  static const int dbg = getenv("ISHARA_GEMM_DBG") ? atoi(getenv("ISHARA_GEMM_DBG")) : 0;
+  static const int force = getenv("ISHARA_GEMM_RESIDENT") ? atoi(getenv("ISHARA_GEMM_RESIDENT")) : -1;
+  static const int pair = getenv("ISHARA_GEMM_PAIR") ? atoi(getenv("ISHARA_GEMM_PAIR")) : 1;
+  GemmPlan p = p_in;
+  p.epi.dbg = dbg;
+  if (force == 0) p.no_resident = true;
+  static const int trace = getenv("ISHARA_GEMM_TRACE") ? atoi(getenv("ISHARA_GEMM_TRACE")) : 0;
+  if (trace > 0) {
+    // debugging aid: timeline of CTA 0 (clock64 at 8 events per tile), printed to stderr after a blocking launch
+    static long long* dbuf = nullptr;
+    const int ntile = 64;
+    if (dbuf == nullptr) ISHARA_CUDA_OK(cudaMalloc(&dbuf, ntile * 8 * sizeof(long long)));
+    ISHARA_CUDA_OK(cudaMemset(dbuf, 0, ntile * 8 * sizeof(long long)));
+    p.epi.trace = dbuf;
+    int rc;
+    if (pair != 0 && !p.no_pair && gemm2_applicable(p, num_sms)) {
+      p.tmB = p.tmBh;
+      rc = gemm2_launch(p, num_sms, stream);
+    } else {
+      p.no_pair = true;
+      GemmPlan q = p;
+      q.epi.trace = dbuf;
+      static const int depth = 0;
+      (void)depth;
+      rc = gemm_launch_inner(q, num_sms, stream);
+    }
+    if (rc) return rc;
+    ISHARA_CUDA_OK(cudaDeviceSynchronize());
+    static int printed = 0;
+    if (printed++ < trace) {
+      long long h[64 * 8];
+      ISHARA_CUDA_OK(cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost));
+      long long t0 = 0;
+      for (int i = 0; i < 8; ++i) if (h[i] != 0 && (t0 == 0 || h[i] < t0)) t0 = h[i];
+      fprintf(stderr, "gemm trace M=%d N=%d K=%d row=%d (cycles since first event; P0 first load issue, P1 last load issue, "
+                      "M2 tempty ok, M3 first full ok, M4 last full ok, M5 tfull commit, E6 tfull seen, E7 epilogue done)\n",
+              p.M, p.N, p.K, (int)p.row_mode);
+      for (int t = 0; t < 14; ++t) {
+        fprintf(stderr, "  tile %2d:", t);
+        for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", h[t * 8 + e] ? h[t * 8 + e] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+    return 0;
+  }
+  if (pair != 0 && !p.no_pair && gemm2_applicable(p, num_sms)) {
+    p.tmB = p.tmBh;
+    return gemm2_launch(p, num_sms, stream);
+  }
+  return gemm_launch_inner(p, num_sms, stream);
+}
+
+int gemm_launch_inner(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   const bool res = !p.no_resident && resident_fits(p.block_n, p.K) && (p.M + kBM - 1) / kBM * (p.N / p.block_n) >= num_sms;
   if (p.row_mode) {
     if (p.block_n == 256 && !p.out_f32)

@@ -57,16 +57,19 @@ struct GemmEpi {
   int rows_per_seq = 1;
   int ld_resid = 0;
   int act = ACT_NONE;
+  long long* trace = nullptr;  // ISHARA_GEMM_TRACE: clock64 timeline of CTA 0, [tile][8 events]
+  int dbg = 0;  // ISHARA_GEMM_DBG bisect bits: 1 skip TMA stores, 2 skip epilogue work, 4 skip MMA issue, 8 skip staging writes
 };
 
 struct GemmPlan {
-  CUtensorMap tmA, tmB, tmO0, tmO1;
+  CUtensorMap tmA, tmB, tmBh, tmO0, tmO1;  // tmBh: 128-row B box for the CTA-pair kernel
   GemmEpi epi;
   int M = 0, N = 0, K = 0;  // N = packed weight rows (MMA N extent), K multiple of 64
   int block_n = 256;        // 64 | 128 | 256
   bool out_f32 = false;
   bool row_mode = false;    // full-row epilogue (LN capable); requires N == block_n
   bool no_resident = false; // force the streaming-B variant (tests / A-B timing)
+  bool no_pair = false;     // force a single-CTA variant
 };
 
 // Fill tensor maps of a plan. A [M,K] bf16 (ld = lda), Wt [N,K] bf16 (ld = K),
