@@ -22,6 +22,8 @@ struct ModelView {
   const ishara_config_t* cfg;
   int device;
   cudaStream_t stream;
+  cudaStream_t copy_stream;
+  cudaEvent_t* copy_done;  // [8]
   float* x_dev;
   float* logits_own;
   int32_t* ids_dev;
@@ -57,6 +59,37 @@ using namespace ishara;
     set_last_error("null model handle");     \
     return ISHARA_ERR_INVALID;               \
   }
+
+// H2D of x in chunks on the copy stream, forward of chunk c as soon as its copy has landed: the PCIe transfer of the
+// 1.1 KB/frame fp32 input (108 MB at batch 256) overlaps the compute of the previous chunk instead of preceding it.
+static int upload_and_forward(ishara_model* m, const ModelView& v, const float* x_host, int batch) {
+  const ishara_config_t& c = *v.cfg;
+  const size_t per_seq = static_cast<size_t>(c.frames) * c.features;
+  int nchunk = batch >= 64 ? 4 : 1;
+  const int per = (batch + nchunk - 1) / nchunk;
+  nchunk = (batch + per - 1) / per;
+  int rc;
+  for (int i = 0; i < nchunk; ++i) {
+    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
+    if (cudaMemcpyAsync(v.x_dev + b0 * per_seq, x_host + b0 * per_seq, nb * per_seq * sizeof(float), cudaMemcpyHostToDevice,
+                        v.copy_stream) != cudaSuccess ||
+        cudaEventRecord(v.copy_done[i], v.copy_stream) != cudaSuccess) {
+      set_last_error(std::string("upload: ") + cudaGetErrorString(cudaGetLastError()));
+      return ISHARA_ERR_CUDA;
+    }
+  }
+  for (int i = 0; i < nchunk; ++i) {
+    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
+    if (cudaStreamWaitEvent(v.stream, v.copy_done[i], 0) != cudaSuccess) {
+      set_last_error(std::string("upload: ") + cudaGetErrorString(cudaGetLastError()));
+      return ISHARA_ERR_CUDA;
+    }
+    if ((rc = model_forward(m, v.x_dev + b0 * per_seq, nb,
+                            v.logits_own + static_cast<size_t>(b0) * c.frames * c.num_classes, v.stream)))
+      return rc;
+  }
+  return 0;
+}
 
 extern "C" {
 
@@ -126,8 +159,7 @@ ishara_status_t ishara_model_forward_host(ishara_model_t* mh, const float* x_hos
   int rc = model_view(m, batch, &v);
   if (rc) return static_cast<ishara_status_t>(rc);
   const size_t M = static_cast<size_t>(batch) * v.cfg->frames;
-  CAPI_CUDA_OK(cudaMemcpyAsync(v.x_dev, x_host, M * v.cfg->features * sizeof(float), cudaMemcpyHostToDevice, v.stream));
-  if ((rc = model_forward(m, v.x_dev, batch, v.logits_own, v.stream))) return static_cast<ishara_status_t>(rc);
+  if ((rc = upload_and_forward(m, v, x_host, batch))) return static_cast<ishara_status_t>(rc);
   CAPI_CUDA_OK(cudaMemcpyAsync(logits_host, v.logits_own, M * v.cfg->num_classes * sizeof(float), cudaMemcpyDeviceToHost,
                                  v.stream));
   CAPI_CUDA_OK(cudaStreamSynchronize(v.stream));
@@ -153,7 +185,6 @@ ishara_status_t ishara_model_infer_host(ishara_model_t* mh, const float* x_host,
   const ishara_config_t& c = *v.cfg;
   const size_t M = static_cast<size_t>(batch) * c.frames;
   const int blank = c.num_classes - 1;  // pad_token_idx = 59 (c1:4-7)
-  CAPI_CUDA_OK(cudaMemcpyAsync(v.x_dev, x_host, M * c.features * sizeof(float), cudaMemcpyHostToDevice, v.stream));
   int32_t* labels_dev = nullptr;
   if (labels_host != nullptr) {
     if ((rc = model_labels_buffer(m, static_cast<size_t>(batch) * max_label_len, &labels_dev)))
@@ -161,7 +192,7 @@ ishara_status_t ishara_model_infer_host(ishara_model_t* mh, const float* x_host,
     CAPI_CUDA_OK(cudaMemcpyAsync(labels_dev, labels_host, static_cast<size_t>(batch) * max_label_len * sizeof(int32_t),
                                    cudaMemcpyHostToDevice, v.stream));
   }
-  if ((rc = model_forward(m, v.x_dev, batch, v.logits_own, v.stream))) return static_cast<ishara_status_t>(rc);
+  if ((rc = upload_and_forward(m, v, x_host, batch))) return static_cast<ishara_status_t>(rc);
   if ((rc = greedy_decode_launch(v.logits_own, batch, c.frames, c.num_classes, blank, v.ids_dev, v.lens_dev, v.stream)))
     return static_cast<ishara_status_t>(rc);
   if (labels_host != nullptr) {

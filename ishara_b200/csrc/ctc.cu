@@ -18,7 +18,7 @@ namespace ishara {
 namespace {
 
 constexpr float kLogZero = -1.0e30f;
-constexpr int kCtcWarps = 4;
+constexpr int kCtcBlk = 32;  // frames staged per shared-memory block
 
 __device__ __forceinline__ float lse2(float a, float b) {
   const float m = fmaxf(a, b);
@@ -31,20 +31,51 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
-// dynamic smem per warp: lse[T] floats + occ[Vpad] floats
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// One warp (= one CTA) per sequence. The recursion over T is strictly sequential, so what matters is the latency of one
+// step: the logits are staged in shared memory in blocks of 32 frames with cp.async, one block ahead of the sweep
+// (the first version read each frame's emissions straight from global one step ahead and spent a DRAM round trip,
+// ~2.5k cycles, on every one of the 384 steps). dynamic smem: lse[T] + occ[Vpad] + 2 x [32 x V] logits blocks.
 template <int SPL>
-__global__ void __launch_bounds__(kCtcWarps * 32)
+__global__ void __launch_bounds__(32)
 ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
            float* __restrict__ nll, float* __restrict__ grad, float* __restrict__ alpha_ws) {
-  extern __shared__ float smem_ctc[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kCtcWarps + warp;
-  if (b >= B) return;
+  extern __shared__ __align__(16) float smem_ctc[];
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
   const int Vpad = (V + 31) & ~31;
-  float* lse = smem_ctc + warp * (T + Vpad);
-  float* occ = lse + T;
+  float* lse = smem_ctc;
+  float* occ = lse + ((T + 3) & ~3);
+  float* blk = occ + Vpad;  // [2][kCtcBlk * V]
+  const int blk_floats = kCtcBlk * V;
   const float* lg = logits + static_cast<size_t>(b) * T * V;
   const int32_t* lab = labels + static_cast<size_t>(b) * L;
+  const int nblk = (T + kCtcBlk - 1) / kCtcBlk;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) && (V % 4 == 0);
+
+  auto stage = [&](int tb) {
+    float* dst = blk + (tb & 1) * blk_floats;
+    const float* src = lg + static_cast<size_t>(tb) * kCtcBlk * V;
+    const int n = min(kCtcBlk, T - tb * kCtcBlk) * V;
+    if (vec_ok) {
+      for (int i = lane * 4; i < n; i += 128) cp_async_16(dst + i, src + i);
+    } else {
+      for (int i = lane; i < n; i += 32) cp_async_4(dst + i, src + i);
+    }
+    cp_async_commit();
+  };
+  stage(0);
 
   // label length = number of non-blank entries (reference: reduce_sum(labels != pad))
   int cnt = 0;
@@ -68,69 +99,68 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
     skip_bwd[i] = (s + 2 < S) && (s & 1) && (lab[(s >> 1) + 1] != lab[s >> 1]);
   }
 
-  // log-sum-exp of every frame (parallel over t)
-  for (int t = lane; t < T; t += 32) {
-    const float* row = lg + static_cast<size_t>(t) * V;
-    float m = -INFINITY;
-    for (int v = 0; v < V; ++v) m = fmaxf(m, row[v]);
-    float z = 0.f;
-    for (int v = 0; v < V; ++v) z += __expf(row[v] - m);
-    lse[t] = m + __logf(z);
-  }
-  __syncwarp();
+  // log-sum-exp of frame (tb*32 + lane) from the staged block; lanes walk the classes in rotated order (bank spread)
+  auto frame_lse = [&](const float* cur, int nf) -> float {
+    float l = 0.f;
+    if (lane < nf) {
+      const float* row = cur + lane * V;
+      float m = -INFINITY;
+      int v = lane % V;
+      for (int k = 0; k < V; ++k) { m = fmaxf(m, row[v]); v = (v + 1 == V) ? 0 : v + 1; }
+      float z = 0.f;
+      for (int k = 0; k < V; ++k) { z += __expf(row[v] - m); v = (v + 1 == V) ? 0 : v + 1; }
+      l = m + __logf(z);
+    }
+    return l;
+  };
 
   float* aw = alpha_ws != nullptr ? alpha_ws + static_cast<size_t>(b) * T * (32 * SPL) : nullptr;
 
   // ---------------- alpha sweep ----------------
   float a[SPL];
-  {
-    const float l0 = lse[0];
+  for (int tb = 0; tb < nblk; ++tb) {
+    if (tb + 1 < nblk) { stage(tb + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncwarp();
+    const float* cur = blk + (tb & 1) * blk_floats;
+    const int nf = min(kCtcBlk, T - tb * kCtcBlk);
+    const float lse_l = frame_lse(cur, nf);
+    if (lane < nf) lse[tb * kCtcBlk + lane] = lse_l;
+    for (int tt = 0; tt < nf; ++tt) {
+      const int t = tb * kCtcBlk + tt;
+      const float lt = __shfl_sync(0xffffffffu, lse_l, tt);
+      const float* row = cur + tt * V;
+      float em[SPL];
 #pragma unroll
-    for (int i = 0; i < SPL; ++i) {
-      const int s = lane * SPL + i;
-      a[i] = (s < 2 && s < S) ? lg[ext[i]] - l0 : kLogZero;
+      for (int i = 0; i < SPL; ++i) em[i] = row[ext[i]] - lt;
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          const int s = lane * SPL + i;
+          a[i] = (s < 2 && s < S) ? em[i] : kLogZero;
+        }
+      } else {
+        float up1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+        float up2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
+        if (lane == 0) { up1 = kLogZero; up2 = kLogZero; }
+        float na[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          const float q1 = (i == 0) ? up1 : a[i - 1];
+          const float q2 = (i == 0) ? up2 : (i == 1 ? up1 : a[i - 2]);
+          const float acc = skip_fwd[i] ? lse3(a[i], q1, q2) : lse2(a[i], q1);
+          const int s = lane * SPL + i;
+          na[i] = (s < S) ? acc + em[i] : kLogZero;
+        }
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) a[i] = na[i];
+      }
+      if (aw != nullptr) {
+        float* dst = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) dst[i] = a[i];
+      }
     }
-    if (aw != nullptr) {
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) aw[lane * SPL + i] = a[i];
-    }
-  }
-  float em_next[SPL];
-  if (T > 1) {
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) em_next[i] = lg[static_cast<size_t>(1) * V + ext[i]];
-  }
-  for (int t = 1; t < T; ++t) {
-    float em[SPL];
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) em[i] = em_next[i];
-    if (t + 1 < T) {
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) em_next[i] = lg[static_cast<size_t>(t + 1) * V + ext[i]];
-    }
-    const float lt = lse[t];
-    float up1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
-    float up2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
-    if (lane == 0) { up1 = kLogZero; up2 = kLogZero; }
-    float na[SPL];
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) {
-      const float p1 = (i >= 1) ? a[i - 1] : up1;
-      const float p2 = (i >= 2) ? a[i - 2] : (i == 1 ? up1 : up2);
-      // i == 0: (s-1, s-2) = (up1, up2); i == 1: (a[0], up1)
-      const float q1 = (i == 0) ? up1 : p1;
-      const float q2 = (i == 0) ? up2 : p2;
-      const float acc = skip_fwd[i] ? lse3(a[i], q1, q2) : lse2(a[i], q1);
-      const int s = lane * SPL + i;
-      na[i] = (s < S) ? acc + (em[i] - lt) : kLogZero;
-    }
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) a[i] = na[i];
-    if (aw != nullptr) {
-      float* dst = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) dst[i] = a[i];
-    }
+    __syncwarp();  // every lane is done with `cur` before the block after next is staged over it
   }
   // log p(l|x) = lse(alpha_T-1(S-1), alpha_T-1(S-2))
   float fin = kLogZero;
@@ -146,70 +176,87 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
   if (lane == 0) nll[b] = feasible ? -logp : INFINITY;
   if (grad == nullptr) return;
 
-  // ---------------- beta sweep + gradient ----------------
+  // ---------------- beta sweep + gradient (blocks in reverse) ----------------
   float* gr = grad + static_cast<size_t>(b) * T * V;
   float bt[SPL];
-  for (int t = T - 1; t >= 0; --t) {
-    const float lt = lse[t];
-    float em[SPL];
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) em[i] = lg[static_cast<size_t>(t) * V + ext[i]] - lt;
-    if (t == T - 1) {
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        const int s = lane * SPL + i;
-        bt[i] = (s == S - 1 || (s == S - 2 && S >= 2)) ? em[i] : kLogZero;
-      }
-    } else {
-      float dn1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
-      float dn2 = __shfl_down_sync(0xffffffffu, bt[SPL > 1 ? 1 : 0], 1);
-      if (lane == 31) { dn1 = kLogZero; dn2 = kLogZero; }
-      float nb[SPL];
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        const float q1 = (i + 1 < SPL) ? bt[i + 1] : dn1;
-        const float q2 = (i + 2 < SPL) ? bt[i + 2] : (i + 1 < SPL ? dn1 : dn2);
-        const float acc = skip_bwd[i] ? lse3(bt[i], q1, q2) : lse2(bt[i], q1);
-        const int s = lane * SPL + i;
-        nb[i] = (s < S) ? acc + em[i] : kLogZero;
-      }
-#pragma unroll
-      for (int i = 0; i < SPL; ++i) bt[i] = nb[i];
-    }
-    // occupancy: alpha_t(s) beta_t(s) / y_t(ext s), scattered by class. In exact arithmetic the sum over s is
-    // p(l|x) at every t; normalising by the per-frame sum instead of exp(logp) keeps fp32 drift out of the
-    // gradient (each row of d nll / d logits then sums to zero to rounding).
-    for (int v = lane; v < Vpad; v += 32) occ[v] = 0.f;
+  stage(nblk - 1);
+  for (int tb = nblk - 1; tb >= 0; --tb) {
+    // note: stage() selects the buffer by block parity, so the block staged next (tb-1) never aliases `cur`
+    if (tb > 0) { stage(tb - 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
-    if (feasible) {
-      const float* asrc = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
-      float e[SPL];
-      float mx = kLogZero;
+    const float* cur = blk + (tb & 1) * blk_floats;
+    const int nf = min(kCtcBlk, T - tb * kCtcBlk);
+    for (int tt = nf - 1; tt >= 0; --tt) {
+      const int t = tb * kCtcBlk + tt;
+      const float lt = lse[t];
+      const float* row = cur + tt * V;
+      float em[SPL];
 #pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        const int s = lane * SPL + i;
-        e[i] = (s < S) ? asrc[i] + bt[i] - em[i] : kLogZero;
-        mx = fmaxf(mx, e[i]);
+      for (int i = 0; i < SPL; ++i) em[i] = row[ext[i]] - lt;
+      // alphas of this frame (written by this thread during the forward sweep)
+      float al[SPL];
+      {
+        const float* asrc = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) al[i] = asrc[i];
       }
+      if (t == T - 1) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f;
+        for (int i = 0; i < SPL; ++i) {
+          const int s = lane * SPL + i;
+          bt[i] = (s == S - 1 || (s == S - 2 && S >= 2)) ? em[i] : kLogZero;
+        }
+      } else {
+        float dn1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+        float dn2 = __shfl_down_sync(0xffffffffu, bt[SPL > 1 ? 1 : 0], 1);
+        if (lane == 31) { dn1 = kLogZero; dn2 = kLogZero; }
+        float nb[SPL];
 #pragma unroll
-      for (int i = 0; i < SPL; ++i) {
-        e[i] = (e[i] - mx > -80.f) ? __expf(e[i] - mx) : 0.f;
-        sum += e[i];
+        for (int i = 0; i < SPL; ++i) {
+          const float q1 = (i + 1 < SPL) ? bt[i + 1] : dn1;
+          const float q2 = (i + 2 < SPL) ? bt[i + 2] : (i + 1 < SPL ? dn1 : dn2);
+          const float acc = skip_bwd[i] ? lse3(bt[i], q1, q2) : lse2(bt[i], q1);
+          const int s = lane * SPL + i;
+          nb[i] = (s < S) ? acc + em[i] : kLogZero;
+        }
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) bt[i] = nb[i];
       }
+      // occupancy: alpha_t(s) beta_t(s) / y_t(ext s), scattered by class. In exact arithmetic the sum over s is
+      // p(l|x) at every t; normalising by the per-frame sum instead of exp(logp) keeps fp32 drift out of the
+      // gradient (each row of d nll / d logits then sums to zero to rounding).
+      for (int v = lane; v < Vpad; v += 32) occ[v] = 0.f;
+      __syncwarp();
+      if (feasible) {
+        float e[SPL];
+        float mx = kLogZero;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float inv = 1.f / sum;
+        for (int i = 0; i < SPL; ++i) {
+          const int s = lane * SPL + i;
+          e[i] = (s < S) ? al[i] + bt[i] - em[i] : kLogZero;
+          mx = fmaxf(mx, e[i]);
+        }
 #pragma unroll
-      for (int i = 0; i < SPL; ++i)
-        if (e[i] != 0.f) atomicAdd(&occ[ext[i]], e[i] * inv);
-    }
-    __syncwarp();
-    for (int v = lane; v < V; v += 32) {
-      const float y = __expf(lg[static_cast<size_t>(t) * V + v] - lt);
-      gr[static_cast<size_t>(t) * V + v] = feasible ? (y - occ[v]) : __int_as_float(0x7fc00000);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          e[i] = (e[i] - mx > -80.f) ? __expf(e[i] - mx) : 0.f;
+          sum += e[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i)
+          if (e[i] != 0.f) atomicAdd(&occ[ext[i]], e[i] * inv);
+      }
+      __syncwarp();
+      for (int v = lane; v < V; v += 32) {
+        const float y = __expf(row[v] - lt);
+        gr[static_cast<size_t>(t) * V + v] = feasible ? (y - occ[v]) : __int_as_float(0x7fc00000);
+      }
+      __syncwarp();
     }
     __syncwarp();
   }
@@ -282,9 +329,9 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
   }
   const int spl = (2 * L + 1 + 31) / 32;
   const int Vpad = (V + 31) & ~31;
-  const size_t smem = static_cast<size_t>(kCtcWarps) * (T + Vpad) * sizeof(float);
+  const size_t smem = (static_cast<size_t>((T + 3) & ~3) + Vpad + 2 * kCtcBlk * V) * sizeof(float);
   if (smem > 200 * 1024) {
-    set_last_error("ctc_loss: T too large for the per-warp frame table");
+    set_last_error("ctc_loss: T / num_classes too large for the per-sequence shared-memory tables");
     return 2;
   }
   const int SPL = spl <= 5 ? 5 : 9;
@@ -304,17 +351,16 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
     }
     ws = g_alpha_ws;
   }
-  const int grid = (B + kCtcWarps - 1) / kCtcWarps;
   if (SPL == 5) {
     auto kern = ctc_kernel<5>;
     if (smem > 48 * 1024)
       ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kCtcWarps * 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
+    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
   } else {
     auto kern = ctc_kernel<9>;
     if (smem > 48 * 1024)
       ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kCtcWarps * 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
+    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
   }
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();

@@ -26,15 +26,19 @@ namespace {
 constexpr int kSlab = 64;    // channels per CTA
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTB = 8;       // outputs per register block
+constexpr int kTBmax = 8;    // outputs per register block (small kernels); wide kernels use 4 to stay under 64 registers
 
 __device__ __forceinline__ float exact_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
 
+template <int K>
+__host__ __device__ constexpr int dw_tb() { return K >= 9 ? 4 : kTBmax; }
+
 template <int K, int POST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (K <= 11 ? 4 : (K <= 15 ? 3 : 1)))
 dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ w,
               const float* __restrict__ bias, const float* __restrict__ eca_w, float* __restrict__ colsum, int T,
               int C, int pad_left, int rows_alloc) {
+  constexpr int kTB = dw_tb<K>();
   extern __shared__ __align__(16) uint8_t smem_dw[];
   uint32_t* tile = reinterpret_cast<uint32_t*>(smem_dw);           // [rows_alloc][32] bf16x2
   float* red = reinterpret_cast<float*>(tile + rows_alloc * 32);   // [kWarps][64]
@@ -67,37 +71,53 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
   const int t_end = min(T, t_begin + rows_per_warp);
 
   float2 scale = make_float2(1.f, 1.f);
+  cg::cluster_group cluster = cg::this_cluster();
   if constexpr (POST == 2) {
     // ---- ECA: mean over T of y = conv + bias, then 5-tap conv over channels, sigmoid ----
+    // The convolution is linear in time, so its mean needs no convolution pass: with S = sum_t x[t],
+    //   sum_t y[t] = T*bias + sum_j w[j] * (S - [rows that tap j shifts out of the window]),
+    // i.e. one add per staged element plus a head/tail correction of at most K-1 rows (ncu: the two-pass version was
+    // issue-bound, 0.6 IPC per scheduler with DRAM at 15 %).
     float2 s = make_float2(0.f, 0.f);
-    for (int t0 = t_begin; t0 < t_end; t0 += kTB) {
-      float2 x[kTB + K - 1];
-#pragma unroll
-      for (int i = 0; i < kTB + K - 1; ++i) {
-        const uint32_t u = tile[(t0 + i) * 32 + lane];
-        x[i] = make_float2(bf16_lo(u), bf16_hi(u));
-      }
-#pragma unroll
-      for (int i = 0; i < kTB; ++i) {
-        if (t0 + i < t_end) {
-          float2 a = bs;
-#pragma unroll
-          for (int j = 0; j < K; ++j) { a.x = fmaf(wt[j].x, x[i + j].x, a.x); a.y = fmaf(wt[j].y, x[i + j].y, a.y); }
-          s.x += a.x; s.y += a.y;
-        }
-      }
+    for (int t = t_begin; t < t_end; ++t) {
+      const uint32_t u = tile[(t + pad_left) * 32 + lane];
+      fadd2(s.x, s.y, s.x, s.y, bf16_lo(u), bf16_hi(u));
     }
     red[warp * kSlab + 2 * lane] = s.x;
     red[warp * kSlab + 2 * lane + 1] = s.y;
     __syncthreads();
-    if (tid < kSlab) {
-      float m = 0.f;
+    if (warp == 0) {
+      float2 S = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int wv = 0; wv < kWarps; ++wv) m += red[wv * kSlab + tid];
-      mean_s[tid] = m / static_cast<float>(T);
+      for (int wv = 0; wv < kWarps; ++wv) {
+        S.x += red[wv * kSlab + 2 * lane];
+        S.y += red[wv * kSlab + 2 * lane + 1];
+      }
+      float2 acc = make_float2(0.f, 0.f);
+      // taps with offset o = j - pad_left < 0 lose the last |o| rows, taps with o > 0 lose the first o rows
+      float2 tail = make_float2(0.f, 0.f);
+      for (int m = 1; m <= pad_left; ++m) {  // tap j = pad_left - m
+        const uint32_t u = tile[(T - m + pad_left) * 32 + lane];
+        tail.x += bf16_lo(u); tail.y += bf16_hi(u);
+        const float2 wj = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(pad_left - m) * C + c0) + lane);
+        acc.x = fmaf(wj.x, S.x - tail.x, acc.x); acc.y = fmaf(wj.y, S.y - tail.y, acc.y);
+      }
+      {
+        const float2 wj = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(pad_left) * C + c0) + lane);
+        acc.x = fmaf(wj.x, S.x, acc.x); acc.y = fmaf(wj.y, S.y, acc.y);
+      }
+      float2 head = make_float2(0.f, 0.f);
+      for (int m = 1; m < K - pad_left; ++m) {  // tap j = pad_left + m
+        const uint32_t u = tile[(m - 1 + pad_left) * 32 + lane];
+        head.x += bf16_lo(u); head.y += bf16_hi(u);
+        const float2 wj = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(pad_left + m) * C + c0) + lane);
+        acc.x = fmaf(wj.x, S.x - head.x, acc.x); acc.y = fmaf(wj.y, S.y - head.y, acc.y);
+      }
+      const float invT = 1.f / static_cast<float>(T);
+      mean_s[2 * lane] = fmaf(acc.x, invT, bs.x);
+      mean_s[2 * lane + 1] = fmaf(acc.y, invT, bs.y);
     }
     // exchange slab-edge means with the neighbouring slabs of the same sequence (DSMEM)
-    cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();
     if (tid < kSlab) {
       const int rank = static_cast<int>(cluster.block_rank());
@@ -118,11 +138,14 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
       }
       red[tid] = exact_sigmoid(acc);  // red[0..63] reused for the per-channel scale
     }
-    cluster.sync();  // neighbours finished reading mean_s; red[] visible to the CTA
+    // neighbours may still be reading mean_s: arrive now, wait only at the very end of the kernel (nothing below
+    // touches mean_s, the wait merely keeps this CTA's shared memory alive)
+    cluster.barrier_arrive();
+    __syncthreads();  // red[] visible to the CTA
     scale = make_float2(red[2 * lane], red[2 * lane + 1]);
   }
 
-  // ---- main pass ----
+  // ---- main pass (packed fp32x2 FMAs: one issue slot per tap for the lane's channel pair) ----
   bf16* dst = out + (static_cast<size_t>(b) * T) * C + c0;
   float2 cs = make_float2(0.f, 0.f);
   for (int t0 = t_begin; t0 < t_end; t0 += kTB) {
@@ -137,12 +160,12 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
       if (t0 + i < t_end) {
         float2 a = bs;
 #pragma unroll
-        for (int j = 0; j < K; ++j) { a.x = fmaf(wt[j].x, x[i + j].x, a.x); a.y = fmaf(wt[j].y, x[i + j].y, a.y); }
+        for (int j = 0; j < K; ++j) ffma2(a.x, a.y, wt[j].x, wt[j].y, x[i + j].x, x[i + j].y, a.x, a.y);
         if constexpr (POST == 1) { a.x = a.x * exact_sigmoid(a.x); a.y = a.y * exact_sigmoid(a.y); }
-        if constexpr (POST == 2) { a.x *= scale.x; a.y *= scale.y; }
+        if constexpr (POST == 2) fmul2(a.x, a.y, a.x, a.y, scale.x, scale.y);
         const uint32_t packed = pack_bf16x2(a.x, a.y);
         reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(t0 + i) * C)[lane] = packed;
-        cs.x += bf16_lo(packed); cs.y += bf16_hi(packed);
+        if (colsum != nullptr) { cs.x += bf16_lo(packed); cs.y += bf16_hi(packed); }
       }
     }
   }
@@ -158,10 +181,12 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
       colsum[static_cast<size_t>(b) * C + c0 + tid] = m;
     }
   }
+  if constexpr (POST == 2) cluster.barrier_wait();
 }
 
 template <int K, int POST>
 int launch_inst(const DwConvArgs& a, cudaStream_t stream) {
+  constexpr int kTB = dw_tb<K>();
   const int rows_per_warp = ((a.T + kWarps - 1) / kWarps + kTB - 1) / kTB * kTB;
   const int rows_alloc = rows_per_warp * kWarps + K - 1;
   const size_t smem = static_cast<size_t>(rows_alloc) * 128 + (kWarps * kSlab + kSlab) * sizeof(float);

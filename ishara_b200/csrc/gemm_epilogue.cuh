@@ -176,22 +176,210 @@ struct WarpStore {
   }
 };
 
-// Walk NCH 32-column chunks of this thread's accumulator row with the NEXT chunk's tcgen05.ld already in flight while
-// the current one is processed (f(raw, chunk)); the load latency disappears behind the epilogue math.
-template <int NCH, class F>
-__device__ __forceinline__ void chunk_loop(uint32_t taddr, F&& f) {
-  static_assert(NCH % 2 == 0, "chunk_loop handles chunk pairs");
-  uint32_t ra[32], rb[32];
-  tmem_ld32(taddr, ra);
-#pragma unroll 1
-  for (int c = 0; c < NCH; c += 2) {
-    tmem_ld_fence(ra);
-    tmem_ld32(taddr + (c + 1) * 32, rb);
-    f(ra, c);
-    tmem_ld_fence(rb);
-    if (c + 2 < NCH) tmem_ld32(taddr + (c + 2) * 32, ra);
-    f(rb, c + 1);
+// Residual prefetch: the 32 bf16 of the NEXT chunk's residual row segment are requested while the current chunk is
+// processed (and, for the first chunk of a tile, before the accumulator is even ready), so the L2/HBM latency of the
+// residual stream never sits on the epilogue's critical path (timeline trace: it used to cost ~1.8k cycles per chunk).
+struct ResidRegs {
+  uint4 q[4];
+};
+__device__ __forceinline__ void resid_load(ResidRegs& r, const GemmEpi& ep, const EpiThread& th, int col0) {
+  if (ep.resid != nullptr && th.valid) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(ep.resid + static_cast<size_t>(th.row) * ep.ld_resid + col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.q[j] = __ldg(r4 + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.q[j] = make_uint4(0u, 0u, 0u, 0u);
   }
+}
+__device__ __forceinline__ void resid_add(float (&v)[32], const ResidRegs& r) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = r.q[j];
+    fadd2(v[8 * j + 0], v[8 * j + 1], v[8 * j + 0], v[8 * j + 1], bf16_lo(q.x), bf16_hi(q.x));
+    fadd2(v[8 * j + 2], v[8 * j + 3], v[8 * j + 2], v[8 * j + 3], bf16_lo(q.y), bf16_hi(q.y));
+    fadd2(v[8 * j + 4], v[8 * j + 5], v[8 * j + 4], v[8 * j + 5], bf16_lo(q.z), bf16_hi(q.z));
+    fadd2(v[8 * j + 6], v[8 * j + 7], v[8 * j + 6], v[8 * j + 7], bf16_lo(q.w), bf16_hi(q.w));
+  }
+}
+
+// Row statistics of the two warps that share a TMEM lane quarter (same 32 rows, alternate 64-column boxes) are
+// combined through a small smem slot + a 64-thread named barrier.
+constexpr int kXchBytes = 2 * 2 * 2 * 128 * 16;  // [tile parity][exchange A|B][column half][row] x float4 = 16 KB
+__device__ __forceinline__ void exchange_stats(RowStats& rs, float4* slot /*[2][128]*/, int h, int r, uint32_t bar_id) {
+  slot[h * 128 + r] = make_float4(rs.s0, rs.s1, rs.q0, rs.q1);
+  named_bar_sync(bar_id, 64);
+  const float4 o = slot[(h ^ 1) * 128 + r];
+  rs.s0 += o.x; rs.s1 += o.y; rs.q0 += o.z; rs.q1 += o.w;
+}
+
+// The whole epilogue of one output tile for ONE warp. All 8 epilogue warps work on the same tile (timeline trace: with
+// two 4-warp groups on alternate tiles one tile's epilogue lasted 4.5k cycles and gated the MMA two tiles later; eight
+// warps halve that): warp (q, h) owns rows [32q, 32q+32) of the tile and the 64-column boxes b = h, h+2, ...
+//   tile_col0: first output column of this tile in the output tensor; acc_col0: first accumulator column (n_tile * BN)
+template <int BN, bool ROW, bool OUT_F32>
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread& th, int n_tile, int N, int row0, int q,
+                                              int h, int lane, WarpStore& st, const CUtensorMap* tmO0,
+                                              const CUtensorMap* tmO1, float4* xch, int tile_parity, ResidRegs rr) {
+  constexpr int CH = OUT_F32 ? 32 : 64;  // output columns per staging box
+  constexpr int SUBS = CH / 32;
+  if constexpr (!ROW) {
+    const bool glu = ep.act == ACT_GLU;
+    const int cols_out = glu ? BN / 2 : BN;
+    const int nbox = cols_out / CH;
+    for (int b = h; b < nbox; b += 2) {
+      const uint32_t buf = st.acquire();
+#pragma unroll 1
+      for (int sub = 0; sub < SUBS; ++sub) {
+        const int tc = b * CH + sub * 32;
+        uint32_t raw[32];
+        float v[32];
+        tmem_ld32(th.taddr + tc, raw);
+        ResidRegs rn;
+        {  // next chunk of this warp (if any)
+          int nb = b, nsub = sub + 1;
+          if (nsub == SUBS) { nsub = 0; nb = b + 2; }
+          if (nb < nbox) {
+            resid_load(rn, ep, th, n_tile * cols_out + nb * CH + nsub * 32);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rn.q[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        tmem_ld_wait();
+        to_float(v, raw);
+        epi_affine(v, ep, th, n_tile * BN + tc, N);
+        if (glu) {
+          float u[32];
+          tmem_ld32(th.taddr + cols_out + tc, raw);
+          tmem_ld_wait();
+          to_float(u, raw);
+          epi_affine(u, ep, th, n_tile * BN + cols_out + tc, N);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(u[j]);
+        } else if (ep.act == ACT_SWISH) {
+          epi_swish(v);
+        } else if (ep.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.resid != nullptr) resid_add(v, rr);
+        rr = rn;
+        stage_write<OUT_F32>(buf, lane, sub, v);
+      }
+      st.release(tmO0, buf, n_tile * cols_out + b * CH, row0);
+    }
+  } else {
+    // ---- full-row epilogue: (resid add) -> [LN0] -> out0 -> [LN1 -> out1]; lane == row; the partner warp (same q,
+    //      other h) holds the other boxes of the same rows, so row statistics are exchanged once per LayerNorm; values
+    //      are parked in TMEM (tcgen05.st) between passes ----
+    static_assert(!OUT_F32 || !ROW, "row epilogue writes bf16");
+    constexpr int nbox = BN / 64;
+    const bool ln0 = ep.ln0_g != nullptr, ln1 = ep.ln1_g != nullptr;
+    const int r = q * 32 + lane;
+    float4* slotA = xch + (tile_parity * 2 + 0) * 256;
+    float4* slotB = xch + (tile_parity * 2 + 1) * 256;
+    RowStats rs;
+    // pass A
+    for (int b = h; b < nbox; b += 2) {
+      uint32_t buf = 0;
+      if (!ln0) buf = st.acquire();
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const int tc = b * 64 + sub * 32;
+        uint32_t raw[32];
+        float v[32];
+        tmem_ld32(th.taddr + tc, raw);
+        ResidRegs rn;
+        {
+          int nb = b, nsub = sub + 1;
+          if (nsub == 2) { nsub = 0; nb = b + 2; }
+          if (nb < nbox) {
+            resid_load(rn, ep, th, nb * 64 + nsub * 32);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rn.q[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        tmem_ld_wait();
+        to_float(v, raw);
+        epi_affine(v, ep, th, tc, N);
+        if (ep.act == ACT_SWISH) epi_swish(v);
+        if (ep.resid != nullptr) resid_add(v, rr);
+        rr = rn;
+        if (ln0 || ln1) {
+          rs.add(v);
+          to_raw(raw, v);
+          tmem_st32(th.taddr + tc, raw);
+        }
+        if (!ln0) stage_write<false>(buf, lane, sub, v);
+      }
+      if (!ln0) st.release(tmO0, buf, b * 64, row0);
+    }
+    if (ln0 || ln1) {
+      tmem_st_wait();
+      exchange_stats(rs, slotA, h, r, 1 + q);
+    }
+    if (ln0) {
+      // pass B: u = LN0(v) -> out0; stats of u for LN1
+      float mean, rstd;
+      rs.finish(BN, ep.ln0_eps, &mean, &rstd);
+      rs = RowStats();
+      for (int b = h; b < nbox; b += 2) {
+        const uint32_t buf = st.acquire();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int tc = b * 64 + sub * 32;
+          uint32_t raw[32];
+          float v[32];
+          tmem_ld32(th.taddr + tc, raw);
+          tmem_ld_wait();
+          to_float(v, raw);
+          epi_layernorm(v, ep.ln0_g, ep.ln0_b, mean, rstd, tc);
+          if (ln1) {
+            rs.add(v);
+            to_raw(raw, v);
+            tmem_st32(th.taddr + tc, raw);
+          }
+          stage_write<false>(buf, lane, sub, v);
+        }
+        st.release(tmO0, buf, b * 64, row0);
+      }
+      if (ln1) {
+        tmem_st_wait();
+        exchange_stats(rs, slotB, h, r, 1 + q);
+      }
+    }
+    if (ln1) {
+      // pass C: out1 = bf16(LN1(stream))
+      float mean, rstd;
+      rs.finish(BN, ep.ln1_eps, &mean, &rstd);
+      for (int b = h; b < nbox; b += 2) {
+        const uint32_t buf = st.acquire();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int tc = b * 64 + sub * 32;
+          uint32_t raw[32];
+          float v[32];
+          tmem_ld32(th.taddr + tc, raw);
+          tmem_ld_wait();
+          to_float(v, raw);
+          epi_layernorm(v, ep.ln1_g, ep.ln1_b, mean, rstd, tc);
+          stage_write<false>(buf, lane, sub, v);
+        }
+        st.release(tmO1, buf, b * 64, row0);
+      }
+    }
+  }
+}
+
+// first residual column a warp needs for a tile (matches the first chunk epilogue_tile processes)
+template <int BN, bool ROW, bool OUT_F32>
+__device__ __forceinline__ int epilogue_first_col(const GemmEpi& ep, int n_tile, int h) {
+  constexpr int CH = OUT_F32 ? 32 : 64;
+  if constexpr (ROW) return h * 64;
+  const int cols_out = ep.act == ACT_GLU ? BN / 2 : BN;
+  return n_tile * cols_out + h * CH;
 }
 
 }  // namespace

@@ -32,7 +32,7 @@ constexpr int kNumStg = 4;            // 2 per epilogue group
 __host__ __device__ constexpr int gemm_stages(int bn) { return bn >= 256 ? 3 : 4; }
 __host__ __device__ constexpr int gemm_stage_bytes(int bn) { return kAStageBytes + bn * kBK * 2; }
 __host__ __device__ constexpr int gemm_smem_bytes(int bn) {
-  return gemm_stages(bn) * gemm_stage_bytes(bn) + kNumStg * kStgBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+  return gemm_stages(bn) * gemm_stage_bytes(bn) + kNumStg * kStgBytes + kXchBytes + 256 /*barriers*/ + 1024 /*align slack*/;
 }
 
 // RESB ("resident B", weight-stationary): the CTA keeps its whole [BN x K] weight slice in shared memory for the
@@ -60,7 +60,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* resb_ptr = smem;                                             // [num_kb][BN x 64] (RESB only)
   uint8_t* stage_ptr = smem + resb_bytes;
   uint8_t* stg_ptr = stage_ptr + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_ptr + NUM_STG * kStgBytes);
+  float4* xch = reinterpret_cast<float4*>(stg_ptr + NUM_STG * kStgBytes);   // row-statistics exchange slots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_ptr + NUM_STG * kStgBytes + kXchBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -89,8 +90,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 128);
-    mbar_init(&tempty[1], 128);
+    mbar_init(&tempty[0], 8);  // one arrive per epilogue warp
+    mbar_init(&tempty[1], 8);
     mbar_init(bfull, 1);
     mbar_fence_init();
   }
@@ -161,9 +162,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue groups =====================
-    const int g = (warp - 4) >> 2;  // 0 | 1: even / odd tiles, TMEM buffer g
+    // ===================== epilogue: all 8 warps on every tile =====================
     const int q = warp & 3;         // TMEM lane quarter this warp may access
+    const int h = (warp - 4) >> 2;  // which alternate 64-column boxes of the tile this warp owns
     WarpStore st;
     st.single = NUM_STG == 2;
     st.base = smem_u32(stg_ptr) + static_cast<uint32_t>((warp - 4) * (st.single ? 1 : 2)) * kWarpStgBytes;
@@ -172,144 +173,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     st.skip_store = (ep.dbg & 1) != 0;
     st.skip_fence = (ep.dbg & 16) != 0;
 
-    constexpr int OC = BN;                 // tile output columns before GLU halving
-    constexpr int CH = OUT_F32 ? 32 : 64;  // output columns per staging box
-
     int it = 0;
     for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++it) {
-      if ((it & 1) != g) continue;
+      const uint32_t buf = it & 1;
       const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
-      const int row0 = m_tile * kBM + q * 32;  // first row of this warp's box
+      const int row0 = m_tile * kBM + q * 32;  // first row of this warp's boxes
       EpiThread th;
       th.row = row0 + lane;
       th.valid = th.row < M;
       th.seq = th.valid ? th.row / ep.rows_per_seq : 0;
       th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
-      th.taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
+      th.taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+      ResidRegs rr;
+      resid_load(rr, ep, th, epilogue_first_col<BN, ROW, OUT_F32>(ep, n_tile, h));  // in flight while the MMAs finish
 
-      mbar_wait(&tfull[g], (it >> 1) & 1);
+      mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
-      if (q == 0 && lane == 0) ISHARA_TRACE(it, 6);
-
-      if (ep.dbg & 2) {
-        tc_fence_before();
-        mbar_arrive(&tempty[g]);
-        continue;
-      }
-      if constexpr (!ROW) {
-        // ---- single pass: bias / gate / rowtab / act / resid -> out0 ----
-        if (ep.act == ACT_GLU) {
-          constexpr int oc = OC / 2;
-          uint32_t buf = 0;
-#pragma unroll 1
-          for (int c = 0; c < oc / 32; ++c) {
-            uint32_t raw[32];
-            float v[32], u[32];
-            const int tc = c * 32;
-            tmem_ld32(th.taddr + tc, raw);
-            tmem_ld_wait();
-            to_float(v, raw);
-            tmem_ld32(th.taddr + oc + tc, raw);
-            tmem_ld_wait();
-            to_float(u, raw);
-            epi_affine(v, ep, th, n_tile * BN + tc, N);
-            epi_affine(u, ep, th, n_tile * BN + oc + tc, N);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(u[j]);
-            epi_resid(v, ep, th, n_tile * oc + tc);
-            const int sub = OUT_F32 ? 0 : (c & 1);
-            if (sub == 0) buf = st.acquire();
-            stage_write<OUT_F32>(buf, lane, sub, v);
-            if (OUT_F32 || sub == 1) st.release(&tmO0, buf, n_tile * oc + (c * 32 / CH) * CH, row0);
-          }
-        } else {
-          uint32_t buf = 0;
-          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-            float v[32];
-            to_float(v, raw);
-            const int tc = c * 32;
-            epi_affine(v, ep, th, n_tile * BN + tc, N);
-            if (ep.act == ACT_SWISH) {
-              epi_swish(v);
-            } else if (ep.act == ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            epi_resid(v, ep, th, n_tile * OC + tc);
-            const int sub = OUT_F32 ? 0 : (c & 1);
-            if (sub == 0) buf = st.acquire();
-            if (!(ep.dbg & 8)) stage_write<OUT_F32>(buf, lane, sub, v);
-            if (OUT_F32 || sub == 1) st.release(&tmO0, buf, n_tile * OC + (c * 32 / CH) * CH, row0);
-          });
-        }
-      } else {
-        // ---- full-row epilogue: (resid add) -> [LN0] -> out0 -> [LN1 -> out1]; lane == row, so row statistics
-        //      are thread-local; values are parked in TMEM (tcgen05.st) between passes ----
-        const bool ln0 = ep.ln0_g != nullptr, ln1 = ep.ln1_g != nullptr;
-        RowStats rs;
-        uint32_t buf = 0;
-        // pass A: v = epi(acc); stats; park if a later pass needs it; emit out0 unless LN0 is pending
-        chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-          float v[32];
-          to_float(v, raw);
-          const int tc = c * 32;
-          epi_affine(v, ep, th, tc, N);
-          if (ep.act == ACT_SWISH) epi_swish(v);
-          epi_resid(v, ep, th, tc);
-          if (ln0 || ln1) {
-            rs.add(v);
-            to_raw(raw, v);
-            tmem_st32(th.taddr + tc, raw);
-          }
-          if (!ln0) {
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO0, buf, (c >> 1) * 64, row0);
-          }
-        });
-        if (ln0 || ln1) tmem_st_wait();
-        if (ln0) {
-          // pass B: u = LN0(v) -> out0; stats of u for LN1
-          float mean, rstd;
-          rs.finish(OC, ep.ln0_eps, &mean, &rstd);
-          rs = RowStats();
-          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-            float v[32];
-            to_float(v, raw);
-            const int tc = c * 32;
-            epi_layernorm(v, ep.ln0_g, ep.ln0_b, mean, rstd, tc);
-            if (ln1) {
-              rs.add(v);
-              to_raw(raw, v);
-              tmem_st32(th.taddr + tc, raw);
-            }
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO0, buf, (c >> 1) * 64, row0);
-          });
-          if (ln1) tmem_st_wait();
-        }
-        if (ln1) {
-          // pass C: out1 = bf16(LN1(stream))
-          float mean, rstd;
-          rs.finish(OC, ep.ln1_eps, &mean, &rstd);
-          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-            float v[32];
-            to_float(v, raw);
-            epi_layernorm(v, ep.ln1_g, ep.ln1_b, mean, rstd, c * 32);
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO1, buf, (c >> 1) * 64, row0);
-          });
-        }
-      }
-      // this tile's accumulator buffer may be overwritten by the MMA warp now
+      if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
+      if (!(ep.dbg & 2))
+        epilogue_tile<BN, ROW, OUT_F32>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+      // this warp is done with accumulator buffer `buf`
       tc_fence_before();
-      mbar_arrive(&tempty[g]);
-      if (q == 0 && lane == 0) ISHARA_TRACE(it, 7);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 7);
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -343,7 +230,7 @@ int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   const int nt = p.N / BN;
   int stages, smem;
   if (RESB) {
-    const int fixed = (p.K / kBK) * BN * kBK * 2 + 2 * kStgBytes + 256 + 1024;
+    const int fixed = (p.K / kBK) * BN * kBK * 2 + 2 * kStgBytes + kXchBytes + 256 + 1024;
     stages = (kMaxSmem - fixed) / kAStageBytes;
     if (stages > 8) stages = 8;
     smem = fixed + stages * kAStageBytes;
@@ -366,7 +253,7 @@ int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
 
 // weight-stationary variant is used when the [BN x K] slice plus >= 3 A stages fit in shared memory
 bool resident_fits(int bn, int K) {
-  const int fixed = (K / kBK) * bn * kBK * 2 + 2 * kStgBytes + 256 + 1024;
+  const int fixed = (K / kBK) * bn * kBK * 2 + 2 * kStgBytes + kXchBytes + 256 + 1024;
   return fixed + 3 * kAStageBytes <= kMaxSmem;
 }
 
@@ -438,8 +325,8 @@ int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* ou
 
 int gemm_launch(const GemmPlan& p_in, int num_sms, cudaStream_t stream) {
   static const int dbg = getenv("ISHARA_GEMM_DBG") ? atoi(getenv("ISHARA_GEMM_DBG")) : 0;
-  static const int force = getenv("ISHARA_GEMM_RESIDENT") ? atoi(getenv("ISHARA_GEMM_RESIDENT")) : -1;
-  static const int pair = getenv("ISHARA_GEMM_PAIR") ? atoi(getenv("ISHARA_GEMM_PAIR")) : 1;
+  static const int force = getenv("ISHARA_GEMM_RESIDENT") ? atoi(getenv("ISHARA_GEMM_RESIDENT")) : 0;  // measured: no gain, off by default
+  static const int pair = getenv("ISHARA_GEMM_PAIR") ? atoi(getenv("ISHARA_GEMM_PAIR")) : 0;  // CTA-pair variant: opt-in (measured slower)
   GemmPlan p = p_in;
   p.epi.dbg = dbg;
   if (force == 0) p.no_resident = true;

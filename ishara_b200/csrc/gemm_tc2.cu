@@ -30,7 +30,7 @@ namespace {
 constexpr int kBN2 = 256;
 constexpr int kBHalfKbBytes = (kBN2 / 2) * kBK * 2;  // one k-block of this CTA's half of the weight tile: 16 KB
 
-template <bool ROW>
+template <bool ROW, int STG_TILES>  // STG_TILES: 4 = two staging boxes per epilogue warp, 2 = one
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const GemmEpi ep, int M,
@@ -49,7 +49,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* resb_ptr = smem;                         // [num_kb][128 x 64] resident half of B
   uint8_t* stage_ptr = smem + resb_bytes;           // A ring
   uint8_t* stg_ptr = stage_ptr + STAGES * kAStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_ptr + 2 * kStgBytes);
+  float4* xch = reinterpret_cast<float4*>(stg_ptr + STG_TILES * kStgBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_ptr + STG_TILES * kStgBytes + kXchBytes);
   uint64_t* full = bars;                            // leader's copy is the live one
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -79,8 +80,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 8);  // buffer g is drained by epilogue group g: 4 warps in each of the two CTAs
-    mbar_init(&tempty[1], 8);
+    mbar_init(&tempty[0], 16);  // 8 epilogue warps in each of the two CTAs
+    mbar_init(&tempty[1], 16);
     mbar_init(bfull, 1);
     mbar_init(bpeer, 1);
     mbar_fence_init();
@@ -151,143 +152,38 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue groups (both CTAs) =====================
-    const int g = (warp - 4) >> 2;  // 0 | 1: even / odd tiles, TMEM buffer g
-    const int q = warp & 3;         // TMEM lane quarter this warp may access
+    // ===================== epilogue (both CTAs): all 8 warps on every tile =====================
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
     WarpStore st;
-    st.single = true;
-    st.base = smem_u32(stg_ptr) + static_cast<uint32_t>(warp - 4) * kWarpStgBytes;
+    st.single = STG_TILES == 2;
+    st.base = smem_u32(stg_ptr) + static_cast<uint32_t>((warp - 4) * (st.single ? 1 : 2)) * kWarpStgBytes;
     st.iter = 0;
     st.lane = lane;
-    constexpr int OC = BN;
 
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      if ((it & 1) != g) continue;
+      const uint32_t buf = it & 1;
       const int m_pair = tile / num_n_tiles, n_tile = tile % num_n_tiles;
-      const int row0 = m_pair * 2 * kBM + static_cast<int>(rank) * kBM + q * 32;  // first row of this warp's box
+      const int row0 = m_pair * 2 * kBM + static_cast<int>(rank) * kBM + q * 32;
       EpiThread th;
       th.row = row0 + lane;
       th.valid = th.row < M;
       th.seq = th.valid ? th.row / ep.rows_per_seq : 0;
       th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
-      th.taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
+      th.taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+      ResidRegs rr;
+      resid_load(rr, ep, th, epilogue_first_col<BN, ROW, false>(ep, n_tile, h));
 
-      mbar_wait(&tfull[g], (it >> 1) & 1);
+      mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
-      if (q == 0 && lane == 0) ISHARA_TRACE(it, 6);
-
-      if constexpr (!ROW) {
-        // ---- single pass: bias / gate / rowtab / act / resid -> out0 ----
-        if (ep.act == ACT_GLU) {
-          constexpr int oc = OC / 2;
-          uint32_t buf = 0;
-#pragma unroll 1
-          for (int c = 0; c < oc / 32; ++c) {
-            uint32_t raw[32];
-            float v[32], u[32];
-            const int tc = c * 32;
-            tmem_ld32(th.taddr + tc, raw);
-            tmem_ld_wait();
-            to_float(v, raw);
-            tmem_ld32(th.taddr + oc + tc, raw);
-            tmem_ld_wait();
-            to_float(u, raw);
-            epi_affine(v, ep, th, n_tile * BN + tc, N);
-            epi_affine(u, ep, th, n_tile * BN + oc + tc, N);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(u[j]);
-            epi_resid(v, ep, th, n_tile * oc + tc);
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO0, buf, n_tile * oc + (c >> 1) * 64, row0);
-          }
-        } else {
-          uint32_t buf = 0;
-          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-            float v[32];
-            to_float(v, raw);
-            const int tc = c * 32;
-            epi_affine(v, ep, th, n_tile * BN + tc, N);
-            if (ep.act == ACT_SWISH) {
-              epi_swish(v);
-            } else if (ep.act == ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            epi_resid(v, ep, th, n_tile * OC + tc);
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO0, buf, n_tile * OC + (c >> 1) * 64, row0);
-          });
-        }
-      } else {
-        // ---- full-row epilogue: (resid add) -> [LN0] -> out0 -> [LN1 -> out1] ----
-        const bool ln0 = ep.ln0_g != nullptr, ln1 = ep.ln1_g != nullptr;
-        RowStats rs;
-        uint32_t buf = 0;
-        chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-          float v[32];
-          to_float(v, raw);
-          const int tc = c * 32;
-          epi_affine(v, ep, th, tc, N);
-          if (ep.act == ACT_SWISH) epi_swish(v);
-          epi_resid(v, ep, th, tc);
-          if (ln0 || ln1) {
-            rs.add(v);
-            to_raw(raw, v);
-            tmem_st32(th.taddr + tc, raw);
-          }
-          if (!ln0) {
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO0, buf, (c >> 1) * 64, row0);
-          }
-        });
-        if (ln0 || ln1) tmem_st_wait();
-        if (ln0) {
-          float mean, rstd;
-          rs.finish(OC, ep.ln0_eps, &mean, &rstd);
-          rs = RowStats();
-          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-            float v[32];
-            to_float(v, raw);
-            const int tc = c * 32;
-            epi_layernorm(v, ep.ln0_g, ep.ln0_b, mean, rstd, tc);
-            if (ln1) {
-              rs.add(v);
-              to_raw(raw, v);
-              tmem_st32(th.taddr + tc, raw);
-            }
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO0, buf, (c >> 1) * 64, row0);
-          });
-          if (ln1) tmem_st_wait();
-        }
-        if (ln1) {
-          float mean, rstd;
-          rs.finish(OC, ep.ln1_eps, &mean, &rstd);
-          chunk_loop<OC / 32>(th.taddr, [&](uint32_t (&raw)[32], int c) {
-            float v[32];
-            to_float(v, raw);
-            epi_layernorm(v, ep.ln1_g, ep.ln1_b, mean, rstd, c * 32);
-            const int sub = c & 1;
-            if (sub == 0) buf = st.acquire();
-            stage_write<false>(buf, lane, sub, v);
-            if (sub == 1) st.release(&tmO1, buf, (c >> 1) * 64, row0);
-          });
-        }
-      }
-      // this CTA's half of accumulator buffer g is drained: one arrive per warp on the LEADER's barrier
+      if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
+      epilogue_tile<BN, ROW, false>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+      // this warp is done with its CTA's half of accumulator buffer `buf`: one arrive on the LEADER's barrier
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty[g], 0);
-      if (q == 0 && lane == 0) ISHARA_TRACE(it, 7);
+      if (lane == 0) mbar_arrive_cluster(&tempty[buf], 0);
+      if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 7);
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -299,9 +195,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
-template <bool ROW>
+template <bool ROW, int STG_TILES>
 int launch2(const GemmPlan& p, int num_sms, int stages, int smem, cudaStream_t stream) {
-  auto kern = gemm2_kernel<ROW>;
+  auto kern = gemm2_kernel<ROW, STG_TILES>;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -320,21 +216,32 @@ int launch2(const GemmPlan& p, int num_sms, int stages, int smem, cudaStream_t s
 
 }  // namespace
 
+int gemm2_fixed_smem(int K, int stg_tiles) {
+  return (K / kBK) * kBHalfKbBytes + stg_tiles * kStgBytes + kXchBytes + 256 + 1024;
+}
+
 // The B tensor map of a pair plan has a 128-row box (each CTA loads its half of the 256-wide weight tile).
 bool gemm2_applicable(const GemmPlan& p, int num_sms) {
   if (p.block_n != kBN2 || p.out_f32 || p.N % kBN2 != 0 || p.K % kBK != 0) return false;
   const int mp = (p.M + 2 * kBM - 1) / (2 * kBM);
   if (mp * (p.N / kBN2) < num_sms / 2) return false;  // not enough pair-tiles to fill the machine
-  const int fixed = (p.K / kBK) * kBHalfKbBytes + 2 * kStgBytes + 256 + 1024;
-  return fixed + 3 * kAStageBytes <= kMaxSmem;
+  return gemm2_fixed_smem(p.K, 2) + 3 * kAStageBytes <= kMaxSmem;
 }
 
 int gemm2_launch(const GemmPlan& p, int num_sms, cudaStream_t stream) {
-  const int fixed = (p.K / kBK) * kBHalfKbBytes + 2 * kStgBytes + 256 + 1024;
+  // two staging boxes per warp when that still leaves >= 6 ring stages, else one
+  static const int force_stg = getenv("ISHARA_GEMM_STG") ? atoi(getenv("ISHARA_GEMM_STG")) : 0;
+  int stg = 4;
+  if ((kMaxSmem - gemm2_fixed_smem(p.K, 4)) / kAStageBytes < 6) stg = 2;
+  if (force_stg == 2 || force_stg == 4) stg = force_stg;
+  if ((kMaxSmem - gemm2_fixed_smem(p.K, stg)) / kAStageBytes < 3) stg = 2;
+  const int fixed = gemm2_fixed_smem(p.K, stg);
   int stages = (kMaxSmem - fixed) / kAStageBytes;
   if (stages > 10) stages = 10;
   const int smem = fixed + stages * kAStageBytes;
-  return p.row_mode ? launch2<true>(p, num_sms, stages, smem, stream) : launch2<false>(p, num_sms, stages, smem, stream);
+  if (stg == 4)
+    return p.row_mode ? launch2<true, 4>(p, num_sms, stages, smem, stream) : launch2<false, 4>(p, num_sms, stages, smem, stream);
+  return p.row_mode ? launch2<true, 2>(p, num_sms, stages, smem, stream) : launch2<false, 2>(p, num_sms, stages, smem, stream);
 }
 
 }  // namespace ishara

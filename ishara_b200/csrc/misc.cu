@@ -48,26 +48,49 @@ se_gate_kernel(SeGateArgs a) {
   extern __shared__ float sm[];
   float* mean = sm;            // [C]
   float* z = mean + a.C;       // [D]
-  float* hid = z + a.D;        // [R]
+  float* part = z + a.D;       // [8][R] partial sums of fc1
+  float* hid = part + 8 * a.R; // [R]
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int c = tid; c < a.C; c += 256) mean[c] = a.colsum[static_cast<size_t>(b) * a.C + c] * a.inv_T;
   __syncthreads();
-  for (int d = warp; d < a.D; d += 8) {
-    const bf16* wr = a.w3t + static_cast<size_t>(d) * a.C;
-    float acc = 0.f;
-    for (int c = lane * 2; c < a.C; c += 64) {
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(wr + c);
-      acc = fmaf(bf16_lo(u), mean[c], acc);
-      acc = fmaf(bf16_hi(u), mean[c + 1], acc);
+  // z = mean @ W3 + b3: four output channels per warp iteration (independent load streams), 16-byte weight loads
+  for (int d0 = warp * 4; d0 < a.D; d0 += 32) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane * 8; c < a.C; c += 256) {
+      const float4 m0 = *reinterpret_cast<const float4*>(mean + c), m1 = *reinterpret_cast<const float4*>(mean + c + 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (d0 + i < a.D) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.w3t + static_cast<size_t>(d0 + i) * a.C + c));
+          acc[i] = fmaf(bf16_lo(u.x), m0.x, acc[i]); acc[i] = fmaf(bf16_hi(u.x), m0.y, acc[i]);
+          acc[i] = fmaf(bf16_lo(u.y), m0.z, acc[i]); acc[i] = fmaf(bf16_hi(u.y), m0.w, acc[i]);
+          acc[i] = fmaf(bf16_lo(u.z), m1.x, acc[i]); acc[i] = fmaf(bf16_hi(u.z), m1.y, acc[i]);
+          acc[i] = fmaf(bf16_lo(u.w), m1.z, acc[i]); acc[i] = fmaf(bf16_hi(u.w), m1.w, acc[i]);
+        }
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) z[d] = acc + a.b3[d];
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      if (lane == 0 && d0 + i < a.D) z[d0 + i] = acc[i] + a.b3[d0 + i];
+    }
+  }
+  __syncthreads();
+  // fc1 (swish): every warp takes a slice of D, lane = hidden unit (R <= 32 handled per pass)
+  for (int r0 = 0; r0 < a.R; r0 += 32) {
+    const int r = r0 + lane;
+    float acc = 0.f;
+    const int dper = (a.D + 7) / 8;
+    if (r < a.R)
+      for (int d = warp * dper; d < min(a.D, (warp + 1) * dper); ++d) acc = fmaf(z[d], a.fc1_w[static_cast<size_t>(d) * a.R + r], acc);
+    if (r < a.R) part[warp * a.R + r] = acc;
   }
   __syncthreads();
   for (int r = tid; r < a.R; r += 256) {
     float acc = a.fc1_b[r];
-    for (int d = 0; d < a.D; ++d) acc = fmaf(z[d], a.fc1_w[static_cast<size_t>(d) * a.R + r], acc);
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) acc += part[wv * a.R + r];
     hid[r] = acc / (1.f + __expf(-acc));  // swish
   }
   __syncthreads();
@@ -130,7 +153,11 @@ int cast_pad_launch(const float* x, bf16* out, int64_t M, int F, int Fpad, cudaS
 }
 
 int se_gate_launch(const SeGateArgs& a, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(a.C + a.D + a.R) * sizeof(float);
+  if (a.C % 8 != 0) {
+    set_last_error("se_gate: C must be a multiple of 8");
+    return 2;
+  }
+  const size_t smem = static_cast<size_t>(a.C + a.D + 9 * a.R) * sizeof(float);
   se_gate_kernel<<<a.B, 256, smem, stream>>>(a);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();

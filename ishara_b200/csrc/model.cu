@@ -8,6 +8,7 @@
 // UMMA "K-major" B operand), bf16, inference BatchNorm folded into the neighbouring linear op.
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <unordered_map>
 #include <vector>
@@ -98,7 +99,11 @@ struct ishara_model {
   std::vector<cudaEvent_t> events;    // [0] before cast_pad, [1] after it, [2+i] after program[i]
   int program_batch = 0;
   float* program_logits = nullptr;
+  // programs built for other (batch, logits pointer) pairs: the chunked host path alternates between a few of them
+  std::map<std::pair<int, float*>, std::vector<Op>> program_cache;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;     // H2D of the chunked host path
+  cudaEvent_t copy_done[8] = {nullptr};
 
   int fpad() const { return (cfg.features + 63) / 64 * 64; }
   int vpad() const { return (cfg.num_classes + 63) / 64 * 64; }
@@ -425,6 +430,7 @@ int ensure_workspace(ishara_model* m, int batch) {
   m->wsallocs.clear();
   m->taps.clear();
   m->program.clear();
+  m->program_cache.clear();
   m->program_batch = 0;
   const ishara_config_t& c = m->cfg;
   const size_t M = static_cast<size_t>(batch) * c.frames;
@@ -733,6 +739,10 @@ int model_destroy(ishara_model* m) {
   for (cudaEvent_t e : m->events) cudaEventDestroy(e);
   if (m->labels_dev) cudaFree(m->labels_dev);
   if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->copy_stream) {
+    cudaStreamDestroy(m->copy_stream);
+    for (auto& e : m->copy_done) if (e) cudaEventDestroy(e);
+  }
   delete m;
   return ISHARA_OK;
 }
@@ -748,10 +758,15 @@ int model_finalize(ishara_model* m) {
   if (major != 10) { set_last_error("ishara_b200 needs a Blackwell (sm_100a) device; no fallback exists"); return ISHARA_ERR_CUDA; }
   m->num_sms = sms;
   if (m->stream == nullptr) ISHARA_CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  if (m->copy_stream == nullptr) {
+    ISHARA_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : m->copy_done) ISHARA_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   int rc = pack_all(m);
   if (rc) return rc;
   m->finalized = true;
   m->program.clear();
+  m->program_cache.clear();
   m->program_batch = 0;
   return ISHARA_OK;
 }
@@ -762,8 +777,27 @@ int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_
   ISHARA_CUDA_OK(cudaSetDevice(m->device));
   int rc;
   if ((rc = ensure_workspace(m, batch))) return rc;
-  if (m->program_batch != batch || m->program_logits != logits_dev || m->program.empty())
-    if ((rc = build_program(m, batch, logits_dev))) return rc;
+  if (m->program_batch != batch || m->program_logits != logits_dev || m->program.empty()) {
+    if (m->debug_taps) {
+      m->program_cache.clear();
+      if ((rc = build_program(m, batch, logits_dev))) return rc;
+    } else {
+      if (!m->program.empty()) {
+        if (m->program_cache.size() >= 16) m->program_cache.clear();
+        m->program_cache[{m->program_batch, m->program_logits}] = std::move(m->program);
+        m->program.clear();
+      }
+      auto it = m->program_cache.find({batch, logits_dev});
+      if (it != m->program_cache.end()) {
+        m->program = std::move(it->second);
+        m->program_cache.erase(it);
+        m->program_batch = batch;
+        m->program_logits = logits_dev;
+      } else if ((rc = build_program(m, batch, logits_dev))) {
+        return rc;
+      }
+    }
+  }
   const ishara_config_t& c = m->cfg;
   const int64_t M = static_cast<int64_t>(batch) * c.frames;
   const bool prof = m->profile;
@@ -841,6 +875,8 @@ struct ModelView {
   const ishara_config_t* cfg;
   int device;
   cudaStream_t stream;
+  cudaStream_t copy_stream;
+  cudaEvent_t* copy_done;  // [8]
   float* x_dev;
   float* logits_own;
   int32_t* ids_dev;
@@ -856,6 +892,8 @@ int model_view(ishara_model* m, int batch, ModelView* v) {
   v->cfg = &m->cfg;
   v->device = m->device;
   v->stream = m->stream;
+  v->copy_stream = m->copy_stream;
+  v->copy_done = m->copy_done;
   v->x_dev = m->x_dev;
   v->logits_own = m->logits_own;
   v->ids_dev = m->ids_dev;
@@ -917,6 +955,7 @@ int model_get_param(const ishara_model* m, const char* name, float* out, int64_t
 int model_set_debug(ishara_model* m, int on) {
   m->debug_taps = on != 0;
   m->program.clear();
+  m->program_cache.clear();
   m->program_batch = 0;
   return 0;
 }

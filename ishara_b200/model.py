@@ -35,6 +35,19 @@ char_to_num: Dict[str, int] = {c: i for i, c in enumerate(_CHARS)}
 char_to_num[pad_token] = pad_token_idx
 num_to_char: Dict[int, str] = {j: i for i, j in char_to_num.items()}
 FALLBACK_IDS = (17, 0, 32, 12, 36, 0, 12, 32, 49, 46, 36)  # c13:22-23
+# id -> ASCII code lookup for vectorised string assembly (ids outside the 59 characters map to "" like num_to_char.get(x, ""))
+_ASCII_LUT = np.zeros(256, np.uint8)
+_ASCII_LUT[: len(_CHARS)] = np.frombuffer(_CHARS.encode("ascii"), np.uint8)
+
+
+def _ids_to_text(ids: np.ndarray) -> str:
+    """"".join(num_to_char_fn(ids)) without a Python loop per character."""
+    ids = np.asarray(ids)
+    ok = (ids >= 0) & (ids < len(_CHARS))
+    if not ok.all():
+        ids = ids[ok]
+    return _ASCII_LUT[ids].tobytes().decode("ascii")
+
 
 ArrayLike = Union[np.ndarray, "DeviceTensor", object]
 
@@ -239,7 +252,7 @@ class IsharaModel:
 
     def decode(self, logits: ArrayLike) -> List[str]:
         """decode_batch_predictions(pred) (c8:15-20)."""
-        return ["".join(num_to_char_fn(ids)) for ids in self.decode_ids(logits)]
+        return [_ids_to_text(ids) for ids in self.decode_ids(logits)]
 
     def infer(self, x: np.ndarray, labels: Optional[np.ndarray] = None, return_logits: bool = False) -> dict:
         """One whole inference step through HOST buffers in a single C-ABI call: H2D, forward, greedy decode,
@@ -262,8 +275,11 @@ class IsharaModel:
         logits = np.empty((B, self.frames, self.num_classes), np.float32) if return_logits else None
         p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         _lib.check(self._lib.ishara_model_infer_host(self._h, p(x), B, p(lab), L, p(logits), p(ids), p(lens), p(nll)))
-        id_list = [ids[b, : lens[b]].astype(np.int64) for b in range(B)]
-        return {"ids": id_list, "text": ["".join(num_to_char_fn(i)) for i in id_list], "nll": nll, "logits": logits}
+        ids64 = ids.astype(np.int64)
+        id_list = [ids64[b, : lens[b]] for b in range(B)]
+        codes = _ASCII_LUT[np.clip(ids, 0, 255)]  # the kernel only emits ids in [0, blank): one LUT pass for the whole batch
+        text = [codes[b, : lens[b]].tobytes().decode("ascii") for b in range(B)]
+        return {"ids": id_list, "text": text, "nll": nll, "logits": logits}
 
     # ---- measurement hook (bench.py) ------------------------------------------------------------
     def profile_forward(self, x: ArrayLike, logits=None) -> List[dict]:
@@ -395,7 +411,7 @@ def num_to_char_fn(y) -> List[str]:  # c8:1-2
 
 
 def decode_batch_predictions(pred: ArrayLike, *, blank: int = pad_token_idx, device: int = 0) -> List[str]:  # c8:15-20
-    return ["".join(num_to_char_fn(ids)) for ids in decode_ids(pred, blank=blank, device=device)]
+    return [_ids_to_text(ids) for ids in decode_ids(pred, blank=blank, device=device)]
 
 
 def tflite_postprocess(ids: Sequence[int]) -> np.ndarray:
