@@ -11,6 +11,8 @@
 // softmax over 64-key chunks with bf16 tensor-core MMAs (fp32 accumulate) and exp2 in fp32.
 // Round-1 note: the two small-K contractions here (K=dh=32 and K=T) use warp-level mma.sync; the
 // tcgen05 port of this kernel is listed in DESIGN.md §"next".
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -434,7 +436,12 @@ int launch_inst(const AttnArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+bool attention_tc_applicable(const AttnArgs& a);
+int attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
+
 int attention_launch(const AttnArgs& a, cudaStream_t stream) {
+  static const int use_tc = getenv("ISHARA_ATTN_TC") ? atoi(getenv("ISHARA_ATTN_TC")) : 1;
+  if (use_tc && attention_tc_applicable(a)) return attention_tc_launch(a, stream);
   if (a.pos != nullptr) {
     if (a.u_bias == nullptr || a.v_bias == nullptr) {
       set_last_error("relpos attention needs u_bias and v_bias");

@@ -20,16 +20,31 @@ namespace {
 constexpr float kLogZero = -1.0e30f;
 constexpr int kCtcBlk = 32;  // frames staged per shared-memory block
 
+// All recursions run in the log2 domain with raw MUFU ex2/lg2 (no range fix-ups, no branches): the sweep is a serial
+// chain of ~T dependent steps executed by ONE warp, so its speed is instructions-per-step times the dependent-issue
+// latency (ncu: 390 instructions and ~2.3k cycles per step with __expf/__logf and early-out branches). kLogZero is a
+// FINITE sentinel: (-1e30) - (-1e30) = 0 and -1e30 + x = -1e30 in fp32, so "log 0" states stay at the sentinel without
+// NaNs or special cases.
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2a(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float lse2(float a, float b) {
   const float m = fmaxf(a, b);
-  if (m <= 0.5f * kLogZero) return kLogZero;
-  return m + __logf(__expf(a - m) + __expf(b - m));
+  return m + lg2a(ex2a(a - m) + ex2a(b - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
-  if (m <= 0.5f * kLogZero) return kLogZero;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+  return m + lg2a(ex2a(a - m) + ex2a(b - m) + ex2a(c - m));
 }
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -131,7 +146,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
       const float* row = cur + tt * V;
       float em[SPL];
 #pragma unroll
-      for (int i = 0; i < SPL; ++i) em[i] = row[ext[i]] - lt;
+      for (int i = 0; i < SPL; ++i) em[i] = (row[ext[i]] - lt) * kLog2e;
       if (t == 0) {
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
@@ -147,7 +162,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
         for (int i = 0; i < SPL; ++i) {
           const float q1 = (i == 0) ? up1 : a[i - 1];
           const float q2 = (i == 0) ? up2 : (i == 1 ? up1 : a[i - 2]);
-          const float acc = skip_fwd[i] ? lse3(a[i], q1, q2) : lse2(a[i], q1);
+          const float acc = lse3(a[i], q1, skip_fwd[i] ? q2 : kLogZero);
           const int s = lane * SPL + i;
           na[i] = (s < S) ? acc + em[i] : kLogZero;
         }
@@ -171,9 +186,9 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fin = lse2(fin, __shfl_xor_sync(0xffffffffu, fin, o));
-  const float logp = fin;
+  const float logp = fin;  // log2 p(l|x)
   const bool feasible = logp > 0.5f * kLogZero;
-  if (lane == 0) nll[b] = feasible ? -logp : INFINITY;
+  if (lane == 0) nll[b] = feasible ? -logp * kLn2 : INFINITY;
   if (grad == nullptr) return;
 
   // ---------------- beta sweep + gradient (blocks in reverse) ----------------
@@ -192,7 +207,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
       const float* row = cur + tt * V;
       float em[SPL];
 #pragma unroll
-      for (int i = 0; i < SPL; ++i) em[i] = row[ext[i]] - lt;
+      for (int i = 0; i < SPL; ++i) em[i] = (row[ext[i]] - lt) * kLog2e;
       // alphas of this frame (written by this thread during the forward sweep)
       float al[SPL];
       {
@@ -215,7 +230,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
         for (int i = 0; i < SPL; ++i) {
           const float q1 = (i + 1 < SPL) ? bt[i + 1] : dn1;
           const float q2 = (i + 2 < SPL) ? bt[i + 2] : (i + 1 < SPL ? dn1 : dn2);
-          const float acc = skip_bwd[i] ? lse3(bt[i], q1, q2) : lse2(bt[i], q1);
+          const float acc = lse3(bt[i], q1, skip_bwd[i] ? q2 : kLogZero);
           const int s = lane * SPL + i;
           nb[i] = (s < S) ? acc + em[i] : kLogZero;
         }
@@ -241,7 +256,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
-          e[i] = (e[i] - mx > -80.f) ? __expf(e[i] - mx) : 0.f;
+          e[i] = (e[i] - mx > -100.f) ? ex2a(e[i] - mx) : 0.f;
           sum += e[i];
         }
 #pragma unroll
@@ -253,7 +268,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
       }
       __syncwarp();
       for (int v = lane; v < V; v += 32) {
-        const float y = __expf(row[v] - lt);
+        const float y = ex2a((row[v] - lt) * kLog2e);
         gr[static_cast<size_t>(t) * V + v] = feasible ? (y - occ[v]) : __int_as_float(0x7fc00000);
       }
       __syncwarp();

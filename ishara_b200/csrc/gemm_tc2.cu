@@ -238,6 +238,8 @@ int gemm2_launch(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   const int fixed = gemm2_fixed_smem(p.K, stg);
   int stages = (kMaxSmem - fixed) / kAStageBytes;
   if (stages > 10) stages = 10;
+  static const int cap = getenv("ISHARA_GEMM_STAGES") ? atoi(getenv("ISHARA_GEMM_STAGES")) : 0;
+  if (cap >= 2 && stages > cap) stages = cap;
   const int smem = fixed + stages * kAStageBytes;
   if (stg == 4)
     return p.row_mode ? launch2<true, 4>(p, num_sms, stages, smem, stream) : launch2<false, 4>(p, num_sms, stages, smem, stream);

@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, sequences sharded across ranks.
+
+Inference, loss and decode have no cross-sequence dependency (BatchNorm uses moving statistics), so the path shards by
+sequence with NO data-path collective; `torch.distributed` is used only to agree on shard boundaries,
+to gather the small results (decoded strings, per-sequence losses) and to reduce timings (max over ranks). The backend
+is NCCL on GPUs and gloo in the CPU tests; nothing here touches the kernels.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [start, stop) of `n` sequences owned by `rank`; the first n % world ranks get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        return None
+    return dist
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Timing reduction the bench contract asks for: the slowest rank defines the step time."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return float(value)
+    import torch
+
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    if t.is_cuda:
+        t = t.float()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_in_rank_order(local: Sequence) -> List:
+    """Concatenate per-rank result lists in rank order (= global sequence order under shard_range)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return list(local)
+    parts: List[Optional[list]] = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, list(local))
+    out: List = []
+    for p in parts:
+        out.extend(p)
+    return out
+
+
+class ShardedInference:
+    """Drop-in for `model.infer` on a GLOBAL batch: every rank passes the same global arrays (or only its shard with
+    `already_sharded=True`), runs its contiguous slice on its own GPU and gets the global, ordered results back."""
+
+    def __init__(self, model, rank: Optional[int] = None, world: Optional[int] = None):
+        dist = _dist()
+        self.model = model
+        self.rank = rank if rank is not None else (dist.get_rank() if dist else 0)
+        self.world = world if world is not None else (dist.get_world_size() if dist else 1)
+
+    def infer(self, x: np.ndarray, labels: Optional[np.ndarray] = None, already_sharded: bool = False) -> dict:
+        if not already_sharded:
+            lo, hi = shard_range(x.shape[0], self.rank, self.world)
+            x = x[lo:hi]
+            labels = labels[lo:hi] if labels is not None else None
+        if x.shape[0] > 0:
+            r = self.model.infer(x, labels=labels)
+            text, ids = r["text"], [i.tolist() for i in r["ids"]]
+            nll = r["nll"].tolist() if r["nll"] is not None else []
+        else:
+            text, ids, nll = [], [], []
+        return {"text": gather_in_rank_order(text), "ids": [np.asarray(i, np.int64) for i in gather_in_rank_order(ids)],
+                "nll": np.asarray(gather_in_rank_order(nll), np.float32) if labels is not None else None}

@@ -144,7 +144,7 @@ def dw_case(B, T, Cc, k, pad_left, post, bias=True, colsum=False):
     return ok
 
 
-def attn_case(B, T, H, dh, mask=False):
+def attn_case(B, T, H, dh, mask=False, time_it=False):
     lib = _lib.load()
     D = H * dh
     qkv = torch.randn(B * T, 3 * D, device=dev).bfloat16()
@@ -160,7 +160,19 @@ def attn_case(B, T, H, dh, mask=False):
     att = q @ k.transpose(-1, -2) * scale
     if mask: att = att + (1 - km.float())[:, None, None, :] * -1e9
     o = (torch.softmax(att, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, D)
-    return report(f"attention B{B} T{T} H{H} dh{dh} mask{int(mask)}", out, o, 2e-2)
+    ok = report(f"attention B{B} T{T} H{H} dh{dh} mask{int(mask)}", out, o, 2e-2)
+    if time_it:
+        for _ in range(3): lib.ishara_op_attention(ptr(qkv), ptr(out), ptr(km), B, T, H, dh, scale, None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s = torch.cuda.default_stream()
+        e0.record(s)
+        for _ in range(10): lib.ishara_op_attention(ptr(qkv), ptr(out), ptr(km), B, T, H, dh, scale, None)
+        e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"   time {ms*1e3:.1f} us  {4.0*B*T*T*D/ms/1e9:.1f} TFLOP/s")
+    return ok
 
 
 def ctc_case(B, T, V, L):
@@ -229,12 +241,15 @@ CASES = {
     "gemm_big_time_row": lambda: gemm_case(98304, 512, 256, 256, bias=True, resid=True, ln1=True, row_mode=True, time_it=True),
     "gemm_big_time_row256": lambda: gemm_case(98304, 256, 256, 256, bias=True, resid=True, ln0=True, ln1=True, row_mode=True, time_it=True),
     "gemm_big_glu": lambda: gemm_case(98304, 256, 512, 256, act=3, bias=True, time_it=True),
+    "gemm_scan_m": lambda: all([gemm_case(m, 256, 768, 256, time_it=True) for m in (18944, 37888, 75776, 151552, 303104)]),
     "gemm_big_qkv": lambda: gemm_case(98304, 256, 768, 256, time_it=True),
     "dw_eca": lambda: dw_case(3, 384, 512, 11, 10, 2),
     "dw_eca_k3": lambda: dw_case(2, 100, 128, 3, 2, 2),
     "dw_swish_colsum": lambda: dw_case(3, 384, 512, 15, 14, 1, bias=False, colsum=True),
     "dw_same": lambda: dw_case(2, 384, 256, 15, 7, 0),
     "attn": lambda: attn_case(2, 384, 8, 32),
+    "attn_t256_mask": lambda: attn_case(3, 256, 4, 32, mask=True),
+    "attn_big_time": lambda: attn_case(256, 384, 8, 32, time_it=True),
     "attn_mask_ragged": lambda: attn_case(2, 200, 4, 32, mask=True),
     "attn_dh48": lambda: attn_case(1, 1024, 8, 48),
     "ctc": lambda: ctc_case(6, 384, 60, 64),
