@@ -146,27 +146,50 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
   }
 
   // ---- main pass (packed fp32x2 FMAs: one issue slot per tap for the lane's channel pair) ----
-  bf16* dst = out + (static_cast<size_t>(b) * T) * C + c0;
+  // Pointers advance incrementally and full kTB-row blocks run without per-row predicates: the first version spent more
+  // issue slots on address arithmetic and bounds checks than on the taps (ncu: 72 thread-instructions per output pair).
   float2 cs = make_float2(0.f, 0.f);
-  for (int t0 = t_begin; t0 < t_end; t0 += kTB) {
-    float2 x[kTB + K - 1];
+  {
+    const uint32_t* trow = tile + t_begin * 32 + lane;  // smem row (t - pad_left) lives at index t, so tap j of output t reads row t + j
+    const int cw = C >> 1;                              // output row pitch in 32-bit words
+    uint32_t* drow = reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * T + t_begin) * C + c0) + lane;
+    const int nrows = max(0, t_end - t_begin);
+    const int nfull = nrows / kTB;
+    for (int blk = 0; blk < nfull; ++blk) {
+      float2 x[kTB + K - 1];
 #pragma unroll
-    for (int i = 0; i < kTB + K - 1; ++i) {
-      const uint32_t u = tile[(t0 + i) * 32 + lane];
-      x[i] = make_float2(bf16_lo(u), bf16_hi(u));
-    }
+      for (int i = 0; i < kTB + K - 1; ++i) {
+        const uint32_t u = trow[i * 32];
+        x[i] = make_float2(bf16_lo(u), bf16_hi(u));
+      }
 #pragma unroll
-    for (int i = 0; i < kTB; ++i) {
-      if (t0 + i < t_end) {
+      for (int i = 0; i < kTB; ++i) {
         float2 a = bs;
 #pragma unroll
         for (int j = 0; j < K; ++j) ffma2(a.x, a.y, wt[j].x, wt[j].y, x[i + j].x, x[i + j].y, a.x, a.y);
         if constexpr (POST == 1) { a.x = a.x * exact_sigmoid(a.x); a.y = a.y * exact_sigmoid(a.y); }
         if constexpr (POST == 2) fmul2(a.x, a.y, a.x, a.y, scale.x, scale.y);
         const uint32_t packed = pack_bf16x2(a.x, a.y);
-        reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(t0 + i) * C)[lane] = packed;
+        *drow = packed;
+        drow += cw;
         if (colsum != nullptr) { cs.x += bf16_lo(packed); cs.y += bf16_hi(packed); }
       }
+      trow += kTB * 32;
+    }
+    for (int i = nfull * kTB; i < nrows; ++i) {  // ragged tail (T not a multiple of the register block)
+      float2 a = bs;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const uint32_t u = trow[j * 32];
+        ffma2(a.x, a.y, wt[j].x, wt[j].y, bf16_lo(u), bf16_hi(u), a.x, a.y);
+      }
+      if constexpr (POST == 1) { a.x = a.x * exact_sigmoid(a.x); a.y = a.y * exact_sigmoid(a.y); }
+      if constexpr (POST == 2) fmul2(a.x, a.y, a.x, a.y, scale.x, scale.y);
+      const uint32_t packed = pack_bf16x2(a.x, a.y);
+      *drow = packed;
+      drow += cw;
+      if (colsum != nullptr) { cs.x += bf16_lo(packed); cs.y += bf16_hi(packed); }
+      trow += 32;
     }
   }
   if (colsum != nullptr) {

@@ -126,6 +126,17 @@ def test_other_configurations(kw):
     _check_logits(m(x), O.forward(params, x, cfg, "float64"), f"cfg {kw}")
 
 
+def test_cfg5_scaled_encoder_long_sequence():
+    """BASELINE configs[4]: dim 384 (dh = 48), 4 squeeze + 4 conform blocks, T = 1024 (batch 1 here; the oracle
+    needs a few seconds per sequence at this size)."""
+    cfg = O.Config(dim=384, num_conv_squeeze_blocks=4, num_conv_conform_blocks=4, frames=1024)
+    params = O.init_params(cfg, seed=5)
+    m = _model_for(cfg, params)
+    assert m.count_params() == 33383028
+    x = O.make_inputs(cfg, 1, seed=8)
+    _check_logits(m(x), O.forward(params, x, cfg, "float64"), "cfg5 logits")
+
+
 # ------------------------------------------------------------------------------------------------
 # CTC
 # ------------------------------------------------------------------------------------------------
