@@ -1,0 +1,302 @@
+// ishara_b200 — fused feed-forward module: S = [LN](S + swish(XN @ W1 + b1) @ W2 + b2), XN' = LN'(S)  (sm_100a only).
+//
+// Reference: the FFN sub-modules of SqueezeformerBlock / ConformerBlock (nb:conv-hybrid-model c5:162-166,187-190,
+// 202-205,237-247,323-326,338-341): Dense(D -> E, swish) -> Dropout -> Dense(E -> D), residual add. As two separate
+// GEMM launches the E-wide intermediate makes a 200 MB round trip through HBM per module and pays two epilogue passes;
+// here it never leaves the SM:
+//
+//   per 128-row tile, E is walked in quarters of 128 columns:
+//     G1(q): acc1[q&1] (TMEM, 128 cols, double buffered) = XN_tile[128 x 256] @ W1[q]^T         tcgen05.mma N=128
+//     epi1(q): +b1, swish, bf16 -> H[128 x 128] in shared memory (K-major, 128B swizzle)         8 epilogue warps
+//     G2(q): acc2 (TMEM, 256 cols) += H @ W2[:, q]^T                                             tcgen05.mma N=256
+//   epi2: +b2, +residual, [LayerNorm], TMA store of the stream and of its normalised copy        gemm_epilogue.cuh
+//
+//   MMA issue order G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3): the tensor pipe always has the next GEMM queued
+//   while the epilogue warps turn acc1 into H. Weights stream from L2 through a ring of 32 KB slots in exactly that
+//   order (W1 quarter = two slots of two [128 x 64] k-blocks, W2 K-slice = two slots of one [256 x 64] k-block).
+//   smem: XN tile 64 KB + H 32 KB (doubles as the epilogue's TMA-store staging: every warp owns the same 4 KB region in
+//   both roles) + 3 weight slots 96 KB + row-statistics exchange.
+//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM alloc | warps 4-11 epilogue.
+// Only D == 256 (full-row LayerNorm epilogue) and E % 128 == 0; other shapes use the two-GEMM path.
+#include "gemm_epilogue.cuh"
+
+namespace ishara {
+namespace {
+
+constexpr int kFD = 256;               // model dim: K of GEMM1, N of GEMM2
+constexpr int kFQ = 128;               // quarter width of the hidden dimension
+constexpr int kFSlot = 32 * 1024;      // weight ring slot
+constexpr int kFStages = 3;
+constexpr int kFA1Bytes = (kFD / kBK) * kAStageBytes;  // 64 KB
+constexpr int kFHBytes = 2 * kAStageBytes;             // 32 KB: H quarter = two k-blocks of [128 x 64]
+
+struct FfnBars {
+  uint64_t a1_full, a1_empty;
+  uint64_t w_full[kFStages], w_empty[kFStages];
+  uint64_t acc1_full[2], acc1_empty[2];
+  uint64_t h_full, h_empty;
+  uint64_t acc2_full, acc2_empty;
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(384, 1)
+ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO0,
+              const __grid_constant__ CUtensorMap tmO1, const GemmEpi ep, const float* __restrict__ bias1, int M, int E,
+              int num_m_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* a1_ptr = smem;                                  // [4][128 x 64] XN tile
+  uint8_t* h_ptr = a1_ptr + kFA1Bytes;                     // [2][128 x 64] H quarter / epilogue staging
+  uint8_t* w_ptr = h_ptr + kFHBytes;                       // [3][32 KB] weight slots
+  float4* xch = reinterpret_cast<float4*>(w_ptr + kFStages * kFSlot);
+  FfnBars* bars = reinterpret_cast<FfnBars*>(reinterpret_cast<uint8_t*>(xch) + kXchBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = E / kFQ;  // quarters of the hidden dimension (4 for E = 512)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmO0);
+    if (ep.ln1_g != nullptr) tma_prefetch_desc(&tmO1);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bars->a1_full, 1);
+    mbar_init(&bars->a1_empty, 1);
+    for (int s = 0; s < kFStages; ++s) {
+      mbar_init(&bars->w_full[s], 1);
+      mbar_init(&bars->w_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->acc1_full[i], 1);
+      mbar_init(&bars->acc1_empty[i], 8);
+    }
+    mbar_init(&bars->h_full, 8);
+    mbar_init(&bars->h_empty, 1);
+    mbar_init(&bars->acc2_full, 1);
+    mbar_init(&bars->acc2_empty, 8);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+  const uint32_t tmem_acc2 = tmem_base + 256;
+  constexpr uint32_t IDESC1 = umma_idesc(kBM, kFQ, 1);
+  constexpr uint32_t IDESC2 = umma_idesc(kBM, kFD, 1);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t ws = 0, wphase = 0;
+      auto slot_acquire = [&]() -> uint8_t* {
+        mbar_wait(&bars->w_empty[ws], wphase ^ 1u);
+        mbar_arrive_expect_tx(&bars->w_full[ws], kFSlot);
+        return w_ptr + ws * kFSlot;
+      };
+      auto slot_advance = [&]() { if (++ws == kFStages) { ws = 0; wphase ^= 1u; } };
+      auto load_g1 = [&](int q) {  // W1 rows [128q, +128), all K = 256: two slots of two k-blocks
+        for (int j = 0; j < 2; ++j) {
+          uint8_t* dst = slot_acquire();
+          tma_load_2d(dst, &tmW1, &bars->w_full[ws], (2 * j) * kBK, q * kFQ);
+          tma_load_2d(dst + kAStageBytes, &tmW1, &bars->w_full[ws], (2 * j + 1) * kBK, q * kFQ);
+          slot_advance();
+        }
+      };
+      auto load_g2 = [&](int q) {  // W2 all 256 rows, K slice [128q, +128): two slots of one k-block
+        for (int j = 0; j < 2; ++j) {
+          uint8_t* dst = slot_acquire();
+          tma_load_2d(dst, &tmW2, &bars->w_full[ws], q * kFQ + j * kBK, 0);
+          slot_advance();
+        }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(&bars->a1_empty, (it & 1) ^ 1u);
+        mbar_arrive_expect_tx(&bars->a1_full, kFA1Bytes);
+        for (int kb = 0; kb < kFD / kBK; ++kb) tma_load_2d(a1_ptr + kb * kAStageBytes, &tmA, &bars->a1_full, kb * kBK, tile * kBM);
+        load_g1(0);
+        if (nq > 1) load_g1(1);
+        for (int q = 0; q < nq; ++q) {
+          load_g2(q);
+          if (q + 2 < nq) load_g1(q + 2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t ws = 0, wphase = 0;
+      uint32_t n_g1 = 0, n_g2 = 0;  // running counts of issued GEMM1 quarters / GEMM2 quarters
+      const uint32_t a1_addr = smem_base, h_addr = a1_addr + kFA1Bytes, w_addr = h_addr + kFHBytes;
+      auto issue_g1 = [&](int q) {
+        const uint32_t buf = n_g1 & 1;
+        mbar_wait(&bars->acc1_empty[buf], ((n_g1 >> 1) & 1) ^ 1u);  // epilogue drained this accumulator buffer
+        tc_fence_after();
+        for (int j = 0; j < 2; ++j) {
+          mbar_wait(&bars->w_full[ws], wphase);
+          tc_fence_after();
+          const uint32_t sb = w_addr + ws * kFSlot;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(tmem_base + buf * kFQ, umma_desc_sw128(a1_addr + (2 * j + kk) * kAStageBytes + k * 32),
+                        umma_desc_sw128(sb + kk * kAStageBytes + k * 32), IDESC1, (j | kk | k) != 0 ? 1u : 0u);
+          umma_commit(&bars->w_empty[ws]);
+          if (++ws == kFStages) { ws = 0; wphase ^= 1u; }
+        }
+        umma_commit(&bars->acc1_full[buf]);
+        ++n_g1;
+        (void)q;
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(&bars->a1_full, it & 1);
+        tc_fence_after();
+        issue_g1(0);
+        if (nq > 1) issue_g1(1);
+        for (int q = 0; q < nq; ++q) {
+          // G2(q): needs H(q) written by the epilogue warps; the first one of a tile also needs acc2 drained
+          if (q == 0) mbar_wait(&bars->acc2_empty, (it & 1) ^ 1u);
+          mbar_wait(&bars->h_full, n_g2 & 1);
+          tc_fence_after();
+          for (int j = 0; j < 2; ++j) {
+            mbar_wait(&bars->w_full[ws], wphase);
+            tc_fence_after();
+            const uint32_t sb = w_addr + ws * kFSlot;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(tmem_acc2, umma_desc_sw128(h_addr + j * kAStageBytes + k * 32), umma_desc_sw128(sb + k * 32), IDESC2,
+                        (q | j | k) != 0 ? 1u : 0u);
+            umma_commit(&bars->w_empty[ws]);
+            if (++ws == kFStages) { ws = 0; wphase ^= 1u; }
+          }
+          umma_commit(&bars->h_empty);  // H may be overwritten once these MMAs retire
+          ++n_g2;
+          if (q == nq - 1) umma_commit(&bars->acc2_full);
+          if (q + 2 < nq) issue_g1(q + 2);
+          if (q + 2 == nq - 1 || (nq <= 2 && q == 0)) umma_commit(&bars->a1_empty);  // last GEMM1 of the tile issued
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int q4 = warp & 3;         // TMEM lane quarter
+    const int h = (warp - 4) >> 2;   // which 64-column box of a 128-column quarter / alternate boxes of the final tile
+    WarpStore st;
+    st.single = true;
+    st.base = smem_u32(h_ptr) + static_cast<uint32_t>(h * 4 + q4) * kWarpStgBytes;  // = H k-block h, rows [32 q4, +32)
+    st.iter = 0;
+    st.lane = lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    uint32_t n_q = 0;  // running count of processed quarters
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * kBM + q4 * 32;
+      EpiThread th;
+      th.row = row0 + lane;
+      th.valid = th.row < M;
+      th.seq = th.valid ? th.row / ep.rows_per_seq : 0;
+      th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
+      th.taddr = tmem_acc2 + lane_addr;
+      for (int q = 0; q < nq; ++q, ++n_q) {
+        const uint32_t buf = n_q & 1;
+        mbar_wait(&bars->acc1_full[buf], (n_q >> 1) & 1);
+        tc_fence_after();
+        // H region free? the previous quarter's GEMM2 has retired; at a tile boundary the previous tile's TMA stores
+        // (which used the same 4 KB region as staging) must have finished reading it as well
+        if (n_q > 0) mbar_wait(&bars->h_empty, (n_q - 1) & 1);
+        if (q == 0) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t raw[32];
+          float v[32];
+          const int tc = h * 64 + sub * 32;
+          tmem_ld32(tmem_base + buf * kFQ + lane_addr + tc, raw);
+          tmem_ld_wait();
+          to_float(v, raw);
+          const float4* b4 = reinterpret_cast<const float4*>(bias1 + q * kFQ + tc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], bb.x, bb.y);
+            fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], bb.z, bb.w);
+          }
+          epi_swish(v);
+          stage_write<false>(st.base, lane, sub, v);
+        }
+        // accumulator buffer drained, H quarter written (generic proxy -> async proxy fence before the MMA reads it)
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->acc1_empty[buf]);
+          mbar_arrive(&bars->h_full);
+        }
+      }
+      // ---- final epilogue of the tile: acc2 -> +b2 -> +residual -> [LN] -> S (and LN'(S)) ----
+      ResidRegs rr;
+      resid_load(rr, ep, th, epilogue_first_col<kFD, true, false>(ep, 0, h));
+      mbar_wait(&bars->acc2_full, it & 1);
+      tc_fence_after();
+      // staging == this warp's H region: every GEMM2 of the tile has retired (acc2_full), so it is free
+      st.iter = 0;
+      epilogue_tile<kFD, true, false>(ep, th, 0, kFD, row0, q4, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc2_empty);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+bool ffn_applicable(int D, int E, int M, int num_sms) {
+  (void)num_sms;
+  return D == kFD && E % kFQ == 0 && E >= 2 * kFQ && M >= 1;
+}
+
+// plan->tmA: XN [M, 256]; tmW1: W1^T [E, 256] box [128 x 64]; tmW2: W2^T [256, E] box [256 x 64]; tmO0 / tmO1: S / LN'(S)
+int ffn_plan_init(FfnPlan* p, const bf16* xn, const bf16* w1t, const bf16* w2t, bf16* out0, bf16* out1) {
+  int rc;
+  if ((rc = make_tmap_2d(&p->tmA, xn, TM_BF16, p->M, kFD, kFD, kBM, kBK))) return rc;
+  if ((rc = make_tmap_2d(&p->tmW1, w1t, TM_BF16, p->E, kFD, kFD, kFQ, kBK))) return rc;
+  if ((rc = make_tmap_2d(&p->tmW2, w2t, TM_BF16, kFD, p->E, p->E, kFD, kBK))) return rc;
+  if ((rc = make_tmap_2d(&p->tmO0, out0, TM_BF16, p->M, kFD, kFD, 32, 64))) return rc;
+  if (out1 != nullptr) {
+    if ((rc = make_tmap_2d(&p->tmO1, out1, TM_BF16, p->M, kFD, kFD, 32, 64))) return rc;
+  } else {
+    p->tmO1 = p->tmO0;
+  }
+  return 0;
+}
+
+int ffn_launch(const FfnPlan& p, int num_sms, cudaStream_t stream) {
+  const int smem = kFA1Bytes + kFHBytes + kFStages * kFSlot + kXchBytes + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int mt = (p.M + kBM - 1) / kBM;
+  const int grid = mt < num_sms ? mt : num_sms;
+  ffn_tc_kernel<<<grid, 384, smem, stream>>>(p.tmA, p.tmW1, p.tmW2, p.tmO0, p.tmO1, p.epi, p.bias1, p.M, p.E, mt);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+}  // namespace ishara

@@ -234,7 +234,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread
         const int tc = b * CH + sub * 32;
         uint32_t raw[32];
         float v[32];
-        tmem_ld32(th.taddr + tc, raw);
+        if (!(ep.dbg & 32)) tmem_ld32(th.taddr + tc, raw);
         ResidRegs rn;
         {  // next chunk of this warp (if any)
           int nb = b, nsub = sub + 1;
@@ -265,7 +265,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread
         }
         if (ep.resid != nullptr) resid_add(v, rr);
         rr = rn;
-        stage_write<OUT_F32>(buf, lane, sub, v);
+        if (!(ep.dbg & 8)) stage_write<OUT_F32>(buf, lane, sub, v);
       }
       st.release(tmO0, buf, n_tile * cols_out + b * CH, row0);
     }

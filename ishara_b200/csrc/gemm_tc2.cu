@@ -160,6 +160,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     st.base = smem_u32(stg_ptr) + static_cast<uint32_t>((warp - 4) * (st.single ? 1 : 2)) * kWarpStgBytes;
     st.iter = 0;
     st.lane = lane;
+    st.skip_store = (ep.dbg & 1) != 0;
+    st.skip_fence = (ep.dbg & 16) != 0;
 
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -178,7 +180,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
       if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
-      epilogue_tile<BN, ROW, false>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+      if (!(ep.dbg & 2)) epilogue_tile<BN, ROW, false>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
       // this warp is done with its CTA's half of accumulator buffer `buf`: one arrive on the LEADER's barrier
       tc_fence_before();
       __syncwarp();

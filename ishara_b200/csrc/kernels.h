@@ -78,6 +78,17 @@ int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* ou
                    bf16* out1, int ldo1);
 int gemm_launch(const GemmPlan& p, int num_sms, cudaStream_t stream);
 
+// ---- fused feed-forward module (ffn_tc.cu): S = [LN0](S + swish(XN @ W1 + b1) @ W2 + b2) [, XN' = LN1(S)] ------
+struct FfnPlan {
+  CUtensorMap tmA, tmW1, tmW2, tmO0, tmO1;
+  GemmEpi epi;                 // epilogue of the second GEMM: bias = b2, resid, ln0 / ln1
+  const float* bias1 = nullptr;  // [E]
+  int M = 0, E = 0;
+};
+bool ffn_applicable(int D, int E, int M, int num_sms);
+int ffn_plan_init(FfnPlan* p, const bf16* xn, const bf16* w1t, const bf16* w2t, bf16* out0, bf16* out1);
+int ffn_launch(const FfnPlan& p, int num_sms, cudaStream_t stream);
+
 // ---- depthwise temporal convolution over a whole sequence per CTA ---------------------------
 // in/out [B, T, C] bf16 channels-last. y[t,c] = post( sum_j w[j,c] * in[t - pad_left + j, c] + bias[c] )
 // (zeros outside [0,T)); BatchNorm is folded into w/bias by the caller.

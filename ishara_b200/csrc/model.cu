@@ -7,6 +7,7 @@
 // (2D / ef*D / 3D) intermediates. Weights are packed once: transposed to [N, K] (K contiguous, the
 // UMMA "K-major" B operand), bf16, inference BatchNorm folded into the neighbouring linear op.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -38,10 +39,11 @@ struct LnRef {
   float eps = 0.f;
 };
 
-enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP };
+enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP, OP_FFN };
 struct Op {
   OpKind kind;
   GemmPlan gemm;
+  FfnPlan ffn;
   DwConvArgs dw;
   AttnArgs at;
   SeGateArgs se;
@@ -597,6 +599,26 @@ struct Builder {
     }
   }
   void ffn(const std::string& base, LnRef next_ln) {
+    static const int fused = getenv("ISHARA_FFN_FUSED") ? atoi(getenv("ISHARA_FFN_FUSED")) : 1;
+    if (fused && !rc && ffn_applicable(D, E, M, m->num_sms)) {
+      // one launch: the E-wide intermediate stays in TMEM / shared memory (ffn_tc.cu)
+      Op op;
+      op.kind = OP_FFN;
+      op.label = "ffn.fused";
+      FfnPlan& p = op.ffn;
+      p.M = M; p.E = E;
+      p.bias1 = pk.get<float>(base + ".0.b");
+      p.epi.bias = pk.get<float>(base + ".2.b");
+      p.epi.resid = m->S;
+      p.epi.ld_resid = D;
+      p.epi.rows_per_seq = T;
+      p.epi.ln1_g = next_ln.g; p.epi.ln1_b = next_ln.b; p.epi.ln1_eps = next_ln.eps;
+      rc = ffn_plan_init(&p, m->XN, pk.get<bf16>(base + ".0.w"), pk.get<bf16>(base + ".2.w"), m->S, next_ln.g ? m->XN : nullptr);
+      op.flops = 4.0 * M * D * E;
+      op.bytes = 2.0 * (static_cast<double>(M) * D * (3 + (next_ln.g ? 1 : 0)) + 2.0 * D * E);
+      ops.push_back(op);
+      return;
+    }
     wide_gemm("ffn.up", m->XN, D, base + ".0.w", base + ".0.b", E, ACT_SWISH, m->H1);
     stream_gemm("ffn.down", m->H1, E, base + ".2.w", base + ".2.b", nullptr, nullptr, true, LnRef(), next_ln);
   }
@@ -818,6 +840,7 @@ int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_
       case OP_DW: rc = dwconv_launch(op.dw, stream); break;
       case OP_ATTN: rc = attention_launch(op.at, stream); break;
       case OP_SEGATE: rc = se_gate_launch(op.se, stream); break;
+      case OP_FFN: rc = ffn_launch(op.ffn, m->num_sms, stream); break;
       case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, M, c.dim, stream); break;
       case OP_TAP:
         rc = cudaMemcpyAsync(m->taps[op.tap], m->S, M * c.dim * sizeof(bf16), cudaMemcpyDeviceToDevice, stream) == cudaSuccess ? 0 : 3;
@@ -850,7 +873,7 @@ int model_profile_entry(ishara_model* m, int i, const char** label, const char**
   ISHARA_CUDA_OK(cudaEventElapsedTime(&t, m->events[i], m->events[i + 1]));
   const ishara_config_t& c = m->cfg;
   const double M = static_cast<double>(m->program_batch) * c.frames;
-  static const char* kinds[] = {"gemm", "dwconv", "attention", "se_gate", "layernorm", "tap"};
+  static const char* kinds[] = {"gemm", "dwconv", "attention", "se_gate", "layernorm", "tap", "gemm"};
   if (i == 0) {
     if (label) *label = "input.cast_pad";
     if (kind) *kind = "cast";
