@@ -65,12 +65,35 @@ using namespace ishara;
 static int upload_and_forward(ishara_model* m, const ModelView& v, const float* x_host, int batch) {
   const ishara_config_t& c = *v.cfg;
   const size_t per_seq = static_cast<size_t>(c.frames) * c.features;
-  int nchunk = batch >= 64 ? 4 : 1;
-  const int per = (batch + nchunk - 1) / nchunk;
-  nchunk = (batch + per - 1) / per;
+  // Chunk boundaries sit on whole waves of 128-row tiles (one wave = num_sms tiles), growing 1 : 2 : rest, so the chunked
+  // forward runs the same number of tile rounds as the unchunked one while the first chunk's copy is short.
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, v.device);
+  const double wave = static_cast<double>(sms) * 128.0 / c.frames;  // sequences per tile wave
+  int bounds[9];
+  int nchunk = 0;
+  bounds[0] = 0;
+  if (batch >= static_cast<int>(3 * wave)) {
+    bounds[1] = static_cast<int>(wave);
+    bounds[2] = static_cast<int>(3 * wave);
+    bounds[3] = batch;
+    nchunk = 3;
+    if (batch - bounds[2] > static_cast<int>(3 * wave)) {  // very large batches: keep the tail chunks at ~3 waves
+      nchunk = 2;
+      while (batch - bounds[nchunk] > static_cast<int>(3 * wave) && nchunk < 7) {
+        bounds[nchunk + 1] = bounds[nchunk] + static_cast<int>(3 * wave);
+        ++nchunk;
+      }
+      bounds[nchunk + 1] = batch;
+      ++nchunk;
+    }
+  } else {
+    bounds[1] = batch;
+    nchunk = 1;
+  }
   int rc;
   for (int i = 0; i < nchunk; ++i) {
-    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
+    const int b0 = bounds[i], nb = bounds[i + 1] - bounds[i];
     if (cudaMemcpyAsync(v.x_dev + b0 * per_seq, x_host + b0 * per_seq, nb * per_seq * sizeof(float), cudaMemcpyHostToDevice,
                         v.copy_stream) != cudaSuccess ||
         cudaEventRecord(v.copy_done[i], v.copy_stream) != cudaSuccess) {
@@ -79,7 +102,7 @@ static int upload_and_forward(ishara_model* m, const ModelView& v, const float* 
     }
   }
   for (int i = 0; i < nchunk; ++i) {
-    const int b0 = i * per, nb = (b0 + per <= batch) ? per : batch - b0;
+    const int b0 = bounds[i], nb = bounds[i + 1] - bounds[i];
     if (cudaStreamWaitEvent(v.stream, v.copy_done[i], 0) != cudaSuccess) {
       set_last_error(std::string("upload: ") + cudaGetErrorString(cudaGetLastError()));
       return ISHARA_ERR_CUDA;

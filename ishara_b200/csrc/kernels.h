@@ -16,6 +16,7 @@ void set_last_error(const std::string& msg);
 const char* get_last_error();
 // every kernel launcher bumps this process-wide counter (bench.py reports it as gpu_launches)
 void note_launch();
+void note_launches(int n);  // a replayed CUDA graph launches n kernels at once
 uint64_t launch_count();
 #define ISHARA_CUDA_OK(expr)                                                                           \
   do {                                                                                                 \

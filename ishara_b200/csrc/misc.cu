@@ -14,6 +14,7 @@ const char* get_last_error() { return tls_error.c_str(); }
 
 static std::atomic<uint64_t> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void note_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 namespace {

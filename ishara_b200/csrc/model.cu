@@ -71,6 +71,22 @@ inline uint16_t f2bf(float f) {
 
 using namespace ishara;
 
+struct GraphKey {
+  int batch;
+  float* logits;
+  const float* x;
+  bool operator<(const GraphKey& o) const {
+    if (batch != o.batch) return batch < o.batch;
+    if (logits != o.logits) return logits < o.logits;
+    return x < o.x;
+  }
+  bool operator!=(const GraphKey& o) const { return batch != o.batch || logits != o.logits || x != o.x; }
+};
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+};
+
 struct ishara_model {
   ishara_config_t cfg;
   int device = 0;
@@ -103,6 +119,8 @@ struct ishara_model {
   float* program_logits = nullptr;
   // programs built for other (batch, logits pointer) pairs: the chunked host path alternates between a few of them
   std::map<std::pair<int, float*>, std::vector<Op>> program_cache;
+  std::map<GraphKey, GraphEntry> graphs;  // captured forwards; dropped whenever programs are rebuilt
+  bool graphs_broken = false;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;     // H2D of the chunked host path
   cudaEvent_t copy_done[8] = {nullptr};
@@ -433,6 +451,8 @@ int ensure_workspace(ishara_model* m, int batch) {
   m->taps.clear();
   m->program.clear();
   m->program_cache.clear();
+  for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
   m->program_batch = 0;
   const ishara_config_t& c = m->cfg;
   const size_t M = static_cast<size_t>(batch) * c.frames;
@@ -759,6 +779,7 @@ int model_destroy(ishara_model* m) {
   for (void* p : m->wallocs) cudaFree(p);
   for (void* p : m->wsallocs) cudaFree(p);
   for (cudaEvent_t e : m->events) cudaEventDestroy(e);
+  for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (m->labels_dev) cudaFree(m->labels_dev);
   if (m->stream) cudaStreamDestroy(m->stream);
   if (m->copy_stream) {
@@ -789,8 +810,16 @@ int model_finalize(ishara_model* m) {
   m->finalized = true;
   m->program.clear();
   m->program_cache.clear();
+  for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
   m->program_batch = 0;
   return ISHARA_OK;
+}
+
+int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t stream, bool prof);
+static void drop_graphs(ishara_model* m) {
+  for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
 }
 
 int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_dev, cudaStream_t stream) {
@@ -805,7 +834,7 @@ int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_
       if ((rc = build_program(m, batch, logits_dev))) return rc;
     } else {
       if (!m->program.empty()) {
-        if (m->program_cache.size() >= 16) m->program_cache.clear();
+        if (m->program_cache.size() >= 16) { m->program_cache.clear(); drop_graphs(m); }
         m->program_cache[{m->program_batch, m->program_logits}] = std::move(m->program);
         m->program.clear();
       }
@@ -820,9 +849,54 @@ int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_
       }
     }
   }
+  const bool prof = m->profile;
+  // CUDA graph path: the 70-odd launches of one forward are captured once per (program, input pointer) on the handle's
+  // own stream and replayed on the caller's stream, which removes the CPU launch cost and most inter-kernel gaps.
+  static const int use_graphs = getenv("ISHARA_GRAPH") ? atoi(getenv("ISHARA_GRAPH")) : 1;
+  if (use_graphs && !prof && !m->debug_taps && !m->graphs_broken) {
+    GraphKey key{batch, logits_dev, x_dev};
+    auto it = m->graphs.find(key);
+    if (it != m->graphs.end()) {
+      if (it->second.exec != nullptr) {
+        ISHARA_CUDA_OK(cudaGraphLaunch(it->second.exec, stream));
+        note_launches(it->second.launches);
+        return ISHARA_OK;
+      }
+      // second call with this key: every kernel has run once (attributes set, lazy state built) -> capture now
+      cudaGraph_t graph = nullptr;
+      const uint64_t before = launch_count();
+      if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        rc = launch_program(m, x_dev, batch, m->stream, false);
+        const cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+        cudaGraphExec_t exec = nullptr;
+        if (rc == 0 && ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          it->second.exec = exec;
+          it->second.launches = static_cast<int>(launch_count() - before);
+          cudaGraphDestroy(graph);
+          if (m->graphs.size() > 32) {  // bound the cache (rotating caller buffers)
+            for (auto& kv : m->graphs) if (kv.second.exec && kv.first != key) cudaGraphExecDestroy(kv.second.exec);
+            GraphEntry keep = it->second;
+            m->graphs.clear();
+            m->graphs[key] = keep;
+          }
+          ISHARA_CUDA_OK(cudaGraphLaunch(exec, stream));
+          return ISHARA_OK;
+        }
+        if (graph != nullptr) cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();  // capture is an optimisation: fall back to direct launches for this handle
+      m->graphs_broken = true;
+    } else {
+      m->graphs[key] = GraphEntry{};
+    }
+  }
+  return launch_program(m, x_dev, batch, stream, prof);
+}
+
+int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t stream, bool prof) {
   const ishara_config_t& c = m->cfg;
   const int64_t M = static_cast<int64_t>(batch) * c.frames;
-  const bool prof = m->profile;
+  int rc;
   if (prof) {
     while (m->events.size() < m->program.size() + 2) {
       cudaEvent_t e;
@@ -979,6 +1053,8 @@ int model_set_debug(ishara_model* m, int on) {
   m->debug_taps = on != 0;
   m->program.clear();
   m->program_cache.clear();
+  for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
   m->program_batch = 0;
   return 0;
 }

@@ -277,7 +277,7 @@ class IsharaModel:
         _lib.check(self._lib.ishara_model_infer_host(self._h, p(x), B, p(lab), L, p(logits), p(ids), p(lens), p(nll)))
         ids64 = ids.astype(np.int64)
         id_list = [ids64[b, : lens[b]] for b in range(B)]
-        codes = _ASCII_LUT[np.clip(ids, 0, 255)]  # the kernel only emits ids in [0, blank): one LUT pass for the whole batch
+        codes = _ASCII_LUT[ids]  # ids are in [-1, blank): one LUT pass for the whole batch (-1 = unused tail slots)
         text = [codes[b, : lens[b]].tobytes().decode("ascii") for b in range(B)]
         return {"ids": id_list, "text": text, "nll": nll, "logits": logits}
 
