@@ -90,6 +90,20 @@ bool ffn_applicable(int D, int E, int M, int num_sms);
 int ffn_plan_init(FfnPlan* p, const bf16* xn, const bf16* w1t, const bf16* w2t, bf16* out0, bf16* out1);
 int ffn_launch(const FfnPlan& p, int num_sms, cudaStream_t stream);
 
+// ---- fused front half of Conv1DBlock (conv1d_front.cu): G = ECA(BN(CausalDW(swish(x @ We + be)))) ----------
+struct Conv1dFrontPlan {
+  CUtensorMap tmA, tmB;
+  const float* bias_e = nullptr;  // [512] expand bias
+  const float* dw_w = nullptr;    // [k, 512] depthwise taps with BatchNorm folded in
+  const float* dw_b = nullptr;    // [512] BatchNorm offset
+  const float* eca_w = nullptr;   // [5]
+  bf16* out = nullptr;            // [B*T, 512]
+  int B = 0, T = 0, k = 0;
+};
+bool conv1d_front_applicable(int D, int T, int k);
+int conv1d_front_plan_init(Conv1dFrontPlan* p, const bf16* x, const bf16* wet);
+int conv1d_front_launch(const Conv1dFrontPlan& p, cudaStream_t stream);
+
 // ---- depthwise temporal convolution over a whole sequence per CTA ---------------------------
 // in/out [B, T, C] bf16 channels-last. y[t,c] = post( sum_j w[j,c] * in[t - pad_left + j, c] + bias[c] )
 // (zeros outside [0,T)); BatchNorm is folded into w/bias by the caller.

@@ -39,11 +39,12 @@ struct LnRef {
   float eps = 0.f;
 };
 
-enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP, OP_FFN };
+enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP, OP_FFN, OP_C1F };
 struct Op {
   OpKind kind;
   GemmPlan gemm;
   FfnPlan ffn;
+  Conv1dFrontPlan c1f;
   DwConvArgs dw;
   AttnArgs at;
   SeGateArgs se;
@@ -610,8 +611,27 @@ struct Builder {
     for (int j = 0; j < c.num_conv_per_block; ++j) {
       const std::string n = "conv" + tag + "_" + std::to_string(i) + "_" + std::to_string(j + 1);
       const int k = conv_kernel_size(c, j);
-      wide_gemm("conv1d.expand", m->S, D, n + "_expand_conv.w", n + "_expand_conv.b", 2 * D, ACT_SWISH, m->H1);
-      dwconv("conv1d.dw_bn_eca", m->H1, m->H2, 2 * D, k, k - 1, n + "_dw.w", n + "_dw.b", n + "_eca.w", 2, nullptr);
+      static const int fused_front = getenv("ISHARA_CONV1D_FUSED") ? atoi(getenv("ISHARA_CONV1D_FUSED")) : 0;  // measured: 118 us vs 55 + 66 us unfused => no gain yet, opt-in
+      if (fused_front && !rc && conv1d_front_applicable(D, T, k)) {
+        // expand GEMM + swish + causal depthwise + BatchNorm + ECA in one launch (conv1d_front.cu)
+        Op op;
+        op.kind = OP_C1F;
+        op.label = "conv1d.front_fused";
+        Conv1dFrontPlan& p = op.c1f;
+        p.B = B; p.T = T; p.k = k;
+        p.bias_e = pk.get<float>(n + "_expand_conv.b");
+        p.dw_w = pk.get<float>(n + "_dw.w");
+        p.dw_b = pk.get<float>(n + "_dw.b");
+        p.eca_w = pk.get<float>(n + "_eca.w");
+        p.out = m->H2;
+        rc = conv1d_front_plan_init(&p, m->S, pk.get<bf16>(n + "_expand_conv.w"));
+        op.flops = 2.0 * M * D * 2 * D + 2.0 * M * 2 * D * k;
+        op.bytes = 2.0 * (static_cast<double>(M) * D + static_cast<double>(M) * 2 * D + 2.0 * D * D);
+        ops.push_back(op);
+      } else {
+        wide_gemm("conv1d.expand", m->S, D, n + "_expand_conv.w", n + "_expand_conv.b", 2 * D, ACT_SWISH, m->H1);
+        dwconv("conv1d.dw_bn_eca", m->H1, m->H2, 2 * D, k, k - 1, n + "_dw.w", n + "_dw.b", n + "_eca.w", 2, nullptr);
+      }
       const bool last = j == c.num_conv_per_block - 1;
       stream_gemm("conv1d.project", m->H2, 2 * D, n + "_project_conv.w", n + "_project_conv.b", nullptr, nullptr, true,
                   LnRef(), last ? next_ln : LnRef());
@@ -915,6 +935,7 @@ int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t 
       case OP_ATTN: rc = attention_launch(op.at, stream); break;
       case OP_SEGATE: rc = se_gate_launch(op.se, stream); break;
       case OP_FFN: rc = ffn_launch(op.ffn, m->num_sms, stream); break;
+      case OP_C1F: rc = conv1d_front_launch(op.c1f, stream); break;
       case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, M, c.dim, stream); break;
       case OP_TAP:
         rc = cudaMemcpyAsync(m->taps[op.tap], m->S, M * c.dim * sizeof(bf16), cudaMemcpyDeviceToDevice, stream) == cudaSuccess ? 0 : 3;
@@ -947,7 +968,7 @@ int model_profile_entry(ishara_model* m, int i, const char** label, const char**
   ISHARA_CUDA_OK(cudaEventElapsedTime(&t, m->events[i], m->events[i + 1]));
   const ishara_config_t& c = m->cfg;
   const double M = static_cast<double>(m->program_batch) * c.frames;
-  static const char* kinds[] = {"gemm", "dwconv", "attention", "se_gate", "layernorm", "tap", "gemm"};
+  static const char* kinds[] = {"gemm", "dwconv", "attention", "se_gate", "layernorm", "tap", "gemm", "gemm"};
   if (i == 0) {
     if (label) *label = "input.cast_pad";
     if (kind) *kind = "cast";
