@@ -162,6 +162,12 @@ ISHARA_API ishara_status_t ishara_op_layernorm(const void* x_bf16, void* out_bf1
 ISHARA_API ishara_status_t ishara_op_cast_pad(const float* x, void* out_bf16, int64_t M, int32_t F, int32_t Fpad, void* stream);
 
 
+/* num_to_char_fn + "".join (c8:1-2, c8:18) for a whole batch on the host: ids_host int32 [B, frames] / lens_host [B] as
+ * returned by ishara_greedy_decode; table[id] is the character of id (ids outside [0, table_len) map to "" like
+ * num_to_char.get(x, "")). Writes the concatenated text to out (capacity >= B*frames) and B+1 offsets. */
+ISHARA_API ishara_status_t ishara_ids_to_text(const int32_t* ids_host, const int32_t* lens_host, int32_t batch, int32_t frames,
+                                   const char* table, int32_t table_len, char* out, int64_t* offsets);
+
 /* ---- raw buffers (so a host without PyTorch can own device / pinned memory; DLPack producers in
  * ishara_b200/_dlpack.py sit on top of these) ------------------------------------------------- */
 ISHARA_API ishara_status_t ishara_device_malloc(int32_t device, int64_t bytes, void** out_dev);

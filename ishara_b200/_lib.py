@@ -98,6 +98,7 @@ SIGNATURES = {
     "ishara_op_conv2d_subsample": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ishara_op_layernorm": (_i32, [_vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp]),
     "ishara_op_cast_pad": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "ishara_ids_to_text": (_i32, [_vp, _vp, _i32, _i32, C.c_char_p, _i32, _vp, _vp]),
     "ishara_device_malloc": (_i32, [_i32, _i64, C.POINTER(_vp)]),
     "ishara_device_free": (_i32, [_i32, _vp]),
     "ishara_host_malloc_pinned": (_i32, [_i64, C.POINTER(_vp)]),

@@ -400,6 +400,26 @@ ishara_status_t ishara_op_cast_pad(const float* x, void* out_bf16, int64_t M, in
       cast_pad_launch(x, static_cast<bf16*>(out_bf16), M, F, Fpad, static_cast<cudaStream_t>(stream)));
 }
 
+ishara_status_t ishara_ids_to_text(const int32_t* ids_host, const int32_t* lens_host, int32_t batch, int32_t frames,
+                                   const char* table, int32_t table_len, char* out, int64_t* offsets) {
+  if (ids_host == nullptr || lens_host == nullptr || table == nullptr || out == nullptr || offsets == nullptr || batch < 0) {
+    set_last_error("ids_to_text: null pointer");
+    return ISHARA_ERR_INVALID;
+  }
+  int64_t n = 0;
+  for (int b = 0; b < batch; ++b) {
+    offsets[b] = n;
+    const int32_t* row = ids_host + static_cast<size_t>(b) * frames;
+    const int len = lens_host[b] < frames ? lens_host[b] : frames;
+    for (int i = 0; i < len; ++i) {
+      const int32_t id = row[i];
+      if (id >= 0 && id < table_len) out[n++] = table[id];
+    }
+  }
+  offsets[batch] = n;
+  return ISHARA_OK;
+}
+
 ishara_status_t ishara_device_malloc(int32_t device, int64_t bytes, void** out_dev) {
   if (out_dev == nullptr || bytes < 0) { set_last_error("device_malloc: bad arguments"); return ISHARA_ERR_INVALID; }
   CAPI_CUDA_OK(cudaSetDevice(device));

@@ -373,6 +373,47 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread
   }
 }
 
+// 16-epilogue-warp variant for the plain BN = 256 GEMMs: warp (q, c) owns rows [32q, +32) and ONE 64-column output box
+// c of the tile (4 boxes; GLU tiles have 2, warps c >= 2 idle). Slim on purpose: 640 threads leave 96 registers each.
+template <int BN>
+__device__ __forceinline__ void epilogue_box16(const GemmEpi& ep, const EpiThread& th, int n_tile, int N, int row0, int c,
+                                               int lane, WarpStore& st, const CUtensorMap* tmO0) {
+  const bool glu = ep.act == ACT_GLU;
+  const int cols_out = glu ? BN / 2 : BN;
+  if (c * 64 >= cols_out) return;
+  const uint32_t buf = st.acquire();
+#pragma unroll 1
+  for (int sub = 0; sub < 2; ++sub) {
+    const int tc = c * 64 + sub * 32;
+    uint32_t raw[32];
+    float v[32];
+    tmem_ld32(th.taddr + tc, raw);
+    tmem_ld_wait();
+    to_float(v, raw);
+    epi_affine(v, ep, th, n_tile * BN + tc, N);
+    if (glu) {
+      tmem_ld32(th.taddr + cols_out + tc, raw);
+      tmem_ld_wait();
+      // gate half: (acc + bias) through the same affine, one column at a time to stay within the register budget
+      const float* gb = ep.bias != nullptr ? ep.bias + n_tile * BN + cols_out + tc : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float g = __uint_as_float(raw[j]);
+        if (gb != nullptr) g += __ldg(gb + j);
+        v[j] *= fast_sigmoid(g);
+      }
+    } else if (ep.act == ACT_SWISH) {
+      epi_swish(v);
+    } else if (ep.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    epi_resid(v, ep, th, n_tile * cols_out + tc);
+    stage_write<false>(buf, lane, sub, v);
+  }
+  st.release(tmO0, buf, n_tile * cols_out + c * 64, row0);
+}
+
 // first residual column a warp needs for a tile (matches the first chunk epilogue_tile processes)
 template <int BN, bool ROW, bool OUT_F32>
 __device__ __forceinline__ int epilogue_first_col(const GemmEpi& ep, int n_tile, int h) {

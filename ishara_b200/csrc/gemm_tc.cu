@@ -39,8 +39,10 @@ __host__ __device__ constexpr int gemm_smem_bytes(int bn) {
 // lifetime of the kernel and streams only A tiles through the ring, so the L2->SM traffic per tile drops from
 // A + B to A alone (ncu on the streaming variant: MMA issue waits on the TMA ring, tensor pipe 22 % active). Each CTA
 // is pinned to one n-tile; m-tiles are strided over the CTAs of that n-tile.
-template <int BN, bool ROW, bool OUT_F32, bool RESB>
-__global__ void __launch_bounds__(384, 1)
+// EW = number of epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter, one 64-column box each — the
+// plain BN = 256 GEMMs are epilogue-paced, so their epilogue gets twice the warps; 640 threads cap registers at 96).
+template <int BN, bool ROW, bool OUT_F32, bool RESB, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                const GemmEpi ep, int M, int N, int K, int num_m_tiles, int num_n_tiles, int num_stages) {
@@ -90,8 +92,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 8);  // one arrive per epilogue warp
-    mbar_init(&tempty[1], 8);
+    mbar_init(&tempty[0], EW);  // one arrive per epilogue warp
+    mbar_init(&tempty[1], EW);
     mbar_init(bfull, 1);
     mbar_fence_init();
   }
@@ -166,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;         // TMEM lane quarter this warp may access
     const int h = (warp - 4) >> 2;  // which alternate 64-column boxes of the tile this warp owns
     WarpStore st;
-    st.single = NUM_STG == 2;
+    st.single = NUM_STG == 2 || EW == 16;  // 16 warps: one staging box each (it is reused a whole tile later)
     st.base = smem_u32(stg_ptr) + static_cast<uint32_t>((warp - 4) * (st.single ? 1 : 2)) * kWarpStgBytes;
     st.iter = 0;
     st.lane = lane;
@@ -185,13 +187,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
       th.taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
       ResidRegs rr;
-      resid_load(rr, ep, th, epilogue_first_col<BN, ROW, OUT_F32>(ep, n_tile, h));  // in flight while the MMAs finish
+      if constexpr (EW != 16) resid_load(rr, ep, th, epilogue_first_col<BN, ROW, OUT_F32>(ep, n_tile, h));  // in flight while the MMAs finish
 
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
       if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
-      if (!(ep.dbg & 2))
-        epilogue_tile<BN, ROW, OUT_F32>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+      if (!(ep.dbg & 2)) {
+        if constexpr (EW == 16) epilogue_box16<BN>(ep, th, n_tile, N, row0, h, lane, st, &tmO0);
+        else epilogue_tile<BN, ROW, OUT_F32>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+      }
       // this warp is done with accumulator buffer `buf`
       tc_fence_before();
       __syncwarp();
@@ -222,9 +226,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool ROW, bool OUT_F32, bool RESB>
+template <int BN, bool ROW, bool OUT_F32, bool RESB, int EW = 8>
 int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<BN, ROW, OUT_F32, RESB>;
+  auto kern = gemm_tc_kernel<BN, ROW, OUT_F32, RESB, EW>;
   static int attr_smem = 0;
   const int mt = (p.M + kBM - 1) / kBM;
   const int nt = p.N / BN;
@@ -245,7 +249,7 @@ int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   int grid = mt * nt;
   if (grid > num_sms) grid = num_sms;
   if (RESB) grid = grid / nt * nt;  // every CTA owns exactly one n-tile
-  kern<<<grid, 384, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.epi, p.M, p.N, p.K, mt, nt, stages);
+  kern<<<grid, 128 + 32 * EW, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.epi, p.M, p.N, p.K, mt, nt, stages);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;
@@ -383,8 +387,12 @@ int gemm_launch_inner(const GemmPlan& p, int num_sms, cudaStream_t stream) {
       return res ? launch_inst<256, true, false, true>(p, num_sms, stream) : launch_inst<256, true, false, false>(p, num_sms, stream);
     if (p.block_n == 128 && !p.out_f32) return launch_inst<128, true, false, false>(p, num_sms, stream);
   } else {
-    if (p.block_n == 256 && !p.out_f32)
-      return res ? launch_inst<256, false, false, true>(p, num_sms, stream) : launch_inst<256, false, false, false>(p, num_sms, stream);
+    if (p.block_n == 256 && !p.out_f32) {
+      static const int ew16 = getenv("ISHARA_GEMM_EW16") ? atoi(getenv("ISHARA_GEMM_EW16")) : 1;
+      if (res) return launch_inst<256, false, false, true>(p, num_sms, stream);
+      return ew16 ? launch_inst<256, false, false, false, 16>(p, num_sms, stream)
+                  : launch_inst<256, false, false, false>(p, num_sms, stream);
+    }
     if (p.block_n == 128 && !p.out_f32) return launch_inst<128, false, false, false>(p, num_sms, stream);
     if (p.block_n == 64 && !p.out_f32) return launch_inst<64, false, false, false>(p, num_sms, stream);
     if (p.block_n == 64 && p.out_f32) return launch_inst<64, false, true, false>(p, num_sms, stream);

@@ -276,9 +276,13 @@ class IsharaModel:
         p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         _lib.check(self._lib.ishara_model_infer_host(self._h, p(x), B, p(lab), L, p(logits), p(ids), p(lens), p(nll)))
         ids64 = ids.astype(np.int64)
-        id_list = [ids64[b, : lens[b]] for b in range(B)]
-        codes = _ASCII_LUT[ids]  # ids are in [-1, blank): one LUT pass for the whole batch (-1 = unused tail slots)
-        text = [codes[b, : lens[b]].tobytes().decode("ascii") for b in range(B)]
+        lens_l = lens.tolist()
+        id_list = [ids64[b, :n] for b, n in enumerate(lens_l)]
+        buf = C.create_string_buffer(B * self.frames + 1)
+        offs = np.empty(B + 1, np.int64)
+        _lib.check(self._lib.ishara_ids_to_text(p(ids), p(lens), B, self.frames, _CHARS.encode("ascii"), len(_CHARS), buf, p(offs)))
+        raw, o = buf.raw, offs.tolist()
+        text = [raw[o[b]:o[b + 1]].decode("ascii") for b in range(B)]
         return {"ids": id_list, "text": text, "nll": nll, "logits": logits}
 
     # ---- measurement hook (bench.py) ------------------------------------------------------------
