@@ -526,6 +526,18 @@ struct Builder {
     p.epi.ld_resid = D;
     p.epi.rows_per_seq = T;
     const bool fused = (D == 256 || D == 128);
+    static const int plain16 = getenv("ISHARA_STREAM_PLAIN16") ? atoi(getenv("ISHARA_STREAM_PLAIN16")) : 0;  // measured: no gain (60 vs 59 us), opt-in
+    if (fused && plain16 && D == 256 && !ln0.g && !ln1.g) {
+      // no LayerNorm to fuse: the plain (non-row) kernel with 16 epilogue warps handles bias / gate / rowtab / residual
+      p.block_n = 256;
+      p.row_mode = false;
+      rc = gemm_plan_init(&p, A, K, pk.get<bf16>(wkey), m->S, D, D, nullptr, 0);
+      op.flops = 2.0 * M * D * klogical;
+      op.bytes = 2.0 * (static_cast<double>(M) * K + static_cast<double>(D) * K + static_cast<double>(M) * D * (1 + (resid ? 1 : 0))) +
+                 (rowtab ? 4.0 * T * D : 0.0) + (gate ? 4.0 * B * D : 0.0);
+      ops.push_back(op);
+      return;
+    }
     if (fused) {
       p.block_n = D;
       p.row_mode = true;

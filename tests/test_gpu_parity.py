@@ -137,6 +137,41 @@ def test_cfg5_scaled_encoder_long_sequence():
     _check_logits(m(x), O.forward(params, x, cfg, "float64"), "cfg5 logits")
 
 
+def test_reference_input_shape_176_frames():
+    """INPUT_SHAPE = [176, 276] is what the reference notebooks actually train and export with (c1:27, FRAME_LEN = 128 + 48);
+    176 is not a multiple of the 128-row tile, so sequences straddle tiles."""
+    cfg = O.Config(frames=176)
+    params = O.init_params(cfg, seed=13)
+    m = _model_for(cfg, params)
+    x = O.make_inputs(cfg, 3, seed=14, ragged=True)
+    got = m(x)
+    _check_logits(got, O.forward(params, x, cfg, "float64"), "T=176 logits")
+    assert m.decode(got) == O.decode_batch_predictions(got)
+
+
+def test_full_batch_properties_and_cache_churn(base):
+    """Size-independent checks at the BASELINE batch (256 x 384): every sequence of the batch equals the same sequence
+    run alone (no cross-sequence leakage through tiles / clusters / the chunked host path), the device path equals the
+    host path bit for bit, and alternating batch sizes (program + CUDA-graph cache churn) does not change results."""
+    torch = pytest.importorskip("torch")
+    cfg, params, m = base
+    rng = np.random.default_rng(99)
+    x = rng.standard_normal((256, cfg.frames, cfg.features)).astype(np.float32)
+    host = m(x)                                            # chunked H2D path
+    assert np.isfinite(host).all()
+    dev = m(torch.from_numpy(x).cuda()).cpu().numpy()      # device-resident path, one program
+    assert np.array_equal(host, dev)
+    for b in (0, 48, 49, 147, 148, 255):                   # chunk boundaries of the host path sit at 49 and 147
+        assert np.array_equal(m(x[b:b + 1])[0], host[b]), b
+    for nb in (3, 256, 5, 64, 256, 3):
+        assert np.array_equal(m(x[:nb]), host[:nb]), nb
+    r = m.infer(x, labels=O.make_labels(cfg, 256), return_logits=True)
+    assert np.array_equal(r["logits"], host)
+    assert r["text"] == m.decode(host)
+    sub = [0, 100, 255]
+    assert [r["text"][i] for i in sub] == O.decode_batch_predictions(host[sub])
+
+
 # ------------------------------------------------------------------------------------------------
 # CTC
 # ------------------------------------------------------------------------------------------------
