@@ -22,6 +22,7 @@ namespace {
 constexpr int kDH = 32;
 constexpr int kQB = 128;           // query rows per block
 constexpr int kMaxT = 384;
+constexpr int kPolyPairs = 0;       // column pairs (of 16 per chunk) whose exp2 runs on the FMA pipe; measured no gain at 9 => off
 constexpr int kThreadsTc = 288;    // warp 0: TMA + MMA issue + TMEM alloc; warps 1-8: softmax / epilogue (2 per lane quarter)
 constexpr int kQKBytes = kMaxT * 128;            // q|k tile: T rows x 128 B
 constexpr int kVtBytes = (kMaxT / 64) * 32 * 128;  // V^T: T/64 k-blocks of [32 x 128 B]
@@ -33,6 +34,51 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-4 polynomial for
+// 2^f (relative error < 5e-5, far below bf16's 4e-3), exponent added with integer arithmetic. Two lanes at a time with
+// the packed fp32 instructions. The exponentials and the fp32->bf16 packs of the softmax share the quarter-rate XU pipe;
+// moving part of the exponentials here is what balances it (same idea as the published FlashAttention-4 softmax).
+__device__ __forceinline__ void exp2_poly2(float& r0, float& r1, float x0, float x1) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, kMagic, kMagic);
+  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
+  fadd2(f0, f1, x0, x1, -n0, -n1);
+  ffma2(p0, p1, f0, f1, 9.618129107628477e-3f, 9.618129107628477e-3f, 5.550410866482158e-2f, 5.550410866482158e-2f);
+  ffma2(p0, p1, p0, p1, f0, f1, 2.402265069591007e-1f, 2.402265069591007e-1f);
+  ffma2(p0, p1, p0, p1, f0, f1, 6.931471805599453e-1f, 6.931471805599453e-1f);
+  ffma2(p0, p1, p0, p1, f0, f1, 1.f, 1.f);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// read 32 bf16 (one 64-byte half of a 128-byte swizzled row) and return their squared L2 norm
+__device__ __forceinline__ float row_half_norm2(const uint8_t* tile, int row, int first_chunk) {
+  const uint8_t* rp = tile + static_cast<size_t>(row) * 128;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 v = *reinterpret_cast<const uint4*>(rp + (((first_chunk + j) ^ (row & 7)) << 4));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+      acc = fmaf(lo, lo, acc);
+      acc = fmaf(hi, hi, acc);
+    }
+  }
+  return acc;
+}
+
+// Pipeline (v3). The softmax is computed against a per-row UPPER BOUND of the scores instead of the exact row maximum:
+// s_ij * scale <= scale * |q_i| * max_j |k_j| (Cauchy-Schwarz). Softmax is invariant to the subtracted constant and bf16
+// has fp32's exponent range, so P keeps its relative precision; a warp whose bound is so loose that 2^(s-bound) could
+// underflow falls back to an exact-maximum pre-pass. Knowing the bound BEFORE the scores exist removes the max pass and
+// lets the key axis be processed in two independent halves with no online rescaling:
+//   MMA thread:   QK(0,0) QK(0,1) | PV(b,0) QK(b+1,0) PV(b,1) QK(b+1,1) ...      (S halves and O double-buffered in TMEM)
+//   softmax warps: sm(0,0) sm(0,1) | sm(b,0) epilogue(b-1) sm(b,1) ...            (never wait for a PV they just enabled)
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict__ qkv, bf16* __restrict__ out,
                const uint8_t* __restrict__ key_mask, int T, int H, float scale_log2) {
@@ -43,27 +89,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
   uint8_t* vt = qk + kQKBytes;                 // [T/64][32][128 B] swizzled V^T
   uint8_t* pp = vt + kVtBytes;                 // [T/64][128][128 B] swizzled P (bf16)
   float* mb = reinterpret_cast<float*>(pp + kPBytes);  // [T] additive key bias (log2 domain), only with a mask
-  float* xch = mb + kMaxT;                     // [2 kinds][2 column halves][128 rows] row max / row sum exchange
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 512);
-  uint64_t* qk_full = bars;      // TMA landed
-  uint64_t* s_full = bars + 1;   // S = Q K^T of the current block is complete
-  uint64_t* p_ready = bars + 2;  // softmax warps wrote P (and are done reading S)
-  uint64_t* o_full = bars + 3;   // O = P V complete
-  uint64_t* o_empty = bars + 4;  // epilogue read O
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* xsum = mb + kMaxT;                    // [2 column halves][128 rows] row-sum exchange (+ spare)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xsum + 512);
+  uint64_t* qk_full = bars;        // TMA landed
+  uint64_t* s_full = bars + 1;     // [2] S half = Q K_half^T complete
+  uint64_t* p_ready = bars + 3;    // [2] softmax warps wrote P half (and are done reading S half)
+  uint64_t* pv_done = bars + 5;    // [2] PV MMAs of that half retired: P half may be overwritten
+  uint64_t* o_full = bars + 7;     // [2] O buffer complete
+  uint64_t* o_empty = bars + 9;    // [2] epilogue read O buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint32_t* kmax_bits = tmem_slot + 1;  // max_j |k_j|^2 as float bits (non-negative floats order like unsigned ints)
 
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nqb = T / kQB, nkb = T / 64;
+  const int nqb = T / kQB, nkb = T / 64, nkb2 = nkb / 2;
   const int ld = 3 * kDH * H;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQK);
     mbar_init(qk_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 256);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 256);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 256);
+    }
+    *kmax_bits = 0u;
     mbar_fence_init();
     mbar_arrive_expect_tx(qk_full, static_cast<uint32_t>(T) * 128u);
     for (int r = 0; r < nqb; ++r) tma_load_2d(qk + r * kQB * 128, &tmQK, qk_full, h * 3 * kDH, b * T + r * kQB);
@@ -101,10 +153,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;          // 384 columns
-  const uint32_t tmem_O = tmem_base + 384;    // 32 columns
-  const int nhalf_cols = T / 2;                              // S is produced as two N = T/2 halves (N <= 256)
-  const uint32_t IDESC_S = umma_idesc(128, nhalf_cols, 1);
+  const int half_cols = T / 2;                 // S is produced as two N = T/2 halves (N <= 192)
+  const uint32_t tmem_O = tmem_base + 384;     // two 32-column O buffers
+  const uint32_t IDESC_S = umma_idesc(128, half_cols, 1);
   constexpr uint32_t IDESC_O = umma_idesc(128, 32, 1);
 
   if (warp == 0) {
@@ -113,125 +164,151 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
       const uint32_t qk_addr = smem_base;
       const uint32_t vt_addr = qk_addr + kQKBytes;
       const uint32_t p_addr = vt_addr + kVtBytes;
+      auto issue_qk = [&](int blk, int half) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tmem_base + half * half_cols, umma_desc_sw128(qk_addr + blk * kQB * 128 + k * 32),
+                    umma_desc_sw128(qk_addr + half * half_cols * 128 + 64 + k * 32), IDESC_S, k);
+        umma_commit(&s_full[half]);
+      };
+      issue_qk(0, 0);
+      issue_qk(0, 1);
       for (int blk = 0; blk < nqb; ++blk) {
-        // S region is free: block blk-1's softmax has signalled p_ready (waited below before its PV MMAs)
-        for (int nh = 0; nh < 2; ++nh)
+        const uint32_t obuf = blk & 1;
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&p_ready[half], blk & 1);
+          if (half == 0 && blk >= 2) mbar_wait(&o_empty[obuf], ((blk >> 1) & 1) ^ 1u);  // block blk-2's epilogue read this O buffer
+          tc_fence_after();
+          for (int j = 0; j < nkb2; ++j) {
+            const int kb = half * nkb2 + j;
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16(tmem_S + nh * nhalf_cols, umma_desc_sw128(qk_addr + blk * kQB * 128 + k * 32),
-                      umma_desc_sw128(qk_addr + nh * nhalf_cols * 128 + 64 + k * 32), IDESC_S, k);
-        umma_commit(s_full);
-        mbar_wait(p_ready, blk & 1);
-        if (blk > 0) mbar_wait(o_empty, (blk - 1) & 1);
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_O, umma_desc_sw128(p_addr + kb * (kQB * 128) + k * 32),
-                      umma_desc_sw128(vt_addr + kb * 4096 + k * 32), IDESC_O, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(o_full);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_O + obuf * 32, umma_desc_sw128(p_addr + kb * (kQB * 128) + k * 32),
+                        umma_desc_sw128(vt_addr + kb * 4096 + k * 32), IDESC_O, (half | j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&pv_done[half]);
+          if (half == 1) umma_commit(&o_full[obuf]);
+          if (blk + 1 < nqb) issue_qk(blk + 1, half);  // this S half was consumed (p_ready): next block's scores can go in
+        }
       }
     }
   } else {
     // ===================== softmax + epilogue =====================
-    // lane == query row (tcgen05.ld 32x32b); the two warps that share a TMEM lane quarter split the key columns in
-    // halves and exchange row max / row sum through smem (64-thread named barrier), so each SM sub-partition has two
-    // warps to overlap the MUFU exponentials of one with the FP32/LSU work of the other.
     const int q = warp & 3;                       // TMEM lane quarter of this warp
-    const int hh = (warp - 1) >> 2;               // which half of the key columns
+    const int hh = (warp - 1) >> 2;               // which part of each key half / which 16 output columns
     const int r = q * 32 + lane;                  // row within the 128-query block
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const bool masked = key_mask != nullptr;
-    const int nc = T / 32, c_lo = hh * (nc / 2), c_hi = c_lo + nc / 2;
-    float* xmax = xch;          // [2][128]
-    float* xsum = xch + 256;    // [2][128]
-    for (int blk = 0; blk < nqb; ++blk) {
-      mbar_wait(s_full, blk & 1);
-      tc_fence_after();
-      // pass 1: exact row maximum of (s * scale + bias) in the log2 domain
-      float mx = -INFINITY;
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, raw);
-        tmem_ld_wait();
-        if (masked) {
+    const int nch = half_cols / 32;               // 32-column chunks per key half (6, 4, 2)
+    const int c_lo = hh * (nch / 2), c_hi = c_lo + nch / 2;
+
+    // max_j |k_j| of this head (for the score bound)
+    mbar_wait(qk_full, 0);
+    {
+      float km = 0.f;
+      for (int key = tid - 32; key < T; key += 256) km = fmaxf(km, row_half_norm2(qk, key, 4));
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(raw[j]), scale_log2, mb[c * 32 + j]));
-        } else {
-          float m0 = __uint_as_float(raw[0]), m1 = __uint_as_float(raw[1]);
-#pragma unroll
-          for (int j = 2; j < 32; j += 2) {
-            m0 = fmaxf(m0, __uint_as_float(raw[j]));
-            m1 = fmaxf(m1, __uint_as_float(raw[j + 1]));
-          }
-          mx = fmaxf(mx, fmaxf(m0, m1) * scale_log2);
-        }
-      }
-      xmax[hh * 128 + r] = mx;
-      named_bar_sync(1 + q, 64);
-      mx = fmaxf(mx, xmax[(hh ^ 1) * 128 + r]);
-      // pass 2: p = 2^(s*scale + bias - max), row sum, bf16 P into the swizzled A-operand tile
-      if (blk > 0) mbar_wait(o_full, (blk - 1) & 1);  // P was being read by the previous block's PV MMAs
-      float s0 = 0.f, s1 = 0.f;
-      const float nmx = -mx;
-      for (int c = c_lo; c < c_hi; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, raw);
-        tmem_ld_wait();
-        float p[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a0, a1;
-          if (masked) {
-            a0 = fmaf(__uint_as_float(raw[2 * j]), scale_log2, mb[c * 32 + 2 * j] + nmx);
-            a1 = fmaf(__uint_as_float(raw[2 * j + 1]), scale_log2, mb[c * 32 + 2 * j + 1] + nmx);
-          } else {
-            ffma2(a0, a1, __uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]), scale_log2, scale_log2, nmx, nmx);
-          }
-          p[2 * j] = ex2f(a0);
-          p[2 * j + 1] = ex2f(a1);
-          fadd2(s0, s1, s0, s1, p[2 * j], p[2 * j + 1]);
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
-        const uint32_t rowbase = smem_base + kQKBytes + kVtBytes + (c >> 1) * (kQB * 128) + static_cast<uint32_t>(r) * 128u;
-        const uint32_t x = static_cast<uint32_t>(r & 7);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_shared_v4(rowbase + ((static_cast<uint32_t>((c & 1) * 4 + j) ^ x) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
-                       pk[4 * j + 3]);
-      }
-      float sum = s0 + s1;
-      xsum[hh * 128 + r] = sum;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_ready);
-      named_bar_sync(1 + q, 64);
-      sum += xsum[(hh ^ 1) * 128 + r];
-      // epilogue of this block: O / rowsum -> bf16 -> global (each warp of the pair writes 16 of the 32 head columns)
-      mbar_wait(o_full, blk & 1);
-      tc_fence_after();
-      {
-        uint32_t raw[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-            : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]), "=r"(raw[6]), "=r"(raw[7]),
-              "=r"(raw[8]), "=r"(raw[9]), "=r"(raw[10]), "=r"(raw[11]), "=r"(raw[12]), "=r"(raw[13]), "=r"(raw[14]), "=r"(raw[15])
-            : "r"(tmem_O + lane_addr + hh * 16)
-            : "memory");
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(o_empty);
-        const float inv = 1.f / sum;
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]) * inv, __uint_as_float(raw[2 * j + 1]) * inv);
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + blk * kQB + r) * (kDH * H) + h * kDH + hh * 16);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
+      for (int o = 16; o > 0; o >>= 1) km = fmaxf(km, __shfl_xor_sync(0xffffffffu, km, o));
+      if (lane == 0) atomicMax(kmax_bits, __float_as_uint(km));
     }
+    named_bar_sync(5, 256);
+    const float kmax = sqrtf(__uint_as_float(*kmax_bits));
+
+    float sum_prev = 0.f;
+    auto epilogue = [&](int blk, float sum) {
+      const uint32_t obuf = blk & 1;
+      mbar_wait(&o_full[obuf], (blk >> 1) & 1);
+      tc_fence_after();
+      uint32_t raw[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]), "=r"(raw[6]), "=r"(raw[7]),
+            "=r"(raw[8]), "=r"(raw[9]), "=r"(raw[10]), "=r"(raw[11]), "=r"(raw[12]), "=r"(raw[13]), "=r"(raw[14]), "=r"(raw[15])
+          : "r"(tmem_O + obuf * 32 + lane_addr + hh * 16)
+          : "memory");
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&o_empty[obuf]);
+      const float inv = 1.f / sum;
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]) * inv, __uint_as_float(raw[2 * j + 1]) * inv);
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + blk * kQB + r) * (kDH * H) + h * kDH + hh * 16);
+      dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
+
+    for (int blk = 0; blk < nqb; ++blk) {
+      // score bound of this query row in the log2 domain
+      float bound = scale_log2 * sqrtf(row_half_norm2(qk, blk * kQB + r, 0)) * kmax;
+      const bool exact = __any_sync(0xffffffffu, bound > 100.f);  // loose bound: 2^(s - bound) could underflow
+      if (exact) {
+        mbar_wait(&s_full[0], blk & 1);
+        mbar_wait(&s_full[1], blk & 1);
+        tc_fence_after();
+        float mx = -INFINITY;
+        for (int c = 0; c < 2 * nch; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + lane_addr + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            mx = fmaxf(mx, fmaf(__uint_as_float(raw[j]), scale_log2, masked ? mb[c * 32 + j] : 0.f));
+        }
+        bound = mx;
+      }
+      const float nb = -bound;
+      float s0 = 0.f, s1 = 0.f;
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&s_full[half], blk & 1);
+        if (blk > 0) mbar_wait(&pv_done[half], (blk - 1) & 1);  // previous block's PV MMAs have finished reading this P half
+        tc_fence_after();
+        for (int c = c_lo; c < c_hi; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + half * half_cols + lane_addr + c * 32, raw);
+          tmem_ld_wait();
+          const int key0 = half * half_cols + c * 32;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a0, a1;
+            if (masked) {
+              a0 = fmaf(__uint_as_float(raw[2 * j]), scale_log2, mb[key0 + 2 * j] + nb);
+              a1 = fmaf(__uint_as_float(raw[2 * j + 1]), scale_log2, mb[key0 + 2 * j + 1] + nb);
+            } else {
+              ffma2(a0, a1, __uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]), scale_log2, scale_log2, nb, nb);
+            }
+            float p0, p1;
+            if (j < kPolyPairs) {
+              exp2_poly2(p0, p1, a0, a1);
+            } else {
+              p0 = ex2f(a0);
+              p1 = ex2f(a1);
+            }
+            fadd2(s0, s1, s0, s1, p0, p1);
+            pk[j] = pack_bf16x2(p0, p1);
+          }
+          const int kc = key0 >> 5;  // global 32-key chunk index
+          const uint32_t rowbase = smem_base + kQKBytes + kVtBytes + (kc >> 1) * (kQB * 128) + static_cast<uint32_t>(r) * 128u;
+          const uint32_t x = static_cast<uint32_t>(r & 7);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(rowbase + ((static_cast<uint32_t>((kc & 1) * 4 + j) ^ x) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
+                         pk[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_ready[half]);
+        if (half == 0 && blk > 0) epilogue(blk - 1, sum_prev);  // overlaps the PV MMAs just enabled
+      }
+      // row sum over both column parts (the partner warp of this lane quarter holds the other chunks)
+      float sum = s0 + s1;
+      xsum[((blk & 1) * 2 + hh) * 128 + r] = sum;
+      named_bar_sync(1 + q, 64);
+      sum += xsum[((blk & 1) * 2 + (hh ^ 1)) * 128 + r];
+      sum_prev = sum;
+    }
+    epilogue(nqb - 1, sum_prev);
   }
   tc_fence_before();
   __syncthreads();
@@ -249,7 +326,7 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
   int rc = make_tmap_2d(&tm, a.qkv, TM_BF16, static_cast<uint64_t>(a.B) * a.T, static_cast<uint64_t>(3) * kDH * a.H,
                         static_cast<uint64_t>(3) * kDH * a.H, kQB, 64);
   if (rc) return rc;
-  const int smem = kQKBytes + kVtBytes + kPBytes + kMaxT * 4 + 2048 + 64 + 1024;
+  const int smem = kQKBytes + kVtBytes + kPBytes + kMaxT * 4 + 2048 + 128 + 1024;
   static bool attr = false;
   if (!attr) {
     ISHARA_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
