@@ -9,6 +9,9 @@
  *   ishara_model_forward[_host]                  <- model(x) / model(x, training=False)   c7:82, c9:15, c13:17
  *   ishara_ctc_loss                              <- CTCLoss(labels, logits)                     c6:1-13
  *   ishara_greedy_decode                         <- decode_phrase / decode_batch_predictions    c8:4-20
+ *   ishara_model_train_*                         <- model.fit's inner step: model(x, training=True), CTCLoss,
+ *                                                   gradients, clip-norm + AdamW        c12:1, c7:67-70,
+ *                                                   integration.py:675-679,750
  *   ishara_op_*                                  <- operator-level building blocks (tests, P-rows of §8a)
  *
  * Conventions
@@ -100,6 +103,48 @@ ISHARA_API ishara_status_t ishara_model_forward_host(ishara_model_t* m, const fl
 ISHARA_API ishara_status_t ishara_model_infer_host(ishara_model_t* m, const float* x_host, int32_t batch,
                                         const int32_t* labels_host, int32_t max_label_len, float* logits_host,
                                         int32_t* ids_host, int32_t* lens_host, float* nll_host);
+
+/* ---- training step ----------------------------------------------------
+ * Keras training-mode forward (BatchNormalization on biased batch statistics over (B,T) + moving-average update,
+ * dropout at the reference's sites), CTCLoss (mean over the batch), gradients of every trainable tensor, then
+ * global-norm clipping and AdamW. Master weights, gradients and Adam moments are fp32 on the device; activations
+ * and activation gradients are bf16. dim must be 128 or 256. The handle's inference path sees the trained weights
+ * after ishara_model_train_sync (called implicitly by forward / get_param / infer when weights are stale). */
+typedef struct {
+  float lr;           /* 4.5e-3  (integration.py:675-679) */
+  float weight_decay; /* 0.08, decoupled, applied to every trainable tensor (torch.optim.AdamW default grouping) */
+  float beta1;        /* 0.9 */
+  float beta2;        /* 0.999 */
+  float eps;          /* 1e-8 */
+  float max_norm;     /* global-norm clip, 1.0 (integration.py:750); <= 0 disables */
+} ishara_adamw_t;
+
+/* dropout_rate = get_model's dropout_rate (0 disables every dropout site; > 0 also enables the head's fixed 0.4,
+ * c7:62; attention-probability dropout c5:113 is not applied); masks are a counter-based hash of (seed, site,
+ * element) so forward and backward agree and a host can reproduce them. debug != 0 keeps named activation
+ * gradients for ishara_model_train_fetch. */
+ISHARA_API ishara_status_t ishara_model_train_configure(ishara_model_t* m, float dropout_rate, uint64_t seed, int32_t debug);
+/* x_dev fp32 [batch, T, F], labels_dev int32 [batch, labels_len] padded with the blank (num_classes-1). Leaves the
+ * mean-reduced gradients in the flat buffer; loss_host (optional) receives mean CTC loss after a stream sync. */
+ISHARA_API ishara_status_t ishara_model_train_forward_backward(ishara_model_t* m, const float* x_dev, const int32_t* labels_dev,
+                                                                int32_t batch, int32_t labels_len, float* loss_host, void* stream);
+/* flat fp32 gradient buffer of all trainable tensors (device pointer, element count): the data-parallel exchange
+ * step is ONE all-reduce over it (torch.distributed / NCCL on the host side), then train_apply(grad_scale=1/world). */
+ISHARA_API ishara_status_t ishara_model_train_grad_buffer(ishara_model_t* m, float** grad_dev, int64_t* numel);
+ISHARA_API ishara_status_t ishara_model_train_apply(ishara_model_t* m, const ishara_adamw_t* opt, float grad_scale, void* stream);
+/* forward_backward + apply in one call (single GPU) */
+ISHARA_API ishara_status_t ishara_model_train_step(ishara_model_t* m, const float* x_dev, const int32_t* labels_dev, int32_t batch,
+                                                    int32_t labels_len, const ishara_adamw_t* opt, float* loss_host, void* stream);
+/* same with host buffers (H2D inside), on the handle's stream; returns after a sync */
+ISHARA_API ishara_status_t ishara_model_train_step_host(ishara_model_t* m, const float* x_host, const int32_t* labels_host,
+                                                         int32_t batch, int32_t labels_len, const ishara_adamw_t* opt, float* loss_host);
+/* device masters -> parameter table (get_param) -> inference packs */
+ISHARA_API ishara_status_t ishara_model_train_sync(ishara_model_t* m);
+/* gradient of one named parameter (Keras layout) after train_forward_backward */
+ISHARA_API ishara_status_t ishara_model_train_param_grad(ishara_model_t* m, const char* name, float* host_out, int64_t numel);
+/* named activation (want_grad = 0) or its gradient (want_grad = 1, debug mode) as fp32 */
+ISHARA_API ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, int32_t want_grad, float* host_out, int64_t numel);
+
 
 /* CTCLoss (c6:1-13): per-sequence negative log-likelihood nll[B] (the reference returns their mean) and,
  * when grad_dev != NULL, d nll_b / d logits [B,T,V]. labels int32 [B,L] padded with `blank`. */

@@ -200,6 +200,22 @@ class DeviceTensor:
         return _api.PyCapsule_New(addr, b"dltensor", C.cast(_capsule_destructor, C.c_void_p))
 
 
+class BorrowedTensor(DeviceTensor):
+    """DLPack producer over device memory owned by someone else (e.g. the model handle's flat gradient buffer).
+    `owner` is kept alive as long as any consumer holds the capsule; nothing is freed here."""
+
+    def __init__(self, ptr: int, shape: Sequence[int], dtype: str, device: int, owner=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = dtype
+        self.device = int(device)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * _ITEMSIZE[dtype]
+        self.ptr = int(ptr)
+        self.owner = owner
+
+    def __del__(self):
+        self.ptr = 0
+
+
 def from_host(a: np.ndarray, device: int = 0, dtype: Optional[str] = None) -> DeviceTensor:
     a = np.ascontiguousarray(a)
     t = DeviceTensor(a.shape, dtype or str(a.dtype), device)

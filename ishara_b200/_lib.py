@@ -40,6 +40,13 @@ class Config(C.Structure):
     ]
 
 
+class AdamW(C.Structure):
+    """ishara_adamw_t — BASELINE optimiser (integration.py:675-679,750)."""
+
+    _fields_ = [("lr", C.c_float), ("weight_decay", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("max_norm", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     """ishara_gemm_args_t"""
 
@@ -113,6 +120,15 @@ SIGNATURES = {
     "ishara_launch_count": (C.c_uint64, []),
     "ishara_model_set_debug": (_i32, [_vp, _i32]),
     "ishara_model_debug_fetch": (_i32, [_vp, C.c_char_p, _vp, _i64]),
+    "ishara_model_train_configure": (_i32, [_vp, _f32, C.c_uint64, _i32]),
+    "ishara_model_train_forward_backward": (_i32, [_vp, _vp, _vp, _i32, _i32, C.POINTER(_f32), _vp]),
+    "ishara_model_train_grad_buffer": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    "ishara_model_train_apply": (_i32, [_vp, _vp, _f32, _vp]),
+    "ishara_model_train_step": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, C.POINTER(_f32), _vp]),
+    "ishara_model_train_step_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, C.POINTER(_f32)]),
+    "ishara_model_train_sync": (_i32, [_vp]),
+    "ishara_model_train_param_grad": (_i32, [_vp, C.c_char_p, _vp, _i64]),
+    "ishara_model_train_fetch": (_i32, [_vp, C.c_char_p, _i32, _vp, _i64]),
 }
 
 _lib = None

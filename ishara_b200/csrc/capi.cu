@@ -41,6 +41,16 @@ int model_set_profile(ishara_model* m, int on);
 int model_profile_count(const ishara_model* m);
 int model_profile_entry(ishara_model* m, int i, const char** label, const char** kind, float* ms, double* flops, double* bytes);
 int model_debug_fetch(ishara_model* m, const char* name, float* host_out, int64_t numel);
+// train.cu
+int train_configure(ishara_model* m, float dropout, uint64_t seed, int debug);
+int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* labels_dev, int batch, int labels_len, float* loss_host,
+                           cudaStream_t stream);
+int train_grad_buffer(ishara_model* m, float** grad_dev, int64_t* numel);
+int train_apply(ishara_model* m, const ishara_adamw_t* opt, float grad_scale, cudaStream_t stream);
+int train_sync(ishara_model* m);
+int train_param_grad(ishara_model* m, const char* name, float* host_out, int64_t numel);
+int train_fetch(ishara_model* m, const char* name, int want_grad, float* host_out, int64_t numel);
+int train_forward_backward_loss(ishara_model* m, float* loss_host, cudaStream_t stream);
 }  // namespace ishara
 
 using namespace ishara;
@@ -456,6 +466,72 @@ ishara_status_t ishara_stream_synchronize(int32_t device, void* stream) {
   CAPI_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return ISHARA_OK;
 }
+
+// ---- training step (train.cu) ---------------------------------------------------------------------
+ishara_status_t ishara_model_train_configure(ishara_model_t* m, float dropout_rate, uint64_t seed, int32_t debug) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_configure(reinterpret_cast<ishara_model*>(m), dropout_rate, seed, debug));
+}
+ishara_status_t ishara_model_train_forward_backward(ishara_model_t* m, const float* x_dev, const int32_t* labels_dev, int32_t batch,
+                                                    int32_t labels_len, float* loss_host, void* stream) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_forward_backward(reinterpret_cast<ishara_model*>(m), x_dev, labels_dev, batch, labels_len,
+                                                             loss_host, static_cast<cudaStream_t>(stream)));
+}
+ishara_status_t ishara_model_train_grad_buffer(ishara_model_t* m, float** grad_dev, int64_t* numel) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_grad_buffer(reinterpret_cast<ishara_model*>(m), grad_dev, numel));
+}
+ishara_status_t ishara_model_train_apply(ishara_model_t* m, const ishara_adamw_t* opt, float grad_scale, void* stream) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_apply(reinterpret_cast<ishara_model*>(m), opt, grad_scale, static_cast<cudaStream_t>(stream)));
+}
+ishara_status_t ishara_model_train_step(ishara_model_t* m, const float* x_dev, const int32_t* labels_dev, int32_t batch, int32_t labels_len,
+                                        const ishara_adamw_t* opt, float* loss_host, void* stream) {
+  CHECK_HANDLE(m);
+  ishara_model* mm = reinterpret_cast<ishara_model*>(m);
+  int rc = train_forward_backward(mm, x_dev, labels_dev, batch, labels_len, nullptr, static_cast<cudaStream_t>(stream));
+  if (rc) return static_cast<ishara_status_t>(rc);
+  rc = train_apply(mm, opt, 1.f, static_cast<cudaStream_t>(stream));
+  if (rc) return static_cast<ishara_status_t>(rc);
+  if (loss_host != nullptr) {
+    // the loss of THIS step's forward; read back after the update was enqueued so the copy overlaps nothing critical
+    rc = train_forward_backward_loss(mm, loss_host, static_cast<cudaStream_t>(stream));
+  }
+  return static_cast<ishara_status_t>(rc);
+}
+ishara_status_t ishara_model_train_step_host(ishara_model_t* mh, const float* x_host, const int32_t* labels_host, int32_t batch,
+                                             int32_t labels_len, const ishara_adamw_t* opt, float* loss_host) {
+  CHECK_HANDLE(mh);
+  if (x_host == nullptr || labels_host == nullptr || batch <= 0 || labels_len <= 0) {
+    set_last_error("train_step_host: bad arguments");
+    return ISHARA_ERR_INVALID;
+  }
+  ishara_model* m = reinterpret_cast<ishara_model*>(mh);
+  ModelView v;
+  int rc = model_view(m, batch, &v);
+  if (rc) return static_cast<ishara_status_t>(rc);
+  int32_t* labels_dev = nullptr;
+  if ((rc = model_labels_buffer(m, static_cast<size_t>(batch) * labels_len, &labels_dev))) return static_cast<ishara_status_t>(rc);
+  const size_t xbytes = static_cast<size_t>(batch) * v.cfg->frames * v.cfg->features * sizeof(float);
+  CAPI_CUDA_OK(cudaMemcpyAsync(v.x_dev, x_host, xbytes, cudaMemcpyHostToDevice, v.stream));
+  CAPI_CUDA_OK(cudaMemcpyAsync(labels_dev, labels_host, static_cast<size_t>(batch) * labels_len * sizeof(int32_t), cudaMemcpyHostToDevice, v.stream));
+  return ishara_model_train_step(mh, v.x_dev, labels_dev, batch, labels_len, opt, loss_host, v.stream);
+}
+ishara_status_t ishara_model_train_sync(ishara_model_t* m) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_sync(reinterpret_cast<ishara_model*>(m)));
+}
+ishara_status_t ishara_model_train_param_grad(ishara_model_t* m, const char* name, float* host_out, int64_t numel) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_param_grad(reinterpret_cast<ishara_model*>(m), name, host_out, numel));
+}
+ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, int32_t want_grad, float* host_out, int64_t numel) {
+  CHECK_HANDLE(m);
+  if (name == nullptr || host_out == nullptr) { set_last_error("train_fetch: null argument"); return ISHARA_ERR_INVALID; }
+  return static_cast<ishara_status_t>(train_fetch(reinterpret_cast<ishara_model*>(m), name, want_grad, host_out, numel));
+}
+
 ishara_status_t ishara_model_set_profile(ishara_model_t* m, int32_t on) {
   CHECK_HANDLE(m);
   return static_cast<ishara_status_t>(model_set_profile(reinterpret_cast<ishara_model*>(m), on));

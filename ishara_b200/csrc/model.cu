@@ -14,123 +14,17 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/ishara_b200.h"
-#include "kernels.h"
 
-namespace ishara {
-
-namespace {
-
-struct Param {
-  std::string name;
-  std::vector<int64_t> shape;
-  std::vector<float> data;
-  bool set = false;
-  int64_t numel() const {
-    int64_t n = 1;
-    for (auto s : shape) n *= s;
-    return n;
-  }
-};
-
-struct LnRef {
-  const float* g = nullptr;
-  const float* b = nullptr;
-  float eps = 0.f;
-};
-
-enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP, OP_FFN, OP_C1F };
-struct Op {
-  OpKind kind;
-  GemmPlan gemm;
-  FfnPlan ffn;
-  Conv1dFrontPlan c1f;
-  DwConvArgs dw;
-  AttnArgs at;
-  SeGateArgs se;
-  // OP_LN
-  const bf16* ln_in = nullptr;
-  bf16* ln_out = nullptr;
-  LnRef ln;
-  int tap = -1;
-  const char* label = "";
-  // algorithmic cost of one launch: useful flops and compulsory HBM bytes (operands read once,
-  // results written once; weights counted once per launch)
-  double flops = 0.0, bytes = 0.0;
-};
-
-inline uint16_t f2bf(float f) {
-  uint32_t u;
-  std::memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;  // NaN
-  u += 0x7fffu + ((u >> 16) & 1u);                      // round to nearest even
-  return static_cast<uint16_t>(u >> 16);
-}
-
-}  // namespace
-}  // namespace ishara
+#include "model_internal.h"
 
 using namespace ishara;
 
-struct GraphKey {
-  int batch;
-  float* logits;
-  const float* x;
-  bool operator<(const GraphKey& o) const {
-    if (batch != o.batch) return batch < o.batch;
-    if (logits != o.logits) return logits < o.logits;
-    return x < o.x;
-  }
-  bool operator!=(const GraphKey& o) const { return batch != o.batch || logits != o.logits || x != o.x; }
-};
-struct GraphEntry {
-  cudaGraphExec_t exec = nullptr;
-  int launches = 0;
-};
-
-struct ishara_model {
-  ishara_config_t cfg;
-  int device = 0;
-  int num_sms = 148;
-  std::vector<Param> params;
-  std::unordered_map<std::string, int> index;
-  bool finalized = false;
-  bool debug_taps = false;
-
-  std::vector<void*> wallocs;  // packed weights
-  std::unordered_map<std::string, void*> packed;
-
-  // workspace
-  int cap_batch = 0;
-  std::vector<void*> wsallocs;
-  bf16 *XIN = nullptr, *S = nullptr, *XN = nullptr, *H1 = nullptr, *H2 = nullptr, *O = nullptr, *HEAD = nullptr;
-  float *colsum = nullptr, *gate = nullptr;
-  float* logits_own = nullptr;
-  int32_t *ids_dev = nullptr, *lens_dev = nullptr, *labels_dev = nullptr;
-  float* nll_dev = nullptr;
-  int labels_cap = 0;
-  float* x_dev = nullptr;
-  std::vector<bf16*> taps;
-  std::vector<std::string> tap_names;
-
-  std::vector<Op> program;
-  bool profile = false;               // record one CUDA event per op during forward
-  std::vector<cudaEvent_t> events;    // [0] before cast_pad, [1] after it, [2+i] after program[i]
-  int program_batch = 0;
-  float* program_logits = nullptr;
-  // programs built for other (batch, logits pointer) pairs: the chunked host path alternates between a few of them
-  std::map<std::pair<int, float*>, std::vector<Op>> program_cache;
-  std::map<GraphKey, GraphEntry> graphs;  // captured forwards; dropped whenever programs are rebuilt
-  bool graphs_broken = false;
-  cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;     // H2D of the chunked host path
-  cudaEvent_t copy_done[8] = {nullptr};
-
-  int fpad() const { return (cfg.features + 63) / 64 * 64; }
-  int vpad() const { return (cfg.num_classes + 63) / 64 * 64; }
-};
-
 namespace ishara {
+// train.cu
+void train_destroy(ishara_model* m);
+void train_invalidate(ishara_model* m);
+int train_sync(ishara_model* m);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -808,6 +702,7 @@ int model_create(const ishara_config_t* cfg, int device, ishara_model** out) {
 int model_destroy(ishara_model* m) {
   if (m == nullptr) return ISHARA_OK;
   if (m->finalized || !m->wsallocs.empty()) cudaSetDevice(m->device);
+  train_destroy(m);
   for (void* p : m->wallocs) cudaFree(p);
   for (void* p : m->wsallocs) cudaFree(p);
   for (cudaEvent_t e : m->events) cudaEventDestroy(e);
@@ -856,6 +751,7 @@ static void drop_graphs(ishara_model* m) {
 
 int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_dev, cudaStream_t stream) {
   if (!m->finalized) { set_last_error("forward before finalize"); return ISHARA_ERR_STATE; }
+  if (m->host_params_stale) { int rcs = train_sync(m); if (rcs) return rcs; }  // weights moved by a training step
   if (batch <= 0 || x_dev == nullptr || logits_dev == nullptr) { set_last_error("forward: bad arguments"); return ISHARA_ERR_INVALID; }
   ISHARA_CUDA_OK(cudaSetDevice(m->device));
   int rc;
@@ -1065,14 +961,18 @@ int model_set_param(ishara_model* m, const char* name, const float* data, int64_
     set_last_error(std::string("set_param ") + name + ": expected " + std::to_string(p.numel()) + " elements, got " + std::to_string(numel));
     return ISHARA_ERR_SHAPE;
   }
+  if (m->host_params_stale) { int rcs = train_sync(m); if (rcs) return rcs; }
+  train_invalidate(m);  // the next training call re-uploads the table
   p.data.assign(data, data + numel);
   p.set = true;
   m->finalized = false;
   return 0;
 }
 
-int model_get_param(const ishara_model* m, const char* name, float* out, int64_t numel) {
+int model_get_param(const ishara_model* mc, const char* name, float* out, int64_t numel) {
   if (name == nullptr || out == nullptr) { set_last_error("get_param: null argument"); return ISHARA_ERR_INVALID; }
+  ishara_model* m = const_cast<ishara_model*>(mc);
+  if (m->host_params_stale) { int rcs = train_sync(m); if (rcs) return rcs; }
   auto it = m->index.find(name);
   if (it == m->index.end()) { set_last_error(std::string("unknown parameter: ") + name); return ISHARA_ERR_INVALID; }
   const Param& p = m->params[it->second];

@@ -1,0 +1,125 @@
+// ishara_b200 — private definition of the model handle, shared by model.cu (inference program), train.cu (training
+// step) and nothing else. Not part of the C ABI.
+#pragma once
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ishara_b200.h"
+#include "kernels.h"
+
+namespace ishara {
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool set = false;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct LnRef {
+  const float* g = nullptr;
+  const float* b = nullptr;
+  float eps = 0.f;
+};
+
+enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP, OP_FFN, OP_C1F };
+struct Op {
+  OpKind kind;
+  GemmPlan gemm;
+  FfnPlan ffn;
+  Conv1dFrontPlan c1f;
+  DwConvArgs dw;
+  AttnArgs at;
+  SeGateArgs se;
+  // OP_LN
+  const bf16* ln_in = nullptr;
+  bf16* ln_out = nullptr;
+  LnRef ln;
+  int tap = -1;
+  const char* label = "";
+  // algorithmic cost of one launch: useful flops and compulsory HBM bytes (operands read once,
+  // results written once; weights counted once per launch)
+  double flops = 0.0, bytes = 0.0;
+};
+
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);                      // round to nearest even
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace ishara
+
+namespace ishara { struct TrainState; }
+using ishara::bf16;
+
+struct GraphKey {
+  int batch;
+  float* logits;
+  const float* x;
+  bool operator<(const GraphKey& o) const {
+    if (batch != o.batch) return batch < o.batch;
+    if (logits != o.logits) return logits < o.logits;
+    return x < o.x;
+  }
+  bool operator!=(const GraphKey& o) const { return batch != o.batch || logits != o.logits || x != o.x; }
+};
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+};
+
+struct ishara_model {
+  ishara_config_t cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::vector<ishara::Param> params;
+  std::unordered_map<std::string, int> index;
+  bool finalized = false;
+  bool debug_taps = false;
+
+  std::vector<void*> wallocs;  // packed weights
+  std::unordered_map<std::string, void*> packed;
+
+  // workspace
+  int cap_batch = 0;
+  std::vector<void*> wsallocs;
+  bf16 *XIN = nullptr, *S = nullptr, *XN = nullptr, *H1 = nullptr, *H2 = nullptr, *O = nullptr, *HEAD = nullptr;
+  float *colsum = nullptr, *gate = nullptr;
+  float* logits_own = nullptr;
+  int32_t *ids_dev = nullptr, *lens_dev = nullptr, *labels_dev = nullptr;
+  float* nll_dev = nullptr;
+  int labels_cap = 0;
+  float* x_dev = nullptr;
+  std::vector<bf16*> taps;
+  std::vector<std::string> tap_names;
+
+  std::vector<ishara::Op> program;
+  bool profile = false;               // record one CUDA event per op during forward
+  std::vector<cudaEvent_t> events;    // [0] before cast_pad, [1] after it, [2+i] after program[i]
+  int program_batch = 0;
+  float* program_logits = nullptr;
+  // programs built for other (batch, logits pointer) pairs: the chunked host path alternates between a few of them
+  std::map<std::pair<int, float*>, std::vector<ishara::Op>> program_cache;
+  std::map<GraphKey, GraphEntry> graphs;  // captured forwards; dropped whenever programs are rebuilt
+  bool graphs_broken = false;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;     // H2D of the chunked host path
+  cudaEvent_t copy_done[8] = {nullptr};
+  ishara::TrainState* train = nullptr;    // training step state (train.cu); null until the first train call
+  bool host_params_stale = false;         // device master weights are newer than params[].data (after a train step)
+
+  int fpad() const { return (cfg.features + 63) / 64 * 64; }
+  int vpad() const { return (cfg.num_classes + 63) / 64 * 64; }
+};
+

@@ -242,6 +242,116 @@ class IsharaModel:
 
     predict = __call__
 
+
+    # ---- training step (Keras fit's inner step c12:1 with BASELINE's AdamW) -----------------
+    def compile(self, lr: float = 4.5e-3, weight_decay: float = 0.08, beta1: float = 0.9, beta2: float = 0.999,
+                eps: float = 1e-8, clipnorm: float = 1.0):
+        """Optimiser of the training step: AdamW + global-norm clipping (integration.py:675-679,750)."""
+        self._opt = _lib.AdamW(lr, weight_decay, beta1, beta2, eps, clipnorm)
+        return self
+
+    def train_config(self, dropout_rate: Optional[float] = None, seed: int = 0, debug: bool = False):
+        """dropout_rate defaults to get_model's; 0 turns every dropout site off (deterministic parity runs)."""
+        self._ensure_finalized()
+        p = self.dropout_rate if dropout_rate is None else float(dropout_rate)
+        _lib.check(self._lib.ishara_model_train_configure(self._h, p, int(seed) & (2 ** 64 - 1), 1 if debug else 0))
+        self._train_configured = True
+        return self
+
+    def _train_args(self, x, labels):
+        if not getattr(self, "_train_configured", False):
+            self.train_config()
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            self._check_x(x.shape)
+            labels = np.ascontiguousarray(labels, dtype=np.int32)
+            if labels.ndim != 2 or labels.shape[0] != x.shape[0]:
+                raise ValueError("labels must be [B, max_label_len]")
+            return x, labels, True
+        xd = _Dev(x, "float32", self.device)
+        self._check_x(xd.shape)
+        if _is_torch(labels) and str(labels.dtype) == "torch.int64":
+            labels = labels.int()
+        ld = _Dev(labels, "int32", self.device)
+        if len(ld.shape) != 2 or ld.shape[0] != xd.shape[0]:
+            raise ValueError("labels must be [B, max_label_len]")
+        return xd, ld, False
+
+    def forward_backward(self, x: ArrayLike, labels: ArrayLike) -> float:
+        """model(x, training=True) -> CTCLoss -> gradients (left in the flat device buffer). Returns the loss."""
+        x, labels, host = self._train_args(x, labels)
+        loss = C.c_float()
+        if host:
+            xt = _dlpack.from_host(x, self.device, "float32")
+            lt = _dlpack.from_host(labels, self.device, "int32")
+            _lib.check(self._lib.ishara_model_train_forward_backward(self._h, _vp(xt.ptr), _vp(lt.ptr), x.shape[0], labels.shape[1],
+                                                                     C.byref(loss), None))
+        else:
+            _lib.check(self._lib.ishara_model_train_forward_backward(self._h, _vp(x.ptr), _vp(labels.ptr), x.shape[0], labels.shape[1],
+                                                                     C.byref(loss), _vp(x.stream)))
+        return float(loss.value)
+
+    def apply_gradients(self, grad_scale: float = 1.0, stream: int = 0):
+        opt = getattr(self, "_opt", None) or _lib.AdamW(4.5e-3, 0.08, 0.9, 0.999, 1e-8, 1.0)
+        _lib.check(self._lib.ishara_model_train_apply(self._h, C.byref(opt), float(grad_scale), _vp(stream)))
+
+    def train_step(self, x: ArrayLike, labels: ArrayLike) -> float:
+        """One optimisation step on one batch; host arrays go through one C-ABI call (H2D inside)."""
+        x, labels, host = self._train_args(x, labels)
+        opt = getattr(self, "_opt", None) or _lib.AdamW(4.5e-3, 0.08, 0.9, 0.999, 1e-8, 1.0)
+        loss = C.c_float()
+        if host:
+            _lib.check(self._lib.ishara_model_train_step_host(self._h, x.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),
+                                                              x.shape[0], labels.shape[1], C.byref(opt), C.byref(loss)))
+        else:
+            _lib.check(self._lib.ishara_model_train_step(self._h, _vp(x.ptr), _vp(labels.ptr), x.shape[0], labels.shape[1], C.byref(opt),
+                                                         C.byref(loss), _vp(x.stream)))
+        return float(loss.value)
+
+    def fit(self, dataset, epochs: int = 1, verbose: bool = False) -> List[float]:
+        """Minimal stand-in for model.fit(train_dataset, epochs=...) (c12:1): iterates (x, labels) batches."""
+        history = []
+        for ep in range(epochs):
+            losses = [self.train_step(x, y) for x, y in dataset]
+            history.append(float(np.mean(losses)) if losses else float("nan"))
+            if verbose:
+                print(f"epoch {ep + 1}/{epochs} loss {history[-1]:.4f}")
+        return history
+
+    def grad_buffer(self) -> Tuple[int, int]:
+        """(device pointer, element count) of the flat fp32 gradient buffer of all trainable tensors."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.ishara_model_train_grad_buffer(self._h, C.byref(ptr), C.byref(n)))
+        return int(ptr.value or 0), int(n.value)
+
+    def grad_tensor(self):
+        """The gradient buffer as a DLPack producer (torch.from_dlpack(model.grad_tensor()) aliases it)."""
+        ptr, n = self.grad_buffer()
+        return _dlpack.BorrowedTensor(ptr, (n,), "float32", self.device, owner=self)
+
+    def gradients(self, names: Optional[Iterable[str]] = None) -> Dict[str, np.ndarray]:
+        """Gradients of the last forward_backward in Keras layouts (trainable tensors only)."""
+        out = {}
+        wanted = set(names) if names is not None else None
+        for name, shape in self._specs:
+            if name.endswith(".moving_mean") or name.endswith(".moving_variance"):
+                continue
+            if wanted is not None and name not in wanted:
+                continue
+            a = np.empty(shape, np.float32)
+            _lib.check(self._lib.ishara_model_train_param_grad(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+            out[name] = a
+        return out
+
+    def train_fetch(self, name: str, shape, grad: bool = False) -> np.ndarray:
+        a = np.empty(tuple(shape), np.float32)
+        _lib.check(self._lib.ishara_model_train_fetch(self._h, name.encode(), 1 if grad else 0, a.ctypes.data_as(C.c_void_p), a.size))
+        return a
+
+    def sync_weights(self):
+        """Make the inference path and get_weights see the trained weights (implicit before forward/get_param)."""
+        _lib.check(self._lib.ishara_model_train_sync(self._h))
+
     # ---- loss / decode on this model's device --------------------------------------------------
     def ctc_loss(self, labels: ArrayLike, logits: ArrayLike, reduction: str = "mean"):
         """CTCLoss(labels, logits) (c6:1-13). reduction 'mean' = what the reference returns; 'none' = per-sequence."""
