@@ -173,7 +173,8 @@ struct TB {
     const int sms = m->num_sms;
     return [plan, sms](cudaStream_t s) { return gemm_launch(*plan, sms, s); };
   }
-  bool rowable(int n) const { return n == 256 || n == 128; }
+  // full-row epilogue only for the D-wide stream tensors (bias / residual / row table; no activation there)
+  bool rowable(int n) const { return n == D && (n == 256 || n == 128); }
   // y = A @ W^T(fwd pack) + bias [+ resid]   -> [M, N] bf16
   Step linear(const bf16* A, int K, const std::string& base, bool bias, int N, bf16* out, const bf16* resid = nullptr, int act = ACT_NONE,
               const float* rowtab = nullptr) {
@@ -423,23 +424,24 @@ struct TB {
   }
 
   // x + drop(FFN(LN(x)))    (FeedForwardModule c5:237-247; Squeezeformer FFN c5:162-166)
-  bf16* ffn(const std::string& base, const std::string& ln, const bf16* S_in, const std::string& out_name) {
+  // branch_drop: SqueezeformerBlock wraps the branch in self.dropout (c5:190,205); ConformerBlock does not (c5:326,341)
+  bf16* ffn(const std::string& base, const std::string& ln, const bf16* S_in, const std::string& out_name, bool branch_drop) {
     bf16* XN = act(D);
     bf16* U = act(E, base + ".u");
     bf16* Hh = act(E);
     bf16* S_out = act(D, out_name);
-    const float p = ts->dropout;
+    const float p = ts->dropout, pb = branch_drop ? ts->dropout : 0.f;
     const int64_t nE = static_cast<int64_t>(M) * E;
     ts->fwd.push_back(ln_fwd(S_in, XN, ln, 1e-6f));
     ts->fwd.push_back(linear(XN, D, base + ".0", true, E, U));
     ts->fwd.push_back([=](cudaStream_t s) { return act_fwd_launch(U, Hh, nE, TACT_SWISH, s); });
     const uint32_t site_h = drop_inplace(ts->fwd, Hh, E, p);
-    const uint32_t site = branch_fwd(Hh, E, base + ".2", true, S_in, S_out, p, false);
+    const uint32_t site = branch_fwd(Hh, E, base + ".2", true, S_in, S_out, pb, false);
 
     std::vector<Step> bw;
     const bf16* dOut = dout();
     snap(bw, out_name, dOut, D);
-    const bf16* dY = branch_bwd(bw, dOut, p, site, false);
+    const bf16* dY = branch_bwd(bw, dOut, pb, site, false);
     bw.push_back(wgrad(Hh, E, E, dY, D, D, base + ".2"));
     bw.push_back(bias_grad(dY, D, D, base + ".2"));
     bw.push_back(dgrad(dY, D, base + ".2", E, gW1));  // dH
@@ -458,13 +460,13 @@ struct TB {
   }
 
   // x + drop(MHSA(LN(x)))   (MultiHeadSelfAttention c5:91-118)
-  bf16* mhsa(const std::string& base, const std::string& ln, const bf16* S_in, const std::string& out_name) {
+  bf16* mhsa(const std::string& base, const std::string& ln, const bf16* S_in, const std::string& out_name, bool branch_drop) {
     const int H = m->cfg.num_heads, dh = D / H;
     bf16* XN = act(D);
     bf16* QKV = act(3 * D, base + ".qkv");
     bf16* O = act(D, base + ".o");
     bf16* S_out = act(D, out_name);
-    const float p = ts->dropout;
+    const float p = branch_drop ? ts->dropout : 0.f;  // attention-probability dropout (c5:113) is not applied
     const float scale = 1.f / std::sqrt(static_cast<float>(D));  // self.scale = dim ** -0.5 (c5:95)
     ts->fwd.push_back(ln_fwd(S_in, XN, ln, 1e-6f));
     ts->fwd.push_back(linear(XN, D, base + ".qkv", false, 3 * D, QKV));
@@ -804,18 +806,18 @@ int build_train_program(ishara_model* m, TrainState* ts, int batch, int labels_l
   for (int i = 0; i < c.num_conv_squeeze_blocks && !b.rc; ++i) {
     conv_blocks("squeeze", i);
     const std::string n = "squeezeformer_" + std::to_string(i);
-    S = b.ffn(n + ".ffn1", n + ".norm1", S, n + ".x1");
-    S = b.mhsa(n + ".mha", n + ".norm2", S, n + ".x2");
+    S = b.ffn(n + ".ffn1", n + ".norm1", S, n + ".x1", true);
+    S = b.mhsa(n + ".mha", n + ".norm2", S, n + ".x2", true);
     S = b.sqz_conv(n, S);
-    S = b.ffn(n + ".ffn2", n + ".norm3", S, n);
+    S = b.ffn(n + ".ffn2", n + ".norm3", S, n, true);
   }
   for (int i = 0; i < c.num_conv_conform_blocks && !b.rc; ++i) {
     conv_blocks("conform", i);
     const std::string n = "conformer_" + std::to_string(i);
-    S = b.ffn(n + ".ffn1", n + ".layer_norm1", S, n + ".x1");
-    S = b.mhsa(n + ".mha", n + ".layer_norm1", S, n + ".x2");  // layer_norm1 reused (c5:330)
+    S = b.ffn(n + ".ffn1", n + ".layer_norm1", S, n + ".x1", false);
+    S = b.mhsa(n + ".mha", n + ".layer_norm1", S, n + ".x2", false);  // layer_norm1 reused (c5:330)
     S = b.conf_conv(n, S);
-    S = b.ffn(n + ".ffn2", n + ".layer_norm2", S, n);
+    S = b.ffn(n + ".ffn2", n + ".layer_norm2", S, n, false);
   }
   if (!b.rc) b.head(S);
   if (b.rc) {

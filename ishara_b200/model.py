@@ -348,6 +348,85 @@ class IsharaModel:
         _lib.check(self._lib.ishara_model_train_fetch(self._h, name.encode(), 1 if grad else 0, a.ctypes.data_as(C.c_void_p), a.size))
         return a
 
+    def dropout_masks(self, batch: int, seed: int, rate: Optional[float] = None) -> Dict[str, np.ndarray]:
+        """The keep/(1-p) masks the training kernels apply for (seed, rate), recomputed on the host from the same
+        counter-based hash (train_ew.cu: mix64). Keys follow the reference's layer structure: '<conv1dblock>.drop'
+        [B,1,1] (c5:83), '<block>.ffnK.drop' [B,T,E] (c5:164,179,242), 'squeezeformer_i.drop{1,2,3}' [B,T,D]
+        (c5:190,196,205), 'head.drop' [B,T,2D] (c7:62, fixed 0.4). Lets a CPU restatement reproduce a step exactly."""
+        p = self.dropout_rate if rate is None else float(rate)
+        if p <= 0:
+            return {}
+        c, T, D = self._cfg, self.frames, self.dim
+        E = c.expansion_factor * D
+        M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+        def mix64(z):
+            with np.errstate(over="ignore"):
+                z = (z + np.uint64(0x9E3779B97F4A7C15)) & M64
+                z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M64
+                z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M64
+                return z ^ (z >> np.uint64(31))
+
+        def key(site):
+            inner = mix64(np.uint64((site << 32) | 0x5bd1e995))
+            return mix64(np.uint64(seed & (2 ** 64 - 1)) ^ inner)
+
+        def thr(q):
+            return np.uint32(np.float32(q) * np.float32(65536.0)), np.float32(1.0) / (np.float32(1.0) - np.float32(q))
+
+        def elementwise(site, cols, q):
+            t16, inv = thr(q)
+            nvec = batch * T * cols // 8
+            with np.errstate(over="ignore"):
+                v = np.arange(nvec, dtype=np.uint64)
+                r0 = mix64(key(site) + np.uint64(2) * v)
+                r1 = mix64(key(site) + np.uint64(2) * v + np.uint64(1))
+            u = np.empty((nvec, 8), np.uint32)
+            for i in range(8):
+                r = r0 if i < 4 else r1
+                u[:, i] = ((r >> np.uint64(16 * (i & 3))) & np.uint64(0xFFFF)).astype(np.uint32)
+            return np.where(u >= t16, inv, np.float32(0)).astype(np.float32).reshape(batch, T, cols)
+
+        def per_sample(site, q):
+            t16, inv = thr(q)
+            with np.errstate(over="ignore"):
+                r = mix64(key(site) + np.arange(batch, dtype=np.uint64))
+            u = (r & np.uint64(0xFFFF)).astype(np.uint32)
+            return np.where(u >= t16, inv, np.float32(0)).astype(np.float32).reshape(batch, 1, 1)
+
+        masks: Dict[str, np.ndarray] = {}
+        site = 0
+
+        def conv_blocks(tag, i):
+            nonlocal site
+            for j in range(c.num_conv_per_block):
+                site += 1
+                masks[f"conv{tag}_{i}_{j + 1}.drop"] = per_sample(site, p)
+
+        def ffn(base, branch_name):
+            nonlocal site
+            site += 1
+            masks[base + ".drop"] = elementwise(site, E, p)
+            if branch_name:
+                site += 1
+                masks[branch_name] = elementwise(site, D, p)
+
+        for i in range(c.num_conv_squeeze_blocks):
+            conv_blocks("squeeze", i)
+            n = f"squeezeformer_{i}"
+            ffn(n + ".ffn1", n + ".drop1")
+            site += 1
+            masks[n + ".drop2"] = elementwise(site, D, p)
+            ffn(n + ".ffn2", n + ".drop3")
+        for i in range(c.num_conv_conform_blocks):
+            conv_blocks("conform", i)
+            n = f"conformer_{i}"
+            ffn(n + ".ffn1", None)
+            ffn(n + ".ffn2", None)
+        site += 1
+        masks["head.drop"] = elementwise(site, 2 * D, 0.4)
+        return masks
+
     def sync_weights(self):
         """Make the inference path and get_weights see the trained weights (implicit before forward/get_param)."""
         _lib.check(self._lib.ishara_model_train_sync(self._h))

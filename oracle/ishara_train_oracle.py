@@ -81,10 +81,13 @@ def _drop(x, mask):
 
 def forward_train(params: Dict[str, np.ndarray], x: np.ndarray, labels: np.ndarray, cfg: Config,
                   dtype: str = "float32", dropout_masks: Optional[Dict[str, np.ndarray]] = None,
-                  want_taps: bool = False):
+                  want_taps: bool = False, relu_gate: Optional[np.ndarray] = None):
     """One training-mode forward + backward. Returns dict(loss, nll[B], grads{name: np}, new_stats{name: np},
     logits, taps{name: (value, grad)}). ``dropout_masks[name]`` are ready-to-multiply masks (keep/(1-p)), broadcastable
-    to the tensor they scale; missing name = dropout off at that site."""
+    to the tensor they scale; missing name = dropout off at that site. ``relu_gate`` (0/1, shape of the head's hidden
+    tensor) replaces the head's ReLU by a fixed gate: a bf16 forward flips the sign of the ~1 % of pre-activations that
+    sit within rounding distance of zero, and each flip is an O(1) gradient difference, so backward kernels are
+    compared "given the same gate" (the un-gated comparison is reported too)."""
     dt = {"float32": torch.float32, "float64": torch.float64}[dtype]
     c = _Ctx(params, dt, want_taps)
     dm = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dt) for k, v in (dropout_masks or {}).items()}
@@ -149,7 +152,11 @@ def forward_train(params: Dict[str, np.ndarray], x: np.ndarray, labels: np.ndarr
         r = c.tap(n + ".conv.r", c.dense(bn, n + ".conv.pointwise_conv2") + res)
         h = c.tap(n + ".x3", c.ln(r, n + ".conv.layer_norm", LN_EPS_CONVMOD))
         h = c.tap(n, h + _drop(ffn(c.ln(h, n + ".layer_norm2", LN_EPS), n + ".ffn2"), dm.get(n + ".drop3")))
-    hh = c.tap("head.h", torch.relu(c.dense(h, "top_conv")))
+    pre = c.dense(h, "top_conv")
+    if relu_gate is None:
+        hh = c.tap("head.h", torch.relu(pre))
+    else:
+        hh = c.tap("head.h", pre * torch.from_numpy(np.ascontiguousarray(relu_gate)).to(dt))
     logits = c.tap("logits", c.dense(_drop(hh, dm.get("head.drop")), "classifier"))
 
     # CTCLoss c6:1-13: label_length = count(labels != pad), logit_length = T, blank = pad index, mean over batch

@@ -75,3 +75,61 @@ def test_world_size_2_gloo_matches_unsharded():
     assert np.allclose(nll, O.ctc_loss(labels, logits), rtol=1e-6)
     assert slowest == 2.0                                   # max over ranks, not the local value
     assert order == [0, 1, 1]
+
+
+# ---- data-parallel training step: one all-reduce over the flat gradient buffer -----------------------
+class _FakeTrainModel:
+    """Host stand-in for IsharaModel's training surface: 'gradient' = mean of the rank's shard, SGD update."""
+
+    def __init__(self):
+        self.w = torch.zeros(4, dtype=torch.float32)
+        self.g = torch.zeros(4, dtype=torch.float32)
+        self.scales = []
+
+    def forward_backward(self, x, labels):
+        self.g.copy_(torch.from_numpy(x.mean(axis=0)))
+        return float(x.sum())
+
+    def grad_tensor(self):
+        return self.g
+
+    def apply_gradients(self, grad_scale=1.0):
+        self.scales.append(grad_scale)
+        self.w -= self.g * grad_scale
+
+
+def _train_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ishara_b200.parallel import DataParallelTrainer
+
+        x = np.arange(24, dtype=np.float32).reshape(6, 4)
+        lo, hi = shard_range(6, rank, world)
+        model = _FakeTrainModel()
+        loss = DataParallelTrainer(model).train_step(x[lo:hi], None)
+        q.put((rank, model.w.tolist(), loss, model.scales))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_trainer_world_2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get() for _ in range(2))
+    x = np.arange(24, dtype=np.float32).reshape(6, 4)
+    want_w = (-x.mean(axis=0)).tolist()                     # equal shards: mean of shard means = global mean
+    for rank, w, loss, scales in got:
+        assert np.allclose(w, want_w)                        # every rank applied the identical averaged gradient
+        assert scales == [0.5]
+        assert np.isclose(loss, x.sum() / 2)                 # mean over ranks of the per-rank losses

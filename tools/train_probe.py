@@ -38,6 +38,10 @@ def run(cfg, B, L, label):
     m.train_config(0.0, seed=1, debug=True)
     loss = m.forward_backward(x, y)
     print(f"gpu:    loss {loss:.5f}   rel diff {abs(loss - ref['loss']) / abs(ref['loss']):.2e}", flush=True)
+    if os.environ.get("PROBE_GATE", "1") == "1":
+        hh = m.train_fetch("head.h", (B, cfg.frames, 2 * cfg.dim))
+        ref = TO.forward_train(p, x, y, cfg, want_taps=True, relu_gate=(hh > 0).astype(np.float32))
+        print(f"oracle re-run with the GPU's ReLU gate: loss {ref['loss']:.5f}", flush=True)
     print(f"{'tensor':44s} {'val relL2':>10s} {'cos':>8s} | {'grad relL2':>10s} {'cos':>8s}")
     for name, (val, grad) in ref["taps"].items():
         line = f"{name:44s}"
