@@ -65,7 +65,7 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int SPL>
 __global__ void __launch_bounds__(32)
 ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
-           float* __restrict__ nll, float* __restrict__ grad, float* __restrict__ alpha_ws) {
+           float* __restrict__ nll, float* __restrict__ grad, float* __restrict__ alpha_ws, float* __restrict__ beta_ws) {
   extern __shared__ __align__(16) float smem_ctc[];
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x;
@@ -192,7 +192,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
   if (grad == nullptr) return;
 
   // ---------------- beta sweep + gradient (blocks in reverse) ----------------
-  float* gr = grad + static_cast<size_t>(b) * T * V;
+  float* bw = beta_ws + static_cast<size_t>(b) * T * (32 * SPL);
   float bt[SPL];
   stage(nblk - 1);
   for (int tb = nblk - 1; tb >= 0; --tb) {
@@ -208,13 +208,6 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
       float em[SPL];
 #pragma unroll
       for (int i = 0; i < SPL; ++i) em[i] = (row[ext[i]] - lt) * kLog2e;
-      // alphas of this frame (written by this thread during the forward sweep)
-      float al[SPL];
-      {
-        const float* asrc = aw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) al[i] = asrc[i];
-      }
       if (t == T - 1) {
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
@@ -237,43 +230,90 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
 #pragma unroll
         for (int i = 0; i < SPL; ++i) bt[i] = nb[i];
       }
-      // occupancy: alpha_t(s) beta_t(s) / y_t(ext s), scattered by class. In exact arithmetic the sum over s is
-      // p(l|x) at every t; normalising by the per-frame sum instead of exp(logp) keeps fp32 drift out of the
-      // gradient (each row of d nll / d logits then sums to zero to rounding).
-      for (int v = lane; v < Vpad; v += 32) occ[v] = 0.f;
-      __syncwarp();
-      if (feasible) {
-        float e[SPL];
-        float mx = kLogZero;
+      // park beta_t next to alpha_t: the gradient of every frame is formed by ctc_grad_kernel, one warp per frame,
+      // instead of ~2k dependent cycles per frame on this single warp
+      {
+        float* bdst = bw + static_cast<size_t>(t) * (32 * SPL) + lane * SPL;
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-          const int s = lane * SPL + i;
-          e[i] = (s < S) ? al[i] + bt[i] - em[i] : kLogZero;
-          mx = fmaxf(mx, e[i]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-          e[i] = (e[i] - mx > -100.f) ? ex2a(e[i] - mx) : 0.f;
-          sum += e[i];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float inv = 1.f / sum;
-#pragma unroll
-        for (int i = 0; i < SPL; ++i)
-          if (e[i] != 0.f) atomicAdd(&occ[ext[i]], e[i] * inv);
+        for (int i = 0; i < SPL; ++i) bdst[i] = bt[i];
       }
-      __syncwarp();
-      for (int v = lane; v < V; v += 32) {
-        const float y = ex2a((row[v] - lt) * kLog2e);
-        gr[static_cast<size_t>(t) * V + v] = feasible ? (y - occ[v]) : __int_as_float(0x7fc00000);
-      }
-      __syncwarp();
     }
     __syncwarp();
+  }
+}
+
+// d nll_b / d logits[b,t,:] = softmax(logits[b,t,:]) - occupancy_t, occupancy_t(v) = sum_{s: ext(s)=v} alpha_t(s) beta_t(s) / y_t(v)
+// normalised per frame (in exact arithmetic the sum over s is p(l|x) at every t; normalising by the per-frame sum keeps
+// fp32 drift out of the gradient: each row sums to zero to rounding). One warp per frame, alphas/betas from the sweep's
+// workspace (log2 domain, state s = lane*SPL + i).
+constexpr int kGradWarps = 8;
+template <int SPL>
+__global__ void __launch_bounds__(kGradWarps * 32)
+ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
+                const float* __restrict__ nll, const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws, float* __restrict__ grad) {
+  extern __shared__ __align__(16) float smem_cg[];  // [kGradWarps][Vpad]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Vpad = (V + 31) & ~31;
+  float* occ = smem_cg + warp * Vpad;
+  const int64_t frame = static_cast<int64_t>(blockIdx.x) * kGradWarps + warp;
+  if (frame >= static_cast<int64_t>(B) * T) return;
+  const int b = static_cast<int>(frame / T), t = static_cast<int>(frame % T);
+  const float* row = logits + frame * V;
+  float* gr = grad + frame * V;
+  const int32_t* lab = labels + static_cast<size_t>(b) * L;
+  const float nl = nll[b];
+  const bool feasible = nl < 1.0e29f;  // +inf = no valid alignment (label longer than the frames allow)
+  // frame log-sum-exp
+  float m = -INFINITY;
+  for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float z = 0.f;
+  for (int v = lane; v < V; v += 32) z += __expf(row[v] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+  const float lt = m + __logf(z);
+  for (int v = lane; v < Vpad; v += 32) occ[v] = 0.f;
+  __syncwarp();
+  if (feasible) {
+    int cnt = 0;
+    for (int i = lane; i < L; i += 32) cnt += (lab[i] != blank) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int S = 2 * cnt + 1;
+    const size_t off = (static_cast<size_t>(b) * T + t) * (32 * SPL) + lane * SPL;
+    float e[SPL];
+    int ext[SPL];
+    float mx = kLogZero;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      const int s = lane * SPL + i;
+      int ex = blank;
+      if (s < S && (s & 1)) ex = lab[s >> 1];
+      ext[i] = ex;
+      const float em = (row[ex] - lt) * kLog2e;
+      e[i] = (s < S) ? alpha_ws[off + i] + beta_ws[off + i] - em : kLogZero;
+      mx = fmaxf(mx, e[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      e[i] = (e[i] - mx > -100.f) ? ex2a(e[i] - mx) : 0.f;
+      sum += e[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i)
+      if (e[i] != 0.f) atomicAdd(&occ[ext[i]], e[i] * inv);
+  }
+  __syncwarp();
+  for (int v = lane; v < V; v += 32) {
+    const float y = ex2a((row[v] - lt) * kLog2e);
+    gr[v] = feasible ? (y - occ[v]) : __int_as_float(0x7fc00000);
   }
 }
 
@@ -356,7 +396,7 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
   }
   float* ws = nullptr;
   if (grad != nullptr) {
-    const size_t need = static_cast<size_t>(B) * T * 32 * SPL * sizeof(float);
+    const size_t need = 2 * static_cast<size_t>(B) * T * 32 * SPL * sizeof(float);  // alphas | betas
     if (need > g_alpha_ws_bytes) {
       if (g_alpha_ws != nullptr) ISHARA_CUDA_OK(cudaFree(g_alpha_ws));
       g_alpha_ws = nullptr;
@@ -370,12 +410,28 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
     auto kern = ctc_kernel<5>;
     if (smem > 48 * 1024)
       ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
+    float* bws = ws != nullptr ? ws + static_cast<size_t>(B) * T * 32 * SPL : nullptr;
+    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws);
+    if (grad != nullptr) {
+      ISHARA_CUDA_OK(cudaGetLastError());
+      note_launch();
+      const int64_t frames = static_cast<int64_t>(B) * T;
+      ctc_grad_kernel<5><<<static_cast<unsigned>((frames + kGradWarps - 1) / kGradWarps), kGradWarps * 32, kGradWarps * Vpad * sizeof(float), stream>>>(
+          logits, labels, B, T, V, L, blank, nll, ws, bws, grad);
+    }
   } else {
     auto kern = ctc_kernel<9>;
     if (smem > 48 * 1024)
       ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws);
+    float* bws = ws != nullptr ? ws + static_cast<size_t>(B) * T * 32 * SPL : nullptr;
+    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws);
+    if (grad != nullptr) {
+      ISHARA_CUDA_OK(cudaGetLastError());
+      note_launch();
+      const int64_t frames = static_cast<int64_t>(B) * T;
+      ctc_grad_kernel<9><<<static_cast<unsigned>((frames + kGradWarps - 1) / kGradWarps), kGradWarps * 32, kGradWarps * Vpad * sizeof(float), stream>>>(
+          logits, labels, B, T, V, L, blank, nll, ws, bws, grad);
+    }
   }
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();

@@ -193,11 +193,13 @@ struct TB {
     e.ld_resid = I;
     return gemm(dy, O, WB(base), I, dx, I, false, rowable(I), e);
   }
-  Step wgrad(const bf16* X, int I, int Ivalid, const bf16* Gy, int O, int Ovalid, const std::string& base) {
+  // dW += X^T Gy  (and, with_bias, dbias += column sums of Gy in the same launch)
+  Step wgrad(const bf16* X, int I, int Ivalid, const bf16* Gy, int O, int Ovalid, const std::string& base, bool with_bias = false) {
     float* dW = G(base + ".kernel");
+    float* db = with_bias ? G(base + ".bias") : nullptr;
     const int sms = m->num_sms;
     const int64_t MM = M;
-    return [=](cudaStream_t s) { return wgrad_launch(X, I, Gy, O, dW, Ovalid, MM, I, O, Ivalid, Ovalid, sms, s); };
+    return [=](cudaStream_t s) { return wgrad_launch(X, I, Gy, O, dW, Ovalid, db, MM, I, O, Ivalid, Ovalid, sms, s); };
   }
   Step bias_grad(const bf16* Gy, int ld, int Cvalid, const std::string& base) {
     float* db = G(base + ".bias");
@@ -282,12 +284,12 @@ struct TB {
 
   // ---- modules -------------------------------------------------------------------------------------
   struct BnSite {
-    float *mean, *rstd, *scale, *shift;
+    float *mean, *rstd, *scale, *shift, *coef;
     size_t sum, sumsq, sum1, sum2;
   };
   BnSite bn_site(int C) {
     BnSite b;
-    b.mean = f32(C); b.rstd = f32(C); b.scale = f32(C); b.shift = f32(C);
+    b.mean = f32(C); b.rstd = f32(C); b.scale = f32(C); b.shift = f32(C); b.coef = f32(2 * static_cast<size_t>(C));
     b.sum = stat(C); b.sumsq = stat(C); b.sum1 = stat(C); b.sum2 = stat(C);
     return b;
   }
@@ -315,7 +317,7 @@ struct TB {
     return [=](cudaStream_t s) {
       int r = bn_bwd_reduce_launch(dG, x, sgate, dm, invT, bs.mean, bs.rstd, t->stats + bs.sum1, t->stats + bs.sum2, BB, TT, C, s);
       if (r) return r;
-      return bn_bwd_apply_launch(dG, x, sgate, dm, invT, bs.mean, bs.rstd, g, t->stats + bs.sum1, t->stats + bs.sum2, count, dx, dg, db,
+      return bn_bwd_apply_launch(dG, x, sgate, dm, invT, bs.mean, bs.rstd, g, t->stats + bs.sum1, t->stats + bs.sum2, count, bs.coef, dx, dg, db,
                                  BB, TT, C, s);
     };
   }
@@ -393,8 +395,7 @@ struct TB {
     const bf16* dOut = dout();
     snap(bw, n, dOut, D);
     const bf16* dY = branch_bwd(bw, dOut, p, site, true);
-    bw.push_back(wgrad(Gb, C, C, dY, D, D, n + "_project_conv"));
-    bw.push_back(bias_grad(dY, D, D, n + "_project_conv"));
+    bw.push_back(wgrad(Gb, C, C, dY, D, D, n + "_project_conv", true));
     bw.push_back(dgrad(dY, D, n + "_project_conv", C, gW1));  // dG
     snap(bw, n + ".g", gW1, C);
     {
@@ -416,8 +417,7 @@ struct TB {
       bw.push_back([=](cudaStream_t s) { return dw_train_launch(a, s); });  // dE
     }
     snap(bw, n + ".e", gW1, C);
-    bw.push_back(wgrad(S_in, D, D, gW1, C, C, n + "_expand_conv"));
-    bw.push_back(bias_grad(gW1, C, C, n + "_expand_conv"));
+    bw.push_back(wgrad(S_in, D, D, gW1, C, C, n + "_expand_conv", true));
     bw.push_back(dgrad(gW1, C, n + "_expand_conv", D, din(), dOut));
     finish_module(bw, "");
     return S_out;
@@ -442,8 +442,7 @@ struct TB {
     const bf16* dOut = dout();
     snap(bw, out_name, dOut, D);
     const bf16* dY = branch_bwd(bw, dOut, pb, site, false);
-    bw.push_back(wgrad(Hh, E, E, dY, D, D, base + ".2"));
-    bw.push_back(bias_grad(dY, D, D, base + ".2"));
+    bw.push_back(wgrad(Hh, E, E, dY, D, D, base + ".2", true));
     bw.push_back(dgrad(dY, D, base + ".2", E, gW1));  // dH
     if (site_h) drop_inplace(bw, gW1, E, p, site_h);
     {
@@ -451,8 +450,7 @@ struct TB {
       bw.push_back([=](cudaStream_t s) { return act_bwd_launch(g1, U, g1, nE, TACT_SWISH, s); });  // dU
     }
     snap(bw, base + ".u", gW1, E);
-    bw.push_back(wgrad(XN, D, D, gW1, E, E, base + ".0"));
-    bw.push_back(bias_grad(gW1, E, E, base + ".0"));
+    bw.push_back(wgrad(XN, D, D, gW1, E, E, base + ".0", true));
     bw.push_back(dgrad(gW1, E, base + ".0", D, gD1));  // dXN
     bw.push_back(ln_bwd(gD1, S_in, ln, 1e-6f, dOut, din()));
     finish_module(bw, "");
@@ -543,8 +541,7 @@ struct TB {
       bw.push_back([=](cudaStream_t s) { return gate_bias_launch(dOut, se.gate, se.dg, se.invT, g1, MM, DD, TT, s); });  // dZ
     }
     snap(bw, n + ".conv.z", gD1, D);
-    bw.push_back(wgrad(H2, E, E, gD1, D, D, n + ".conv.conv3"));
-    bw.push_back(bias_grad(gD1, D, D, n + ".conv.conv3"));
+    bw.push_back(wgrad(H2, E, E, gD1, D, D, n + ".conv.conv3", true));
     bw.push_back(dgrad(gD1, D, n + ".conv.conv3", E, gW1));  // dH2
     {
       bf16* g1 = gW1;
@@ -556,8 +553,7 @@ struct TB {
       bw.push_back([=](cudaStream_t s) { return dw_train_launch(a, s); });  // dC1
     }
     snap(bw, n + ".conv.c1", gW2, E);
-    bw.push_back(wgrad(XN, D, D, gW2, E, E, n + ".conv.conv1"));
-    bw.push_back(bias_grad(gW2, E, E, n + ".conv.conv1"));
+    bw.push_back(wgrad(XN, D, D, gW2, E, E, n + ".conv.conv1", true));
     bw.push_back(dgrad(gW2, E, n + ".conv.conv1", D, gD1));  // dXN
     bw.push_back(ln_bwd(gD1, S_in, n + ".conv.norm", 1e-6f, dOut, din()));
     finish_module(bw, "");
@@ -596,8 +592,7 @@ struct TB {
     snap(bw, n + ".x3", dOut, D);
     bw.push_back(ln_bwd(dOut, Rb, n + ".conv.layer_norm", 1e-3f, nullptr, gD1));  // dR
     snap(bw, n + ".conv.r", gD1, D);
-    bw.push_back(wgrad(BNb, D, D, gD1, D, D, n + ".conv.pointwise_conv2"));
-    bw.push_back(bias_grad(gD1, D, D, n + ".conv.pointwise_conv2"));
+    bw.push_back(wgrad(BNb, D, D, gD1, D, D, n + ".conv.pointwise_conv2", true));
     bw.push_back(dgrad(gD1, D, n + ".conv.pointwise_conv2", D, gD2));  // dBN
     bw.push_back(bn_bwd_step(gD2, DWb, nullptr, nullptr, bs, D, n + ".conv.batch_norm", gD2));  // dDW (in place)
     snap(bw, n + ".conv.dw", gD2, D);
@@ -614,8 +609,7 @@ struct TB {
       bw.push_back([=](cudaStream_t s) { return glu_bwd_launch(g2, P1, g1, MM, DD, s); });  // dP1 [M, 2D]
     }
     snap(bw, n + ".conv.p1", gW1, 2 * D);
-    bw.push_back(wgrad(S_in, D, D, gW1, 2 * D, 2 * D, n + ".conv.pointwise_conv1"));
-    bw.push_back(bias_grad(gW1, 2 * D, 2 * D, n + ".conv.pointwise_conv1"));
+    bw.push_back(wgrad(S_in, D, D, gW1, 2 * D, 2 * D, n + ".conv.pointwise_conv1", true));
     bw.push_back(dgrad(gW1, 2 * D, n + ".conv.pointwise_conv1", D, din(), gD1));  // + dR (residual path)
     finish_module(bw, "");
     return S_out;
@@ -643,8 +637,7 @@ struct TB {
       const float alpha = 1.f / static_cast<float>(B);
       bw.push_back([=](cudaStream_t s) { return scale_cast_pad_launch(t->dlogits, dL, MM, V, Vp, alpha, s); });
     }
-    bw.push_back(wgrad(HH, C, C, dL, Vp, V, "classifier"));
-    bw.push_back(bias_grad(dL, Vp, V, "classifier"));
+    bw.push_back(wgrad(HH, C, C, dL, Vp, V, "classifier", true));
     bw.push_back(dgrad(dL, Vp, "classifier", C, gW1));  // dHH
     if (site) drop_inplace(bw, gW1, C, p, site);
     {
@@ -652,8 +645,7 @@ struct TB {
       bw.push_back([=](cudaStream_t s) { return act_bwd_launch(g1, HH, g1, nC, TACT_RELU, s); });
     }
     snap(bw, "head.h", gW1, C);
-    bw.push_back(wgrad(S_in, D, D, gW1, C, C, "top_conv"));
-    bw.push_back(bias_grad(gW1, C, C, "top_conv"));
+    bw.push_back(wgrad(S_in, D, D, gW1, C, C, "top_conv", true));
     bw.push_back(dgrad(gW1, C, "top_conv", D, din()));
     finish_module(bw, "");
   }

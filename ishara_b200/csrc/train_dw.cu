@@ -16,7 +16,7 @@ namespace {
 
 constexpr int kDwThreads = 128;  // x 2 channels = 256-channel slab
 constexpr int kDwChunk = 32;     // output time steps per CTA (forward / data gradient)
-constexpr int kDwWgChunk = 128;  // time steps per CTA (tap gradient): fewer atomics per tap
+constexpr int kDwWgChunk = 64;   // time steps per CTA (tap gradient)
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float swish_f(float x) { return x * sigm(x); }
@@ -25,12 +25,15 @@ __device__ __forceinline__ float swish_d(float x) {
   return s * (1.f + x * (1.f - s));
 }
 
+constexpr int kDwBatch = 8;  // time steps whose loads are issued together (memory-level parallelism; the walk is latency-bound otherwise)
+
 template <int K>
 __global__ void __launch_bounds__(kDwThreads) dw_train_kernel(DwTrainArgs a) {
   const int c = (blockIdx.x * kDwThreads + threadIdx.x) * 2;
   if (c >= a.C) return;
   const int t0 = blockIdx.y * kDwChunk, b = blockIdx.z;
   const int T = a.T, C = a.C;
+  const int t_end = t0 + kDwChunk < T ? t0 + kDwChunk : T;  // exclusive
   float w0[K], w1[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
@@ -40,37 +43,48 @@ __global__ void __launch_bounds__(kDwThreads) dw_train_kernel(DwTrainArgs a) {
   }
   float b0 = 0.f, b1 = 0.f;
   if (a.bias != nullptr) { b0 = a.bias[c]; b1 = a.bias[c + 1]; }
-  const bf16* in = a.in + static_cast<size_t>(b) * T * C + c;
-  bf16* out = a.out + static_cast<size_t>(b) * T * C + c;
-  const bf16* ref = a.mul_ref != nullptr ? a.mul_ref + static_cast<size_t>(b) * T * C + c : nullptr;
+  const bf16* __restrict__ in = a.in + static_cast<size_t>(b) * T * C + c;
+  bf16* __restrict__ out = a.out + static_cast<size_t>(b) * T * C + c;
+  const bf16* __restrict__ ref = a.mul_ref != nullptr ? a.mul_ref + static_cast<size_t>(b) * T * C + c : nullptr;
   float x0[K], x1[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) { x0[j] = 0.f; x1[j] = 0.f; }
   // step s pushes in[s]; afterwards the window holds in[s-K+1 .. s] and produces out[t], t = s - (K-1) + pad_left
-  const int s_begin = t0 - a.pad_left, s_end = t0 + kDwChunk - 1 - a.pad_left + (K - 1);
-  for (int s = s_begin; s <= s_end; ++s) {
+  const int s_begin = t0 - a.pad_left, s_end = t_end - 1 - a.pad_left + (K - 1);
+  const int dt = a.pad_left - (K - 1);  // t = s + dt
+  for (int sb = s_begin; sb <= s_end; sb += kDwBatch) {
+    uint32_t raw[kDwBatch], rr[kDwBatch];
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) { x0[j] = x0[j + 1]; x1[j] = x1[j + 1]; }
-    float v0 = 0.f, v1 = 0.f;
-    if (s >= 0 && s < T) {
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(in + static_cast<size_t>(s) * C);
-      v0 = bf16_lo(u);
-      v1 = bf16_hi(u);
-      if (a.pre_act == TACT_SWISH) { v0 = swish_f(v0); v1 = swish_f(v1); }
+    for (int u = 0; u < kDwBatch; ++u) {
+      const int s = sb + u;
+      raw[u] = (s >= 0 && s < T) ? __ldg(reinterpret_cast<const uint32_t*>(in + static_cast<size_t>(s) * C)) : 0u;  // swish(0) = 0
     }
-    x0[K - 1] = v0;
-    x1[K - 1] = v1;
-    const int t = s - (K - 1) + a.pad_left;
-    if (t >= t0 && t < T) {
-      float y0 = b0, y1 = b1;
+    if (ref != nullptr) {
 #pragma unroll
-      for (int j = 0; j < K; ++j) { y0 = fmaf(w0[j], x0[j], y0); y1 = fmaf(w1[j], x1[j], y1); }
-      if (ref != nullptr) {
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(ref + static_cast<size_t>(t) * C);
-        y0 *= swish_d(bf16_lo(u));
-        y1 *= swish_d(bf16_hi(u));
+      for (int u = 0; u < kDwBatch; ++u) {
+        const int t = sb + u + dt;
+        rr[u] = (t >= t0 && t < t_end) ? __ldg(reinterpret_cast<const uint32_t*>(ref + static_cast<size_t>(t) * C)) : 0u;
       }
-      *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(t) * C) = pack_bf16x2(y0, y1);
+    }
+#pragma unroll
+    for (int u = 0; u < kDwBatch; ++u) {
+#pragma unroll
+      for (int j = 0; j < K - 1; ++j) { x0[j] = x0[j + 1]; x1[j] = x1[j + 1]; }
+      float v0 = bf16_lo(raw[u]), v1 = bf16_hi(raw[u]);
+      if (a.pre_act == TACT_SWISH) { v0 = swish_f(v0); v1 = swish_f(v1); }
+      x0[K - 1] = v0;
+      x1[K - 1] = v1;
+      const int t = sb + u + dt;
+      if (t >= t0 && t < t_end) {
+        float y0 = b0, y1 = b1;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { y0 = fmaf(w0[j], x0[j], y0); y1 = fmaf(w1[j], x1[j], y1); }
+        if (ref != nullptr) {
+          y0 *= swish_d(bf16_lo(rr[u]));
+          y1 *= swish_d(bf16_hi(rr[u]));
+        }
+        *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(t) * C) = pack_bf16x2(y0, y1);
+      }
     }
   }
 }
@@ -81,30 +95,32 @@ __global__ void __launch_bounds__(kDwThreads) dw_wgrad_kernel(const bf16* __rest
   const int c = (blockIdx.x * kDwThreads + threadIdx.x) * 2;
   if (c >= C) return;
   const int t0 = blockIdx.y * kDwWgChunk, b = blockIdx.z;
-  const bf16* in = in_all + static_cast<size_t>(b) * T * C + c;
-  const bf16* dy = dOut + static_cast<size_t>(b) * T * C + c;
+  const bf16* __restrict__ in = in_all + static_cast<size_t>(b) * T * C + c;
+  const bf16* __restrict__ dy = dOut + static_cast<size_t>(b) * T * C + c;
   float x0[K], x1[K], g0[K], g1[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) { x0[j] = x1[j] = g0[j] = g1[j] = 0.f; }
   float sb0 = 0.f, sb1 = 0.f;
-  const int t_hi = (t0 + kDwWgChunk < T ? t0 + kDwWgChunk : T) - 1;
-  const int s_begin = t0 - pad_left, s_end = t_hi - pad_left + (K - 1);
-  for (int s = s_begin; s <= s_end; ++s) {
+  const int t_end = t0 + kDwWgChunk < T ? t0 + kDwWgChunk : T;  // exclusive
+  const int s_begin = t0 - pad_left, s_end = t_end - 1 - pad_left + (K - 1);
+  const int dt = pad_left - (K - 1);
+  for (int sb = s_begin; sb <= s_end; sb += kDwBatch) {
+    uint32_t raw[kDwBatch], dd[kDwBatch];
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) { x0[j] = x0[j + 1]; x1[j] = x1[j + 1]; }
-    float v0 = 0.f, v1 = 0.f;
-    if (s >= 0 && s < T) {
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(in + static_cast<size_t>(s) * C);
-      v0 = bf16_lo(u);
-      v1 = bf16_hi(u);
-      if (pre_act == TACT_SWISH) { v0 = swish_f(v0); v1 = swish_f(v1); }
+    for (int u = 0; u < kDwBatch; ++u) {
+      const int s = sb + u, t = sb + u + dt;
+      raw[u] = (s >= 0 && s < T) ? __ldg(reinterpret_cast<const uint32_t*>(in + static_cast<size_t>(s) * C)) : 0u;
+      dd[u] = (t >= t0 && t < t_end) ? __ldg(reinterpret_cast<const uint32_t*>(dy + static_cast<size_t>(t) * C)) : 0u;  // 0 gradient outside
     }
-    x0[K - 1] = v0;
-    x1[K - 1] = v1;
-    const int t = s - (K - 1) + pad_left;
-    if (t >= t0 && t <= t_hi) {
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(dy + static_cast<size_t>(t) * C);
-      const float d0 = bf16_lo(u), d1 = bf16_hi(u);
+#pragma unroll
+    for (int u = 0; u < kDwBatch; ++u) {
+#pragma unroll
+      for (int j = 0; j < K - 1; ++j) { x0[j] = x0[j + 1]; x1[j] = x1[j + 1]; }
+      float v0 = bf16_lo(raw[u]), v1 = bf16_hi(raw[u]);
+      if (pre_act == TACT_SWISH) { v0 = swish_f(v0); v1 = swish_f(v1); }
+      x0[K - 1] = v0;
+      x1[K - 1] = v1;
+      const float d0 = bf16_lo(dd[u]), d1 = bf16_hi(dd[u]);
       sb0 += d0;
       sb1 += d1;
 #pragma unroll

@@ -301,28 +301,34 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const bf16* _
   }
 }
 
+// per-channel constants of the BatchNorm backward (fp64 sums -> fp32 once, instead of per element) + dgamma / dbeta
+__global__ void bn_bwd_coeff_kernel(const double* __restrict__ sum1, const double* __restrict__ sum2, double inv_count, float* __restrict__ coef,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sum1[c], s2 = sum2[c];
+  coef[c] = static_cast<float>(s1 * inv_count);
+  coef[C + c] = static_cast<float>(s2 * inv_count);
+  dgamma[c] += static_cast<float>(s2);
+  dbeta[c] += static_cast<float>(s1);
+}
+
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const bf16* __restrict__ dG, const bf16* __restrict__ x, const float* __restrict__ sgate,
                                                                     const float* __restrict__ dm, float invT, const float* __restrict__ mean,
                                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                                    const double* __restrict__ sum1, const double* __restrict__ sum2, float inv_count,
-                                                                    bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M,
-                                                                    int C, int T) {
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += kEwThreads) {
-      dgamma[c] += static_cast<float>(sum2[c]);
-      dbeta[c] += static_cast<float>(sum1[c]);
-    }
-  }
+                                                                    const float* __restrict__ coef, bf16* __restrict__ dx, int64_t M, int C, int T) {
   const int c8 = C / 8;
   EW_LOOP(v, M * c8) {
     const int64_t row = v / c8;
     const int c = static_cast<int>(v % c8) * 8;
-    float f[8], d[8], mu[8], rs[8], ga[8];
+    float f[8], d[8], mu[8], rs[8], ga[8], s1[8], s2[8];
     ld8(x + row * C + c, f);
     ld8(dG + row * C + c, d);
     ld8f(mean + c, mu);
     ld8f(rstd + c, rs);
     ld8f(gamma + c, ga);
+    ld8f(coef + c, s1);
+    ld8f(coef + C + c, s2);
     if (sgate != nullptr) {
       float sg[8];
       ld8f(sgate + (row / T) * C + c, sg);
@@ -338,8 +344,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const bf16* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float xh = (f[i] - mu[i]) * rs[i];
-      const float s1 = static_cast<float>(sum1[c + i]) * inv_count, s2 = static_cast<float>(sum2[c + i]) * inv_count;
-      d[i] = ga[i] * rs[i] * (d[i] - s1 - xh * s2);
+      d[i] = ga[i] * rs[i] * (d[i] - s1[i] - xh * s2[i]);
     }
     st8(dx + row * C + c, d);
   }
@@ -399,14 +404,22 @@ __global__ void eca_bwd_kernel(const float* __restrict__ ds, const float* __rest
     dw[j] = (ok && cm >= 0 && cm < C) ? du * m[static_cast<size_t>(b) * C + cm] : 0.f;
   }
   if (ok) dm[i] = acc;
+  __shared__ float wred[8][5];
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     const float s = warp_sum(dw[j]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&dw5[j], s);
+    if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += wred[w][threadIdx.x];
+    atomicAdd(&dw5[threadIdx.x], s);
   }
 }
 
-// ---- LayerNorm backward: one warp per row, lane owns 4-column groups (j*32 + lane)*4 ------------------------
+// ---- LayerNorm backward: a warp takes two rows per iteration (their loads are issued together), lane owns the
+// 4-column groups (j*32 + lane)*4 ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma, float eps,
                                                        const bf16* __restrict__ dresid, bf16* __restrict__ dx, float* __restrict__ dgamma,
                                                        float* __restrict__ dbeta, int64_t M, int D) {
@@ -420,59 +433,72 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
       const float4 g4 = *reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4);
       gam[j][0] = g4.x; gam[j][1] = g4.y; gam[j][2] = g4.z; gam[j][3] = g4.w;
     }
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < M; row += static_cast<int64_t>(gridDim.x) * 8) {
-    float xv[4][4], dv[4][4];
-    float s = 0.f;
+  for (int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * 2; row0 < M; row0 += static_cast<int64_t>(gridDim.x) * 16) {
+    uint2 ux[2][4], ud[2][4], ur[2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < nj) {
-        const size_t o = static_cast<size_t>(row) * D + (j * 32 + lane) * 4;
-        const uint2 ux = *reinterpret_cast<const uint2*>(x + o), ud = *reinterpret_cast<const uint2*>(dy + o);
-        xv[j][0] = bf16_lo(ux.x); xv[j][1] = bf16_hi(ux.x); xv[j][2] = bf16_lo(ux.y); xv[j][3] = bf16_hi(ux.y);
-        dv[j][0] = bf16_lo(ud.x); dv[j][1] = bf16_hi(ud.x); dv[j][2] = bf16_lo(ud.y); dv[j][3] = bf16_hi(ud.y);
-        s += (xv[j][0] + xv[j][1]) + (xv[j][2] + xv[j][3]);
-      }
-    const float mean = warp_sum(s) * invD;
-    float q = 0.f;
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < nj)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { xv[j][e] -= mean; q = fmaf(xv[j][e], xv[j][e], q); }
-    const float rstd = rsqrtf(warp_sum(q) * invD + eps);
-    float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < nj)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float xh = xv[j][e] * rstd;
-          xv[j][e] = xh;
-          ag[j][e] = fmaf(dv[j][e], xh, ag[j][e]);
-          ab[j][e] += dv[j][e];
-          const float dxh = dv[j][e] * gam[j][e];
-          dv[j][e] = dxh;
-          m1 += dxh;
-          m2 = fmaf(dxh, xh, m2);
+      for (int j = 0; j < 4; ++j)
+        if (j < nj) {
+          const bool ok = row0 + r < M;
+          const size_t o = static_cast<size_t>(ok ? row0 + r : row0) * D + (j * 32 + lane) * 4;
+          ux[r][j] = *reinterpret_cast<const uint2*>(x + o);
+          ud[r][j] = *reinterpret_cast<const uint2*>(dy + o);
+          if (dresid != nullptr) ur[r][j] = *reinterpret_cast<const uint2*>(dresid + o);
         }
-    m1 = warp_sum(m1) * invD;
-    m2 = warp_sum(m2) * invD;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < nj) {
-        const size_t o = static_cast<size_t>(row) * D + (j * 32 + lane) * 4;
-        float r[4];
+    for (int r = 0; r < 2; ++r) {
+      if (row0 + r >= M) break;  // warp-uniform
+      float xv[4][4], dv[4][4];
+      float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) r[e] = rstd * (dv[j][e] - m1 - xv[j][e] * m2);
-        if (dresid != nullptr) {
-          const uint2 ur = *reinterpret_cast<const uint2*>(dresid + o);
-          r[0] += bf16_lo(ur.x); r[1] += bf16_hi(ur.x); r[2] += bf16_lo(ur.y); r[3] += bf16_hi(ur.y);
+      for (int j = 0; j < 4; ++j)
+        if (j < nj) {
+          xv[j][0] = bf16_lo(ux[r][j].x); xv[j][1] = bf16_hi(ux[r][j].x); xv[j][2] = bf16_lo(ux[r][j].y); xv[j][3] = bf16_hi(ux[r][j].y);
+          dv[j][0] = bf16_lo(ud[r][j].x); dv[j][1] = bf16_hi(ud[r][j].x); dv[j][2] = bf16_lo(ud[r][j].y); dv[j][3] = bf16_hi(ud[r][j].y);
+          s += (xv[j][0] + xv[j][1]) + (xv[j][2] + xv[j][3]);
         }
-        uint2 uo;
-        uo.x = pack_bf16x2(r[0], r[1]);
-        uo.y = pack_bf16x2(r[2], r[3]);
-        *reinterpret_cast<uint2*>(dx + o) = uo;
-      }
+      const float mean = warp_sum(s) * invD;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nj)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { xv[j][e] -= mean; q = fmaf(xv[j][e], xv[j][e], q); }
+      const float rstd = rsqrtf(warp_sum(q) * invD + eps);
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nj)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float xh = xv[j][e] * rstd;
+            xv[j][e] = xh;
+            ag[j][e] = fmaf(dv[j][e], xh, ag[j][e]);
+            ab[j][e] += dv[j][e];
+            const float dxh = dv[j][e] * gam[j][e];
+            dv[j][e] = dxh;
+            m1 += dxh;
+            m2 = fmaf(dxh, xh, m2);
+          }
+      m1 = warp_sum(m1) * invD;
+      m2 = warp_sum(m2) * invD;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nj) {
+          const size_t o = static_cast<size_t>(row0 + r) * D + (j * 32 + lane) * 4;
+          float rr[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rr[e] = rstd * (dv[j][e] - m1 - xv[j][e] * m2);
+          if (dresid != nullptr) {
+            rr[0] += bf16_lo(ur[r][j].x); rr[1] += bf16_hi(ur[r][j].x); rr[2] += bf16_lo(ur[r][j].y); rr[3] += bf16_hi(ur[r][j].y);
+          }
+          uint2 uo;
+          uo.x = pack_bf16x2(rr[0], rr[1]);
+          uo.y = pack_bf16x2(rr[2], rr[3]);
+          *reinterpret_cast<uint2*>(dx + o) = uo;
+        }
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -680,18 +706,20 @@ int bn_bwd_reduce_launch(const bf16* dG, const bf16* x, const float* sgate, cons
 }
 int bn_bwd_apply_launch(const bf16* dG, const bf16* x, const float* sgate, const float* dm, float invT,
                         const float* mean, const float* rstd, const float* gamma, const double* sum1,
-                        const double* sum2, double count, bf16* dx, float* dgamma, float* dbeta, int B, int T, int C,
+                        const double* sum2, double count, float* coef, bf16* dx, float* dgamma, float* dbeta, int B, int T, int C,
                         cudaStream_t s) {
   REQUIRE(C % 8 == 0, "bn_bwd_apply: C % 8 != 0");
   const int64_t M = static_cast<int64_t>(B) * T;
-  bn_bwd_apply_kernel<<<ew_grid(M * C / 8), kEwThreads, 0, s>>>(dG, x, sgate, dm, invT, mean, rstd, gamma, sum1, sum2,
-                                                                static_cast<float>(1.0 / count), dx, dgamma, dbeta, M, C, T);
+  bn_bwd_coeff_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum1, sum2, 1.0 / count, coef, dgamma, dbeta, C);
+  int r = check("bn_bwd_coeff");
+  if (r) return r;
+  bn_bwd_apply_kernel<<<ew_grid(M * C / 8), kEwThreads, 0, s>>>(dG, x, sgate, dm, invT, mean, rstd, gamma, coef, dx, M, C, T);
   return check("bn_bwd_apply");
 }
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* gamma, float eps, const bf16* dresid, bf16* dx,
                   float* dgamma, float* dbeta, int64_t M, int D, cudaStream_t s) {
   REQUIRE(D % 128 == 0 && D <= 512, "ln_bwd: D must be a multiple of 128, <= 512");
-  const int64_t want = (M + 7) / 8;
+  const int64_t want = (M + 15) / 16;
   const int grid = static_cast<int>(want < 148 * 4 ? want : 148 * 4);
   ln_bwd_kernel<<<grid, 256, 0, s>>>(dy, x, gamma, eps, dresid, dx, dgamma, dbeta, M, D);
   return check("ln_bwd");

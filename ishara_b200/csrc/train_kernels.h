@@ -58,8 +58,8 @@ int bn_bwd_reduce_launch(const bf16* dG, const bf16* x, const float* sgate, cons
                          cudaStream_t s);
 int bn_bwd_apply_launch(const bf16* dG, const bf16* x, const float* sgate, const float* dm, float invT,
                         const float* mean, const float* rstd, const float* gamma, const double* sum1,
-                        const double* sum2, double count, bf16* dx, float* dgamma, float* dbeta, int B, int T, int C,
-                        cudaStream_t s);
+                        const double* sum2, double count, float* coef /* [2C] scratch */, bf16* dx, float* dgamma,
+                        float* dbeta, int B, int T, int C, cudaStream_t s);
 // LayerNorm backward over rows of x [M,D] (statistics recomputed from x): dx = LN'(dy) (+ dresid if non-null);
 // dgamma/dbeta += column sums. D multiple of 128, D <= 512.
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* gamma, float eps, const bf16* dresid, bf16* dx,
@@ -100,7 +100,8 @@ int dw_wgrad_launch(const bf16* dOut, const bf16* in, int pre_act, float* dw, fl
 
 // ---- dense weight gradient (train_wgrad.cu): dW[I,O] += X[M,I]^T @ G[M,O] --------------------------
 // X, G bf16 row-major (ldx, ldg); dW fp32 row-major [Ivalid, ldw] (Keras [in,out]); only i < Ivalid, o < Ovalid stored.
-int wgrad_launch(const bf16* X, int ldx, const bf16* G, int ldg, float* dW, int ldw, int64_t M, int I, int O,
+// dbias (optional): [Ovalid] += column sums of G (the Dense bias gradient), taken from the tiles already in smem.
+int wgrad_launch(const bf16* X, int ldx, const bf16* G, int ldg, float* dW, int ldw, float* dbias, int64_t M, int I, int O,
                  int Ivalid, int Ovalid, int num_sms, cudaStream_t s);
 
 // ---- attention backward (train_attn.cu) ----------------------------------------------------------

@@ -16,8 +16,8 @@ namespace {
 constexpr int kWgBI = 128, kWgBO = 128, kWgBK = 32, kWgLd = 136, kWgThreads = 256;
 
 __global__ void __launch_bounds__(kWgThreads)
-wgrad_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ G, int ldg, float* __restrict__ dW, int ldw, int64_t M,
-             int I, int O, int Ivalid, int Ovalid, int rows_per_split) {
+wgrad_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ G, int ldg, float* __restrict__ dW, int ldw,
+             float* __restrict__ dbias, int64_t M, int I, int O, int Ivalid, int Ovalid, int rows_per_split) {
   __shared__ __align__(16) bf16 Xs[2][kWgBK][kWgLd];
   __shared__ __align__(16) bf16 Gs[2][kWgBK][kWgLd];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -26,6 +26,8 @@ wgrad_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ G, in
   const int64_t m_end = m_begin + rows_per_split < M ? m_begin + rows_per_split : M;
   if (m_begin >= m_end) return;
   const int wi = (warp & 3) * 32, wo = (warp >> 2) * 64;
+  const bool do_bias = dbias != nullptr && blockIdx.y == 0;  // the i-tile-0 CTAs see every row of G for their columns
+  float bsum = 0.f;
   float acc[2][8][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -59,6 +61,11 @@ wgrad_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ G, in
       cp_async_wait<0>();
     }
     __syncthreads();
+    if (do_bias) {
+      const int col = tid & 127, r0 = (tid >> 7) * 16;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) bsum += __bfloat162float(Gs[st][r0 + r][col]);
+    }
 #pragma unroll
     for (int kk = 0; kk < kWgBK / 16; ++kk) {
       uint32_t af[2][4];
@@ -78,6 +85,12 @@ wgrad_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ G, in
     }
     __syncthreads();
   }
+  if (do_bias) {
+    __shared__ float bred[kWgThreads];
+    bred[tid] = bsum;
+    __syncthreads();
+    if (tid < 128 && o0 + tid < Ovalid) atomicAdd(&dbias[o0 + tid], bred[tid] + bred[tid + 128]);
+  }
   const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -93,7 +106,7 @@ wgrad_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ G, in
 
 }  // namespace
 
-int wgrad_launch(const bf16* X, int ldx, const bf16* G, int ldg, float* dW, int ldw, int64_t M, int I, int O,
+int wgrad_launch(const bf16* X, int ldx, const bf16* G, int ldg, float* dW, int ldw, float* dbias, int64_t M, int I, int O,
                  int Ivalid, int Ovalid, int num_sms, cudaStream_t s) {
   if (I % 8 != 0 || O % 8 != 0 || ldx % 8 != 0 || ldg % 8 != 0 || ldw % 2 != 0 || Ovalid % 2 != 0 || Ivalid > I || Ovalid > O) {
     set_last_error("wgrad: I, O, ldx, ldg must be multiples of 8; ldw and Ovalid even");
@@ -108,7 +121,7 @@ int wgrad_launch(const bf16* X, int ldx, const bf16* G, int ldg, float* dW, int 
   int64_t rps = (M + splits - 1) / splits;
   rps = (rps + kWgBK - 1) / kWgBK * kWgBK;
   splits = static_cast<int>((M + rps - 1) / rps);
-  wgrad_kernel<<<dim3(to, ti, splits), kWgThreads, 0, s>>>(X, ldx, G, ldg, dW, ldw, M, I, O, Ivalid, Ovalid, static_cast<int>(rps));
+  wgrad_kernel<<<dim3(to, ti, splits), kWgThreads, 0, s>>>(X, ldx, G, ldg, dW, ldw, dbias, M, I, O, Ivalid, Ovalid, static_cast<int>(rps));
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error(std::string("wgrad: ") + cudaGetErrorString(e)); return 3; }
   note_launch();
