@@ -199,6 +199,13 @@ struct TB {
     float* db = with_bias ? G(base + ".bias") : nullptr;
     const int sms = m->num_sms;
     const int64_t MM = M;
+    static const int use_tc = getenv("ISHARA_WGRAD_TC") ? atoi(getenv("ISHARA_WGRAD_TC")) : 1;
+    if (use_tc && O % 64 == 0) {
+      // tcgen05 path: MN-major operands via TMA; the bias gradient rides along (idle epilogue warps sum the G tiles)
+      auto plan = std::make_shared<WgradTcPlan>();
+      if (!rc) rc = wgrad_tc_plan_init(plan.get(), X, I, Gy, O, MM, I, O, sms);
+      return [=](cudaStream_t s) { return wgrad_tc_launch(plan.get(), dW, Ovalid, db, Ivalid, Ovalid, s); };
+    }
     return [=](cudaStream_t s) { return wgrad_launch(X, I, Gy, O, dW, Ovalid, db, MM, I, O, Ivalid, Ovalid, sms, s); };
   }
   Step bias_grad(const bf16* Gy, int ld, int Cvalid, const std::string& base) {

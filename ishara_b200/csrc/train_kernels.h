@@ -104,6 +104,12 @@ int dw_wgrad_launch(const bf16* dOut, const bf16* in, int pre_act, float* dw, fl
 int wgrad_launch(const bf16* X, int ldx, const bf16* G, int ldg, float* dW, int ldw, float* dbias, int64_t M, int I, int O,
                  int Ivalid, int Ovalid, int num_sms, cudaStream_t s);
 
+// tcgen05 version (train_wgrad_tc.cu): operands read MN-major straight from the row-major activations through TMA.
+// The plan holds the two tensor maps and the grid; build once, launch every step. O must be a multiple of 64.
+struct alignas(64) WgradTcPlan { unsigned char storage[384]; };
+int wgrad_tc_plan_init(WgradTcPlan* p, const bf16* X, int ldx, const bf16* G, int ldg, int64_t M, int I, int O, int num_sms);
+int wgrad_tc_launch(const WgradTcPlan* p, float* dW, int ldw, float* dbias, int Ivalid, int Ovalid, cudaStream_t s);
+
 // ---- attention backward (train_attn.cu) ----------------------------------------------------------
 // qkv / dqkv [B*T, 3*H*dh] per-head interleaved; o / dO [B*T, H*dh]; lse2, dsum scratch [B*H*T] fp32
 struct AttnBwdArgs {
