@@ -284,6 +284,44 @@ def run_ours(args):
            "d2h_bytes_per_step": int(world * (B * T * 4 + B * 4 + B * 4)),
            "api": "IsharaModel.infer(x_host, labels) -> ishara_model_infer_host"}
 
+    # ---- training step (64 sequences per GPU, fwd + CTC + bwd + clip + AdamW) ----
+    train = None
+    if not args.no_train:
+        from ishara_b200.parallel import DataParallelTrainer
+
+        Bt = args.train_batch
+        mt = ib.get_model(device=local, seed=77)  # same weights on every rank (data-parallel replicas)
+        mt.train_config(0.2, seed=1000 + rank)    # dropout_rate=0.2 as in the reference's get_model call (c7:80)
+        mt.compile()                              # AdamW lr 4.5e-3, wd 0.08, clip-norm 1.0 (BASELINE.json cfg3)
+        trainer = DataParallelTrainer(mt)
+        txs = [torch.randn(Bt, T, F, device=dev, generator=torch.Generator(dev).manual_seed(9000 + 100 * rank + i)) for i in range(N_ROT)]
+        tlab = labels[:Bt].contiguous() if Bt <= B else labels.repeat((Bt + B - 1) // B, 1)[:Bt].contiguous()
+        k_train = max(3, min(args.steps, 20))
+        losses = []
+        for i in range(3):
+            losses.append(trainer.train_step(txs[i % N_ROT], tlab))
+        sync_all()
+        l0 = lib.ishara_launch_count()
+        e0.record(stream)
+        for i in range(k_train):
+            losses.append(trainer.train_step(txs[i % N_ROT], tlab))
+        e1.record(stream)
+        sync_all()
+        tms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([tms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t.item())
+        train = {"metric": "training sequences/sec at T=384 (forward + CTC + backward + clip-norm + AdamW)",
+                 "value": world * Bt * k_train / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms / k_train, "steps": k_train,
+                 "warmup": 3, "batch_per_gpu": Bt, "scaling": "weak", "dtype": "bf16 activations, fp32 master weights/gradients/moments",
+                 "gpu_launches_per_step": int(lib.ishara_launch_count() - l0) // k_train,
+                 "step_tflops": world * Bt * k_train * 3 * 6.367e9 / (tms * 1e-3) / 1e12,
+                 "loss_first": losses[0], "loss_last": losses[-1], "dropout_rate": 0.2,
+                 "exchange": None if world == 1 else "one NCCL all-reduce (sum) over the flat fp32 gradient buffer per step",
+                 "api": "DataParallelTrainer.train_step -> ishara_model_train_forward_backward / _apply"}
+        mt.close()
+
     # ---- per-launch device times of the same step (rank 0), profiled pass ----
     roof = kernels = None
     if rank == 0:
@@ -344,6 +382,7 @@ def run_ours(args):
             "model_flops_per_seq": 6.367e9,
             "whole_step_tflops": value / world * 6.367e9 / 1e12,
             "kernels": kernels,
+            "train": train,
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
@@ -361,6 +400,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
+    ap.add_argument("--train-batch", type=int, default=64, help="sequences per GPU per training step (cfg3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -113,9 +113,19 @@ class DataParallelTrainer:
     def train_step(self, x, labels) -> float:
         """x/labels = THIS rank's shard. Returns the mean loss over all ranks."""
         loss = self.model.forward_backward(x, labels)
+        stream = 0
         if self.world > 1:
-            allreduce_sum_(self._grad_view())
-        self.model.apply_gradients(grad_scale=1.0 / self.world)
+            g = self._grad_view()
+            allreduce_sum_(g)
+            if g.is_cuda:  # the update must queue behind the all-reduce: same (torch current) stream
+                import torch
+
+                stream = int(torch.cuda.current_stream(g.device).cuda_stream)
+        elif hasattr(x, "is_cuda") and x.is_cuda:
+            import torch
+
+            stream = int(torch.cuda.current_stream(x.device).cuda_stream)
+        self.model.apply_gradients(1.0 / self.world, stream) if stream else self.model.apply_gradients(1.0 / self.world)
         if self.world > 1:
             import torch
 
