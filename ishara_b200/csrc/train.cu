@@ -165,8 +165,12 @@ struct TB {
     GemmPlan& p = *plan;
     p.M = M; p.N = N; p.K = K;
     p.out_f32 = out_f32;
+    // ISHARA_TRAIN_BN: tile shape of the D-wide (N == 256) products. 0 = full-row kernel (192 tiles at B = 64: 1.3 waves
+    // on 148 SMs), 128 = plain kernel with 128-column tiles (384 tiles: better tail), 256 = plain kernel, full width.
+    static const int train_bn = getenv("ISHARA_TRAIN_BN") ? atoi(getenv("ISHARA_TRAIN_BN")) : 0;
+    if (row_mode && N == 256 && (train_bn == 128 || train_bn == 256)) row_mode = false;
     p.row_mode = row_mode;
-    p.block_n = out_f32 ? 64 : (row_mode ? N : wide_bn(N));
+    p.block_n = out_f32 ? 64 : (row_mode ? N : (N == 256 && train_bn == 128 ? 128 : wide_bn(N)));
     epi.rows_per_seq = T;
     p.epi = epi;
     if (!rc) rc = gemm_plan_init(&p, A, K, Wt, out, nout, nout, nullptr, 0);
