@@ -420,25 +420,27 @@ __global__ void eca_bwd_kernel(const float* __restrict__ ds, const float* __rest
 
 // ---- LayerNorm backward: a warp takes two rows per iteration (their loads are issued together), lane owns the
 // 4-column groups (j*32 + lane)*4 ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma, float eps,
-                                                       const bf16* __restrict__ dresid, bf16* __restrict__ dx, float* __restrict__ dgamma,
-                                                       float* __restrict__ dbeta, int64_t M, int D) {
-  __shared__ float red[2][8][512];
-  const int nj = D / 128, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <int NJ>
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma, float eps,
+                                                          const bf16* __restrict__ dresid, bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, int64_t M, int D) {
+  __shared__ float red[2][8][NJ * 128];
+  constexpr int nj = NJ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float invD = 1.f / static_cast<float>(D);
-  float gam[4][4], ag[4][4] = {}, ab[4][4] = {};
+  float gam[NJ][4], ag[NJ][4] = {}, ab[NJ][4] = {};
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < NJ; ++j)
     if (j < nj) {
       const float4 g4 = *reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4);
       gam[j][0] = g4.x; gam[j][1] = g4.y; gam[j][2] = g4.z; gam[j][3] = g4.w;
     }
   for (int64_t row0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * 2; row0 < M; row0 += static_cast<int64_t>(gridDim.x) * 16) {
-    uint2 ux[2][4], ud[2][4], ur[2][4];
+    uint2 ux[2][NJ], ud[2][NJ], ur[2][NJ];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NJ; ++j)
         if (j < nj) {
           const bool ok = row0 + r < M;
           const size_t o = static_cast<size_t>(ok ? row0 + r : row0) * D + (j * 32 + lane) * 4;
@@ -449,10 +451,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       if (row0 + r >= M) break;  // warp-uniform
-      float xv[4][4], dv[4][4];
+      float xv[NJ][4], dv[NJ][4];
       float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NJ; ++j)
         if (j < nj) {
           xv[j][0] = bf16_lo(ux[r][j].x); xv[j][1] = bf16_hi(ux[r][j].x); xv[j][2] = bf16_lo(ux[r][j].y); xv[j][3] = bf16_hi(ux[r][j].y);
           dv[j][0] = bf16_lo(ud[r][j].x); dv[j][1] = bf16_hi(ud[r][j].x); dv[j][2] = bf16_lo(ud[r][j].y); dv[j][3] = bf16_hi(ud[r][j].y);
@@ -461,14 +463,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
       const float mean = warp_sum(s) * invD;
       float q = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NJ; ++j)
         if (j < nj)
 #pragma unroll
           for (int e = 0; e < 4; ++e) { xv[j][e] -= mean; q = fmaf(xv[j][e], xv[j][e], q); }
       const float rstd = rsqrtf(warp_sum(q) * invD + eps);
       float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NJ; ++j)
         if (j < nj)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
       m1 = warp_sum(m1) * invD;
       m2 = warp_sum(m2) * invD;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NJ; ++j)
         if (j < nj) {
           const size_t o = static_cast<size_t>(row0 + r) * D + (j * 32 + lane) * 4;
           float rr[4];
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < NJ; ++j)
     if (j < nj)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -720,8 +722,13 @@ int ln_bwd_launch(const bf16* dy, const bf16* x, const float* gamma, float eps, 
                   float* dgamma, float* dbeta, int64_t M, int D, cudaStream_t s) {
   REQUIRE(D % 128 == 0 && D <= 512, "ln_bwd: D must be a multiple of 128, <= 512");
   const int64_t want = (M + 15) / 16;
-  const int grid = static_cast<int>(want < 148 * 4 ? want : 148 * 4);
-  ln_bwd_kernel<<<grid, 256, 0, s>>>(dy, x, gamma, eps, dresid, dx, dgamma, dbeta, M, D);
+  const int grid = static_cast<int>(want < 148 * 2 ? want : 148 * 2);  // 2 resident CTAs per SM: fewer, fatter CTAs = fewer gamma/beta atomics
+  switch (D / 128) {
+    case 1: ln_bwd_kernel<1><<<grid, 256, 0, s>>>(dy, x, gamma, eps, dresid, dx, dgamma, dbeta, M, D); break;
+    case 2: ln_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, x, gamma, eps, dresid, dx, dgamma, dbeta, M, D); break;
+    case 3: ln_bwd_kernel<3><<<grid, 256, 0, s>>>(dy, x, gamma, eps, dresid, dx, dgamma, dbeta, M, D); break;
+    default: ln_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, x, gamma, eps, dresid, dx, dgamma, dbeta, M, D); break;
+  }
   return check("ln_bwd");
 }
 int colsum_launch(const bf16* g, int ld, float* out, int64_t M, int Cvalid, cudaStream_t s) {

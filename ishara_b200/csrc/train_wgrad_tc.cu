@@ -9,6 +9,7 @@
 // per-warp smem transpose -> coalesced fp32 red.global.add). Reads X and G once per tile row/column (L2-resident
 // re-reads), so the launch is HBM-bound for I, O <= 768.
 #include <cstdio>
+#include <cstdlib>
 
 #include "ptx.cuh"
 #include "train_kernels.h"
@@ -38,7 +39,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, float* __restrict__ dW, int ldw,
-                float* __restrict__ dbias, int M, int Ivalid, int Ovalid, int BN, int rows_per_split) {
+                float* __restrict__ dbias, int M, int Ivalid, int Ovalid, int BN, int rows_per_split, int dbg) {
   extern __shared__ uint8_t smem_wg_raw[];
   uint8_t* smem_wg = smem_wg_raw + (((smem_u32(smem_wg_raw) + 1023u) & ~1023u) - smem_u32(smem_wg_raw));  // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* stages = smem_wg;
@@ -145,7 +146,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
           const int i = i0 + q * 32 + rr;
-          if (i < Ivalid) atomicAdd(dW + static_cast<size_t>(i) * ldw + o, buf[rr * 33 + lane]);
+          if (i < Ivalid && !(dbg & 1)) atomicAdd(dW + static_cast<size_t>(i) * ldw + o, buf[rr * 33 + lane]);
         }
       }
       __syncwarp();
@@ -189,12 +190,13 @@ int wgrad_tc_plan_init(WgradTcPlan* p, const bf16* X, int ldx, const bf16* G, in
 int wgrad_tc_launch(const WgradTcPlan* p, float* dW, int ldw, float* dbias, int Ivalid, int Ovalid, cudaStream_t s) {
   const WgradTcPlanImpl* q = reinterpret_cast<const WgradTcPlanImpl*>(p);
   const size_t smem = static_cast<size_t>(kTcStages) * kTcStageBytes + 128 + 4 * kTcEpiFloats * sizeof(float) + 1024;
+  static const int dbg = getenv("ISHARA_WGRAD_DBG") ? atoi(getenv("ISHARA_WGRAD_DBG")) : 0;  // bit 0: skip the atomics (timing bisect only)
   static bool attr_done = false;
   if (!attr_done) {
     ISHARA_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_done = true;
   }
-  wgrad_tc_kernel<<<dim3(q->to, q->ti, q->splits), kTcThreads, smem, s>>>(q->tmX, q->tmG, dW, ldw, dbias, q->M, Ivalid, Ovalid, q->BN, q->rps);
+  wgrad_tc_kernel<<<dim3(q->to, q->ti, q->splits), kTcThreads, smem, s>>>(q->tmX, q->tmG, dW, ldw, dbias, q->M, Ivalid, Ovalid, q->BN, q->rps, dbg);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;
