@@ -120,7 +120,7 @@ typedef struct {
 } ishara_adamw_t;
 
 /* dropout_rate = get_model's dropout_rate (0 disables every dropout site; > 0 also enables the head's fixed 0.4,
- * c7:62; attention-probability dropout c5:113 is not applied); masks are a counter-based hash of (seed, site,
+ * c7:62 and ConformerBlock's default attention dropout 0.1, c5:312); masks are a counter-based hash of (seed, site,
  * element) so forward and backward agree and a host can reproduce them. debug != 0 keeps named activation
  * gradients for ishara_model_train_fetch. */
 ISHARA_API ishara_status_t ishara_model_train_configure(ishara_model_t* m, float dropout_rate, uint64_t seed, int32_t debug);

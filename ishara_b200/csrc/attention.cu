@@ -13,6 +13,7 @@
 // tcgen05 port of this kernel is listed in DESIGN.md §"next".
 #include <cstdlib>
 
+#include "dropout_hash.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -37,7 +38,7 @@ __device__ __forceinline__ float ex2(float x) {
 template <int DH>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const uint8_t* __restrict__ key_mask, int T, int H,
-            int Tp, float scale_log2) {
+            int Tp, float scale_log2, uint32_t drop_thr16, float drop_inv_keep, uint64_t drop_key) {
   constexpr int KS = DH + 8;  // K row stride (elements): conflict-free fragment reads
   extern __shared__ __align__(16) uint8_t smem_at[];
   bf16* Ks = reinterpret_cast<bf16*>(smem_at);                 // [Tp][KS]
@@ -149,6 +150,20 @@ attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const uint8_t*
       l1 = l1 * a1 + ps1;
 #pragma unroll
       for (int n = 0; n < DH / 8; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+      if (drop_thr16 != 0) {
+        // training: dropout on the normalised probabilities = mask the numerators that feed P V, keep the row sums
+        const uint64_t Tpair = static_cast<uint64_t>((T + 1) & ~1);
+        const uint64_t rb0 = ((static_cast<uint64_t>(b) * H + h) * T + r0) * Tpair, rb1 = rb0 + 8 * Tpair;
+#pragma unroll
+        for (int n = 0; n < kKeyChunk / 8; ++n) {
+          const int j = kc + n * 8 + tg * 2;
+          float k0, k1;
+          attn_keep2(drop_key, rb0, j, drop_thr16, drop_inv_keep, k0, k1);
+          s[n][0] *= k0; s[n][1] *= k1;
+          attn_keep2(drop_key, rb1, j, drop_thr16, drop_inv_keep, k0, k1);
+          s[n][2] *= k0; s[n][3] *= k1;
+        }
+      }
       // O += P V : P (C-fragment layout) re-packed as the A operand of the next MMA
 #pragma unroll
       for (int kk = 0; kk < kKeyChunk / 16; ++kk) {
@@ -428,7 +443,7 @@ int launch_inst(const AttnArgs& a, cudaStream_t stream) {
     smem_attr = smem;
   }
   kern<<<dim3(a.H, a.B), kAttnThreads, smem, stream>>>(a.qkv, a.out, a.key_mask, a.T, a.H, Tp,
-                                                      a.scale * 1.4426950408889634f);
+                                                      a.scale * 1.4426950408889634f, a.drop_thr16, a.drop_inv_keep, a.drop_key);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;
@@ -441,7 +456,11 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream);
 
 int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   static const int use_tc = getenv("ISHARA_ATTN_TC") ? atoi(getenv("ISHARA_ATTN_TC")) : 1;
-  if (use_tc && attention_tc_applicable(a)) return attention_tc_launch(a, stream);
+  if (use_tc && a.drop_thr16 == 0 && attention_tc_applicable(a)) return attention_tc_launch(a, stream);
+  if (a.drop_thr16 != 0 && a.pos != nullptr) {
+    set_last_error("attention: dropout is not supported by the relative-position kernel");
+    return 2;
+  }
   if (a.pos != nullptr) {
     if (a.u_bias == nullptr || a.v_bias == nullptr) {
       set_last_error("relpos attention needs u_bias and v_bias");

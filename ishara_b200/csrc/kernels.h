@@ -134,6 +134,10 @@ struct AttnArgs {
   const float* v_bias = nullptr;
   int B = 0, T = 0, H = 0, dh = 0;
   float scale = 1.f;
+  // training only: dropout on the attention probabilities (c5:113); thr16 = 0 disables. See dropout_hash.cuh.
+  uint32_t drop_thr16 = 0;
+  float drop_inv_keep = 1.f;
+  uint64_t drop_key = 0;
 };
 int attention_launch(const AttnArgs& a, cudaStream_t stream);
 

@@ -19,6 +19,7 @@
 #include <functional>
 #include <memory>
 
+#include "dropout_hash.cuh"
 #include "model_internal.h"
 #include "train_kernels.h"
 
@@ -469,20 +470,31 @@ struct TB {
   }
 
   // x + drop(MHSA(LN(x)))   (MultiHeadSelfAttention c5:91-118)
-  bf16* mhsa(const std::string& base, const std::string& ln, const bf16* S_in, const std::string& out_name, bool branch_drop) {
+  // p_attn: dropout on the attention probabilities (c5:113): SqueezeformerBlock passes its dropout, ConformerBlock its
+  // own attn_dropout default 0.1 (c5:312,315)
+  bf16* mhsa(const std::string& base, const std::string& ln, const bf16* S_in, const std::string& out_name, bool branch_drop, float p_attn) {
     const int H = m->cfg.num_heads, dh = D / H;
     bf16* XN = act(D);
     bf16* QKV = act(3 * D, base + ".qkv");
     bf16* O = act(D, base + ".o");
     bf16* S_out = act(D, out_name);
-    const float p = branch_drop ? ts->dropout : 0.f;  // attention-probability dropout (c5:113) is not applied
+    const float p = branch_drop ? ts->dropout : 0.f;
     const float scale = 1.f / std::sqrt(static_cast<float>(D));  // self.scale = dim ** -0.5 (c5:95)
+    const uint32_t site_a = p_attn > 0.f ? ++site_counter : 0;
+    const uint32_t thr_a = p_attn > 0.f ? dropout_thr16(p_attn) : 0;
+    const float inv_a = p_attn > 0.f ? 1.f / (1.f - p_attn) : 1.f;
+    const uint64_t* seedp = &ts->seed;
     ts->fwd.push_back(ln_fwd(S_in, XN, ln, 1e-6f));
     ts->fwd.push_back(linear(XN, D, base + ".qkv", false, 3 * D, QKV));
     {
       AttnArgs a;
       a.qkv = QKV; a.out = O; a.B = B; a.T = T; a.H = H; a.dh = dh; a.scale = scale;
-      ts->fwd.push_back([=](cudaStream_t s) { return attention_launch(a, s); });
+      a.drop_thr16 = thr_a; a.drop_inv_keep = inv_a;
+      ts->fwd.push_back([=](cudaStream_t s) {
+        AttnArgs aa = a;
+        if (site_a) aa.drop_key = dropout_key(*seedp, site_a);
+        return attention_launch(aa, s);
+      });
     }
     const uint32_t site = branch_fwd(O, D, base + ".proj", false, S_in, S_out, p, false);
 
@@ -496,7 +508,12 @@ struct TB {
     {
       AttnBwdArgs a;
       a.qkv = QKV; a.o = O; a.dO = gD1; a.dqkv = gW1; a.lse2 = lse; a.dsum = dsum; a.B = B; a.T = T; a.H = H; a.dh = dh; a.scale = scale;
-      bw.push_back([=](cudaStream_t s) { return attention_bwd_launch(a, s); });
+      a.drop_thr16 = thr_a; a.drop_inv_keep = inv_a;
+      bw.push_back([=](cudaStream_t s) {
+        AttnBwdArgs aa = a;
+        if (site_a) aa.drop_key = dropout_key(*seedp, site_a);
+        return attention_bwd_launch(aa, s);
+      });
     }
     snap(bw, base + ".qkv", gW1, 3 * D);
     bw.push_back(wgrad(XN, D, D, gW1, 3 * D, 3 * D, base + ".qkv"));
@@ -810,7 +827,7 @@ int build_train_program(ishara_model* m, TrainState* ts, int batch, int labels_l
     conv_blocks("squeeze", i);
     const std::string n = "squeezeformer_" + std::to_string(i);
     S = b.ffn(n + ".ffn1", n + ".norm1", S, n + ".x1", true);
-    S = b.mhsa(n + ".mha", n + ".norm2", S, n + ".x2", true);
+    S = b.mhsa(n + ".mha", n + ".norm2", S, n + ".x2", true, ts->dropout);
     S = b.sqz_conv(n, S);
     S = b.ffn(n + ".ffn2", n + ".norm3", S, n, true);
   }
@@ -818,7 +835,7 @@ int build_train_program(ishara_model* m, TrainState* ts, int batch, int labels_l
     conv_blocks("conform", i);
     const std::string n = "conformer_" + std::to_string(i);
     S = b.ffn(n + ".ffn1", n + ".layer_norm1", S, n + ".x1", false);
-    S = b.mhsa(n + ".mha", n + ".layer_norm1", S, n + ".x2", false);  // layer_norm1 reused (c5:330)
+    S = b.mhsa(n + ".mha", n + ".layer_norm1", S, n + ".x2", false, ts->dropout > 0.f ? 0.1f : 0.f);  // layer_norm1 reused (c5:330)
     S = b.conf_conv(n, S);
     S = b.ffn(n + ".ffn2", n + ".layer_norm2", S, n, false);
   }

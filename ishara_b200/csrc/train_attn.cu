@@ -11,6 +11,7 @@
 // Q/dO (kernel 2) are staged once per CTA in shared memory, row-major and transposed.
 #include <cstdio>
 
+#include "dropout_hash.cuh"
 #include "mma.cuh"
 #include "ptx.cuh"
 #include "train_kernels.h"
@@ -108,7 +109,8 @@ __device__ __forceinline__ void strip_acc(float (&out)[DH / 8][4], const float (
 template <int DH>
 __global__ void __launch_bounds__(kAbThreads)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
-                   float* __restrict__ lse_out, float* __restrict__ dsum_out, int T, int H, int Tp, float scale) {
+                   float* __restrict__ lse_out, float* __restrict__ dsum_out, int T, int H, int Tp, float scale, uint32_t drop_thr16,
+                   float drop_inv_keep, uint64_t drop_key) {
   constexpr int KS = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_ab[];
   const int VS = Tp + 8;
@@ -198,6 +200,15 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, con
         const float k0 = key < T ? 0.f : -INFINITY, k1 = key + 1 < T ? 0.f : -INFINITY;
         const float p0 = ex2f(fmaf(s[n][0], scale_log2, k0) - lse0), p1 = ex2f(fmaf(s[n][1], scale_log2, k1) - lse0);
         const float p2 = ex2f(fmaf(s[n][2], scale_log2, k0) - lse1), p3 = ex2f(fmaf(s[n][3], scale_log2, k1) - lse1);
+        if (drop_thr16 != 0) {  // O = (P o M) V  =>  dP = M o (dO V^T); rowsum(dO o O) already includes the mask
+          const uint64_t Tpair = static_cast<uint64_t>((T + 1) & ~1);
+          const uint64_t rb0 = ((static_cast<uint64_t>(b) * H + h) * T + r0) * Tpair;
+          float m0, m1;
+          attn_keep2(drop_key, rb0, key, drop_thr16, drop_inv_keep, m0, m1);
+          dp[n][0] *= m0; dp[n][1] *= m1;
+          attn_keep2(drop_key, rb0 + 8 * Tpair, key, drop_thr16, drop_inv_keep, m0, m1);
+          dp[n][2] *= m0; dp[n][3] *= m1;
+        }
         s[n][0] = p0 * (dp[n][0] - d0); s[n][1] = p1 * (dp[n][1] - d0);
         s[n][2] = p2 * (dp[n][2] - d1); s[n][3] = p3 * (dp[n][3] - d1);
       }
@@ -216,7 +227,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, con
 template <int DH>
 __global__ void __launch_bounds__(kAbThreads)
 attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, bf16* __restrict__ dqkv, const float* __restrict__ lse_in,
-                    const float* __restrict__ dsum_in, int T, int H, int Tp, float scale) {
+                    const float* __restrict__ dsum_in, int T, int H, int Tp, float scale, uint32_t drop_thr16, float drop_inv_keep,
+                    uint64_t drop_key) {
   constexpr int KS = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_ab[];
   const int VS = Tp + 8;
@@ -265,9 +277,18 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, b
         const float2 ls = *reinterpret_cast<const float2*>(lse + q), dd = *reinterpret_cast<const float2*>(dsum + q);
         const float p0 = ex2f(fmaf(st[n][0], scale_log2, -ls.x)), p1 = ex2f(fmaf(st[n][1], scale_log2, -ls.y));
         const float p2 = ex2f(fmaf(st[n][2], scale_log2, -ls.x)), p3 = ex2f(fmaf(st[n][3], scale_log2, -ls.y));
-        st[n][0] = p0; st[n][1] = p1; st[n][2] = p2; st[n][3] = p3;
-        dpt[n][0] = p0 * (dpt[n][0] - dd.x); dpt[n][1] = p1 * (dpt[n][1] - dd.y);
-        dpt[n][2] = p2 * (dpt[n][2] - dd.x); dpt[n][3] = p3 * (dpt[n][3] - dd.y);
+        float m00 = 1.f, m01 = 1.f, m10 = 1.f, m11 = 1.f;  // mask[query q / q+1][key r0 / r1]
+        if (drop_thr16 != 0) {
+          const uint64_t Tpair = static_cast<uint64_t>((T + 1) & ~1);
+          const uint64_t rbq = ((static_cast<uint64_t>(b) * H + h) * T + q) * Tpair;
+          m00 = attn_keep(drop_key, rbq, r0, drop_thr16, drop_inv_keep);
+          m01 = attn_keep(drop_key, rbq + Tpair, r0, drop_thr16, drop_inv_keep);
+          m10 = attn_keep(drop_key, rbq, r1, drop_thr16, drop_inv_keep);
+          m11 = attn_keep(drop_key, rbq + Tpair, r1, drop_thr16, drop_inv_keep);
+        }
+        st[n][0] = p0 * m00; st[n][1] = p1 * m01; st[n][2] = p2 * m10; st[n][3] = p3 * m11;  // (P o M)^T feeds dV
+        dpt[n][0] = p0 * (dpt[n][0] * m00 - dd.x); dpt[n][1] = p1 * (dpt[n][1] * m01 - dd.y);
+        dpt[n][2] = p2 * (dpt[n][2] * m10 - dd.x); dpt[n][3] = p3 * (dpt[n][3] * m11 - dd.y);
       }
       strip_acc<DH>(dv, st, Dt32, VS, qc, g, tg);   // dV += P^T dO
       strip_acc<DH>(dk, dpt, Qt32, VS, qc, g, tg);  // dK += dS^T Q
@@ -305,10 +326,12 @@ int launch_dh(const AttnBwdArgs& a, cudaStream_t s) {
     attr_done = true;
   }
   const dim3 grid(a.H, a.B);
-  attn_bwd_dq_kernel<DH><<<grid, kAbThreads, smem1, s>>>(a.qkv, a.o, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale);
+  attn_bwd_dq_kernel<DH><<<grid, kAbThreads, smem1, s>>>(a.qkv, a.o, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale, a.drop_thr16,
+                                                           a.drop_inv_keep, a.drop_key);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
-  attn_bwd_dkv_kernel<DH><<<grid, kAbThreads, smem2, s>>>(a.qkv, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale);
+  attn_bwd_dkv_kernel<DH><<<grid, kAbThreads, smem2, s>>>(a.qkv, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale, a.drop_thr16, a.drop_inv_keep,
+                                                            a.drop_key);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

@@ -5,6 +5,7 @@
 // grid sized to a few CTAs per SM); the reductions accumulate per-CTA fp32 partials into fp64 / fp32 atomics.
 #include <cstdio>
 
+#include "dropout_hash.cuh"
 #include "ptx.cuh"
 #include "train_kernels.h"
 
@@ -161,12 +162,6 @@ __global__ void __launch_bounds__(kEwThreads) scale_cast_pad_kernel(const float*
 }
 
 // ---- dropout ------------------------------------------------------------------------------------------
-__host__ __device__ inline uint64_t mix64(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
 __global__ void __launch_bounds__(kEwThreads) dropout_kernel(const bf16* __restrict__ x, const bf16* __restrict__ resid, bf16* __restrict__ y, int64_t M,
                                                                int C, int T, uint32_t thr16, float inv_keep, uint64_t key, int per_sample) {
   const int c8 = C / 8;
@@ -666,8 +661,8 @@ int scale_cast_pad_launch(const float* in, bf16* out, int64_t M, int V, int Vpad
 int dropout_launch(const bf16* x, const bf16* resid, bf16* y, int64_t M, int C, int T, float p, uint64_t seed,
                    uint32_t site, int per_sample, cudaStream_t s) {
   REQUIRE(C % 8 == 0 && p >= 0.f && p < 1.f, "dropout: bad arguments");
-  const uint32_t thr = static_cast<uint32_t>(p * 65536.f);
-  const uint64_t key = mix64(seed ^ mix64((static_cast<uint64_t>(site) << 32) | 0x5bd1e995ull));
+  const uint32_t thr = dropout_thr16(p);
+  const uint64_t key = dropout_key(seed, site);
   dropout_kernel<<<ew_grid(M * C / 8), kEwThreads, 0, s>>>(x, resid, y, M, C, T, thr, 1.f / (1.f - p), key, per_sample);
   return check("dropout");
 }

@@ -118,6 +118,9 @@ struct AttnBwdArgs {
   float *lse2 = nullptr, *dsum = nullptr;
   int B = 0, T = 0, H = 0, dh = 0;
   float scale = 1.f;
+  uint32_t drop_thr16 = 0;  // same dropout mask as the forward (AttnArgs)
+  float drop_inv_keep = 1.f;
+  uint64_t drop_key = 0;
 };
 int attention_bwd_launch(const AttnBwdArgs& a, cudaStream_t s);
 

@@ -352,7 +352,9 @@ class IsharaModel:
         """The keep/(1-p) masks the training kernels apply for (seed, rate), recomputed on the host from the same
         counter-based hash (train_ew.cu: mix64). Keys follow the reference's layer structure: '<conv1dblock>.drop'
         [B,1,1] (c5:83), '<block>.ffnK.drop' [B,T,E] (c5:164,179,242), 'squeezeformer_i.drop{1,2,3}' [B,T,D]
-        (c5:190,196,205), 'head.drop' [B,T,2D] (c7:62, fixed 0.4). Lets a CPU restatement reproduce a step exactly."""
+        (c5:190,196,205), '<block>.mha.attn_drop' [B,H,T,T] (c5:113; rate = dropout_rate in SqueezeformerBlock, the
+        default attn_dropout 0.1 in ConformerBlock), 'head.drop' [B,T,2D] (c7:62, fixed 0.4). Lets a CPU restatement
+        reproduce a step exactly."""
         p = self.dropout_rate if rate is None else float(rate)
         if p <= 0:
             return {}
@@ -394,6 +396,25 @@ class IsharaModel:
             u = (r & np.uint64(0xFFFF)).astype(np.uint32)
             return np.where(u >= t16, inv, np.float32(0)).astype(np.float32).reshape(batch, 1, 1)
 
+        def attention(site, q):
+            t16, inv = thr(q)
+            H, Tp = c.num_heads, (T + 1) & ~1
+            k = int(key(site))
+            with np.errstate(over="ignore"):
+                rows = np.arange(batch * H * T, dtype=np.uint64)[:, None]
+                j = np.arange(T, dtype=np.uint64)[None, :]
+                idx = (rows * np.uint64(Tp) + j) >> np.uint64(1)
+                x = ((idx & np.uint64(0xFFFFFFFF)).astype(np.uint32) * np.uint32(0x9E3779B1)
+                     + (idx >> np.uint64(32)).astype(np.uint32) * np.uint32(0x85EBCA77) + np.uint32(k & 0xFFFFFFFF))
+                x ^= x >> np.uint32(16)
+                x *= np.uint32(0x85EBCA6B)
+                x ^= x >> np.uint32(13)
+                x *= np.uint32(0xC2B2AE35)
+                x ^= x >> np.uint32(16)
+                x ^= np.uint32(k >> 32)
+                u = (x >> (np.uint32(16) * (j & np.uint64(1)).astype(np.uint32))) & np.uint32(0xFFFF)
+            return np.where(u >= t16, inv, np.float32(0)).astype(np.float32).reshape(batch, H, T, T)
+
         masks: Dict[str, np.ndarray] = {}
         site = 0
 
@@ -416,12 +437,16 @@ class IsharaModel:
             n = f"squeezeformer_{i}"
             ffn(n + ".ffn1", n + ".drop1")
             site += 1
+            masks[n + ".mha.attn_drop"] = attention(site, p)
+            site += 1
             masks[n + ".drop2"] = elementwise(site, D, p)
             ffn(n + ".ffn2", n + ".drop3")
         for i in range(c.num_conv_conform_blocks):
             conv_blocks("conform", i)
             n = f"conformer_{i}"
             ffn(n + ".ffn1", None)
+            site += 1
+            masks[n + ".mha.attn_drop"] = attention(site, 0.1)
             ffn(n + ".ffn2", None)
         site += 1
         masks["head.drop"] = elementwise(site, 2 * D, 0.4)

@@ -149,6 +149,8 @@ def test_dropout_masks_reproduce_on_the_host():
     masks = m.dropout_masks(B, 1234, 0.2)
     assert abs(float((masks["squeezeformer_0.ffn1.drop"] == 0).mean()) - 0.2) < 0.01
     assert abs(float((masks["head.drop"] == 0).mean()) - 0.4) < 0.01
+    assert abs(float((masks["squeezeformer_0.mha.attn_drop"] == 0).mean()) - 0.2) < 0.01
+    assert abs(float((masks["conformer_0.mha.attn_drop"] == 0).mean()) - 0.1) < 0.01   # ConformerBlock default (c5:312)
     ref = TO.forward_train(p, x, y, cfg, dropout_masks=masks)
     assert abs(loss - ref["loss"]) <= 2e-3 * abs(ref["loss"]), (loss, ref["loss"])
     names = sorted(ref["grads"])
