@@ -12,6 +12,8 @@
  *   ishara_model_train_*                         <- model.fit's inner step: model(x, training=True), CTCLoss,
  *                                                   gradients, clip-norm + AdamW        c12:1, c7:67-70,
  *                                                   integration.py:675-679,750
+ *   ishara_preprocess                            <- pre_process00 + pre_process1 (landmark gather, hand-frame filter,
+ *                                                   resize_pad, normalise)       c3:1-115, c13:9-15
  *   ishara_op_*                                  <- operator-level building blocks (tests, P-rows of §8a)
  *
  * Conventions
@@ -103,6 +105,17 @@ ISHARA_API ishara_status_t ishara_model_forward_host(ishara_model_t* m, const fl
 ISHARA_API ishara_status_t ishara_model_infer_host(ishara_model_t* m, const float* x_host, int32_t batch,
                                         const int32_t* labels_host, int32_t max_label_len, float* logits_host,
                                         int32_t* ids_host, int32_t* lens_host, float* nll_host);
+
+/* ---- landmark preprocessing -----------------------------------------------
+ * The step in front of the model call: TFLiteModel.__call__ c13:9-15 = pre_process00 (c3:57-101) + pre_process1
+ * (c3:103-115). frames_dev fp32 [total_frames, 276] holds the batch's sequences back to back in the reference's SEL_COLS
+ * order (c1:22-26); offsets_dev int32 [batch+1] are frame offsets (a sequence may be empty: it becomes one zero frame,
+ * c13:11); mean_dev / std_dev fp32 [276] are the per-group statistics laid out in OUTPUT column order (lip, rhand,
+ * lhand, rpose, lpose; landmark-major, xyz-minor); out_dev fp32 [batch, frame_len, 276] is the model input.
+ * filter_frames != 0 applies the hand-frame filter (inference path); 0 = training path (pre_process1 only). */
+ISHARA_API ishara_status_t ishara_preprocess(const float* frames_dev, const int32_t* offsets_dev, int32_t batch, int32_t max_frames,
+                                             const float* mean_dev, const float* std_dev, int32_t frame_len, int32_t filter_frames,
+                                             float* out_dev, void* stream);
 
 /* ---- training step ----------------------------------------------------
  * Keras training-mode forward (BatchNormalization on biased batch statistics over (B,T) + moving-average update,

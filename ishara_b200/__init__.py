@@ -11,11 +11,12 @@ from ._lib import IsharaError
 from .model import (CTCLoss, FALLBACK_IDS, IsharaModel, char_to_num, decode_batch_predictions, decode_ids,
                     decode_phrase, get_model, num_to_char, num_to_char_fn, pad_token, pad_token_idx,
                     tflite_postprocess)
+from .preprocess import LandmarkPreprocessor, sel_cols
 
 _lib.load()  # fail at import time if the CUDA library is missing
 
 __all__ = [
     "get_model", "IsharaModel", "CTCLoss", "decode_phrase", "decode_batch_predictions", "decode_ids",
     "num_to_char_fn", "tflite_postprocess", "char_to_num", "num_to_char", "pad_token", "pad_token_idx",
-    "FALLBACK_IDS", "DeviceTensor", "from_host", "IsharaError",
+    "FALLBACK_IDS", "DeviceTensor", "from_host", "IsharaError", "LandmarkPreprocessor", "sel_cols",
 ]

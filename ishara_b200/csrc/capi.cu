@@ -467,6 +467,17 @@ ishara_status_t ishara_stream_synchronize(int32_t device, void* stream) {
   return ISHARA_OK;
 }
 
+ishara_status_t ishara_preprocess(const float* frames_dev, const int32_t* offsets_dev, int32_t batch, int32_t max_frames,
+                                  const float* mean_dev, const float* std_dev, int32_t frame_len, int32_t filter_frames, float* out_dev,
+                                  void* stream) {
+  if (offsets_dev == nullptr || mean_dev == nullptr || std_dev == nullptr || out_dev == nullptr || (frames_dev == nullptr && max_frames > 0)) {
+    set_last_error("preprocess: null argument");
+    return ISHARA_ERR_INVALID;
+  }
+  return static_cast<ishara_status_t>(preprocess_launch(frames_dev, offsets_dev, batch, max_frames, mean_dev, std_dev, frame_len,
+                                                        filter_frames, out_dev, static_cast<cudaStream_t>(stream)));
+}
+
 // ---- training step (train.cu) ---------------------------------------------------------------------
 ishara_status_t ishara_model_train_configure(ishara_model_t* m, float dropout_rate, uint64_t seed, int32_t debug) {
   CHECK_HANDLE(m);

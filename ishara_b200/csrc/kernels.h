@@ -184,6 +184,12 @@ struct Conv2dSubsampleArgs {
 };
 int conv2d_subsample_launch(const Conv2dSubsampleArgs& a, cudaStream_t stream);
 
+// ---- landmark preprocessing (preprocess.cu) --------------------------------
+// frames fp32 [total_frames, 276] (SEL_COLS order), offsets int32 [B+1]; mean / stdv [276] in OUTPUT column order;
+// out fp32 [B, T, 276]. filter != 0 applies the hand-frame filter of pre_process00.
+int preprocess_launch(const float* frames, const int32_t* offsets, int B, int max_frames, const float* mean, const float* stdv, int T,
+                      int filter, float* out, cudaStream_t stream);
+
 // ---- CTC + greedy decode ----------------------------------------------------------------------
 // logits fp32 [B,T,V]; labels int32 [B,L] padded with `blank`; nll [B]; grad [B,T,V] or null
 // (grad = d nll_b / d logits, unreduced).
