@@ -106,6 +106,12 @@ ISHARA_API ishara_status_t ishara_model_infer_host(ishara_model_t* m, const floa
                                         const int32_t* labels_host, int32_t max_label_len, float* logits_host,
                                         int32_t* ids_host, int32_t* lens_host, float* nll_host);
 
+/* ---- scorer -----------------------------------------------------------------
+ * Levenshtein distances of n (prediction, target) byte-string pairs, the `distance` call of the evaluation loop
+ * c18:1-15 (score = (len(target) - distance) / len(target)). Host function; strings need not be NUL-terminated. */
+ISHARA_API ishara_status_t ishara_edit_distances(const char* const* preds, const int32_t* pred_lens, const char* const* targets,
+                                                 const int32_t* target_lens, int32_t n, int32_t* out_distances);
+
 /* ---- landmark preprocessing -----------------------------------------------
  * The step in front of the model call: TFLiteModel.__call__ c13:9-15 = pre_process00 (c3:57-101) + pre_process1
  * (c3:103-115). frames_dev fp32 [total_frames, 276] holds the batch's sequences back to back in the reference's SEL_COLS

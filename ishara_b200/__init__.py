@@ -12,6 +12,7 @@ from .model import (CTCLoss, FALLBACK_IDS, IsharaModel, char_to_num, decode_batc
                     decode_phrase, get_model, num_to_char, num_to_char_fn, pad_token, pad_token_idx,
                     tflite_postprocess)
 from .preprocess import LandmarkPreprocessor, sel_cols
+from .deploy import TFLiteModel, edit_distances, levenshtein_scores
 
 _lib.load()  # fail at import time if the CUDA library is missing
 
@@ -19,4 +20,5 @@ __all__ = [
     "get_model", "IsharaModel", "CTCLoss", "decode_phrase", "decode_batch_predictions", "decode_ids",
     "num_to_char_fn", "tflite_postprocess", "char_to_num", "num_to_char", "pad_token", "pad_token_idx",
     "FALLBACK_IDS", "DeviceTensor", "from_host", "IsharaError", "LandmarkPreprocessor", "sel_cols",
+    "TFLiteModel", "edit_distances", "levenshtein_scores",
 ]

@@ -467,6 +467,37 @@ ishara_status_t ishara_stream_synchronize(int32_t device, void* stream) {
   return ISHARA_OK;
 }
 
+ishara_status_t ishara_edit_distances(const char* const* preds, const int32_t* pred_lens, const char* const* targets,
+                                      const int32_t* target_lens, int32_t n, int32_t* out) {
+  if (n < 0 || (n > 0 && (preds == nullptr || pred_lens == nullptr || targets == nullptr || target_lens == nullptr || out == nullptr))) {
+    set_last_error("edit_distances: null argument");
+    return ISHARA_ERR_INVALID;
+  }
+  std::vector<int32_t> row;
+  for (int32_t i = 0; i < n; ++i) {
+    const char *a = preds[i], *b = targets[i];
+    const int la = pred_lens[i], lb = target_lens[i];
+    if (la < 0 || lb < 0 || (la > 0 && a == nullptr) || (lb > 0 && b == nullptr)) {
+      set_last_error("edit_distances: bad string");
+      return ISHARA_ERR_INVALID;
+    }
+    row.resize(static_cast<size_t>(lb) + 1);
+    for (int j = 0; j <= lb; ++j) row[j] = j;
+    for (int p = 1; p <= la; ++p) {
+      int32_t diag = row[0];
+      row[0] = p;
+      for (int j = 1; j <= lb; ++j) {
+        const int32_t sub = diag + (a[p - 1] == b[j - 1] ? 0 : 1);
+        diag = row[j];
+        const int32_t del = row[j] + 1, ins = row[j - 1] + 1;
+        row[j] = sub < del ? (sub < ins ? sub : ins) : (del < ins ? del : ins);
+      }
+    }
+    out[i] = row[lb];
+  }
+  return ISHARA_OK;
+}
+
 ishara_status_t ishara_preprocess(const float* frames_dev, const int32_t* offsets_dev, int32_t batch, int32_t max_frames,
                                   const float* mean_dev, const float* std_dev, int32_t frame_len, int32_t filter_frames, float* out_dev,
                                   void* stream) {

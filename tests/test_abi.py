@@ -151,3 +151,28 @@ def test_dlpack_view_of_numpy_is_rejected_as_device_operand():
     assert v.shape == (2, 3) and v.dtype == "float32" and not v.on_cuda
     with pytest.raises(ValueError):
         _dlpack.view(np.zeros((4, 4), np.float32)[:, ::2])
+
+
+def test_edit_distances_host_function():
+    """ishara_edit_distances is a host function: known answers + a brute-force DP (c18:1-15 scorer)."""
+    import random
+
+    from ishara_b200 import edit_distances, levenshtein_scores
+
+    def dp(a, b):
+        prev = list(range(len(b) + 1))
+        for i, ca in enumerate(a, 1):
+            cur = [i]
+            for j, cb in enumerate(b, 1):
+                cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+            prev = cur
+        return prev[-1]
+
+    assert edit_distances(["kitten", "", "abc", "flaw"], ["sitting", "abc", "", "lawn"]).tolist() == [3, 3, 3, 2]
+    rnd = random.Random(0)
+    pairs = [("".join(rnd.choice("abc -") for _ in range(rnd.randint(0, 20))), "".join(rnd.choice("abc -") for _ in range(rnd.randint(1, 20))))
+             for _ in range(200)]
+    got = edit_distances([p for p, _ in pairs], [t for _, t in pairs])
+    assert got.tolist() == [dp(p, t) for p, t in pairs]
+    s = levenshtein_scores(["3 creekhouse", "x"], ["3 creekhouse", "ab"])
+    assert s[0] == 1.0 and s[1] == 0.0
