@@ -165,6 +165,16 @@ ISHARA_API ishara_status_t ishara_model_train_param_grad(ishara_model_t* m, cons
 ISHARA_API ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, int32_t want_grad, float* host_out, int64_t numel);
 
 
+/* Pipelined form of infer_host for back-to-back batches (serving / evaluation loops, c9:15-26 run over a dataset):
+ * submit enqueues the upload (copy stream), forward, decode, optional CTC and the read-back for one batch and returns
+ * immediately; collect blocks until the OLDEST submitted batch is complete. Up to two batches may be in flight, so the
+ * H2D copy of batch i+1 runs under the kernels of batch i. All host buffers (pinned for overlap) must stay valid and
+ * untouched until the matching collect returns. */
+ISHARA_API ishara_status_t ishara_model_infer_submit(ishara_model_t* m, const float* x_host, int32_t batch, const int32_t* labels_host,
+                                                     int32_t max_label_len, float* logits_host, int32_t* ids_host,
+                                                     int32_t* lens_host, float* nll_host);
+ISHARA_API ishara_status_t ishara_model_infer_collect(ishara_model_t* m);
+
 /* CTCLoss (c6:1-13): per-sequence negative log-likelihood nll[B] (the reference returns their mean) and,
  * when grad_dev != NULL, d nll_b / d logits [B,T,V]. labels int32 [B,L] padded with `blank`. */
 ISHARA_API ishara_status_t ishara_ctc_loss(const float* logits_dev, const int32_t* labels_dev, int32_t batch, int32_t frames,

@@ -120,6 +120,8 @@ SIGNATURES = {
     "ishara_launch_count": (C.c_uint64, []),
     "ishara_model_set_debug": (_i32, [_vp, _i32]),
     "ishara_model_debug_fetch": (_i32, [_vp, C.c_char_p, _vp, _i64]),
+    "ishara_model_infer_submit": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "ishara_model_infer_collect": (_i32, [_vp]),
     "ishara_edit_distances": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "ishara_preprocess": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "ishara_model_train_configure": (_i32, [_vp, _f32, C.c_uint64, _i32]),

@@ -41,6 +41,9 @@ int model_set_profile(ishara_model* m, int on);
 int model_profile_count(const ishara_model* m);
 int model_profile_entry(ishara_model* m, int i, const char** label, const char** kind, float* ms, double* flops, double* bytes);
 int model_debug_fetch(ishara_model* m, const char* name, float* host_out, int64_t numel);
+int model_infer_submit(ishara_model* m, const float* x_host, int batch, const int32_t* labels_host, int max_label_len, float* logits_host,
+                       int32_t* ids_host, int32_t* lens_host, float* nll_host);
+int model_infer_collect(ishara_model* m);
 // train.cu
 int train_configure(ishara_model* m, float dropout, uint64_t seed, int debug);
 int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* labels_dev, int batch, int labels_len, float* loss_host,
@@ -241,6 +244,26 @@ ishara_status_t ishara_model_infer_host(ishara_model_t* mh, const float* x_host,
                                    v.stream));
   CAPI_CUDA_OK(cudaStreamSynchronize(v.stream));
   return ISHARA_OK;
+}
+
+ishara_status_t ishara_model_infer_submit(ishara_model_t* mh, const float* x_host, int32_t batch, const int32_t* labels_host,
+                                          int32_t max_label_len, float* logits_host, int32_t* ids_host, int32_t* lens_host,
+                                          float* nll_host) {
+  CHECK_HANDLE(mh);
+  if (x_host == nullptr || batch <= 0 || ids_host == nullptr || lens_host == nullptr) {
+    set_last_error("infer_submit: bad arguments");
+    return ISHARA_ERR_INVALID;
+  }
+  if (labels_host != nullptr && (nll_host == nullptr || max_label_len <= 0)) {
+    set_last_error("infer_submit: labels need nll_host and max_label_len > 0");
+    return ISHARA_ERR_INVALID;
+  }
+  return static_cast<ishara_status_t>(model_infer_submit(reinterpret_cast<ishara_model*>(mh), x_host, batch, labels_host, max_label_len,
+                                                         logits_host, ids_host, lens_host, nll_host));
+}
+ishara_status_t ishara_model_infer_collect(ishara_model_t* mh) {
+  CHECK_HANDLE(mh);
+  return static_cast<ishara_status_t>(model_infer_collect(reinterpret_cast<ishara_model*>(mh)));
 }
 
 ishara_status_t ishara_ctc_loss(const float* logits_dev, const int32_t* labels_dev, int32_t batch, int32_t frames,

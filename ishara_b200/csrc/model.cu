@@ -709,6 +709,11 @@ int model_destroy(ishara_model* m) {
   for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (m->labels_dev) cudaFree(m->labels_dev);
   if (m->stream) cudaStreamDestroy(m->stream);
+  for (auto& sl : m->pipe) {
+    if (sl.x) cudaFree(sl.x);
+    if (sl.labels) cudaFree(sl.labels);
+    if (sl.h2d_done) { cudaEventDestroy(sl.h2d_done); cudaEventDestroy(sl.x_free); cudaEventDestroy(sl.done); }
+  }
   if (m->copy_stream) {
     cudaStreamDestroy(m->copy_stream);
     for (auto& e : m->copy_done) if (e) cudaEventDestroy(e);
@@ -925,6 +930,79 @@ int model_view(ishara_model* m, int batch, ModelView* v) {
   v->ids_dev = m->ids_dev;
   v->lens_dev = m->lens_dev;
   v->nll_dev = m->nll_dev;
+  return 0;
+}
+
+// ---- pipelined host inference --------------------------------------------------------------------------------------
+// submit: enqueue H2D (copy stream) + forward + decode [+ CTC] + D2H (main stream) for one batch and return at once;
+// collect: wait for the oldest submitted batch. Up to two batches in flight, so batch i+1 uploads while batch i computes.
+int model_infer_submit(ishara_model* m, const float* x_host, int batch, const int32_t* labels_host, int max_label_len, float* logits_host,
+                       int32_t* ids_host, int32_t* lens_host, float* nll_host) {
+  if (!m->finalized) { set_last_error("model not finalized"); return ISHARA_ERR_STATE; }
+  if (m->pipe_submitted - m->pipe_collected >= 2) { set_last_error("infer_submit: two batches already in flight, collect one first"); return ISHARA_ERR_STATE; }
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  if (m->host_params_stale) { int rcs = train_sync(m); if (rcs) return rcs; }
+  if (batch > m->cap_batch && m->pipe_submitted != m->pipe_collected) {
+    set_last_error("infer_submit: a larger batch needs a bigger workspace; collect the batch in flight first");
+    return ISHARA_ERR_STATE;
+  }
+  int rc;
+  if ((rc = ensure_workspace(m, batch))) return rc;
+  const ishara_config_t& c = m->cfg;
+  const size_t M = static_cast<size_t>(batch) * c.frames;
+  const int slot_i = static_cast<int>(m->pipe_submitted & 1);
+  ishara_model::PipeSlot& sl = m->pipe[slot_i];
+  if (sl.h2d_done == nullptr) {
+    ISHARA_CUDA_OK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    ISHARA_CUDA_OK(cudaEventCreateWithFlags(&sl.x_free, cudaEventDisableTiming));
+    ISHARA_CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  if (sl.x_cap < M * c.features) {
+    if (m->pipe_submitted != m->pipe_collected) ISHARA_CUDA_OK(cudaDeviceSynchronize());
+    if (sl.x) ISHARA_CUDA_OK(cudaFree(sl.x));
+    sl.x = nullptr; sl.x_cap = 0;
+    for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);  // graphs hold the old input pointer
+    m->graphs.clear();
+    ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&sl.x), M * c.features * sizeof(float)));
+    sl.x_cap = M * c.features;
+  }
+  const size_t nlab = labels_host != nullptr ? static_cast<size_t>(batch) * max_label_len : 0;
+  if (sl.labels_cap < nlab) {
+    if (sl.labels) ISHARA_CUDA_OK(cudaFree(sl.labels));
+    sl.labels = nullptr; sl.labels_cap = 0;
+    ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&sl.labels), nlab * sizeof(int32_t)));
+    sl.labels_cap = nlab;
+  }
+  // upload on the copy stream, once the forward that last read this slot is done
+  ISHARA_CUDA_OK(cudaStreamWaitEvent(m->copy_stream, sl.x_free, 0));
+  ISHARA_CUDA_OK(cudaMemcpyAsync(sl.x, x_host, M * c.features * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
+  if (nlab) ISHARA_CUDA_OK(cudaMemcpyAsync(sl.labels, labels_host, nlab * sizeof(int32_t), cudaMemcpyHostToDevice, m->copy_stream));
+  ISHARA_CUDA_OK(cudaEventRecord(sl.h2d_done, m->copy_stream));
+  // compute + read-back on the main stream
+  cudaStream_t s = m->stream;
+  ISHARA_CUDA_OK(cudaStreamWaitEvent(s, sl.h2d_done, 0));
+  if ((rc = model_forward(m, sl.x, batch, m->logits_own, s))) return rc;
+  ISHARA_CUDA_OK(cudaEventRecord(sl.x_free, s));
+  const int blank = c.num_classes - 1;
+  if ((rc = greedy_decode_launch(m->logits_own, batch, c.frames, c.num_classes, blank, m->ids_dev, m->lens_dev, s))) return rc;
+  if (nlab) {
+    if ((rc = ctc_loss_launch(m->logits_own, sl.labels, batch, c.frames, c.num_classes, max_label_len, blank, m->nll_dev, nullptr, s))) return rc;
+    ISHARA_CUDA_OK(cudaMemcpyAsync(nll_host, m->nll_dev, batch * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  ISHARA_CUDA_OK(cudaMemcpyAsync(ids_host, m->ids_dev, M * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  ISHARA_CUDA_OK(cudaMemcpyAsync(lens_host, m->lens_dev, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (logits_host != nullptr)
+    ISHARA_CUDA_OK(cudaMemcpyAsync(logits_host, m->logits_own, M * c.num_classes * sizeof(float), cudaMemcpyDeviceToHost, s));
+  ISHARA_CUDA_OK(cudaEventRecord(sl.done, s));
+  ++m->pipe_submitted;
+  return 0;
+}
+
+int model_infer_collect(ishara_model* m) {
+  if (m->pipe_submitted == m->pipe_collected) { set_last_error("infer_collect: nothing in flight"); return ISHARA_ERR_STATE; }
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  ISHARA_CUDA_OK(cudaEventSynchronize(m->pipe[m->pipe_collected & 1].done));
+  ++m->pipe_collected;
   return 0;
 }
 

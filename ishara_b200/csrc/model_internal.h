@@ -116,6 +116,15 @@ struct ishara_model {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;     // H2D of the chunked host path
   cudaEvent_t copy_done[8] = {nullptr};
+  // pipelined host inference (model_infer_submit / _collect): two input slots so the H2D copy of batch i+1 runs under
+  // the kernels of batch i
+  struct PipeSlot {
+    float* x = nullptr;
+    int32_t* labels = nullptr;
+    size_t x_cap = 0, labels_cap = 0;
+    cudaEvent_t h2d_done = nullptr, x_free = nullptr, done = nullptr;
+  } pipe[2];
+  uint64_t pipe_submitted = 0, pipe_collected = 0;
   ishara::TrainState* train = nullptr;    // training step state (train.cu); null until the first train call
   bool host_params_stale = false;         // device master weights are newer than params[].data (after a train step)
 

@@ -135,6 +135,9 @@ class IsharaModel:
         if getattr(self, "_h", None):
             self._lib.ishara_model_destroy(self._h)
             self._h = None
+        for ptr in getattr(self, "_pinned_ptrs", []):
+            self._lib.ishara_host_free_pinned(ptr)
+        self._pinned_ptrs = []
 
     def __del__(self):
         try:
@@ -498,6 +501,76 @@ class IsharaModel:
         raw, o = buf.raw, offs.tolist()
         text = [raw[o[b]:o[b + 1]].decode("ascii") for b in range(B)]
         return {"ids": id_list, "text": text, "nll": nll, "logits": logits}
+
+    def _pinned(self, shape, dtype):
+        """numpy array over page-locked host memory (freed with the model)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        _lib.check(self._lib.ishara_host_malloc_pinned(max(n, 16), C.byref(ptr)))
+        if not hasattr(self, "_pinned_ptrs"):
+            self._pinned_ptrs = []
+        self._pinned_ptrs.append(ptr)
+        buf = (C.c_char * max(n, 16)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def infer_pipelined(self, batches, return_logits: bool = False):
+        """Generator over an iterable of host batches — ``x`` or ``(x, labels)`` — yielding what ``infer`` returns, in
+        order, with up to two batches in flight: the H2D copy of batch i+1 and the host-side string assembly of batch
+        i-1 overlap the kernels of batch i (``ishara_model_infer_submit`` / ``_collect``). Inputs should be pinned
+        (``pin_host``) for the copy to be asynchronous; every batch must stay untouched until its result is yielded."""
+        self._ensure_finalized()
+        p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        slots = [None, None]
+        pending = []  # (slot index, B, has_labels, keep-alive inputs)
+
+        def finish():
+            si, B, has_lab, _keep = pending.pop(0)
+            _lib.check(self._lib.ishara_model_infer_collect(self._h))
+            s = slots[si]
+            ids, lens = s["ids"][:B], s["lens"][:B]
+            ids64 = ids.astype(np.int64)
+            lens_l = lens.tolist()
+            buf = C.create_string_buffer(B * self.frames + 1)
+            offs = np.empty(B + 1, np.int64)
+            idc = np.ascontiguousarray(ids)
+            _lib.check(self._lib.ishara_ids_to_text(p(idc), p(lens), B, self.frames, _CHARS.encode("ascii"), len(_CHARS), buf, p(offs)))
+            raw, o = buf.raw, offs.tolist()
+            return {"ids": [ids64[b, :n] for b, n in enumerate(lens_l)], "text": [raw[o[b]:o[b + 1]].decode("ascii") for b in range(B)],
+                    "nll": s["nll"][:B].copy() if has_lab else None,
+                    "logits": s["logits"][:B].copy() if return_logits else None}
+
+        n = 0
+        for item in batches:
+            x, labels = item if isinstance(item, tuple) else (item, None)
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            self._check_x(x.shape)
+            B = x.shape[0]
+            lab, L = None, 0
+            if labels is not None:
+                lab = np.ascontiguousarray(labels, dtype=np.int32)
+                if lab.ndim != 2 or lab.shape[0] != B:
+                    raise ValueError("labels must be [B, max_label_len]")
+                L = lab.shape[1]
+            if len(pending) == 2:
+                yield finish()
+            si = n & 1
+            if slots[si] is None or slots[si]["cap"] < B:
+                slots[si] = {"cap": B, "ids": self._pinned((B, self.frames), np.int32), "lens": self._pinned((B,), np.int32),
+                             "nll": self._pinned((B,), np.float32),
+                             "logits": self._pinned((B, self.frames, self.num_classes), np.float32) if return_logits else None}
+            s = slots[si]
+            _lib.check(self._lib.ishara_model_infer_submit(self._h, p(x), B, p(lab), L, p(s["logits"]) if return_logits else None,
+                                                           p(s["ids"]), p(s["lens"]), p(s["nll"]) if lab is not None else None))
+            pending.append((si, B, lab is not None, (x, lab)))
+            n += 1
+        while pending:
+            yield finish()
+
+    def pin_host(self, a: np.ndarray) -> np.ndarray:
+        """Copy of ``a`` in page-locked host memory (so uploads run asynchronously at full PCIe rate)."""
+        out = self._pinned(a.shape, a.dtype)
+        out[...] = a
+        return out
 
     # ---- measurement hook (bench.py) ------------------------------------------------------------
     def profile_forward(self, x: ArrayLike, logits=None) -> List[dict]:

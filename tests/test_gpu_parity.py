@@ -276,3 +276,21 @@ def test_decode_full_size_properties():
     for b in range(B):
         assert (ids[b] != V - 1).all() and len(ids[b]) <= T - 1
         assert len(ids[b]) == int(((am[b, :-1] != am[b, 1:]) & (am[b, :-1] != V - 1)).sum())
+
+
+def test_pipelined_inference_matches_blocking_calls():
+    """infer_pipelined (two batches in flight, H2D of batch i+1 under the kernels of batch i) = infer, batch by batch."""
+    cfg = O.Config()
+    m = ib.get_model().load_weights(O.init_params(cfg))
+    batches = [(m.pin_host(O.make_inputs(cfg, b, seed=50 + i)), O.make_labels(cfg, b, seed=60 + i)) for i, b in enumerate((5, 3, 8, 8, 2))]
+    want = [m.infer(x, labels=y, return_logits=True) for x, y in batches]
+    got = list(m.infer_pipelined(batches, return_logits=True))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g["text"] == w["text"]
+        assert all(np.array_equal(a, b) for a, b in zip(g["ids"], w["ids"]))
+        assert np.array_equal(g["nll"], w["nll"]) and np.array_equal(g["logits"], w["logits"])
+    # without labels, and a generator that is abandoned half way must not wedge the handle
+    g2 = list(m.infer_pipelined([x for x, _ in batches[:3]]))
+    assert [r["text"] for r in g2] == [w["text"] for w in want[:3]] and g2[0]["nll"] is None
+    m.close()
