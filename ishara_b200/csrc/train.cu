@@ -213,11 +213,6 @@ struct TB {
     }
     return [=](cudaStream_t s) { return wgrad_launch(X, I, Gy, O, dW, Ovalid, db, MM, I, O, Ivalid, Ovalid, sms, s); };
   }
-  Step bias_grad(const bf16* Gy, int ld, int Cvalid, const std::string& base) {
-    float* db = G(base + ".bias");
-    const int64_t MM = M;
-    return [=](cudaStream_t s) { return colsum_launch(Gy, ld, db, MM, Cvalid, s); };
-  }
   Step ln_fwd(const bf16* x, bf16* out, const std::string& base, float eps) {
     const float *g = W(base + ".gamma"), *b = W(base + ".beta");
     const int64_t MM = M;
@@ -861,10 +856,6 @@ int ensure_train(ishara_model* m, int batch, int labels_len) {
     if (rc) return rc;
   }
   ISHARA_CUDA_OK(cudaSetDevice(m->device));
-  if (m->cfg.dim != 256 && m->cfg.dim != 128) {
-    set_last_error("train: dim must be 128 or 256 (full-row tcgen05 epilogue); got " + std::to_string(m->cfg.dim));
-    return ISHARA_ERR_SHAPE;
-  }
   if (m->train == nullptr) {
     auto ts = std::make_unique<TrainState>();
     int rc = init_storage(m, ts.get());
@@ -906,7 +897,6 @@ int train_configure(ishara_model* m, float dropout, uint64_t seed, int debug) {
   if (m->train == nullptr) {
     if (!m->finalized) { int rc = model_finalize(m); if (rc) return rc; }
     ISHARA_CUDA_OK(cudaSetDevice(m->device));
-    if (m->cfg.dim != 256 && m->cfg.dim != 128) { set_last_error("train: dim must be 128 or 256"); return ISHARA_ERR_SHAPE; }
     auto ts = std::make_unique<TrainState>();
     int rc = init_storage(m, ts.get());
     if (rc) return rc;

@@ -135,8 +135,8 @@ struct AdamWArgs {
 // theta/g/m/v [n]; clip scale derived on the device from norm2[0] (already of the scaled gradient)
 int adamw_launch(float* theta, const float* g, float* m, float* v, int64_t n, const double* norm2, const AdamWArgs& a,
                  cudaStream_t s);
-// bf16 working copies of a dense kernel W [I, O] fp32: fwd [Opad, Ipad] (= W^T, K-major for the forward GEMM) and
-// bwd [Ipad? no: I, Opad] (= W, K-major for the data-gradient GEMM); zero padding.
+// bf16 working copies of a dense kernel W [I, O] fp32: fwd [Opad, Ipad] (= W^T, K-major B operand of y = x W) and
+// bwd [I, Opad] (= W, K-major B operand of dx = dy W^T); zero padding; either pointer may be null.
 struct RepackEntry {
   const float* src;
   bf16* fwd;

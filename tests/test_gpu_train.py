@@ -178,9 +178,17 @@ def test_batch_size_change_rebuilds_the_program():
     m.close()
 
 
-def test_training_rejects_unsupported_dim():
-    cfg = O.Config(dim=192, num_heads=4, frames=64, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=0)
-    m = _model(cfg, O.init_params(cfg))
-    with pytest.raises(ishara_b200.IsharaError):
-        m.train_config(0.0)
+def test_other_widths_train_too():
+    """dim = 192 (head dim 48): no full-row epilogue, plain 64/128-column tiles, mma.sync attention forward."""
+    cfg = O.Config(dim=192, num_heads=4, frames=64, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
+    p = O.init_params(cfg)
+    x = O.make_inputs(cfg, 3)
+    y = O.make_labels(cfg, 3, max_len=12, min_len=3)
+    m = _model(cfg, p)
+    m.train_config(0.0, debug=True)
+    loss = m.forward_backward(x, y)
+    hh = m.train_fetch("head.h", (3, cfg.frames, 2 * cfg.dim))
+    ref = TO.forward_train(p, x, y, cfg, relu_gate=(hh > 0).astype(np.float32))
+    assert abs(loss - ref["loss"]) <= 1e-3 * abs(ref["loss"])
+    _check_grads(m.gradients(), ref["grads"])
     m.close()

@@ -69,3 +69,40 @@ def test_opt_in_variants_match_oracle_and_default(tmp_path):
     assert np.array_equal(outs["no_graph"], base)
     assert np.array_equal(outs["gemm_resident"], base)
     assert np.array_equal(outs["gemm_pair"], base)
+
+
+TRAIN_SNIPPET = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+import ishara_b200
+from oracle import ishara_oracle as O
+cfg = O.Config(dim=128, num_heads=4, frames=128, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
+p = O.init_params(cfg)
+x = O.make_inputs(cfg, 4); y = O.make_labels(cfg, 4, max_len=24, min_len=6)
+m = ishara_b200.get_model(dim=128, num_heads=4, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, dropout_rate=0.0,
+                          input_shape=(128, 20)).load_weights(p)
+m.train_config(0.0)
+loss = m.forward_backward(x, y)
+g = m.gradients()
+flat = np.concatenate([g[k].ravel() for k in sorted(g)] + [np.array([loss], np.float32)])
+np.save(sys.argv[1], flat)
+""" % ROOT
+
+
+def test_weight_gradient_kernels_agree(tmp_path):
+    """tcgen05 weight gradients (MN-major operands, default) vs the mma.sync + ldmatrix.trans kernel (ISHARA_WGRAD_TC=0)."""
+    import numpy as np
+
+    outs = {}
+    for name, env_extra in (("tc", {}), ("mma_sync", {"ISHARA_WGRAD_TC": "0"})):
+        out = tmp_path / f"train_{name}.npy"
+        env = {k: v for k, v in os.environ.items() if not k.startswith("ISHARA_")}
+        env.update(env_extra)
+        r = subprocess.run([sys.executable, "-c", TRAIN_SNIPPET, str(out)], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, f"{name}: {r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+        outs[name] = np.load(out)
+    a, b = outs["tc"].astype(np.float64), outs["mma_sync"].astype(np.float64)
+    assert abs(a[-1] - b[-1]) <= 1e-5 * abs(b[-1])                       # same forward => same loss
+    rel = np.linalg.norm(a[:-1] - b[:-1]) / np.linalg.norm(b[:-1])
+    assert rel < 2e-3, rel                                              # fp32 accumulation order only
