@@ -127,7 +127,7 @@ ISHARA_API ishara_status_t ishara_preprocess(const float* frames_dev, const int3
  * Keras training-mode forward (BatchNormalization on biased batch statistics over (B,T) + moving-average update,
  * dropout at the reference's sites), CTCLoss (mean over the batch), gradients of every trainable tensor, then
  * global-norm clipping and AdamW. Master weights, gradients and Adam moments are fp32 on the device; activations
- * and activation gradients are bf16. The handle's inference path sees the trained weights
+ * and activation gradients are bf16. dim must be a multiple of 128 (<= 512). The handle's inference path sees the trained weights
  * after ishara_model_train_sync (called implicitly by forward / get_param / infer when weights are stale). */
 typedef struct {
   float lr;           /* 4.5e-3  (integration.py:675-679) */

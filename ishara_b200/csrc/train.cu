@@ -856,6 +856,10 @@ int ensure_train(ishara_model* m, int batch, int labels_len) {
     if (rc) return rc;
   }
   ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  if (m->cfg.dim % 128 != 0 || m->cfg.dim > 512) {
+    set_last_error("train: dim must be a multiple of 128, at most 512 (LayerNorm backward lane layout); got " + std::to_string(m->cfg.dim));
+    return ISHARA_ERR_SHAPE;
+  }
   if (m->train == nullptr) {
     auto ts = std::make_unique<TrainState>();
     int rc = init_storage(m, ts.get());
@@ -897,6 +901,10 @@ int train_configure(ishara_model* m, float dropout, uint64_t seed, int debug) {
   if (m->train == nullptr) {
     if (!m->finalized) { int rc = model_finalize(m); if (rc) return rc; }
     ISHARA_CUDA_OK(cudaSetDevice(m->device));
+    if (m->cfg.dim % 128 != 0 || m->cfg.dim > 512) {
+      set_last_error("train: dim must be a multiple of 128, at most 512 (LayerNorm backward lane layout); got " + std::to_string(m->cfg.dim));
+      return ISHARA_ERR_SHAPE;
+    }
     auto ts = std::make_unique<TrainState>();
     int rc = init_storage(m, ts.get());
     if (rc) return rc;

@@ -40,6 +40,11 @@ def _check_grads(grads, ref, tol_tensor=8e-2, tol_flat=2e-2):
     total = float(np.linalg.norm(_flat(ref, names)))
     worst = (0.0, "")
     for k in names:
+        if k.endswith(".conv.depthwise_conv.bias"):
+            # BatchNorm follows this bias, so its true gradient is exactly zero; what comes out is the rounding noise of
+            # summing bf16 activation gradients, checked on the scale of the whole gradient
+            assert float(np.linalg.norm(grads[k])) <= 5e-4 * total, k
+            continue
         e = float(np.linalg.norm(grads[k].astype(np.float64) - ref[k])) / max(float(np.linalg.norm(ref[k])), 1e-3 * total)
         worst = max(worst, (e, k))
     assert worst[0] <= tol_tensor, f"worst per-tensor gradient error {worst}"
@@ -179,8 +184,14 @@ def test_batch_size_change_rebuilds_the_program():
 
 
 def test_other_widths_train_too():
-    """dim = 192 (head dim 48): no full-row epilogue, plain 64/128-column tiles, mma.sync attention forward."""
-    cfg = O.Config(dim=192, num_heads=4, frames=64, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
+    """dim = 384 (cfg5's width, head dim 48): no full-row epilogue, plain 128-column tiles, mma.sync attention forward;
+    dim = 192 is refused up front (LayerNorm backward needs a multiple of 128)."""
+    bad = O.Config(dim=192, num_heads=4, frames=64, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=0)
+    mb = _model(bad, O.init_params(bad))
+    with pytest.raises(ishara_b200.IsharaError):
+        mb.train_config(0.0)
+    mb.close()
+    cfg = O.Config(dim=384, num_heads=8, frames=64, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
     p = O.init_params(cfg)
     x = O.make_inputs(cfg, 3)
     y = O.make_labels(cfg, 3, max_len=12, min_len=3)

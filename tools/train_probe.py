@@ -95,5 +95,7 @@ if __name__ == "__main__":
     if which in ("small", "both"):
         cfg = O.Config(dim=128, num_heads=4, frames=128, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
         run(cfg, 4, 24, "small")
+    if which == "d384":
+        run(O.Config(dim=384, num_heads=8, frames=64, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1), 3, 12, "dim 384")
     if which in ("full", "both"):
         run(O.Config(), 4, 64, "cfg3-shape (B=4)")
