@@ -128,11 +128,15 @@ def cpu_baseline(budget_s=20.0):
     per_seq = (time.perf_counter() - t0) / 2
     b = int(max(2, min(64, budget_s / max(per_seq, 1e-3))))
     x, y = O.make_inputs(cfg, b), O.make_labels(cfg, b)
-    t0 = time.perf_counter()
-    cpu_step(O, params, cfg, x, y)
-    dt = time.perf_counter() - t0
-    return {"value": b / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{b} sequences of the same workload (oracle torch-CPU fp32 forward + CTC + decode), one pass, {dt:.1f} s"}
+    # batches of <= 64 sequences (the batched torch ops are fastest there) repeated until ~budget_s of CPU work is done
+    passes, dt = 0, 0.0
+    while passes == 0 or (dt < 0.6 * budget_s and passes < 64):
+        t0 = time.perf_counter()
+        cpu_step(O, params, cfg, x, y)
+        dt += time.perf_counter() - t0
+        passes += 1
+    return {"value": b * passes / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{passes} pass(es) over {b} sequences of the same workload (oracle torch-CPU fp32 forward + CTC + decode), {dt:.1f} s"}
 
 
 def run_reference(args):
