@@ -38,7 +38,7 @@ __device__ __forceinline__ float ex2(float x) {
 template <int DH>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const uint8_t* __restrict__ key_mask, int T, int H,
-            int Tp, float scale_log2, uint32_t drop_thr16, float drop_inv_keep, uint64_t drop_key) {
+            int Tp, float scale_log2, uint32_t drop_thr16, float drop_inv_keep, uint64_t drop_key, float* __restrict__ lse_out) {
   constexpr int KS = DH + 8;  // K row stride (elements): conflict-free fragment reads
   extern __shared__ __align__(16) uint8_t smem_at[];
   bf16* Ks = reinterpret_cast<bf16*>(smem_at);                 // [Tp][KS]
@@ -188,6 +188,11 @@ attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const uint8_t*
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.f / l0, i1 = 1.f / l1;
+    if (lse_out != nullptr && tg == 0) {  // training: row log-sum-exp (log2 domain) for the backward pass
+      const size_t rowbase = (static_cast<size_t>(b) * H + h) * T;
+      if (r0 < T) lse_out[rowbase + r0] = m0 + log2f(l0);
+      if (r1 < T) lse_out[rowbase + r1] = m1 + log2f(l1);
+    }
     bf16* ob = out + static_cast<size_t>(b) * T * (DH * H) + h * DH;
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n) {
@@ -443,7 +448,7 @@ int launch_inst(const AttnArgs& a, cudaStream_t stream) {
     smem_attr = smem;
   }
   kern<<<dim3(a.H, a.B), kAttnThreads, smem, stream>>>(a.qkv, a.out, a.key_mask, a.T, a.H, Tp,
-                                                      a.scale * 1.4426950408889634f, a.drop_thr16, a.drop_inv_keep, a.drop_key);
+                                                      a.scale * 1.4426950408889634f, a.drop_thr16, a.drop_inv_keep, a.drop_key, a.lse_out);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

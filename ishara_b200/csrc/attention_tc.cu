@@ -81,7 +81,7 @@ __device__ __forceinline__ float row_half_norm2(const uint8_t* tile, int row, in
 //   softmax warps: sm(0,0) sm(0,1) | sm(b,0) epilogue(b-1) sm(b,1) ...            (never wait for a PV they just enabled)
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-               const uint8_t* __restrict__ key_mask, int T, int H, float scale_log2) {
+               const uint8_t* __restrict__ key_mask, int T, int H, float scale_log2, float* __restrict__ lse_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -307,6 +307,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
       named_bar_sync(1 + q, 64);
       sum += xsum[((blk & 1) * 2 + (hh ^ 1)) * 128 + r];
       sum_prev = sum;
+      // training: P = 2^(s*scale_log2 - bound) / sum  =>  row log-sum-exp (log2 domain) = bound + log2(sum)
+      if (lse_out != nullptr && hh == 0) lse_out[(static_cast<size_t>(b) * H + h) * T + blk * kQB + r] = bound + log2f(sum);
     }
     epilogue(nqb - 1, sum_prev);
   }
@@ -333,7 +335,7 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
     attr = true;
   }
   attn_tc_kernel<<<dim3(a.H, a.B), kThreadsTc, smem, stream>>>(tm, a.qkv, a.out, a.key_mask, a.T, a.H,
-                                                             a.scale * 1.4426950408889634f);
+                                                             a.scale * 1.4426950408889634f, a.lse_out);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

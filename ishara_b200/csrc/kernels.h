@@ -134,6 +134,8 @@ struct AttnArgs {
   const float* v_bias = nullptr;
   int B = 0, T = 0, H = 0, dh = 0;
   float scale = 1.f;
+  // training only: row log-sum-exp of the scaled scores in the log2 domain, [B*H*T] fp32 (saved for the backward pass)
+  float* lse_out = nullptr;
   // training only: dropout on the attention probabilities (c5:113); thr16 = 0 disables. See dropout_hash.cuh.
   uint32_t drop_thr16 = 0;
   float drop_inv_keep = 1.f;

@@ -473,6 +473,7 @@ struct TB {
     bf16* QKV = act(3 * D, base + ".qkv");
     bf16* O = act(D, base + ".o");
     bf16* S_out = act(D, out_name);
+    float* lse_save = f32(static_cast<size_t>(B) * H * T);  // row log-sum-exp of this layer's scores, forward -> backward
     const float p = branch_drop ? ts->dropout : 0.f;
     const float scale = 1.f / std::sqrt(static_cast<float>(D));  // self.scale = dim ** -0.5 (c5:95)
     const uint32_t site_a = p_attn > 0.f ? ++site_counter : 0;
@@ -485,6 +486,7 @@ struct TB {
       AttnArgs a;
       a.qkv = QKV; a.out = O; a.B = B; a.T = T; a.H = H; a.dh = dh; a.scale = scale;
       a.drop_thr16 = thr_a; a.drop_inv_keep = inv_a;
+      a.lse_out = lse_save;
       ts->fwd.push_back([=](cudaStream_t s) {
         AttnArgs aa = a;
         if (site_a) aa.drop_key = dropout_key(*seedp, site_a);
@@ -502,7 +504,7 @@ struct TB {
     snap(bw, base + ".o", gD1, D);
     {
       AttnBwdArgs a;
-      a.qkv = QKV; a.o = O; a.dO = gD1; a.dqkv = gW1; a.lse2 = lse; a.dsum = dsum; a.B = B; a.T = T; a.H = H; a.dh = dh; a.scale = scale;
+      a.qkv = QKV; a.o = O; a.dO = gD1; a.dqkv = gW1; a.lse2 = lse_save; a.have_lse = 1; a.dsum = dsum; a.B = B; a.T = T; a.H = H; a.dh = dh; a.scale = scale;
       a.drop_thr16 = thr_a; a.drop_inv_keep = inv_a;
       bw.push_back([=](cudaStream_t s) {
         AttnBwdArgs aa = a;

@@ -110,7 +110,7 @@ template <int DH>
 __global__ void __launch_bounds__(kAbThreads)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
                    float* __restrict__ lse_out, float* __restrict__ dsum_out, int T, int H, int Tp, float scale, uint32_t drop_thr16,
-                   float drop_inv_keep, uint64_t drop_key) {
+                   float drop_inv_keep, uint64_t drop_key, int have_lse) {
   constexpr int KS = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_ab[];
   const int VS = Tp + 8;
@@ -148,42 +148,51 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, con
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
 
-    // sweep 1: row log-sum-exp in the log2 domain
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int kc = 0; kc < Tp; kc += kAbChunk) {
-      float s[kAbChunk / 8][4];
-      strip_mma<DH>(s, qa, Ks32, kc, g, tg);
-      float cm0 = -INFINITY, cm1 = -INFINITY;
-#pragma unroll
-      for (int n = 0; n < kAbChunk / 8; ++n) {
-        const int key = kc + n * 8 + tg * 2;
-        const float k0 = key < T ? 0.f : -INFINITY, k1 = key + 1 < T ? 0.f : -INFINITY;
-        s[n][0] = fmaf(s[n][0], scale_log2, k0); s[n][1] = fmaf(s[n][1], scale_log2, k1);
-        s[n][2] = fmaf(s[n][2], scale_log2, k0); s[n][3] = fmaf(s[n][3], scale_log2, k1);
-        cm0 = fmaxf(cm0, fmaxf(s[n][0], s[n][1]));
-        cm1 = fmaxf(cm1, fmaxf(s[n][2], s[n][3]));
+    float lse0, lse1;
+    if (have_lse) {
+      // the forward kernel saved the row log-sum-exp (log2 domain): no recompute sweep
+      const size_t rowbase = (static_cast<size_t>(b) * H + h) * T;
+      lse0 = r0 < T ? lse_out[rowbase + r0] : 0.f;
+      lse1 = r1 < T ? lse_out[rowbase + r1] : 0.f;
+    } else {
+      // sweep 1: row log-sum-exp in the log2 domain
+      float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+      for (int kc = 0; kc < Tp; kc += kAbChunk) {
+        float s[kAbChunk / 8][4];
+        strip_mma<DH>(s, qa, Ks32, kc, g, tg);
+        float cm0 = -INFINITY, cm1 = -INFINITY;
+  #pragma unroll
+        for (int n = 0; n < kAbChunk / 8; ++n) {
+          const int key = kc + n * 8 + tg * 2;
+          const float k0 = key < T ? 0.f : -INFINITY, k1 = key + 1 < T ? 0.f : -INFINITY;
+          s[n][0] = fmaf(s[n][0], scale_log2, k0); s[n][1] = fmaf(s[n][1], scale_log2, k1);
+          s[n][2] = fmaf(s[n][2], scale_log2, k0); s[n][3] = fmaf(s[n][3], scale_log2, k1);
+          cm0 = fmaxf(cm0, fmaxf(s[n][0], s[n][1]));
+          cm1 = fmaxf(cm1, fmaxf(s[n][2], s[n][3]));
+        }
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+        const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+        const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;
+        float ps0 = 0.f, ps1 = 0.f;
+  #pragma unroll
+        for (int n = 0; n < kAbChunk / 8; ++n) {
+          ps0 += ex2f(s[n][0] - ms0) + ex2f(s[n][1] - ms0);
+          ps1 += ex2f(s[n][2] - ms1) + ex2f(s[n][3] - ms1);
+        }
+        l0 = l0 * ex2f(m0 - ms0) + ps0;
+        l1 = l1 * ex2f(m1 - ms1) + ps1;
+        m0 = mn0; m1 = mn1;
       }
-      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
-      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
-      const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
-      const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;
-      float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-      for (int n = 0; n < kAbChunk / 8; ++n) {
-        ps0 += ex2f(s[n][0] - ms0) + ex2f(s[n][1] - ms0);
-        ps1 += ex2f(s[n][2] - ms1) + ex2f(s[n][3] - ms1);
-      }
-      l0 = l0 * ex2f(m0 - ms0) + ps0;
-      l1 = l1 * ex2f(m1 - ms1) + ps1;
-      m0 = mn0; m1 = mn1;
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      lse0 = m0 + log2f(l0);
+      lse1 = m1 + log2f(l1);
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float lse0 = m0 + log2f(l0), lse1 = m1 + log2f(l1);
     if (tg == 0) {
       const size_t rowbase = (static_cast<size_t>(b) * H + h) * T;
-      if (r0 < T) { lse_out[rowbase + r0] = lse0; dsum_out[rowbase + r0] = d0; }
-      if (r1 < T) { lse_out[rowbase + r1] = lse1; dsum_out[rowbase + r1] = d1; }
+      if (r0 < T) { if (!have_lse) lse_out[rowbase + r0] = lse0; dsum_out[rowbase + r0] = d0; }
+      if (r1 < T) { if (!have_lse) lse_out[rowbase + r1] = lse1; dsum_out[rowbase + r1] = d1; }
     }
 
     // sweep 2: dQ = scale * (P o (dP - D)) K
@@ -327,7 +336,7 @@ int launch_dh(const AttnBwdArgs& a, cudaStream_t s) {
   }
   const dim3 grid(a.H, a.B);
   attn_bwd_dq_kernel<DH><<<grid, kAbThreads, smem1, s>>>(a.qkv, a.o, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale, a.drop_thr16,
-                                                           a.drop_inv_keep, a.drop_key);
+                                                           a.drop_inv_keep, a.drop_key, a.have_lse);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   attn_bwd_dkv_kernel<DH><<<grid, kAbThreads, smem2, s>>>(a.qkv, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale, a.drop_thr16, a.drop_inv_keep,

@@ -116,6 +116,7 @@ struct AttnBwdArgs {
   const bf16 *qkv = nullptr, *o = nullptr, *dO = nullptr;
   bf16* dqkv = nullptr;
   float *lse2 = nullptr, *dsum = nullptr;
+  int have_lse = 0;  // lse2 already holds the forward's row log-sum-exp (AttnArgs::lse_out): skip the recompute sweep
   int B = 0, T = 0, H = 0, dh = 0;
   float scale = 1.f;
   uint32_t drop_thr16 = 0;  // same dropout mask as the forward (AttnArgs)
