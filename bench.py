@@ -202,6 +202,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line (rank 0). Libraries that print to the C-level stdout (NCCL's version banner)
+    # are sent to stderr for the duration of the run; the saved descriptor is restored for the final print.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -367,12 +372,12 @@ def run_ours(args):
 
         for _ in range(3):
             prep_step()
-        sync_all()
+        torch.cuda.synchronize(dev)  # rank-0-only section: no collectives here (the other ranks are already at the final barrier)
         e0.record(stream)
         for _ in range(20):
             prep_step()
         e1.record(stream)
-        sync_all()
+        torch.cuda.synchronize(dev)  # rank-0-only section: no collectives here (the other ranks are already at the final barrier)
         pms = e0.elapsed_time(e1) / 20
         pbytes = float(offs[-1]) * F * 4 + B * T * F * 4            # every raw frame read once + the model input written once
         t0 = time.perf_counter()
@@ -453,7 +458,10 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
