@@ -90,8 +90,8 @@ def test_host_dropout_masks_structure():
     assert "conformer_0.drop1" not in a and "conformer_0.ffn2.drop" in a
     for k, v in a.items():
         rate = 0.4 if k == "head.drop" else (0.1 if k == "conformer_0.mha.attn_drop" else 0.25)
-        vals = np.unique(v)
-        assert set(np.round(vals, 5)) <= {0.0, round(1 / (1 - rate), 5)}, k
+        nz = v[v != 0]
+        assert nz.size == 0 or np.allclose(nz, 1 / (1 - rate), rtol=1e-6), k
         if v.size > 1000:
             assert abs(float((v == 0).mean()) - rate) < 0.02, k
     m.close()
