@@ -982,13 +982,13 @@ int model_infer_submit(ishara_model* m, const float* x_host, int batch, const in
   cudaStream_t s = m->stream;
   ISHARA_CUDA_OK(cudaStreamWaitEvent(s, sl.h2d_done, 0));
   if ((rc = model_forward(m, sl.x, batch, m->logits_own, s))) return rc;
-  ISHARA_CUDA_OK(cudaEventRecord(sl.x_free, s));
   const int blank = c.num_classes - 1;
   if ((rc = greedy_decode_launch(m->logits_own, batch, c.frames, c.num_classes, blank, m->ids_dev, m->lens_dev, s))) return rc;
   if (nlab) {
     if ((rc = ctc_loss_launch(m->logits_own, sl.labels, batch, c.frames, c.num_classes, max_label_len, blank, m->nll_dev, nullptr, s))) return rc;
     ISHARA_CUDA_OK(cudaMemcpyAsync(nll_host, m->nll_dev, batch * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
+  ISHARA_CUDA_OK(cudaEventRecord(sl.x_free, s));  // every reader of this slot's x AND labels has been enqueued before this point
   ISHARA_CUDA_OK(cudaMemcpyAsync(ids_host, m->ids_dev, M * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   ISHARA_CUDA_OK(cudaMemcpyAsync(lens_host, m->lens_dev, batch * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   if (logits_host != nullptr)

@@ -539,6 +539,14 @@ class IsharaModel:
                     "nll": s["nll"][:B].copy() if has_lab else None,
                     "logits": s["logits"][:B].copy() if return_logits else None}
 
+        try:
+            yield from self._pipelined_loop(batches, slots, pending, finish, return_logits, p)
+        finally:
+            while pending:  # generator closed early: drain what is in flight so the handle stays usable
+                pending.pop(0)
+                _lib.check(self._lib.ishara_model_infer_collect(self._h))
+
+    def _pipelined_loop(self, batches, slots, pending, finish, return_logits, p):
         n = 0
         for item in batches:
             x, labels = item if isinstance(item, tuple) else (item, None)
