@@ -108,7 +108,6 @@ struct TB {
   bf16 *gD1 = nullptr, *gD2 = nullptr, *tD = nullptr;  // [M, D] scratch
   float *lse = nullptr, *dsum = nullptr;            // attention backward scratch [B*H*T]
   size_t stats_used = 0;
-  std::vector<size_t> stat_offsets;                 // resolved to pointers once the arena exists
 
   template <typename Tp>
   Tp* alloc(size_t count) {
@@ -135,7 +134,6 @@ struct TB {
     stats_used += n;
     return o;
   }
-  double* sp(size_t off) const { return ts->stats + off; }
 
   int pidx(const std::string& name) {
     auto it = m->index.find(name);
