@@ -362,7 +362,7 @@ def forward(params: Dict[str, np.ndarray], x: np.ndarray, cfg: Config, dtype: st
     mask_mode "dropped" (default) = the reference as executed: the Keras mask is lost at ``x + pe``
     (a TFOpLambda) so every downstream layer sees mask=None. "propagated" = the
     authors' apparent intent: mask reaches ECA / SE / Softmax inside the Conv1DBlocks and
-    SqueezeformerBlocks (ConformerBlock still drops it, c5:311-319,335)."""
+    SqueezeformerBlocks; the first ConformerBlock drops it for everything downstream (c5:311-319,335)."""
     assert torch is not None, "torch is required for oracle.forward"
     dt = {"float32": torch.float32, "float64": torch.float64}[dtype]
     p = params
@@ -397,6 +397,7 @@ def forward(params: Dict[str, np.ndarray], x: np.ndarray, cfg: Config, dtype: st
         for i in range(cfg.num_conv_conform_blocks):
             h = conv_blocks(h, "conform", i)
             h = _conformer_block(h, p, f"conformer_{i}", cfg, dt)
+            mask = None  # ConformerBlock has no supports_masking / compute_mask: its output carries no Keras mask (c5:311-343)
             if taps is not None:
                 taps[f"conformer_{i}"] = h.float().numpy()
         h = torch.relu(_dense(h, p, "top_conv", dt))                                  # c7:61
