@@ -106,22 +106,24 @@ ISHARA_API ishara_status_t ishara_model_infer_host(ishara_model_t* m, const floa
                                         const int32_t* labels_host, int32_t max_label_len, float* logits_host,
                                         int32_t* ids_host, int32_t* lens_host, float* nll_host);
 
-/* ---- scorer (SURVEY.md §8f rank 2) -----------------------------------------------------------------
- * Levenshtein distances of n (prediction, target) byte-string pairs, the `distance` call of the evaluation loop
- * c18:1-15 (score = (len(target) - distance) / len(target)). Host function; strings need not be NUL-terminated. */
-ISHARA_API ishara_status_t ishara_edit_distances(const char* const* preds, const int32_t* pred_lens, const char* const* targets,
-                                                 const int32_t* target_lens, int32_t n, int32_t* out_distances);
+/* Pipelined form of infer_host for back-to-back batches (serving / evaluation loops, c9:15-26 run over a dataset):
+ * submit enqueues the upload (copy stream), forward, decode, optional CTC and the read-back for one batch and returns
+ * immediately; collect blocks until the OLDEST submitted batch is complete. Up to two batches may be in flight, so the
+ * H2D copy of batch i+1 runs under the kernels of batch i. All host buffers (pinned for overlap) must stay valid and
+ * untouched until the matching collect returns. */
+ISHARA_API ishara_status_t ishara_model_infer_submit(ishara_model_t* m, const float* x_host, int32_t batch, const int32_t* labels_host,
+                                                     int32_t max_label_len, float* logits_host, int32_t* ids_host,
+                                                     int32_t* lens_host, float* nll_host);
+ISHARA_API ishara_status_t ishara_model_infer_collect(ishara_model_t* m);
 
-/* ---- landmark preprocessing (SURVEY.md §8f rank 1) -----------------------------------------------
- * The step in front of the model call: TFLiteModel.__call__ c13:9-15 = pre_process00 (c3:57-101) + pre_process1
- * (c3:103-115). frames_dev fp32 [total_frames, 276] holds the batch's sequences back to back in the reference's SEL_COLS
- * order (c1:22-26); offsets_dev int32 [batch+1] are frame offsets (a sequence may be empty: it becomes one zero frame,
- * c13:11); mean_dev / std_dev fp32 [276] are the per-group statistics laid out in OUTPUT column order (lip, rhand,
- * lhand, rpose, lpose; landmark-major, xyz-minor); out_dev fp32 [batch, frame_len, 276] is the model input.
- * filter_frames != 0 applies the hand-frame filter (inference path); 0 = training path (pre_process1 only). */
-ISHARA_API ishara_status_t ishara_preprocess(const float* frames_dev, const int32_t* offsets_dev, int32_t batch, int32_t max_frames,
-                                             const float* mean_dev, const float* std_dev, int32_t frame_len, int32_t filter_frames,
-                                             float* out_dev, void* stream);
+/* CTCLoss (c6:1-13): per-sequence negative log-likelihood nll[B] (the reference returns their mean) and,
+ * when grad_dev != NULL, d nll_b / d logits [B,T,V]. labels int32 [B,L] padded with `blank`. */
+ISHARA_API ishara_status_t ishara_ctc_loss(const float* logits_dev, const int32_t* labels_dev, int32_t batch, int32_t frames,
+                                int32_t num_classes, int32_t max_label_len, int32_t blank, float* nll_dev,
+                                float* grad_dev, void* stream);
+/* decode_phrase (c8:4-12) for a batch: ids_dev int32 [B,T] (first lens[b] entries valid, rest -1). */
+ISHARA_API ishara_status_t ishara_greedy_decode(const float* logits_dev, int32_t batch, int32_t frames, int32_t num_classes,
+                                     int32_t blank, int32_t* ids_dev, int32_t* lens_dev, void* stream);
 
 /* ---- training step ----------------------------------------------------
  * Keras training-mode forward (BatchNormalization on biased batch statistics over (B,T) + moving-average update,
@@ -164,25 +166,22 @@ ISHARA_API ishara_status_t ishara_model_train_param_grad(ishara_model_t* m, cons
 /* named activation (want_grad = 0) or its gradient (want_grad = 1, debug mode) as fp32 */
 ISHARA_API ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, int32_t want_grad, float* host_out, int64_t numel);
 
+/* ---- landmark preprocessing (SURVEY.md §8f rank 1) -----------------------------------------------
+ * The step in front of the model call: TFLiteModel.__call__ c13:9-15 = pre_process00 (c3:57-101) + pre_process1
+ * (c3:103-115). frames_dev fp32 [total_frames, 276] holds the batch's sequences back to back in the reference's SEL_COLS
+ * order (c1:22-26); offsets_dev int32 [batch+1] are frame offsets (a sequence may be empty: it becomes one zero frame,
+ * c13:11); mean_dev / std_dev fp32 [276] are the per-group statistics laid out in OUTPUT column order (lip, rhand,
+ * lhand, rpose, lpose; landmark-major, xyz-minor); out_dev fp32 [batch, frame_len, 276] is the model input.
+ * filter_frames != 0 applies the hand-frame filter (inference path); 0 = training path (pre_process1 only). */
+ISHARA_API ishara_status_t ishara_preprocess(const float* frames_dev, const int32_t* offsets_dev, int32_t batch, int32_t max_frames,
+                                             const float* mean_dev, const float* std_dev, int32_t frame_len, int32_t filter_frames,
+                                             float* out_dev, void* stream);
 
-/* Pipelined form of infer_host for back-to-back batches (serving / evaluation loops, c9:15-26 run over a dataset):
- * submit enqueues the upload (copy stream), forward, decode, optional CTC and the read-back for one batch and returns
- * immediately; collect blocks until the OLDEST submitted batch is complete. Up to two batches may be in flight, so the
- * H2D copy of batch i+1 runs under the kernels of batch i. All host buffers (pinned for overlap) must stay valid and
- * untouched until the matching collect returns. */
-ISHARA_API ishara_status_t ishara_model_infer_submit(ishara_model_t* m, const float* x_host, int32_t batch, const int32_t* labels_host,
-                                                     int32_t max_label_len, float* logits_host, int32_t* ids_host,
-                                                     int32_t* lens_host, float* nll_host);
-ISHARA_API ishara_status_t ishara_model_infer_collect(ishara_model_t* m);
-
-/* CTCLoss (c6:1-13): per-sequence negative log-likelihood nll[B] (the reference returns their mean) and,
- * when grad_dev != NULL, d nll_b / d logits [B,T,V]. labels int32 [B,L] padded with `blank`. */
-ISHARA_API ishara_status_t ishara_ctc_loss(const float* logits_dev, const int32_t* labels_dev, int32_t batch, int32_t frames,
-                                int32_t num_classes, int32_t max_label_len, int32_t blank, float* nll_dev,
-                                float* grad_dev, void* stream);
-/* decode_phrase (c8:4-12) for a batch: ids_dev int32 [B,T] (first lens[b] entries valid, rest -1). */
-ISHARA_API ishara_status_t ishara_greedy_decode(const float* logits_dev, int32_t batch, int32_t frames, int32_t num_classes,
-                                     int32_t blank, int32_t* ids_dev, int32_t* lens_dev, void* stream);
+/* ---- scorer (SURVEY.md §8f rank 2) -----------------------------------------------------------------
+ * Levenshtein distances of n (prediction, target) byte-string pairs, the `distance` call of the evaluation loop
+ * c18:1-15 (score = (len(target) - distance) / len(target)). Host function; strings need not be NUL-terminated. */
+ISHARA_API ishara_status_t ishara_edit_distances(const char* const* preds, const int32_t* pred_lens, const char* const* targets,
+                                                 const int32_t* target_lens, int32_t n, int32_t* out_distances);
 
 /* ---- operator-level entry points (device pointers; bf16 tensors are raw uint16 bit patterns) --- */
 typedef struct {
