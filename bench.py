@@ -291,107 +291,119 @@ def run_ours(args):
         e2e_s = float(t.item())
     assert r["nll"].shape == (B,) and len(r["text"]) == B
     sync_value = world * B * args.steps / e2e_s
-    # same work through the pipelined public API: every batch is still uploaded from pinned host memory and its results
-    # (ids, lengths, losses -> strings) read back inside the timed region, but batch i+1 uploads while batch i computes
-    for _ in m.infer_pipelined(((xh[i % 2], lab_np) for i in range(4))):
-        pass
-    sync_all()
-    t0 = time.perf_counter()
-    n_out = 0
-    for r in m.infer_pipelined(((xh[i % 2], lab_np) for i in range(args.steps))):
-        n_out += len(r["text"])
-    pipe_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([pipe_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pipe_s = float(t.item())
-    assert n_out == B * args.steps and r["nll"].shape == (B,)
-    e2e = {"value": world * B * args.steps / pipe_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(world * (B * T * F * 4 + B * L * 4)),
-           "d2h_bytes_per_step": int(world * (B * T * 4 + B * 4 + B * 4)),
-           "api": "IsharaModel.infer_pipelined(batches) -> ishara_model_infer_submit / _collect (two batches in flight)",
-           "sync_value": sync_value, "sync_api": "IsharaModel.infer(x_host, labels) -> ishara_model_infer_host (one blocking call per batch)"}
+    h2d_b, d2h_b = int(world * (B * T * F * 4 + B * L * 4)), int(world * (B * T * 4 + B * 4 + B * 4))
+    try:
+        # same work through the pipelined public API: every batch is still uploaded from pinned host memory and its results
+        # (ids, lengths, losses -> strings) read back inside the timed region, but batch i+1 uploads while batch i computes
+        for _ in m.infer_pipelined(((xh[i % 2], lab_np) for i in range(4))):
+            pass
+        sync_all()
+        t0 = time.perf_counter()
+        n_out = 0
+        for r in m.infer_pipelined(((xh[i % 2], lab_np) for i in range(args.steps))):
+            n_out += len(r["text"])
+        pipe_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([pipe_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pipe_s = float(t.item())
+        assert n_out == B * args.steps and r["nll"].shape == (B,)
+        e2e = {"value": world * B * args.steps / pipe_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(world * (B * T * F * 4 + B * L * 4)),
+               "d2h_bytes_per_step": int(world * (B * T * 4 + B * 4 + B * 4)),
+               "api": "IsharaModel.infer_pipelined(batches) -> ishara_model_infer_submit / _collect (two batches in flight)",
+               "sync_value": sync_value, "sync_api": "IsharaModel.infer(x_host, labels) -> ishara_model_infer_host (one blocking call per batch)"}
+    except Exception as ex:  # the auxiliary leg must never cost the headline line: fall back to the blocking figure
+        e2e = {"value": sync_value, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "api": "IsharaModel.infer(x_host, labels) -> ishara_model_infer_host (one blocking call per batch)",
+               "pipelined_error": repr(ex)}
 
     # ---- training step (64 sequences per GPU, fwd + CTC + bwd + clip + AdamW) ----
     train = None
     if not args.no_train:
-        from ishara_b200.parallel import DataParallelTrainer
+        try:
+            from ishara_b200.parallel import DataParallelTrainer
 
-        Bt = args.train_batch
-        mt = ib.get_model(device=local, seed=77)  # same weights on every rank (data-parallel replicas)
-        mt.train_config(0.2, seed=1000 + rank)    # dropout_rate=0.2 as in the reference's get_model call (c7:80)
-        mt.compile()                              # AdamW lr 4.5e-3, wd 0.08, clip-norm 1.0 (BASELINE.json cfg3)
-        trainer = DataParallelTrainer(mt)
-        txs = [torch.randn(Bt, T, F, device=dev, generator=torch.Generator(dev).manual_seed(9000 + 100 * rank + i)) for i in range(N_ROT)]
-        tlab = labels[:Bt].contiguous() if Bt <= B else labels.repeat((Bt + B - 1) // B, 1)[:Bt].contiguous()
-        k_train = max(3, min(args.steps, 20))
-        losses = []
-        for i in range(3):
-            losses.append(trainer.train_step(txs[i % N_ROT], tlab))
-        sync_all()
-        l0 = lib.ishara_launch_count()
-        e0.record(stream)
-        for i in range(k_train):
-            losses.append(trainer.train_step(txs[i % N_ROT], tlab))
-        e1.record(stream)
-        sync_all()
-        tms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([tms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tms = float(t.item())
-        train = {"metric": "training sequences/sec at T=384 (forward + CTC + backward + clip-norm + AdamW)",
-                 "value": world * Bt * k_train / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms / k_train, "steps": k_train,
-                 "warmup": 3, "batch_per_gpu": Bt, "scaling": "weak", "dtype": "bf16 activations, fp32 master weights/gradients/moments",
-                 "gpu_launches_per_step": int(lib.ishara_launch_count() - l0) // k_train,
-                 "step_tflops": world * Bt * k_train * 3 * 6.367e9 / (tms * 1e-3) / 1e12,
-                 "loss_first": losses[0], "loss_last": losses[-1], "dropout_rate": 0.2,
-                 "exchange": None if world == 1 else "one NCCL all-reduce (sum) over the flat fp32 gradient buffer per step",
-                 "api": "DataParallelTrainer.train_step -> ishara_model_train_forward_backward / _apply"}
-        mt.close()
+            Bt = args.train_batch
+            mt = ib.get_model(device=local, seed=77)  # same weights on every rank (data-parallel replicas)
+            mt.train_config(0.2, seed=1000 + rank)    # dropout_rate=0.2 as in the reference's get_model call (c7:80)
+            mt.compile()                              # AdamW lr 4.5e-3, wd 0.08, clip-norm 1.0 (BASELINE.json cfg3)
+            trainer = DataParallelTrainer(mt)
+            txs = [torch.randn(Bt, T, F, device=dev, generator=torch.Generator(dev).manual_seed(9000 + 100 * rank + i)) for i in range(N_ROT)]
+            tlab = labels[:Bt].contiguous() if Bt <= B else labels.repeat((Bt + B - 1) // B, 1)[:Bt].contiguous()
+            k_train = max(3, min(args.steps, 20))
+            losses = []
+            for i in range(3):
+                losses.append(trainer.train_step(txs[i % N_ROT], tlab))
+            sync_all()
+            l0 = lib.ishara_launch_count()
+            e0.record(stream)
+            for i in range(k_train):
+                losses.append(trainer.train_step(txs[i % N_ROT], tlab))
+            e1.record(stream)
+            sync_all()
+            tms = e0.elapsed_time(e1)
+            if dist is not None:
+                t = torch.tensor([tms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                tms = float(t.item())
+            train = {"metric": "training sequences/sec at T=384 (forward + CTC + backward + clip-norm + AdamW)",
+                     "value": world * Bt * k_train / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms / k_train, "steps": k_train,
+                     "warmup": 3, "batch_per_gpu": Bt, "scaling": "weak", "dtype": "bf16 activations, fp32 master weights/gradients/moments",
+                     "gpu_launches_per_step": int(lib.ishara_launch_count() - l0) // k_train,
+                     "step_tflops": world * Bt * k_train * 3 * 6.367e9 / (tms * 1e-3) / 1e12,
+                     "loss_first": losses[0], "loss_last": losses[-1], "dropout_rate": 0.2,
+                     "exchange": None if world == 1 else "one NCCL all-reduce (sum) over the flat fp32 gradient buffer per step",
+                     "api": "DataParallelTrainer.train_step -> ishara_model_train_forward_backward / _apply"}
+            mt.close()
+        except Exception as ex:
+            train = {"error": repr(ex)}
 
     # ---- landmark preprocessing in front of the model, rank 0 only ----
     prep = None
     if rank == 0 and not args.no_train:
-        from oracle import ishara_preprocess_oracle as PO
-        from ishara_b200.preprocess import _flatten_stats
+        try:
+            from oracle import ishara_preprocess_oracle as PO
+            from ishara_b200.preprocess import _flatten_stats
 
-        prng = np.random.default_rng(5)
-        plens = prng.integers(100, 801, size=B)                      # raw frames per sequence
-        offs = np.zeros(B + 1, np.int32)
-        offs[1:] = np.cumsum(plens)
-        raw = torch.rand(int(offs[-1]), F, device=dev)
-        raw[torch.rand(int(offs[-1]), device=dev) < 0.3, :42] = float("nan")   # missing hands, as MediaPipe reports them
-        st = PO.make_stats()
-        pm, ps = (torch.from_numpy(a).to(dev) for a in _flatten_stats(st))
-        offs_d = torch.from_numpy(offs).to(dev)
-        pout = torch.empty(B, T, F, device=dev)
+            prng = np.random.default_rng(5)
+            plens = prng.integers(100, 801, size=B)                      # raw frames per sequence
+            offs = np.zeros(B + 1, np.int32)
+            offs[1:] = np.cumsum(plens)
+            raw = torch.rand(int(offs[-1]), F, device=dev)
+            raw[torch.rand(int(offs[-1]), device=dev) < 0.3, :42] = float("nan")   # missing hands, as MediaPipe reports them
+            st = PO.make_stats()
+            pm, ps = (torch.from_numpy(a).to(dev) for a in _flatten_stats(st))
+            offs_d = torch.from_numpy(offs).to(dev)
+            pout = torch.empty(B, T, F, device=dev)
 
-        def prep_step():
-            _lib.check(lib.ishara_preprocess(vp(raw), vp(offs_d), B, int(plens.max()), vp(pm), vp(ps), T, 1, vp(pout), sp))
+            def prep_step():
+                _lib.check(lib.ishara_preprocess(vp(raw), vp(offs_d), B, int(plens.max()), vp(pm), vp(ps), T, 1, vp(pout), sp))
 
-        for _ in range(3):
-            prep_step()
-        torch.cuda.synchronize(dev)  # rank-0-only section: no collectives here (the other ranks are already at the final barrier)
-        e0.record(stream)
-        for _ in range(20):
-            prep_step()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)  # rank-0-only section: no collectives here (the other ranks are already at the final barrier)
-        pms = e0.elapsed_time(e1) / 20
-        pbytes = float(offs[-1]) * F * 4 + B * T * F * 4            # every raw frame read once + the model input written once
-        t0 = time.perf_counter()
-        raw_h = raw[: int(offs[8])].cpu().numpy()
-        for i in range(8):
-            PO.preprocess(raw_h[offs[i]:offs[i + 1]], st, T)
-        cpu_s = (time.perf_counter() - t0) / 8
-        peaks_p = load_peaks()
-        prep = {"metric": "preprocessed sequences/sec (gather + hand-frame filter + resize_pad + normalise -> [T,276])",
-                "value": B / (pms * 1e-3), "unit": UNIT, "ms_per_launch": pms, "batch": B, "mean_raw_frames": float(plens.mean()),
-                "roofline": {"bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peaks_p["hbm_gbs"], "unit": "GB/s",
-                             "frac": pbytes / (pms * 1e-3) / 1e9 / peaks_p["hbm_gbs"], "algorithmic_bytes_per_launch": pbytes},
-                "cpu_baseline": {"value": 1.0 / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
-                                 "sample": "8 sequences through the numpy oracle"}}
+            for _ in range(3):
+                prep_step()
+            torch.cuda.synchronize(dev)  # rank-0-only section: no collectives here (the other ranks are already at the final barrier)
+            e0.record(stream)
+            for _ in range(20):
+                prep_step()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)  # rank-0-only section: no collectives here (the other ranks are already at the final barrier)
+            pms = e0.elapsed_time(e1) / 20
+            pbytes = float(offs[-1]) * F * 4 + B * T * F * 4            # every raw frame read once + the model input written once
+            t0 = time.perf_counter()
+            raw_h = raw[: int(offs[8])].cpu().numpy()
+            for i in range(8):
+                PO.preprocess(raw_h[offs[i]:offs[i + 1]], st, T)
+            cpu_s = (time.perf_counter() - t0) / 8
+            peaks_p = load_peaks()
+            prep = {"metric": "preprocessed sequences/sec (gather + hand-frame filter + resize_pad + normalise -> [T,276])",
+                    "value": B / (pms * 1e-3), "unit": UNIT, "ms_per_launch": pms, "batch": B, "mean_raw_frames": float(plens.mean()),
+                    "roofline": {"bound": "hbm", "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peaks_p["hbm_gbs"], "unit": "GB/s",
+                                 "frac": pbytes / (pms * 1e-3) / 1e9 / peaks_p["hbm_gbs"], "algorithmic_bytes_per_launch": pbytes},
+                    "cpu_baseline": {"value": 1.0 / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
+                                     "sample": "8 sequences through the numpy oracle"}}
+        except Exception as ex:
+            prep = {"error": repr(ex)}
 
     # ---- per-launch device times of the same step (rank 0), profiled pass ----
     roof = kernels = None
