@@ -176,3 +176,35 @@ def test_edit_distances_host_function():
     assert got.tolist() == [dp(p, t) for p, t in pairs]
     s = levenshtein_scores(["3 creekhouse", "x"], ["3 creekhouse", "ab"])
     assert s[0] == 1.0 and s[1] == 0.0
+
+
+def test_new_entry_points_report_errors_without_gpu():
+    """Training, preprocessing, pipelined inference and scorer entry points: argument and state errors are status codes
+    with a message; no compute is attempted without a device and nothing falls back to the CPU."""
+    lib = _lib.load()
+    m = ib.get_model(dim=128, num_conv_squeeze_blocks=0, num_conv_conform_blocks=1, num_heads=4, input_shape=(32, 20),
+                     num_classes=12)
+    # state errors: nothing submitted / no training state yet
+    assert lib.ishara_model_infer_collect(m._h) == _lib.ERR_STATE and b"nothing in flight" in lib.ishara_last_error()
+    assert lib.ishara_model_train_apply(m._h, None, 1.0, None) == _lib.ERR_STATE
+    ptr, n = C.c_void_p(), C.c_int64()
+    assert lib.ishara_model_train_grad_buffer(m._h, C.byref(ptr), C.byref(n)) == _lib.ERR_STATE
+    a = np.zeros(4, np.float32)
+    assert lib.ishara_model_train_param_grad(m._h, b"stem_conv.kernel", a.ctypes.data_as(C.c_void_p), 4) == _lib.ERR_STATE
+    assert lib.ishara_model_train_sync(m._h) == _lib.OK                      # nothing to sync is not an error
+    # argument errors
+    assert lib.ishara_model_train_configure(None, 0.0, 0, 0) == _lib.ERR_INVALID
+    assert lib.ishara_model_train_configure(m._h, 1.5, 0, 0) == _lib.ERR_INVALID and b"dropout" in lib.ishara_last_error()
+    assert lib.ishara_model_infer_submit(m._h, None, 1, None, 0, None, None, None, None) == _lib.ERR_INVALID
+    assert lib.ishara_model_train_step_host(m._h, None, None, 1, 1, None, None) == _lib.ERR_INVALID
+    assert lib.ishara_preprocess(None, None, 1, 0, None, None, 32, 1, None, None) == _lib.ERR_INVALID
+    assert lib.ishara_edit_distances(None, None, None, None, 3, None) == _lib.ERR_INVALID
+    assert lib.ishara_edit_distances(None, None, None, None, 0, None) == _lib.OK
+    if lib.ishara_device_count() == 0:
+        # compute needs the device: loud CUDA error, no fallback
+        with pytest.raises(ib.IsharaError) as e:
+            m.train_step(np.zeros((1, 32, 20), np.float32), np.zeros((1, 4), np.int32))
+        assert e.value.status == _lib.ERR_CUDA
+        with pytest.raises(ib.IsharaError):
+            ib.LandmarkPreprocessor({g: (0.0, 1.0) for g in ("lip", "rhand", "lhand", "rpose", "lpose")}, frame_len=32)
+    m.close()
