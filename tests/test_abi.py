@@ -208,3 +208,23 @@ def test_new_entry_points_report_errors_without_gpu():
         with pytest.raises(ib.IsharaError):
             ib.LandmarkPreprocessor({g: (0.0, 1.0) for g in ("lip", "rhand", "lhand", "rpose", "lpose")}, frame_len=32)
     m.close()
+
+
+def test_c_host_example_builds_and_uses_the_abi(tmp_path):
+    """examples/infer.c: a plain-C host (no Python, no torch) drives the ABI; 235 tensors / 7,591,096 parameters are the
+    reference's model.summary() count for the BASELINE configuration. Without a GPU the first compute call fails loudly."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "infer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "infer.c"),
+                    "-L", libdir, "-lishara_b200", f"-Wl,-rpath,{libdir}", "-lm", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert "235 tensors, 7591096 parameters" in r.stdout
+    if _lib.load().ishara_device_count() == 0:
+        assert r.returncode == 3 and "status 3" in r.stderr
+    else:
+        assert r.returncode == 0 and "sequence 1:" in r.stdout
