@@ -186,10 +186,13 @@ class IsharaModel:
         self.load_weights(w)
 
     def load_weights(self, src: Union[str, os.PathLike, Mapping[str, np.ndarray]]):
-        """Named tensors in Keras layouts, from a mapping or an .npz written by save_weights."""
+        """Named tensors in Keras layouts, from a mapping, an .npz or a .safetensors file written by save_weights."""
         if isinstance(src, (str, os.PathLike)):
-            with np.load(src) as z:
-                src = {k: z[k] for k in z.files}
+            if str(src).endswith(".safetensors"):
+                src = _read_safetensors(src)
+            else:
+                with np.load(src) as z:
+                    src = {k: z[k] for k in z.files}
         known = dict(self._specs)
         for name, arr in src.items():
             if name not in known:
@@ -199,6 +202,7 @@ class IsharaModel:
                 raise ValueError(f"{name}: expected shape {known[name]}, got {tuple(a.shape)}")
             _lib.check(self._lib.ishara_model_set_param(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size))
         self._finalized = False
+        self._train_configured = False  # the library dropped its training state (masters, Adam moments): re-configure lazily
         return self
 
     def get_weights(self) -> Dict[str, np.ndarray]:
@@ -212,7 +216,11 @@ class IsharaModel:
     state_dict = get_weights
 
     def save_weights(self, path):
-        np.savez(path, **self.get_weights())
+        """Keras names and layouts; ``.safetensors`` (fp32, header + raw little-endian data) or ``.npz`` by extension."""
+        if str(path).endswith(".safetensors"):
+            _write_safetensors(path, self.get_weights())
+        else:
+            np.savez(path, **self.get_weights())
 
     def _ensure_finalized(self):
         if not self._finalized:
@@ -259,11 +267,12 @@ class IsharaModel:
         p = self.dropout_rate if dropout_rate is None else float(dropout_rate)
         _lib.check(self._lib.ishara_model_train_configure(self._h, p, int(seed) & (2 ** 64 - 1), 1 if debug else 0))
         self._train_configured = True
+        self._train_cfg = (p, seed, debug)  # re-applied if load_weights resets the library's training state
         return self
 
     def _train_args(self, x, labels):
         if not getattr(self, "_train_configured", False):
-            self.train_config()
+            self.train_config(*getattr(self, "_train_cfg", (None, 0, False)))
         if isinstance(x, np.ndarray):
             x = np.ascontiguousarray(x, dtype=np.float32)
             self._check_x(x.shape)
@@ -636,6 +645,44 @@ def get_model(dim=256, num_conv_squeeze_blocks=2, num_conv_conform_blocks=2, ker
     return IsharaModel(dim, num_conv_squeeze_blocks, num_conv_conform_blocks, kernel_sizes, num_conv_per_block,
                        dropout_rate, num_heads, expansion_factor, transformer_kernel_size, input_shape=input_shape,
                        num_classes=num_classes, device=device, mask_mode=mask_mode, seed=seed)
+
+
+def _write_safetensors(path, tensors: Mapping[str, np.ndarray]) -> None:
+    """safetensors container: u64 header length, JSON header {name: {dtype, shape, data_offsets}}, raw data."""
+    import json
+
+    header, blobs, off = {}, [], 0
+    for name, a in tensors.items():
+        b = np.ascontiguousarray(a, dtype="<f4").tobytes()
+        header[name] = {"dtype": "F32", "shape": list(a.shape), "data_offsets": [off, off + len(b)]}
+        blobs.append(b)
+        off += len(b)
+    header["__metadata__"] = {"format": "ishara_b200 keras-layout weights"}
+    hj = json.dumps(header, separators=(",", ":")).encode()
+    hj += b" " * ((8 - len(hj) % 8) % 8)
+    with open(path, "wb") as f:
+        f.write(len(hj).to_bytes(8, "little"))
+        f.write(hj)
+        for b in blobs:
+            f.write(b)
+
+
+def _read_safetensors(path) -> Dict[str, np.ndarray]:
+    import json
+
+    with open(path, "rb") as f:
+        n = int.from_bytes(f.read(8), "little")
+        header = json.loads(f.read(n))
+        data = f.read()
+    out = {}
+    for name, meta in header.items():
+        if name == "__metadata__":
+            continue
+        if meta["dtype"] != "F32":
+            raise TypeError(f"{name}: dtype {meta['dtype']} (only F32 weights are stored)")
+        b, e = meta["data_offsets"]
+        out[name] = np.frombuffer(data[b:e], dtype="<f4").reshape(meta["shape"]).astype(np.float32)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

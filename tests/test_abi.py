@@ -90,6 +90,18 @@ def test_weights_round_trip_and_keras_default_init(tmp_path):
                       num_classes=12).load_weights(str(path))
     for k, v in m2.get_weights().items():
         assert np.array_equal(v, p[k]), k
+    # same through the safetensors container (readable by the `safetensors` package: u64 header length + JSON + raw fp32)
+    sp = tmp_path / "w.safetensors"
+    m.save_weights(sp)
+    raw = open(sp, "rb").read()
+    n = int.from_bytes(raw[:8], "little")
+    import json
+    hdr = json.loads(raw[8:8 + n])
+    assert hdr["stem_conv.kernel"]["dtype"] == "F32" and hdr["stem_conv.kernel"]["shape"] == [20, 64] and n % 8 == 0
+    m3 = ib.get_model(dim=64, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, num_heads=4, input_shape=(32, 20),
+                      num_classes=12).load_weights(sp)
+    for k, v in m3.get_weights().items():
+        assert np.array_equal(v, p[k]), k
 
 
 def test_error_reporting_without_gpu():
