@@ -9,7 +9,7 @@ from . import _lib
 from ._dlpack import DeviceTensor, from_host
 from ._lib import IsharaError
 from .model import (CTCLoss, FALLBACK_IDS, IsharaModel, char_to_num, decode_batch_predictions, decode_ids,
-                    decode_phrase, get_model, num_to_char, num_to_char_fn, pad_token, pad_token_idx,
+                    decode_phrase, get_model, lr_schedule, lrfn, num_to_char, num_to_char_fn, pad_token, pad_token_idx,
                     tflite_postprocess)
 from .preprocess import LandmarkPreprocessor, sel_cols
 from .deploy import TFLiteModel, edit_distances, levenshtein_scores
@@ -20,5 +20,5 @@ __all__ = [
     "get_model", "IsharaModel", "CTCLoss", "decode_phrase", "decode_batch_predictions", "decode_ids",
     "num_to_char_fn", "tflite_postprocess", "char_to_num", "num_to_char", "pad_token", "pad_token_idx",
     "FALLBACK_IDS", "DeviceTensor", "from_host", "IsharaError", "LandmarkPreprocessor", "sel_cols",
-    "TFLiteModel", "edit_distances", "levenshtein_scores",
+    "TFLiteModel", "edit_distances", "levenshtein_scores", "lrfn", "lr_schedule",
 ]

@@ -320,14 +320,29 @@ class IsharaModel:
                                                          C.byref(loss), _vp(x.stream)))
         return float(loss.value)
 
-    def fit(self, dataset, epochs: int = 1, verbose: bool = False) -> List[float]:
-        """Minimal stand-in for model.fit(train_dataset, epochs=...) (c12:1): iterates (x, labels) batches."""
-        history = []
+    def fit(self, dataset, epochs: int = 1, validation_data=None, lr_schedule: Optional[Sequence[float]] = None,
+            wd_ratio: Optional[float] = None, verbose: bool = False) -> Dict[str, List[float]]:
+        """Stand-in for ``model.fit(train_dataset, validation_data=..., epochs=N, callbacks=[lr_callback,
+        WeightDecayCallback()])`` (c12:1-9): iterates ``(x, labels)`` batches; ``lr_schedule[epoch]`` is what
+        ``LearningRateScheduler`` sets (c11:59), ``wd_ratio`` what ``WeightDecayCallback`` does at every epoch start
+        (weight_decay = learning_rate * wd_ratio, c11:62-70). Returns Keras-history-like ``{"loss": [...], "val_loss": [...]}``
+        (validation loss = mean CTC loss through the inference path)."""
+        history: Dict[str, List[float]] = {"loss": []}
+        if validation_data is not None:
+            history["val_loss"] = []
+        base = getattr(self, "_opt", None) or _lib.AdamW(4.5e-3, 0.08, 0.9, 0.999, 1e-8, 1.0)
         for ep in range(epochs):
+            lr = float(lr_schedule[ep]) if lr_schedule is not None else float(base.lr)
+            wd = lr * float(wd_ratio) if wd_ratio is not None else float(base.weight_decay)
+            self._opt = _lib.AdamW(lr, wd, base.beta1, base.beta2, base.eps, base.max_norm)
             losses = [self.train_step(x, y) for x, y in dataset]
-            history.append(float(np.mean(losses)) if losses else float("nan"))
+            history["loss"].append(float(np.mean(losses)) if losses else float("nan"))
+            if validation_data is not None:
+                nll = [np.asarray(self.infer(np.asarray(x, np.float32), labels=np.asarray(y))["nll"]) for x, y in validation_data]
+                history["val_loss"].append(float(np.concatenate(nll).mean()) if nll else float("nan"))
             if verbose:
-                print(f"epoch {ep + 1}/{epochs} loss {history[-1]:.4f}")
+                extra = f" val_loss {history['val_loss'][-1]:.4f}" if validation_data is not None else ""
+                print(f"epoch {ep + 1}/{epochs} learning rate: {lr:.2e}, weight decay: {wd:.2e} loss {history['loss'][-1]:.4f}{extra}")
         return history
 
     def grad_buffer(self) -> Tuple[int, int]:
@@ -645,6 +660,26 @@ def get_model(dim=256, num_conv_squeeze_blocks=2, num_conv_conform_blocks=2, ker
     return IsharaModel(dim, num_conv_squeeze_blocks, num_conv_conform_blocks, kernel_sizes, num_conv_per_block,
                        dropout_rate, num_heads, expansion_factor, transformer_kernel_size, input_shape=input_shape,
                        num_classes=num_classes, device=device, mask_mode=mask_mode, seed=seed)
+
+
+def lrfn(current_step: int, num_warmup_steps: int, lr_max: float, num_cycles: float = 0.50, num_training_steps: int = 50,
+         warmup_method: str = "exp") -> float:
+    """The reference's per-epoch learning-rate rule (c11:1-12): exponential ('exp': x2 per epoch) or 'log' (x10 per epoch)
+    warm-up to ``lr_max``, then a half-cosine decay over the remaining epochs."""
+    import math
+
+    if current_step < num_warmup_steps:
+        if warmup_method == "log":
+            return lr_max * 0.10 ** (num_warmup_steps - current_step)
+        return lr_max * 2 ** -(num_warmup_steps - current_step)
+    progress = float(current_step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress))) * lr_max
+
+
+def lr_schedule(n_epochs: int = 50, n_warmup_epochs: int = 5, lr_max: float = 4e-3, num_cycles: float = 0.50,
+                warmup_method: str = "exp") -> List[float]:
+    """LR_SCHEDULE of the reference (c10:1-5, c11:57): one learning rate per epoch."""
+    return [lrfn(step, n_warmup_epochs, lr_max, num_cycles, n_epochs, warmup_method) for step in range(n_epochs)]
 
 
 def _write_safetensors(path, tensors: Mapping[str, np.ndarray]) -> None:

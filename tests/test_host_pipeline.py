@@ -80,3 +80,27 @@ def test_early_close_drains_the_pipeline_and_bad_input_raises():
         pass
     assert m._lib.inflight == []                                          # the batch in flight was collected
     assert [r["nll"] for r in m.infer_pipelined(batches[:1])] == [None]   # no labels -> no losses
+
+
+def test_lr_schedule_and_fit_callbacks_host_logic():
+    """lrfn / LR_SCHEDULE (c11:1-12,57) and fit()'s per-epoch learning-rate + weight-decay callbacks (c11:59-70, c12:1-9)."""
+    import math
+
+    import ishara_b200 as ib
+
+    s = ib.lr_schedule(n_epochs=50, n_warmup_epochs=5, lr_max=4e-3)              # the reference's constants (c10:1-5)
+    assert len(s) == 50 and s[:6] == [4e-3 * 2 ** -5, 4e-3 * 2 ** -4, 4e-3 * 2 ** -3, 4e-3 * 2 ** -2, 4e-3 * 2 ** -1, 4e-3]
+    assert abs(s[27] - 0.5 * (1 + math.cos(math.pi * 22 / 45)) * 4e-3) < 1e-15 and s[-1] < 1e-5
+    assert all(a >= b for a, b in zip(s[5:], s[6:]))                            # monotone decay after the warm-up
+    assert abs(ib.lrfn(1, 3, 1.0, warmup_method="log") - 0.01) < 1e-15
+
+    m = _model()
+    seen = []
+    m.train_step = lambda x, y: (seen.append((m._opt.lr, m._opt.weight_decay)), 2.0 * len(seen))[1]
+    m.infer = lambda x, labels=None: {"nll": np.full(len(x), 3.0, np.float32)}
+    data = [(np.zeros((2, 8, 4), np.float32), np.zeros((2, 5), np.int32))] * 3
+    h = m.fit(data, epochs=2, validation_data=data[:1], lr_schedule=[1e-3, 5e-4], wd_ratio=0.05)
+    assert h["loss"] == [4.0, 10.0] and h["val_loss"] == [3.0, 3.0]
+    lrs = [round(a, 9) for a, _ in seen]
+    assert lrs == [1e-3] * 3 + [5e-4] * 3
+    assert all(abs(wd - lr * 0.05) < 1e-9 for lr, wd in seen)                   # WeightDecayCallback: wd = lr * WD_RATIO
