@@ -95,3 +95,27 @@ def test_host_dropout_masks_structure():
         if v.size > 1000:
             assert abs(float((v == 0).mean()) - rate) < 0.02, k
     m.close()
+
+
+def test_oracle_against_tf_training_golden_if_present():
+    """tools/dump_tf_reference.py (run where TensorFlow is available) pins the training-mode oracle: loss, gradients
+    and the BatchNorm moving-statistics update of the real Keras model with dropout switched off."""
+    import os
+
+    import pytest
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_reference_train.npz")
+    if not os.path.exists(path):
+        pytest.skip("no TensorFlow golden vectors (parity unpinned; see tools/dump_tf_reference.py)")
+    z = np.load(path, allow_pickle=True)
+    p = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    cfg = O.Config(frames=int(z["x"].shape[1]))
+    r = TO.forward_train(p, z["x"], z["labels"], cfg)
+    assert abs(r["loss"] - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+    assert np.abs(r["logits"] - z["logits_train"]).max() <= 1e-3 * np.abs(z["logits_train"]).max()
+    for k in z.files:
+        if k.startswith("g:"):
+            ref = z[k]
+            assert np.linalg.norm(r["grads"][k[2:]] - ref) <= 2e-3 * max(np.linalg.norm(ref), 1e-6), k
+        if k.startswith("s:"):
+            assert np.allclose(r["new_stats"][k[2:]], z[k], rtol=1e-4, atol=1e-6), k

@@ -6,7 +6,9 @@ It does not contain reference code: it loads cells c5-c8 of `Test Notebooks/conv
 checkout you point it at, executes them, builds get_model() with the BASELINE kwargs, loads the seeded weights
 that oracle.init_params generates (so both sides share weights), runs seeded inputs and writes
 
-    tests/golden/tf_reference.npz   weights (Keras names), x, labels, logits, per-sequence CTC loss, decoded ids
+    tests/golden/tf_reference.npz        weights (Keras names), x, labels, logits, per-sequence CTC loss, decoded ids
+    tests/golden/tf_reference_train.npz  one training-mode step with every Dropout layer switched off: mean CTC loss,
+                                         gradients of all trainable variables, updated BatchNorm moving statistics
 
 usage: python tools/dump_tf_reference.py /path/to/ishara [--frames 384] [--batch 4]
 """
@@ -73,6 +75,30 @@ def main():
     out = os.path.join(ROOT, "tests", "golden", "tf_reference.npz")
     np.savez(out, x=x, labels=y, logits=logits, nll=nll, ids=np.array(ids, dtype=object), **{"w:" + k: v for k, v in params.items()})
     print("wrote", out)
+
+    # ---- training-mode step. The head's Dropout(0.4) and ConformerBlock's attention dropout cannot
+    # be disabled through get_model's kwargs, so every Dropout layer is made the identity for this dump: what is pinned is
+    # BatchNormalization on batch statistics + its moving-average update, the loss and the gradients.
+    tf.keras.layers.Dropout.call = lambda self, inputs, training=None: inputs
+    name_of = {}
+    for v in model.variables:
+        cand = v.name.split(":")[0].replace("/", ".")
+        for name in params:
+            if cand.endswith(name) or name.replace("_eca.", ".").endswith(cand):
+                name_of[v.ref()] = name
+                break
+    with tf.GradientTape() as tape:
+        lg = model(x, training=True)
+        loss = ns["CTCLoss"](tf.constant(y), lg)
+    grads = tape.gradient(loss, model.trainable_variables)
+    gout = {"g:" + name_of[v.ref()]: (np.zeros(v.shape, np.float32) if g is None else tf.convert_to_tensor(g).numpy().reshape(v.shape))
+            for v, g in zip(model.trainable_variables, grads)}
+    stats = {"s:" + name_of[v.ref()]: v.numpy() for v in model.variables
+             if name_of[v.ref()].endswith(("moving_mean", "moving_variance"))}
+    out_t = os.path.join(ROOT, "tests", "golden", "tf_reference_train.npz")
+    np.savez(out_t, x=x, labels=y, loss=np.float32(loss.numpy()), logits_train=lg.numpy(), **gout, **stats,
+             **{"w:" + k: v for k, v in params.items()})
+    print("wrote", out_t)
 
 
 if __name__ == "__main__":
