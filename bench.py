@@ -490,10 +490,10 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     ap.add_argument("--train-batch", type=int, default=64, help="sequences per GPU per training step (cfg3)")
     args = ap.parse_args()
-    # safety net: a hung collective or kernel must not hold the box — dump every thread's stack and exit after 20 minutes
+    # safety net: a hung collective or kernel must not hold the box — dump every thread's stack and exit after 15 minutes
     import faulthandler
 
-    faulthandler.dump_traceback_later(1200, exit=True)
+    faulthandler.dump_traceback_later(900, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
