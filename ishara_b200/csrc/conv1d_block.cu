@@ -1,0 +1,545 @@
+// ishara_b200 — the whole Conv1DBlock in ONE launch (sm_100a only):
+//   S <- S + (ECA(BN(CausalDWConv1D_k(swish(S @ We + be)))) @ Wp + bp)      [, XN <- LayerNorm(S) for the next module]
+//
+// Reference: Conv1DBlock (nb:conv-hybrid-model c5:41-89) = Dense(2D, swish) c5:61-65 -> CausalDWConv1D(k) c5:17-39,68-71
+// -> BatchNorm c5:73 -> ECA c5:1-15,75 -> Dense(D) c5:77-80 -> (+ skip) c5:85-86; 12 of them per forward (c7:20-29).
+// As three launches (expand GEMM, depthwise kernel, project GEMM) the 2D-wide tensor crossed HBM four times
+// (571 MB per block at B = 256 against 100.7 MB of compulsory traffic). Here it exists only in shared memory / TMEM:
+// the kernel reads the [T, D] stream once and writes it once.
+//
+//   cluster = the T/128 CTAs of ONE sequence; CTA r owns frames [128 r, 128 r + 128); 640 threads:
+//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4-19: 16 worker warps
+//
+//   1. expand:  acc[128 x 512] fp32 (all 512 TMEM columns, two N = 256 halves) = S_tile @ We^T, operands through three
+//      48 KB TMA slots; the first half is drained while the second half's MMAs run
+//   2. drain:   + be, swish, bf16 -> H[128 x 512] in shared memory, laid out as the eight [128 x 64] K-major
+//      128B-swizzled boxes that tcgen05.mma consumes as the A operand of the project GEMM (16 halo rows in front of
+//      each box hold the k-1 frames of the previous CTA)
+//   3. ECA:     mean over the VALID frames of the BatchNorm'd conv output. The conv is linear in time, so the mean is
+//      wsum * colsum(H) - (a correction from the last k-1 valid frames): every CTA publishes its partial sums,
+//      cluster barrier, every CTA derives all 512 channel scales (5-tap conv across channels + sigmoid) from DSMEM
+//   4. stencil: IN PLACE, box pair by box pair: warp = (box, 16-frame group), lane = channel pair, register sliding
+//      window walking DOWN the frames (so a frame is overwritten only after every tap that needs it has read it);
+//      BatchNorm and the ECA scale are folded into the taps. As soon as a box is finished the MMA warp issues its
+//      four project MMAs (K = 64) against the matching Wp slice streamed through a two-slot ring
+//   5. epilogue (16 warps, lane = row): + bp, + residual, [LayerNorm statistics exchanged between the four warps of a
+//      lane quarter, values parked in TMEM], TMA stores of S and of LN(S)
+// Only D == 256 (2D = 512 TMEM columns), T % 128 == 0, T <= 1024; other shapes use the three-kernel path.
+#include "gemm_epilogue.cuh"
+
+namespace ishara {
+namespace {
+
+constexpr int kKD = 256;                      // model dim
+constexpr int kKC = 512;                      // expanded channels
+constexpr int kBoxHalo = 2048;                // 16 halo rows x 128 B in front of every box
+constexpr int kBoxStride = kBoxHalo + kAStageBytes;  // 18 KB (keeps every box 1024-byte aligned)
+constexpr int kHRegion = 8 * kBoxStride;      // 144 KB
+constexpr int kWSlot = 32 * 1024;             // one [256 x 64] k-slice of Wp^T
+constexpr int kWRing = 2 * kWSlot;
+constexpr int kXSlot = 48 * 1024;             // expand slot: S chunk [128 x 64] + We chunk [256 x 64]
+constexpr int kFloatBytes = 12 * 1024;        // part2 / corr2 / mean / scale (LN exchange aliases part2)
+constexpr int kCbSmem = kHRegion + kWRing + kFloatBytes + 256 + 1024;
+constexpr int kWorkers = 16;
+constexpr int kCbThreads = 128 + 32 * kWorkers;
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + __expf(-x)); }
+
+struct CbBars {
+  uint64_t full[3], empty[3];   // expand slots
+  uint64_t accf[2];             // expand accumulator half ready
+  uint64_t wfull[2], wempty[2]; // Wp ring
+  uint64_t boxr[8];             // stencil finished box b (8 warps each)
+  uint64_t acc2f;               // project accumulator ready
+  uint32_t tmem_slot;
+};
+
+struct CbParams {
+  const float* bias_e;   // [512]
+  const float* dw_w;     // [k, 512] taps, BatchNorm folded
+  const float* dw_b;     // [512]
+  const float* eca_w;    // [5]
+  const float* bias_p;   // [256]
+  const bf16* resid;     // S [M, 256]
+  const float* ln_g;     // LayerNorm of the NEXT module (null: none)
+  const float* ln_b;
+  float ln_eps;
+  const int32_t* seq_len;  // [B] valid frames per sequence for the ECA mean (mask_mode="propagated"), null = all T
+  int T;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kCbThreads, 1)
+conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
+                    const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmO0,
+                    const __grid_constant__ CUtensorMap tmO1, const CbParams pr) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* part2 = reinterpret_cast<float*>(smem + kHRegion + kWRing);  // [2][512] column sums (valid frames) of the row halves
+  float* corr2 = part2 + 2 * kKC;                                     // [2][512] tail-correction shares
+  float* mean = corr2 + 2 * kKC;                                      // [512]
+  float* scale = mean + kKC;                                          // [512]
+  CbBars* bars = reinterpret_cast<CbBars*>(smem + kHRegion + kWRing + kFloatBytes);
+
+  const int rank = blockIdx.x, nrank = gridDim.x;   // tile index inside the sequence == rank in the cluster
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = pr.T;
+  const int row_g0 = b * T + rank * kBM;
+  const uint32_t w_base = smem_base + kHRegion;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWe);
+    tma_prefetch_desc(&tmWp);
+    tma_prefetch_desc(&tmO0);
+    if (pr.ln_g != nullptr) tma_prefetch_desc(&tmO1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 3; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->accf[s], 1); mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
+    for (int s = 0; s < 8; ++s) mbar_init(&bars->boxr[s], 8);
+    mbar_init(&bars->acc2f, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+  constexpr uint32_t IDESC = umma_idesc(kBM, 256, 1);
+
+  // Expand operand slots. Loads 0-3 feed accumulator half 0, loads 4-7 half 1; the second half only uses the two slots
+  // that do not overlap boxes 0-3, so the drain of half 0 can run under the MMAs of half 1.
+  //   slot 0 = [0, 48K) (boxes 0-2), slot 1 = [72K, 120K) (boxes 4-6), slot 2 = [120K, 168K) (boxes 6-7 + Wp slot 0)
+  const uint32_t slot_off[3] = {0u, 72u * 1024u, 120u * 1024u};
+  const int slot_of[8] = {0, 1, 2, 0, 1, 2, 1, 2};
+  const int use_of[8] = {0, 0, 0, 1, 1, 1, 2, 2};
+
+  // ======================================= phase 1: expand GEMM + drain =======================================
+  if (warp == 0) {
+    if (lane == 0) {
+      // Wp slice 1 lives in [176K, 208K): never touched by the expand slots, prefetch it right away
+      mbar_arrive_expect_tx(&bars->wfull[1], kWSlot);
+      tma_load_2d(smem + kHRegion + kWSlot, &tmWp, &bars->wfull[1], 1 * kBK, 0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int s = slot_of[i], u = use_of[i];
+        const int nh = i >> 2, kb = i & 3;
+        if (u > 0) mbar_wait(&bars->empty[s], static_cast<uint32_t>((u - 1) & 1));
+        mbar_arrive_expect_tx(&bars->full[s], kXSlot);
+        uint8_t* dst = smem + slot_off[s];
+        tma_load_2d(dst, &tmX, &bars->full[s], kb * kBK, row_g0);
+        tma_load_2d(dst + kAStageBytes, &tmWe, &bars->full[s], kb * kBK, nh * 256);
+      }
+      // every expand MMA has retired -> slot 2 is dead -> Wp slice 0 may land in [144K, 176K)
+      mbar_wait(&bars->accf[1], 0);
+      mbar_arrive_expect_tx(&bars->wfull[0], kWSlot);
+      tma_load_2d(smem + kHRegion, &tmWp, &bars->wfull[0], 0, 0);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int s = slot_of[i], u = use_of[i];
+        const int nh = i >> 2, kb = i & 3;
+        mbar_wait(&bars->full[s], static_cast<uint32_t>(u & 1));
+        tc_fence_after();
+        const uint32_t sa = smem_base + slot_off[s];
+        const uint32_t sb = sa + kAStageBytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_bf16(tmem_base + nh * 256, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC,
+                    (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&bars->empty[s]);
+        if (kb == 3) umma_commit(&bars->accf[nh]);
+      }
+    }
+  } else if (warp >= 4) {
+    // drain: warp (q, c) turns rows [32q, +32) x channels [256 nh + 64 c, +64) into box 4 nh + c
+    const int ww = warp - 4;
+    const int q = warp & 3, c = ww >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+#pragma unroll 1
+    for (int nh = 0; nh < 2; ++nh) {
+      mbar_wait(&bars->accf[nh], 0);
+      tc_fence_after();
+      const uint32_t box = smem_base + static_cast<uint32_t>(4 * nh + c) * kBoxStride + kBoxHalo + static_cast<uint32_t>(q) * 4096u;
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        uint32_t raw[32];
+        float v[32];
+        const int col = nh * 256 + c * 64 + sub * 32;
+        tmem_ld32(tmem_base + lane_addr + col, raw);
+        tmem_ld_wait();
+        to_float(v, raw);
+        const float4* b4 = reinterpret_cast<const float4*>(pr.bias_e + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], bb.x, bb.y);
+          fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], bb.z, bb.w);
+        }
+        epi_swish(v);
+        stage_write<false>(box, lane, sub, v);
+      }
+    }
+    tc_fence_before();
+    named_bar_sync(3, 32 * kWorkers);  // the whole H tile is in shared memory
+
+    // ---- column sums over the valid frames of this tile + this tile's share of the tail correction ----
+    //   sum_{t<L} y[t] = L*b + sum_j w_j * (S_L - [last K-1-j valid frames]),  S_L = sum_{u<L} h[u]
+    //                  = L*b + wsum*S_L - sum_{i=1..K-1} cw_i * h[L-i],         cw_i = w_0 + ... + w_{K-1-i}
+    {
+      const int box = ww >> 1, rh = ww & 1;
+      const int L = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
+      const int lloc = L - rank * kBM;  // valid frames of the sequence that end inside / before / after this tile
+      const int lo = rh * 64, hi = min(lo + 64, lloc);
+      const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
+      const uint32_t lsw = static_cast<uint32_t>(lane >> 2), lw = static_cast<uint32_t>(lane & 3) << 2;
+      float2 s = make_float2(0.f, 0.f);
+      for (int r = lo; r < hi; ++r) {
+        const uint32_t u = ld_shared_u32(bx + static_cast<uint32_t>(r) * 128u + (((lsw ^ static_cast<uint32_t>(r & 7)) << 4) | lw));
+        fadd2(s.x, s.y, s.x, s.y, bf16_lo(u), bf16_hi(u));
+      }
+      float2 cr = make_float2(0.f, 0.f);
+      if (lloc >= 1 && lloc - (K - 1) < lo + 64 && lloc > lo) {  // some of the frames L-1 .. L-(K-1) fall into this row half
+        const int ch = box * 64 + 2 * lane;
+        float2 cw = make_float2(0.f, 0.f);  // running prefix sum of the taps: after adding tap j it equals cw_{K-1-j}
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) {
+          const float2 wj = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
+          cw.x += wj.x; cw.y += wj.y;
+          const int i = K - 1 - j;     // cw now = cw_i, pairs with frame L - i
+          const int r = lloc - i;
+          if (r >= lo && r < lo + 64 && r < kBM) {
+            const uint32_t u = ld_shared_u32(bx + static_cast<uint32_t>(r) * 128u + (((lsw ^ static_cast<uint32_t>(r & 7)) << 4) | lw));
+            cr.x = fmaf(cw.x, bf16_lo(u), cr.x);
+            cr.y = fmaf(cw.y, bf16_hi(u), cr.y);
+          }
+        }
+      }
+      *reinterpret_cast<float2*>(part2 + rh * kKC + box * 64 + 2 * lane) = s;
+      *reinterpret_cast<float2*>(corr2 + rh * kKC + box * 64 + 2 * lane) = cr;
+    }
+  }
+  __syncwarp();
+  cluster_arrive();   // #1: every CTA of the sequence has its H tile and its partial sums in shared memory
+  cluster_wait();
+
+  if (warp >= 4) {
+    const int ww = warp - 4;
+    // ---- halo: the previous CTA's last K-1 frames (zeros in front of the sequence) -> rows -(K-1)..-1 of every box.
+    //      (128 - j) & 7 == (-j) & 7, so a physical 128-byte row keeps its swizzle phase and is copied word by word ----
+    {
+      const int box = ww >> 1;
+      const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
+      for (int j = 1 + (ww & 1); j <= K - 1; j += 2) {
+        uint32_t u = 0u;
+        if (rank > 0) u = ld_dsmem_u32(mapa_shared(bx + static_cast<uint32_t>(kBM - j) * 128u + static_cast<uint32_t>(lane) * 4u, rank - 1));
+        st_shared_u32(bx - static_cast<uint32_t>(j) * 128u + static_cast<uint32_t>(lane) * 4u, u);
+      }
+    }
+    // ---- channel means of the BatchNorm'd conv output over the valid frames (every CTA computes all 512) ----
+    const int wt = threadIdx.x - 128;
+    if (wt < kKC / 2) {
+      const int ch = 2 * wt;
+      float2 S = make_float2(0.f, 0.f), C = make_float2(0.f, 0.f);
+      for (int rr = 0; rr < nrank; ++rr) {
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          const float2 a = ld_dsmem_f32x2(mapa_shared(smem_u32(part2 + rh * kKC + ch), rr));
+          const float2 c2 = ld_dsmem_f32x2(mapa_shared(smem_u32(corr2 + rh * kKC + ch), rr));
+          S.x += a.x; S.y += a.y;
+          C.x += c2.x; C.y += c2.y;
+        }
+      }
+      float2 wsum = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float2 wj = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
+        wsum.x += wj.x; wsum.y += wj.y;
+      }
+      const int L = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
+      const float invL = L > 0 ? 1.f / static_cast<float>(L) : 0.f;
+      const float2 bdw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
+      mean[ch] = fmaf(fmaf(wsum.x, S.x, -C.x), invL, bdw.x);
+      mean[ch + 1] = fmaf(fmaf(wsum.y, S.y, -C.y), invL, bdw.y);
+    }
+  }
+  __syncwarp();
+  cluster_arrive();   // #2 (arrive): this CTA no longer reads its neighbours' shared memory
+  if (warp >= 4) {
+    named_bar_sync(3, 32 * kWorkers);  // mean[] complete
+    const int wt = threadIdx.x - 128;  // one channel per worker thread
+    float z = 0.f;
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) {
+      const int cc = wt + d;
+      if (cc >= 0 && cc < kKC) z = fmaf(__ldg(pr.eca_w + d + 2), mean[cc], z);
+    }
+    scale[wt] = sigmoid_exact(z);
+    named_bar_sync(3, 32 * kWorkers);  // scale[] complete, halo rows written
+  }
+  cluster_wait();     // #2 (wait): the neighbour has copied its halo, this CTA's H tile may now be overwritten in place
+
+  // ======================================= phase 2: stencil -> project GEMM -> epilogue =======================================
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 2; c < 8; ++c) {
+        const int s = c & 1;
+        mbar_wait(&bars->wempty[s], static_cast<uint32_t>(((c >> 1) - 1) & 1));
+        mbar_arrive_expect_tx(&bars->wfull[s], kWSlot);
+        tma_load_2d(smem + kHRegion + s * kWSlot, &tmWp, &bars->wfull[s], c * kBK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int c = 0; c < 8; ++c) {
+        const int s = c & 1;
+        mbar_wait(&bars->wfull[s], static_cast<uint32_t>((c >> 1) & 1));
+        mbar_wait(&bars->boxr[c], 0);
+        tc_fence_after();
+        const uint32_t sa = smem_base + static_cast<uint32_t>(c) * kBoxStride + kBoxHalo;
+        const uint32_t sb = w_base + static_cast<uint32_t>(s) * kWSlot;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_bf16(tmem_base, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&bars->wempty[s]);
+      }
+      umma_commit(&bars->acc2f);
+    }
+  } else if (warp >= 4) {
+    const int ww = warp - 4;
+    // ---- stencil, in place: 4 rounds of two boxes; warp = (box of the round, 16-frame group), lane = channel pair ----
+    {
+      const int bi = ww >> 3, g = ww & 7;
+      constexpr int TB = 4;
+      const uint32_t lsw = static_cast<uint32_t>(lane >> 2), lw = static_cast<uint32_t>(lane & 3) << 2;
+      uint32_t sw[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sw[e] = ((lsw ^ static_cast<uint32_t>(e)) << 4) | lw;
+#pragma unroll 1
+      for (int round = 0; round < 4; ++round) {
+        const int box = 2 * round + bi;
+        const int ch = box * 64 + 2 * lane;
+        const uint32_t base = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo + static_cast<uint32_t>(g) * 16u * 128u;
+        const float2 sc = *reinterpret_cast<const float2*>(scale + ch);
+        float2 wt[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float2 wj = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
+          wt[j] = make_float2(wj.x * sc.x, wj.y * sc.y);
+        }
+        float2 bs = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
+        bs.x *= sc.x; bs.y *= sc.y;
+        // the K-1 frames in front of this group belong to the previous group (or to the halo rows): read them before
+        // anybody overwrites them
+        uint32_t hw[K - 1];
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) {
+          const int r = j - (K - 1);  // -(K-1) .. -1
+          hw[j] = ld_shared_u32(base + static_cast<uint32_t>(r * 128) + sw[r & 7]);
+        }
+        named_bar_sync(1 + bi, 256);
+        float2 x[TB + K - 1];
+#pragma unroll
+        for (int blk = 16 / TB - 1; blk >= 0; --blk) {
+          // window index i <-> frame 4 blk - (K-1) + i of the group
+#pragma unroll
+          for (int i = 0; i < TB + K - 1; ++i) {
+            if (blk == 16 / TB - 1 || i < TB) {
+              const int r = TB * blk - (K - 1) + i;
+              const uint32_t u = r >= 0 ? ld_shared_u32(base + static_cast<uint32_t>(r * 128) + sw[r & 7]) : hw[r + (K - 1)];
+              x[i] = make_float2(bf16_lo(u), bf16_hi(u));
+            }
+          }
+          uint32_t o[TB];
+#pragma unroll
+          for (int t = 0; t < TB; ++t) {
+            float2 a = bs;
+#pragma unroll
+            for (int j = 0; j < K; ++j) ffma2(a.x, a.y, wt[j].x, wt[j].y, x[t + j].x, x[t + j].y, a.x, a.y);
+            o[t] = pack_bf16x2(a.x, a.y);
+          }
+#pragma unroll
+          for (int t = 0; t < TB; ++t) {
+            const int r = TB * blk + t;
+            st_shared_u32(base + static_cast<uint32_t>(r * 128) + sw[r & 7], o[t]);
+          }
+          // keep the lowest K-1 frames of the window for the next (lower) block
+#pragma unroll
+          for (int i = K - 2; i >= 0; --i) x[i + TB] = x[i];
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->boxr[box]);
+      }
+    }
+
+    // ---- epilogue: warp (q, c) owns rows [32q, +32) x columns [64c, +64) ----
+    const int q = warp & 3, c = ww >> 2;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int row = row_g0 + q * 32 + lane;
+    const bool ln = pr.ln_g != nullptr;
+    const uint32_t stg0 = smem_base + static_cast<uint32_t>(ww) * kWarpStgBytes;             // H region is dead once acc2f fires
+    const uint32_t stg1 = smem_base + static_cast<uint32_t>(kWorkers + ww) * kWarpStgBytes;
+    const bf16* rrow = pr.resid + static_cast<size_t>(row) * kKD + c * 64;
+    uint4 rq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);  // in flight while the MMAs finish
+    mbar_wait(&bars->acc2f, 0);
+    tc_fence_after();
+    RowStats rs;
+#pragma unroll 1
+    for (int sub = 0; sub < 2; ++sub) {
+      const int col = c * 64 + sub * 32;
+      uint32_t raw[32];
+      float v[32];
+      tmem_ld32(tmem_base + lane_addr + col, raw);
+      uint4 rn[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rn[j] = sub == 0 ? __ldg(reinterpret_cast<const uint4*>(rrow + 32) + j) : make_uint4(0u, 0u, 0u, 0u);
+      tmem_ld_wait();
+      to_float(v, raw);
+      const float4* b4 = reinterpret_cast<const float4*>(pr.bias_p + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = __ldg(b4 + j);
+        fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], bb.x, bb.y);
+        fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], bb.z, bb.w);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 r4 = rq[j];
+        fadd2(v[8 * j + 0], v[8 * j + 1], v[8 * j + 0], v[8 * j + 1], bf16_lo(r4.x), bf16_hi(r4.x));
+        fadd2(v[8 * j + 2], v[8 * j + 3], v[8 * j + 2], v[8 * j + 3], bf16_lo(r4.y), bf16_hi(r4.y));
+        fadd2(v[8 * j + 4], v[8 * j + 5], v[8 * j + 4], v[8 * j + 5], bf16_lo(r4.z), bf16_hi(r4.z));
+        fadd2(v[8 * j + 6], v[8 * j + 7], v[8 * j + 6], v[8 * j + 7], bf16_lo(r4.w), bf16_hi(r4.w));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rq[j] = rn[j];
+      if (ln) {
+        rs.add(v);
+        to_raw(raw, v);
+        tmem_st32(tmem_base + lane_addr + col, raw);  // parked for the LayerNorm pass
+      }
+      stage_write<false>(stg0, lane, sub, v);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&tmO0, smem + static_cast<uint32_t>(ww) * kWarpStgBytes, c * 64, row_g0 + q * 32);
+      tma_store_commit();
+    }
+    if (ln) {
+      // row statistics of the four warps sharing this lane quarter
+      float4* xch = reinterpret_cast<float4*>(part2);  // [4 q][4 c][32] (aliases the column sums: dead since barrier #2)
+      tmem_st_wait();
+      xch[(q * 4 + c) * 32 + lane] = make_float4(rs.s0, rs.s1, rs.q0, rs.q1);
+      named_bar_sync(4 + q, 128);
+      float s = 0.f, qq = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 o = xch[(q * 4 + cc) * 32 + lane];
+        s += o.x + o.y;
+        qq += o.z + o.w;
+      }
+      const float m = s * (1.f / kKD);
+      const float var = fmaxf(qq * (1.f / kKD) - m * m, 0.f);
+      const float rstd = rsqrtf(var + pr.ln_eps);
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const int col = c * 64 + sub * 32;
+        uint32_t raw[32];
+        float v[32];
+        tmem_ld32(tmem_base + lane_addr + col, raw);
+        tmem_ld_wait();
+        to_float(v, raw);
+        epi_layernorm(v, pr.ln_g, pr.ln_b, m, rstd, col);
+        stage_write<false>(stg1, lane, sub, v);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmO1, smem + static_cast<uint32_t>(kWorkers + ww) * kWarpStgBytes, c * 64, row_g0 + q * 32);
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int K>
+int launch_k(const Conv1dBlockPlan& p, cudaStream_t stream) {
+  auto kern = conv1d_block_kernel<K>;
+  static bool attr = false;
+  if (!attr) {
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCbSmem));
+    attr = true;
+  }
+  CbParams pr;
+  pr.bias_e = p.bias_e; pr.dw_w = p.dw_w; pr.dw_b = p.dw_b; pr.eca_w = p.eca_w; pr.bias_p = p.bias_p;
+  pr.resid = p.resid; pr.ln_g = p.ln_g; pr.ln_b = p.ln_b; pr.ln_eps = p.ln_eps; pr.seq_len = p.seq_len; pr.T = p.T;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.T / kBM, p.B, 1);
+  cfg.blockDim = dim3(kCbThreads, 1, 1);
+  cfg.dynamicSmemBytes = kCbSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = p.T / kBM;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  ISHARA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p.tmX, p.tmWe, p.tmWp, p.tmO0, p.tmO1, pr));
+  note_launch();
+  return 0;
+}
+
+}  // namespace
+
+bool conv1d_block_applicable(int D, int T, int k) {
+  return D == kKD && T % kBM == 0 && T / kBM >= 1 && T / kBM <= 8 && (k == 3 || k == 5 || k == 7 || k == 9 || k == 11);
+}
+
+// x = S [B*T, 256] (read as the expand operand and as the residual, overwritten in place); wet = We^T [512, 256];
+// wpt = Wp^T [256, 512]; xn = LN(S) output or null
+int conv1d_block_plan_init(Conv1dBlockPlan* p, bf16* s, const bf16* wet, const bf16* wpt, bf16* xn) {
+  static_assert(kCbSmem <= kMaxSmem, "conv1d_block: shared memory budget");
+  static_assert(120 * 1024 + kXSlot <= kHRegion + kWSlot, "expand slot 2 must end before Wp slot 1");
+  static_assert(kXSlot <= 4 * kBoxStride && 72 * 1024 == 4 * kBoxStride, "expand slots 1-2 must not overlap boxes 0-3");
+  const uint64_t M = static_cast<uint64_t>(p->B) * p->T;
+  int rc;
+  if ((rc = make_tmap_2d(&p->tmX, s, TM_BF16, M, kKD, kKD, kBM, kBK))) return rc;
+  if ((rc = make_tmap_2d(&p->tmWe, wet, TM_BF16, kKC, kKD, kKD, 256, kBK))) return rc;
+  if ((rc = make_tmap_2d(&p->tmWp, wpt, TM_BF16, kKD, kKC, kKC, 256, kBK))) return rc;
+  if ((rc = make_tmap_2d(&p->tmO0, s, TM_BF16, M, kKD, kKD, 32, 64))) return rc;
+  if (xn != nullptr) {
+    if ((rc = make_tmap_2d(&p->tmO1, xn, TM_BF16, M, kKD, kKD, 32, 64))) return rc;
+  } else {
+    p->tmO1 = p->tmO0;
+  }
+  p->resid = s;
+  return 0;
+}
+
+int conv1d_block_launch(const Conv1dBlockPlan& p, cudaStream_t stream) {
+  switch (p.k) {
+    case 3: return launch_k<3>(p, stream);
+    case 5: return launch_k<5>(p, stream);
+    case 7: return launch_k<7>(p, stream);
+    case 9: return launch_k<9>(p, stream);
+    case 11: return launch_k<11>(p, stream);
+  }
+  set_last_error("conv1d_block: unsupported kernel size");
+  return 2;
+}
+
+}  // namespace ishara

@@ -104,6 +104,25 @@ bool conv1d_front_applicable(int D, int T, int k);
 int conv1d_front_plan_init(Conv1dFrontPlan* p, const bf16* x, const bf16* wet);
 int conv1d_front_launch(const Conv1dFrontPlan& p, cudaStream_t stream);
 
+// ---- the whole Conv1DBlock in one launch (conv1d_block.cu): S <- S + ECA(BN(CausalDW(swish(S We + be)))) Wp + bp ----
+struct Conv1dBlockPlan {
+  CUtensorMap tmX, tmWe, tmWp, tmO0, tmO1;
+  const float* bias_e = nullptr;  // [512] expand bias
+  const float* dw_w = nullptr;    // [k, 512] depthwise taps with BatchNorm folded in
+  const float* dw_b = nullptr;    // [512] BatchNorm offset
+  const float* eca_w = nullptr;   // [5]
+  const float* bias_p = nullptr;  // [256] project bias
+  const bf16* resid = nullptr;    // = S (set by plan_init)
+  const float* ln_g = nullptr;    // LayerNorm of the next module: XN = LN(S) (null: none)
+  const float* ln_b = nullptr;
+  float ln_eps = 0.f;
+  const int32_t* seq_len = nullptr;  // [B] valid frames for the ECA mean (mask_mode="propagated") or null
+  int B = 0, T = 0, k = 0;
+};
+bool conv1d_block_applicable(int D, int T, int k);
+int conv1d_block_plan_init(Conv1dBlockPlan* p, bf16* s, const bf16* wet, const bf16* wpt, bf16* xn);
+int conv1d_block_launch(const Conv1dBlockPlan& p, cudaStream_t stream);
+
 // ---- depthwise temporal convolution over a whole sequence per CTA ---------------------------
 // in/out [B, T, C] bf16 channels-last. y[t,c] = post( sum_j w[j,c] * in[t - pad_left + j, c] + bias[c] )
 // (zeros outside [0,T)); BatchNorm is folded into w/bias by the caller.

@@ -518,6 +518,31 @@ struct Builder {
       const std::string n = "conv" + tag + "_" + std::to_string(i) + "_" + std::to_string(j + 1);
       const int k = conv_kernel_size(c, j);
       static const int fused_front = getenv("ISHARA_CONV1D_FUSED") ? atoi(getenv("ISHARA_CONV1D_FUSED")) : 0;  // measured: 118 us vs 55 + 66 us unfused => no gain yet, opt-in
+      static const int fused_block = getenv("ISHARA_CONV1D_BLOCK") ? atoi(getenv("ISHARA_CONV1D_BLOCK")) : 1;
+      const bool last_blk = j == c.num_conv_per_block - 1;
+      if (fused_block && !fused_front && !rc && conv1d_block_applicable(D, T, k)) {
+        // the whole block in one launch: the 2D-wide intermediate never leaves the SM (conv1d_block.cu)
+        Op op;
+        op.kind = OP_C1B;
+        op.label = "conv1d.block_fused";
+        Conv1dBlockPlan& p = op.c1b;
+        p.B = B; p.T = T; p.k = k;
+        p.bias_e = pk.get<float>(n + "_expand_conv.b");
+        p.dw_w = pk.get<float>(n + "_dw.w");
+        p.dw_b = pk.get<float>(n + "_dw.b");
+        p.eca_w = pk.get<float>(n + "_eca.w");
+        p.bias_p = pk.get<float>(n + "_project_conv.b");
+        const LnRef nl = last_blk ? next_ln : LnRef();
+        p.ln_g = nl.g; p.ln_b = nl.b; p.ln_eps = nl.eps;
+        p.seq_len = m->seq_len_active;
+        rc = conv1d_block_plan_init(&p, m->S, pk.get<bf16>(n + "_expand_conv.w"), pk.get<bf16>(n + "_project_conv.w"),
+                                    nl.g ? m->XN : nullptr);
+        op.flops = 2.0 * M * D * 2 * D * 2 + 2.0 * M * 2 * D * k;
+        op.bytes = 2.0 * (static_cast<double>(M) * D * (2 + (nl.g ? 1 : 0)) + 4.0 * D * D);
+        ops.push_back(op);
+        tap(n);
+        continue;
+      }
       if (fused_front && !rc && conv1d_front_applicable(D, T, k)) {
         // expand GEMM + swish + causal depthwise + BatchNorm + ECA in one launch (conv1d_front.cu)
         Op op;
@@ -849,6 +874,7 @@ int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t 
       case OP_SEGATE: rc = se_gate_launch(op.se, stream); break;
       case OP_FFN: rc = ffn_launch(op.ffn, m->num_sms, stream); break;
       case OP_C1F: rc = conv1d_front_launch(op.c1f, stream); break;
+      case OP_C1B: rc = conv1d_block_launch(op.c1b, stream); break;
       case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, M, c.dim, stream); break;
       case OP_TAP:
         rc = cudaMemcpyAsync(m->taps[op.tap], m->S, M * c.dim * sizeof(bf16), cudaMemcpyDeviceToDevice, stream) == cudaSuccess ? 0 : 3;
@@ -881,7 +907,7 @@ int model_profile_entry(ishara_model* m, int i, const char** label, const char**
   ISHARA_CUDA_OK(cudaEventElapsedTime(&t, m->events[i], m->events[i + 1]));
   const ishara_config_t& c = m->cfg;
   const double M = static_cast<double>(m->program_batch) * c.frames;
-  static const char* kinds[] = {"gemm", "dwconv", "attention", "se_gate", "layernorm", "tap", "gemm", "gemm"};
+  static const char* kinds[] = {"gemm", "dwconv", "attention", "se_gate", "layernorm", "tap", "gemm", "gemm", "conv1d_block"};
   if (i == 0) {
     if (label) *label = "input.cast_pad";
     if (kind) *kind = "cast";

@@ -30,12 +30,13 @@ struct LnRef {
   float eps = 0.f;
 };
 
-enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP, OP_FFN, OP_C1F };
+enum OpKind { OP_GEMM, OP_DW, OP_ATTN, OP_SEGATE, OP_LN, OP_TAP, OP_FFN, OP_C1F, OP_C1B };
 struct Op {
   OpKind kind;
   GemmPlan gemm;
   FfnPlan ffn;
   Conv1dFrontPlan c1f;
+  Conv1dBlockPlan c1b;
   DwConvArgs dw;
   AttnArgs at;
   SeGateArgs se;
@@ -96,6 +97,9 @@ struct ishara_model {
   std::vector<void*> wsallocs;
   bf16 *XIN = nullptr, *S = nullptr, *XN = nullptr, *H1 = nullptr, *H2 = nullptr, *O = nullptr, *HEAD = nullptr;
   float *colsum = nullptr, *gate = nullptr;
+  int32_t* seq_len_dev = nullptr;      // [cap_batch] valid frames per sequence (mask_mode="propagated")
+  uint8_t* key_mask_dev = nullptr;     // [cap_batch * frames] 1 = frame carries data
+  const int32_t* seq_len_active = nullptr;  // = seq_len_dev while a propagated-mask program is being built, else null
   float* logits_own = nullptr;
   int32_t *ids_dev = nullptr, *lens_dev = nullptr, *labels_dev = nullptr;
   float* nll_dev = nullptr;

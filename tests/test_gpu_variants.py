@@ -1,5 +1,5 @@
 """GPU parity of the opt-in kernel variants (selected by environment variables that the library reads once per process,
-hence one subprocess per variant): CTA-pair GEMM, weight-stationary GEMM, fused Conv1DBlock front kernel, the legacy
+hence one subprocess per variant): CTA-pair GEMM, weight-stationary GEMM, the unfused three-kernel Conv1DBlock, the fused Conv1DBlock front kernel, the legacy
 mma.sync attention, the unfused FFN, and direct launches instead of CUDA-graph replay. Each must match the oracle and
 the default path."""
 import os
@@ -36,6 +36,7 @@ VARIANTS = {
     "default": {},
     "gemm_pair": {"ISHARA_GEMM_PAIR": "1"},
     "gemm_resident": {"ISHARA_GEMM_RESIDENT": "1"},
+    "conv1d_unfused": {"ISHARA_CONV1D_BLOCK": "0"},           # three-kernel Conv1DBlock instead of conv1d_block.cu
     "conv1d_fused": {"ISHARA_CONV1D_FUSED": "1"},
     "attn_mma_sync": {"ISHARA_ATTN_TC": "0"},
     "ffn_unfused": {"ISHARA_FFN_FUSED": "0"},

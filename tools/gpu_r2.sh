@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round-2 GPU checks; every step has its own short timeout. usage: bash tools/gpu_r2.sh <stage> [tag]
+set -u
+mkdir -p gpurun_out
+TAG="${2:-r2}"
+kern_table() {
+python - "$1" <<'PY'
+import json, sys
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
+print("value", round(d["value"]), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "launches", d.get("gpu_launches"))
+for k in d.get("kernels", []):
+    print("  %-22s n=%2d share=%.3f us=%7.1f tf=%6.1f frac_t=%.3f frac_h=%.3f" % (k["label"], k["launches_per_step"], k["share"], k["us_per_launch"], k["tflops"], k["frac_tensor"], k["frac_hbm"]))
+print("roofline", json.dumps(d["roofline"])[:400])
+if d.get("train"): print("train", d["train"]["value"], d["train"]["ms_per_step"], d["train"]["gpu_launches_per_step"])
+PY
+}
+case "${1:-quick}" in
+  quick)   # parity of the forward + variants + a short bench with the per-kernel table
+    timeout 400 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -15
+    timeout 600 python -m pytest tests/test_gpu_variants.py -x -q -m gpu -k opt_in -s 2>&1 | tail -25
+    timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-train > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+    tail -3 gpurun_out/${TAG}_bench.err
+    kern_table gpurun_out/${TAG}_bench.json
+    ;;
+  tests)
+    timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+    timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+    ;;
+  bench)
+    timeout 500 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+    tail -3 gpurun_out/${TAG}_bench.err
+    kern_table gpurun_out/${TAG}_bench.json
+    ;;
+esac
