@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libishara_b200.so")
+# ISHARA_B200_LIB selects another build of the SAME library (the profiling build with timeline tracing, `make TRACE=1`)
+LIB_PATH = os.environ.get("ISHARA_B200_LIB") or os.path.join(_HERE, "lib", "libishara_b200.so")
 
 OK, ERR_INVALID, ERR_SHAPE, ERR_CUDA, ERR_STATE = 0, 1, 2, 3, 4
 

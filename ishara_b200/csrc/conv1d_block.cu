@@ -25,6 +25,9 @@
 //   5. epilogue (16 warps, lane = row): + bp, + residual, [LayerNorm statistics exchanged between the four warps of a
 //      lane quarter, values parked in TMEM], TMA stores of S and of LN(S)
 // Only D == 256 (2D = 512 TMEM columns), T % 128 == 0, T <= 1024; other shapes use the three-kernel path.
+#include <cstdio>
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 
 namespace ishara {
@@ -44,6 +47,14 @@ constexpr int kWorkers = 16;
 constexpr int kCbThreads = 128 + 32 * kWorkers;
 
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// Timeline tracing (profiling builds only: make TRACE=1 -> libishara_b200_trace.so): clock64 at phase boundaries of one
+// sequence's CTAs. Compiled out of the production library.
+#ifdef ISHARA_C1B_TRACE
+#define CB_TRACE(ev_) do { if (pr.trace != nullptr && blockIdx.y == pr.trace_b) pr.trace[blockIdx.x * 32 + (ev_)] = clock64(); } while (0)
+#else
+#define CB_TRACE(ev_) do { } while (0)
+#endif
 
 struct CbBars {
   uint64_t full[3], empty[3];   // expand slots
@@ -66,6 +77,8 @@ struct CbParams {
   float ln_eps;
   const int32_t* seq_len;  // [B] valid frames per sequence for the ECA mean (mask_mode="propagated"), null = all T
   int T;
+  long long* trace;        // ISHARA_C1B_TRACE builds only
+  int trace_b;
 };
 
 template <int K>
@@ -109,6 +122,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
   constexpr uint32_t IDESC = umma_idesc(kBM, 256, 1);
+  if (threadIdx.x == 0) CB_TRACE(0);
 
   // Expand operand slots. Loads 0-3 feed accumulator half 0, loads 4-7 half 1; the second half only uses the two slots
   // that do not overlap boxes 0-3, so the drain of half 0 can run under the MMAs of half 1.
@@ -154,6 +168,9 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     (kb | k) != 0 ? 1u : 0u);
         umma_commit(&bars->empty[s]);
         if (kb == 3) umma_commit(&bars->accf[nh]);
+        if (i == 0) CB_TRACE(1);
+        if (i == 3) CB_TRACE(2);
+        if (i == 7) CB_TRACE(3);
       }
     }
   } else if (warp >= 4) {
@@ -165,6 +182,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int nh = 0; nh < 2; ++nh) {
       mbar_wait(&bars->accf[nh], 0);
       tc_fence_after();
+      if (warp == 4 && lane == 0) CB_TRACE(4 + 2 * nh);
       const uint32_t box = smem_base + static_cast<uint32_t>(4 * nh + c) * kBoxStride + kBoxHalo + static_cast<uint32_t>(q) * 4096u;
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
@@ -184,9 +202,11 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         epi_swish(v);
         stage_write<false>(box, lane, sub, v);
       }
+      if (warp == 4 && lane == 0) CB_TRACE(5 + 2 * nh);
     }
     tc_fence_before();
     named_bar_sync(3, 32 * kWorkers);  // the whole H tile is in shared memory
+    if (warp == 4 && lane == 0) CB_TRACE(8);
 
     // ---- column sums over the valid frames of this tile + this tile's share of the tail correction ----
     //   sum_{t<L} y[t] = L*b + sum_j w_j * (S_L - [last K-1-j valid frames]),  S_L = sum_{u<L} h[u]
@@ -225,8 +245,10 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   }
   __syncwarp();
+  if (warp == 4 && lane == 0) CB_TRACE(9);
   cluster_arrive();   // #1: every CTA of the sequence has its H tile and its partial sums in shared memory
   cluster_wait();
+  if (warp == 4 && lane == 0) CB_TRACE(10);
 
   if (warp >= 4) {
     const int ww = warp - 4;
@@ -269,6 +291,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   }
   __syncwarp();
+  if (warp == 4 && lane == 0) CB_TRACE(11);
   cluster_arrive();   // #2 (arrive): this CTA no longer reads its neighbours' shared memory
   if (warp >= 4) {
     named_bar_sync(3, 32 * kWorkers);  // mean[] complete
@@ -282,7 +305,9 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     scale[wt] = sigmoid_exact(z);
     named_bar_sync(3, 32 * kWorkers);  // scale[] complete, halo rows written
   }
+  if (warp == 4 && lane == 0) CB_TRACE(12);
   cluster_wait();     // #2 (wait): the neighbour has copied its halo, this CTA's H tile may now be overwritten in place
+  if (warp == 4 && lane == 0) CB_TRACE(13);
 
   // ======================================= phase 2: stencil -> project GEMM -> epilogue =======================================
   if (warp == 0) {
@@ -301,6 +326,8 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(&bars->wfull[s], static_cast<uint32_t>((c >> 1) & 1));
         mbar_wait(&bars->boxr[c], 0);
         tc_fence_after();
+        if (c == 0) CB_TRACE(20);
+        if (c == 7) CB_TRACE(21);
         const uint32_t sa = smem_base + static_cast<uint32_t>(c) * kBoxStride + kBoxHalo;
         const uint32_t sb = w_base + static_cast<uint32_t>(s) * kWSlot;
 #pragma unroll
@@ -375,6 +402,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->boxr[box]);
+        if (warp == 4 && lane == 0) CB_TRACE(14 + round);
       }
     }
 
@@ -391,6 +419,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int j = 0; j < 4; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);  // in flight while the MMAs finish
     mbar_wait(&bars->acc2f, 0);
     tc_fence_after();
+    if (warp == 4 && lane == 0) CB_TRACE(18);
     RowStats rs;
 #pragma unroll 1
     for (int sub = 0; sub < 2; ++sub) {
@@ -467,7 +496,9 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tma_store_commit();
       }
     }
+    if (warp == 4 && lane == 0) CB_TRACE(19);
     if (lane == 0) tma_store_wait_all<0>();
+    if (warp == 4 && lane == 0) CB_TRACE(22);
   }
 
   tc_fence_before();
@@ -486,6 +517,19 @@ int launch_k(const Conv1dBlockPlan& p, cudaStream_t stream) {
   CbParams pr;
   pr.bias_e = p.bias_e; pr.dw_w = p.dw_w; pr.dw_b = p.dw_b; pr.eca_w = p.eca_w; pr.bias_p = p.bias_p;
   pr.resid = p.resid; pr.ln_g = p.ln_g; pr.ln_b = p.ln_b; pr.ln_eps = p.ln_eps; pr.seq_len = p.seq_len; pr.T = p.T;
+  pr.trace = nullptr; pr.trace_b = 0;
+#ifdef ISHARA_C1B_TRACE
+  static long long* tbuf = nullptr;
+  static int printed = 0;
+  const int want = getenv("ISHARA_C1B_TRACE_N") ? atoi(getenv("ISHARA_C1B_TRACE_N")) : 6;
+  const bool tracing = printed < want && p.B >= 8;
+  if (tracing) {
+    if (tbuf == nullptr) ISHARA_CUDA_OK(cudaMalloc(&tbuf, 8 * 32 * sizeof(long long)));
+    ISHARA_CUDA_OK(cudaMemsetAsync(tbuf, 0, 8 * 32 * sizeof(long long), stream));
+    pr.trace = tbuf;
+    pr.trace_b = p.B * 3 / 5;  // a sequence from the middle of the launch
+  }
+#endif
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.T / kBM, p.B, 1);
   cfg.blockDim = dim3(kCbThreads, 1, 1);
@@ -500,6 +544,24 @@ int launch_k(const Conv1dBlockPlan& p, cudaStream_t stream) {
   cfg.numAttrs = 1;
   ISHARA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p.tmX, p.tmWe, p.tmWp, p.tmO0, p.tmO1, pr));
   note_launch();
+#ifdef ISHARA_C1B_TRACE
+  if (tracing) {
+    ISHARA_CUDA_OK(cudaStreamSynchronize(stream));
+    long long h[8 * 32];
+    ISHARA_CUDA_OK(cudaMemcpy(h, tbuf, sizeof(h), cudaMemcpyDeviceToHost));
+    ++printed;
+    fprintf(stderr, "c1b trace K=%d B=%d seq=%d ln=%d (cycles since CTA start): 0 start | 1,2,3 expand MMA issued: first, half0, half1 | "
+                    "4/5 drain0 begin/end | 6/7 drain1 begin/end | 8 H complete | 9 sums | 10 cluster#1 | 11 halo+mean | 12 scale | 13 cluster#2 | "
+                    "14-17 stencil rounds | 20/21 project MMA box0/box7 | 18 acc2 ready | 19 epilogue issued | 22 stores drained\n",
+            K, p.B, pr.trace_b, p.ln_g != nullptr);
+    for (int r = 0; r < p.T / kBM; ++r) {
+      fprintf(stderr, "  rank %d:", r);
+      const int order[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 20, 21, 18, 19, 22};
+      for (int e : order) fprintf(stderr, " %d:%lld", e, h[r * 32 + e] ? h[r * 32 + e] - h[r * 32] : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   return 0;
 }
 

@@ -50,7 +50,9 @@ struct TrainState {
   // program
   int batch = 0, labels_len = 0;
   float dropout = 0.f;
-  uint64_t seed = 0;
+  uint64_t seed = 0;       // effective dropout seed of the CURRENT forward/backward = step_seed(seed_base, fb_count)
+  uint64_t seed_base = 0;  // as configured
+  int64_t fb_count = 0;    // forward/backward passes since train_configure: fresh dropout noise every step (Keras Dropout)
   bool debug = false;
   std::vector<Step> fwd, bwd;
   std::vector<void*> allocs;
@@ -353,7 +355,7 @@ struct TB {
     const int F = c.features;
     ts->fwd.push_back([=](cudaStream_t s) { return cast_pad_launch(x_dev, XIN, MM, F, fpad, s); });
     ts->fwd.push_back(linear(XIN, fpad, "stem_conv", false, D, Z, nullptr, ACT_NONE, pe));
-    ts->fwd.push_back(bn_stats_step(Z, seqsum, bs, D, "stem_bn", 0.99f));
+    ts->fwd.push_back(bn_stats_step(Z, seqsum, bs, D, "stem_bn", 0.95f));  // BatchNormalization(momentum=0.95, name='stem_bn') c7:17
     {
       const int DD = D, TT = T;
       ts->fwd.push_back([=](cudaStream_t s) { return affine_gate_add_launch(Z, bs.scale, bs.shift, nullptr, nullptr, S0, MM, DD, TT, s); });
@@ -913,8 +915,24 @@ int train_configure(ishara_model* m, float dropout, uint64_t seed, int debug) {
   TrainState* ts = m->train;
   if (ts->dropout != dropout || ts->debug != (debug != 0)) free_program(ts);  // dropout sites / taps are baked into the program
   ts->dropout = dropout;
+  ts->seed_base = seed;
   ts->seed = seed;
+  ts->fb_count = 0;
   ts->debug = debug != 0;
+  return 0;
+}
+
+// Dropout seed of the n-th forward/backward after train_configure(seed): step 0 uses the configured seed itself (so a
+// host can reproduce the masks of a freshly configured step from the seed alone), later steps mix the counter in.
+// IsharaModel.dropout_masks(step=n) evaluates the same function.
+uint64_t train_step_seed(uint64_t seed_base, int64_t n) {
+  return n == 0 ? seed_base : seed_base ^ mix64(0x5eedull + static_cast<uint64_t>(n));
+}
+
+int train_counters(ishara_model* m, int64_t* fb_steps, int64_t* opt_steps) {
+  if (m->train == nullptr) { set_last_error("train_counters: no training state"); return ISHARA_ERR_STATE; }
+  if (fb_steps) *fb_steps = m->train->fb_count;
+  if (opt_steps) *opt_steps = m->train->step;
   return 0;
 }
 
@@ -927,6 +945,8 @@ int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* l
   TrainState* ts = m->train;
   const ishara_config_t& c = m->cfg;
   const size_t M = static_cast<size_t>(batch) * c.frames;
+  ts->seed = train_step_seed(ts->seed_base, ts->fb_count);  // the step closures read ts->seed at launch time
+  ++ts->fb_count;
   ISHARA_CUDA_OK(cudaMemcpyAsync(ts->x_dev, x_dev, M * c.features * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   ISHARA_CUDA_OK(cudaMemcpyAsync(ts->labels_dev, labels_dev, static_cast<size_t>(batch) * labels_len * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
   ISHARA_CUDA_OK(cudaMemsetAsync(ts->grad, 0, static_cast<size_t>(ts->n_total) * sizeof(float), stream));

@@ -27,7 +27,8 @@ import torch.nn.functional as F
 from .ishara_oracle import (BN_EPS, LN_EPS, LN_EPS_CONVMOD, Config, _dwconv, _swish, param_specs, positional_encoding)
 
 BN_MOMENTUM_CONV1D = 0.95   # c5:73
-BN_MOMENTUM_DEFAULT = 0.99  # Keras default (c7:17, c5:281)
+BN_MOMENTUM_STEM = 0.95     # BatchNormalization(momentum=0.95, name='stem_bn') c7:17
+BN_MOMENTUM_DEFAULT = 0.99  # Keras default: ConvolutionModule.batch_norm (c5:281)
 
 
 def is_trainable(name: str) -> bool:
@@ -125,7 +126,7 @@ def forward_train(params: Dict[str, np.ndarray], x: np.ndarray, labels: np.ndarr
 
     h = c.dense(xt, "stem_conv", bias=False) + torch.from_numpy(positional_encoding(T, D)).to(dt)
     h = c.tap("stem.z", h)
-    h = c.tap("stem", c.bn_train(h, "stem_bn", BN_MOMENTUM_DEFAULT))
+    h = c.tap("stem", c.bn_train(h, "stem_bn", BN_MOMENTUM_STEM))
     for i in range(cfg.num_conv_squeeze_blocks):
         h = conv_blocks(h, "squeeze", i)
         n = f"squeezeformer_{i}"

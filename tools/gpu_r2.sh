@@ -26,6 +26,11 @@ case "${1:-quick}" in
     timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
     timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
     ;;
+  c1b_prof)  # timeline trace (profiling build) + ncu --set full of the fused Conv1DBlock kernel
+    ISHARA_B200_LIB=$PWD/ishara_b200/lib/libishara_b200_trace.so timeout 200 python tools/fwd_once.py 256 2 > gpurun_out/${TAG}_trace.log 2>&1
+    grep -A4 "c1b trace" gpurun_out/${TAG}_trace.log | head -40
+    CMD="python tools/fwd_once.py 256 2" timeout 600 bash tools/ncu_capture.sh ${TAG}_prof_c1b:conv1d_block:3:3
+    ;;
   bench)
     timeout 500 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
     tail -3 gpurun_out/${TAG}_bench.err

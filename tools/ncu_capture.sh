@@ -2,7 +2,7 @@
 # Targeted `ncu --set full` captures of the hot kernels of one bench step (run under gpurun, one GPU).
 # Reports are post-processed ON the box into small CSVs; a .ncu-rep above 20 MB is dropped (gpurun_out/ <= 64 MiB).
 set -u
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu"
+CMD="${CMD:-python bench.py --steps 1 --warmup 3 --no-cpu --no-train}"
 OUT=gpurun_out
 $CMD > $OUT/plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain.log; exit 1; }
 cap() {  # name regex skip count
