@@ -375,13 +375,14 @@ class IsharaModel:
         _lib.check(self._lib.ishara_model_train_fetch(self._h, name.encode(), 1 if grad else 0, a.ctypes.data_as(C.c_void_p), a.size))
         return a
 
-    def dropout_masks(self, batch: int, seed: int, rate: Optional[float] = None) -> Dict[str, np.ndarray]:
+    def dropout_masks(self, batch: int, seed: int, rate: Optional[float] = None, step: int = 0) -> Dict[str, np.ndarray]:
         """The keep/(1-p) masks the training kernels apply for (seed, rate), recomputed on the host from the same
         counter-based hash (train_ew.cu: mix64). Keys follow the reference's layer structure: '<conv1dblock>.drop'
         [B,1,1] (c5:83), '<block>.ffnK.drop' [B,T,E] (c5:164,179,242), 'squeezeformer_i.drop{1,2,3}' [B,T,D]
         (c5:190,196,205), '<block>.mha.attn_drop' [B,H,T,T] (c5:113; rate = dropout_rate in SqueezeformerBlock, the
         default attn_dropout 0.1 in ConformerBlock), 'head.drop' [B,T,2D] (c7:62, fixed 0.4). Lets a CPU restatement
-        reproduce a step exactly."""
+        reproduce a step exactly. ``step`` = index of the forward/backward pass since ``train_config(seed=...)``: every
+        pass draws fresh noise like Keras ``Dropout`` (train.cu ``train_step_seed``); step 0 uses ``seed`` itself."""
         p = self.dropout_rate if rate is None else float(rate)
         if p <= 0:
             return {}
@@ -395,6 +396,10 @@ class IsharaModel:
                 z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M64
                 z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M64
                 return z ^ (z >> np.uint64(31))
+
+        seed = int(seed) & (2 ** 64 - 1)
+        if step:
+            seed ^= int(mix64(np.uint64((0x5eed + int(step)) & (2 ** 64 - 1))))
 
         def key(site):
             inner = mix64(np.uint64((site << 32) | 0x5bd1e995))

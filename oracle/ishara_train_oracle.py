@@ -7,8 +7,8 @@ the Keras training-mode forward, so the only hand-written arithmetic is the forw
 
 What it restates (``nb:conv-hybrid-model cN:L``):
   * ``model(x, training=True)`` c7:12-65 with c5:1-343: BatchNormalization uses the biased batch statistics over
-    (B, T) and updates ``moving = m*moving + (1-m)*batch`` (m = 0.95 for ``Conv1DBlock`` c5:73, Keras default 0.99 for
-    ``stem_bn`` c7:17 and ``ConvolutionModule.batch_norm`` c5:281); dropout sites: FFN inner + residual branches
+    (B, T) and updates ``moving = m*moving + (1-m)*batch`` (m = 0.95 for ``Conv1DBlock`` c5:73 and ``stem_bn`` c7:17, Keras default
+    0.99 for ``ConvolutionModule.batch_norm`` c5:281); dropout sites: FFN inner + residual branches
     (c5:162-166,183,190,204), attention probabilities (c5:113), per-sample ``noise_shape=(None,1,1)`` on the
     Conv1DBlock branch (c5:83), head 0.4 (c7:62). Dropout is driven by explicit keep-masks (or off) so the CUDA path
     can be compared deterministically.

@@ -66,7 +66,7 @@ def test_moving_statistics_rule():
     p, x, y = _setup()
     r = TO.forward_train(p, x, y, TINY, want_taps=True)
     z = r["taps"]["stem.z"][0]
-    want = 0.99 * p["stem_bn.moving_mean"] + 0.01 * z.mean(axis=(0, 1))
+    want = 0.95 * p["stem_bn.moving_mean"] + 0.05 * z.mean(axis=(0, 1))  # BatchNormalization(momentum=0.95, name='stem_bn') c7:17
     assert np.allclose(r["new_stats"]["stem_bn.moving_mean"], want, atol=1e-6)
     d = r["taps"]["convsqueeze_0_1.d"][0]
     want_v = 0.95 * p["convsqueeze_0_1_bn.moving_variance"] + 0.05 * d.var(axis=(0, 1))
