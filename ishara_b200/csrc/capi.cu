@@ -233,7 +233,7 @@ ishara_status_t ishara_model_infer_host(ishara_model_t* mh, const float* x_host,
     return static_cast<ishara_status_t>(rc);
   if (labels_host != nullptr) {
     if ((rc = ctc_loss_launch(v.logits_own, labels_dev, batch, c.frames, c.num_classes, max_label_len, blank, v.nll_dev,
-                              nullptr, v.stream)))
+                              nullptr, nullptr, 0, v.stream)))
       return static_cast<ishara_status_t>(rc);
     CAPI_CUDA_OK(cudaMemcpyAsync(nll_host, v.nll_dev, batch * sizeof(float), cudaMemcpyDeviceToHost, v.stream));
   }
@@ -273,8 +273,19 @@ ishara_status_t ishara_ctc_loss(const float* logits_dev, const int32_t* labels_d
     set_last_error("ctc_loss: null pointer");
     return ISHARA_ERR_INVALID;
   }
-  return static_cast<ishara_status_t>(ctc_loss_launch(logits_dev, labels_dev, batch, frames, num_classes, max_label_len,
-                                                      blank, nll_dev, grad_dev, static_cast<cudaStream_t>(stream)));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  if (grad_dev != nullptr) {
+    // this entry point has no handle to own the alpha/beta workspace: a stream-ordered allocation on the caller's stream
+    // and device lives exactly as long as the two kernels that use it
+    ws_bytes = ctc_workspace_bytes(batch, frames, max_label_len);
+    CAPI_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), ws_bytes, s));
+  }
+  const int rc = ctc_loss_launch(logits_dev, labels_dev, batch, frames, num_classes, max_label_len, blank, nll_dev, grad_dev, ws,
+                                 ws_bytes, s);
+  if (ws != nullptr) cudaFreeAsync(ws, s);
+  return static_cast<ishara_status_t>(rc);
 }
 
 ishara_status_t ishara_greedy_decode(const float* logits_dev, int32_t batch, int32_t frames, int32_t num_classes,

@@ -41,7 +41,7 @@ constexpr int kHRegion = 8 * kBoxStride;      // 144 KB
 constexpr int kWSlot = 32 * 1024;             // one [256 x 64] k-slice of Wp^T
 constexpr int kWRing = 2 * kWSlot;
 constexpr int kXSlot = 48 * 1024;             // expand slot: S chunk [128 x 64] + We chunk [256 x 64]
-constexpr int kFloatBytes = 12 * 1024;        // part2 / corr2 / mean / scale (LN exchange aliases part2)
+constexpr int kFloatBytes = 16 * 1024;        // part2 | corr2 (later: tap staging, LN exchange) | mean (first: expand bias) | scale | constants
 constexpr int kCbSmem = kHRegion + kWRing + kFloatBytes + 256 + 1024;
 constexpr int kWorkers = 16;
 constexpr int kCbThreads = 128 + 32 * kWorkers;
@@ -91,8 +91,10 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   float* part2 = reinterpret_cast<float*>(smem + kHRegion + kWRing);  // [2][512] column sums (valid frames) of the row halves
   float* corr2 = part2 + 2 * kKC;                                     // [2][512] tail-correction shares
-  float* mean = corr2 + 2 * kKC;                                      // [512]
+  float* mean = corr2 + 2 * kKC;                                      // [512] (holds the expand bias until the drain is over)
   float* scale = mean + kKC;                                          // [512]
+  float* cvec = scale + kKC;                                          // bias_p[256] | ln_g[256] | ln_b[256] | eca_w[5]
+  float* tapbuf = part2;                                              // [(K+1)][128] taps + offset of the NEXT stencil round
   CbBars* bars = reinterpret_cast<CbBars*>(smem + kHRegion + kWRing + kFloatBytes);
 
   const int rank = blockIdx.x, nrank = gridDim.x;   // tile index inside the sequence == rank in the cluster
@@ -174,33 +176,65 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // drain: warp (q, c) turns rows [32q, +32) x channels [256 nh + 64 c, +64) into box 4 nh + c
+    // constants the later phases need go to shared memory now, while the expand GEMM runs: with the shared-memory
+    // carve-out at its maximum the L1 is ~2 KB, so every __ldg on a critical path costs an L2 round trip
     const int ww = warp - 4;
+    {
+      const int wt = threadIdx.x - 128;
+      if (wt < 128) {
+        reinterpret_cast<float4*>(mean)[wt] = __ldg(reinterpret_cast<const float4*>(pr.bias_e) + wt);
+      } else if (wt < 192) {
+        reinterpret_cast<float4*>(cvec)[wt - 128] = __ldg(reinterpret_cast<const float4*>(pr.bias_p) + (wt - 128));
+      } else if (wt < 256) {
+        if (pr.ln_g != nullptr) reinterpret_cast<float4*>(cvec)[wt - 128] = __ldg(reinterpret_cast<const float4*>(pr.ln_g) + (wt - 192));
+      } else if (wt < 320) {
+        if (pr.ln_g != nullptr) reinterpret_cast<float4*>(cvec)[wt - 128] = __ldg(reinterpret_cast<const float4*>(pr.ln_b) + (wt - 256));
+      } else if (wt < 325) {
+        cvec[768 + (wt - 320)] = __ldg(pr.eca_w + (wt - 320));
+      }
+      named_bar_sync(3, 32 * kWorkers);
+    }
+    // drain: warp (q, c) turns rows [32q, +32) x channels [256 nh + 64 c, +64) into box 4 nh + c; 16 columns at a time,
+    // the TMEM read of the next 16 in flight under the math of the current ones
     const int q = warp & 3, c = ww >> 2;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float* bias_s = mean;
 #pragma unroll 1
     for (int nh = 0; nh < 2; ++nh) {
       mbar_wait(&bars->accf[nh], 0);
       tc_fence_after();
       if (warp == 4 && lane == 0) CB_TRACE(4 + 2 * nh);
-      const uint32_t box = smem_base + static_cast<uint32_t>(4 * nh + c) * kBoxStride + kBoxHalo + static_cast<uint32_t>(q) * 4096u;
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        uint32_t raw[32];
-        float v[32];
-        const int col = nh * 256 + c * 64 + sub * 32;
-        tmem_ld32(tmem_base + lane_addr + col, raw);
-        tmem_ld_wait();
-        to_float(v, raw);
-        const float4* b4 = reinterpret_cast<const float4*>(pr.bias_e + col);
+      const uint32_t rowbase = smem_base + static_cast<uint32_t>(4 * nh + c) * kBoxStride + kBoxHalo + static_cast<uint32_t>(q * 32 + lane) * 128u;
+      const uint32_t xr = static_cast<uint32_t>(lane & 7);
+      const int col0 = nh * 256 + c * 64;
+      const uint32_t t0 = tmem_base + lane_addr + static_cast<uint32_t>(col0);
+      uint32_t ra[16], rb[16];
+      tmem_ld16(t0, ra);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = __ldg(b4 + j);
-          fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], bb.x, bb.y);
-          fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], bb.z, bb.w);
+      for (int i = 0; i < 4; ++i) {
+        uint32_t (&cur)[16] = (i & 1) ? rb : ra;
+        uint32_t (&nxt)[16] = (i & 1) ? ra : rb;
+        tmem_ld_fence16(cur);
+        if (i < 3) tmem_ld16(t0 + 16u * (i + 1), nxt);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 16 * i + 4 * j);
+          fadd2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(cur[4 * j + 0]), __uint_as_float(cur[4 * j + 1]), bb.x, bb.y);
+          fadd2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3]), bb.z, bb.w);
         }
-        epi_swish(v);
-        stage_write<false>(box, lane, sub, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // swish(x) = h + h tanh(h), h = x / 2
+          float h0, h1;
+          fmul2(h0, h1, v[2 * j], v[2 * j + 1], 0.5f, 0.5f);
+          const float t0f = fast_tanh(h0), t1f = fast_tanh(h1);
+          ffma2(v[2 * j], v[2 * j + 1], h0, h1, t0f, t1f, h0, h1);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          st_shared_v4(rowbase + ((static_cast<uint32_t>(2 * i + j) ^ xr) << 4), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
+                       pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                       pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
       }
       if (warp == 4 && lane == 0) CB_TRACE(5 + 2 * nh);
     }
@@ -218,11 +252,24 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int lo = rh * 64, hi = min(lo + 64, lloc);
       const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
       const uint32_t lsw = static_cast<uint32_t>(lane >> 2), lw = static_cast<uint32_t>(lane & 3) << 2;
-      float2 s = make_float2(0.f, 0.f);
-      for (int r = lo; r < hi; ++r) {
+      float2 s = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+      int r = lo;
+      for (; r + 8 <= hi; r += 8) {  // lo is a multiple of 8: frame r + i has swizzle phase i; eight loads in flight
+        uint32_t u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          u[i] = ld_shared_u32(bx + static_cast<uint32_t>(r + i) * 128u + (((lsw ^ static_cast<uint32_t>(i)) << 4) | lw));
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          fadd2(s.x, s.y, s.x, s.y, bf16_lo(u[i]), bf16_hi(u[i]));
+          fadd2(s2.x, s2.y, s2.x, s2.y, bf16_lo(u[i + 1]), bf16_hi(u[i + 1]));
+        }
+      }
+      for (; r < hi; ++r) {
         const uint32_t u = ld_shared_u32(bx + static_cast<uint32_t>(r) * 128u + (((lsw ^ static_cast<uint32_t>(r & 7)) << 4) | lw));
         fadd2(s.x, s.y, s.x, s.y, bf16_lo(u), bf16_hi(u));
       }
+      s.x += s2.x; s.y += s2.y;
       float2 cr = make_float2(0.f, 0.f);
       if (lloc >= 1 && lloc - (K - 1) < lo + 64 && lloc > lo) {  // some of the frames L-1 .. L-(K-1) fall into this row half
         const int ch = box * 64 + 2 * lane;
@@ -257,10 +304,19 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     {
       const int box = ww >> 1;
       const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
-      for (int j = 1 + (ww & 1); j <= K - 1; j += 2) {
-        uint32_t u = 0u;
-        if (rank > 0) u = ld_dsmem_u32(mapa_shared(bx + static_cast<uint32_t>(kBM - j) * 128u + static_cast<uint32_t>(lane) * 4u, rank - 1));
-        st_shared_u32(bx - static_cast<uint32_t>(j) * 128u + static_cast<uint32_t>(lane) * 4u, u);
+      constexpr int NH = K / 2;  // ceil((K - 1) / 2) rows per warp
+      uint32_t u[NH];
+#pragma unroll
+      for (int jj = 0; jj < NH; ++jj) {  // all remote loads first (a DSMEM load is ~200 cycles)
+        const int j = 1 + (ww & 1) + 2 * jj;
+        u[jj] = 0u;
+        if (rank > 0 && j <= K - 1)
+          u[jj] = ld_dsmem_u32(mapa_shared(bx + static_cast<uint32_t>(kBM - j) * 128u + static_cast<uint32_t>(lane) * 4u, rank - 1));
+      }
+#pragma unroll
+      for (int jj = 0; jj < NH; ++jj) {
+        const int j = 1 + (ww & 1) + 2 * jj;
+        if (j <= K - 1) st_shared_u32(bx - static_cast<uint32_t>(j) * 128u + static_cast<uint32_t>(lane) * 4u, u[jj]);
       }
     }
     // ---- channel means of the BatchNorm'd conv output over the valid frames (every CTA computes all 512) ----
@@ -268,24 +324,36 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (wt < kKC / 2) {
       const int ch = 2 * wt;
       float2 S = make_float2(0.f, 0.f), C = make_float2(0.f, 0.f);
-      for (int rr = 0; rr < nrank; ++rr) {
-#pragma unroll
-        for (int rh = 0; rh < 2; ++rh) {
-          const float2 a = ld_dsmem_f32x2(mapa_shared(smem_u32(part2 + rh * kKC + ch), rr));
-          const float2 c2 = ld_dsmem_f32x2(mapa_shared(smem_u32(corr2 + rh * kKC + ch), rr));
-          S.x += a.x; S.y += a.y;
-          C.x += c2.x; C.y += c2.y;
-        }
-      }
       float2 wsum = make_float2(0.f, 0.f);
+      float2 wj[K];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const float2 wj = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
-        wsum.x += wj.x; wsum.y += wj.y;
+      for (int j = 0; j < K; ++j) wj[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
+      const float2 bdw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
+      for (int r0 = 0; r0 < nrank; r0 += 4) {  // four CTAs' partial sums in flight at a time
+        float2 a[4][2], c2[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            a[i][rh] = make_float2(0.f, 0.f);
+            c2[i][rh] = make_float2(0.f, 0.f);
+            if (r0 + i < nrank) {
+              a[i][rh] = ld_dsmem_f32x2(mapa_shared(smem_u32(part2 + rh * kKC + ch), r0 + i));
+              c2[i][rh] = ld_dsmem_f32x2(mapa_shared(smem_u32(corr2 + rh * kKC + ch), r0 + i));
+            }
+          }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            S.x += a[i][rh].x; S.y += a[i][rh].y;
+            C.x += c2[i][rh].x; C.y += c2[i][rh].y;
+          }
       }
+#pragma unroll
+      for (int j = 0; j < K; ++j) { wsum.x += wj[j].x; wsum.y += wj[j].y; }
       const int L = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
       const float invL = L > 0 ? 1.f / static_cast<float>(L) : 0.f;
-      const float2 bdw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
       mean[ch] = fmaf(fmaf(wsum.x, S.x, -C.x), invL, bdw.x);
       mean[ch + 1] = fmaf(fmaf(wsum.y, S.y, -C.y), invL, bdw.y);
     }
@@ -293,14 +361,22 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __syncwarp();
   if (warp == 4 && lane == 0) CB_TRACE(11);
   cluster_arrive();   // #2 (arrive): this CTA no longer reads its neighbours' shared memory
+  float2 wraw[K];                  // taps (BatchNorm folded) of this thread's channel pair in the CURRENT stencil round
+  float2 braw = make_float2(0.f, 0.f);
   if (warp >= 4) {
+    {  // round 0 straight from global memory, requested now so the L2 latency hides under the barriers below
+      const int ch0 = ((warp - 4) >> 3) * 64 + 2 * lane;
+#pragma unroll
+      for (int j = 0; j < K; ++j) wraw[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch0));
+      braw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch0));
+    }
     named_bar_sync(3, 32 * kWorkers);  // mean[] complete
     const int wt = threadIdx.x - 128;  // one channel per worker thread
     float z = 0.f;
 #pragma unroll
     for (int d = -2; d <= 2; ++d) {
       const int cc = wt + d;
-      if (cc >= 0 && cc < kKC) z = fmaf(__ldg(pr.eca_w + d + 2), mean[cc], z);
+      if (cc >= 0 && cc < kKC) z = fmaf(cvec[768 + d + 2], mean[cc], z);
     }
     scale[wt] = sigmoid_exact(z);
     named_bar_sync(3, 32 * kWorkers);  // scale[] complete, halo rows written
@@ -324,6 +400,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int c = 0; c < 8; ++c) {
         const int s = c & 1;
         mbar_wait(&bars->wfull[s], static_cast<uint32_t>((c >> 1) & 1));
+        if (c == 7) CB_TRACE(23);
         mbar_wait(&bars->boxr[c], 0);
         tc_fence_after();
         if (c == 0) CB_TRACE(20);
@@ -336,6 +413,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         umma_commit(&bars->wempty[s]);
       }
       umma_commit(&bars->acc2f);
+      CB_TRACE(24);
     }
   } else if (warp >= 4) {
     const int ww = warp - 4;
@@ -347,20 +425,22 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       uint32_t sw[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) sw[e] = ((lsw ^ static_cast<uint32_t>(e)) << 4) | lw;
+      // taps of round r+1 are copied global -> tapbuf (the dead column-sum area) by cp.async while round r computes
+      const int wtid = threadIdx.x - 128;
+      auto stage_taps = [&](int round) {
+        if (wtid < (K + 1) * 32) {
+          const int j = wtid >> 5, part = wtid & 31;  // row j of the tap table (row K = offsets), 16-byte piece `part` of 128 channels
+          const float* src = (j < K ? pr.dw_w + static_cast<size_t>(j) * kKC : pr.dw_b) + round * 128 + part * 4;
+          cpa_16(smem_u32(tapbuf + j * 128 + part * 4), src);
+        }
+        cpa_commit();
+      };
+      stage_taps(1);
 #pragma unroll 1
       for (int round = 0; round < 4; ++round) {
         const int box = 2 * round + bi;
         const int ch = box * 64 + 2 * lane;
         const uint32_t base = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo + static_cast<uint32_t>(g) * 16u * 128u;
-        const float2 sc = *reinterpret_cast<const float2*>(scale + ch);
-        float2 wt[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const float2 wj = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
-          wt[j] = make_float2(wj.x * sc.x, wj.y * sc.y);
-        }
-        float2 bs = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
-        bs.x *= sc.x; bs.y *= sc.y;
         // the K-1 frames in front of this group belong to the previous group (or to the halo rows): read them before
         // anybody overwrites them
         uint32_t hw[K - 1];
@@ -369,7 +449,22 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const int r = j - (K - 1);  // -(K-1) .. -1
           hw[j] = ld_shared_u32(base + static_cast<uint32_t>(r * 128) + sw[r & 7]);
         }
-        named_bar_sync(1 + bi, 256);
+        if (round > 0) cpa_wait_all();
+        named_bar_sync(3, 32 * kWorkers);  // halo frames read by everybody; this round's taps have landed
+        if (round > 0) {
+#pragma unroll
+          for (int j = 0; j < K; ++j) wraw[j] = *reinterpret_cast<const float2*>(tapbuf + j * 128 + bi * 64 + 2 * lane);
+          braw = *reinterpret_cast<const float2*>(tapbuf + K * 128 + bi * 64 + 2 * lane);
+          if (round < 3) {
+            named_bar_sync(3, 32 * kWorkers);  // everybody holds this round's taps in registers: tapbuf may be refilled
+            stage_taps(round + 1);
+          }
+        }
+        const float2 sc = *reinterpret_cast<const float2*>(scale + ch);
+        float2 wt[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) wt[j] = make_float2(wraw[j].x * sc.x, wraw[j].y * sc.y);
+        const float2 bs = make_float2(braw.x * sc.x, braw.y * sc.y);
         float2 x[TB + K - 1];
 #pragma unroll
         for (int blk = 16 / TB - 1; blk >= 0; --blk) {
@@ -379,7 +474,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             if (blk == 16 / TB - 1 || i < TB) {
               const int r = TB * blk - (K - 1) + i;
               const uint32_t u = r >= 0 ? ld_shared_u32(base + static_cast<uint32_t>(r * 128) + sw[r & 7]) : hw[r + (K - 1)];
-              x[i] = make_float2(bf16_lo(u), bf16_hi(u));
+              x[i] = make_float2(bf16_lo_prmt(u), bf16_hi(u));
             }
           }
           uint32_t o[TB];
@@ -414,41 +509,35 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t stg0 = smem_base + static_cast<uint32_t>(ww) * kWarpStgBytes;             // H region is dead once acc2f fires
     const uint32_t stg1 = smem_base + static_cast<uint32_t>(kWorkers + ww) * kWarpStgBytes;
     const bf16* rrow = pr.resid + static_cast<size_t>(row) * kKD + c * 64;
-    uint4 rq[4];
+    uint4 rq[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);  // in flight while the MMAs finish
+    for (int j = 0; j < 8; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);  // in flight while the MMAs finish
     mbar_wait(&bars->acc2f, 0);
     tc_fence_after();
     if (warp == 4 && lane == 0) CB_TRACE(18);
     RowStats rs;
-#pragma unroll 1
+#pragma unroll
     for (int sub = 0; sub < 2; ++sub) {
       const int col = c * 64 + sub * 32;
       uint32_t raw[32];
       float v[32];
       tmem_ld32(tmem_base + lane_addr + col, raw);
-      uint4 rn[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rn[j] = sub == 0 ? __ldg(reinterpret_cast<const uint4*>(rrow + 32) + j) : make_uint4(0u, 0u, 0u, 0u);
       tmem_ld_wait();
       to_float(v, raw);
-      const float4* b4 = reinterpret_cast<const float4*>(pr.bias_p + col);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 bb = __ldg(b4 + j);
+        const float4 bb = *reinterpret_cast<const float4*>(cvec + col + 4 * j);
         fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], bb.x, bb.y);
         fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], bb.z, bb.w);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 r4 = rq[j];
+        const uint4 r4 = rq[4 * sub + j];
         fadd2(v[8 * j + 0], v[8 * j + 1], v[8 * j + 0], v[8 * j + 1], bf16_lo(r4.x), bf16_hi(r4.x));
         fadd2(v[8 * j + 2], v[8 * j + 3], v[8 * j + 2], v[8 * j + 3], bf16_lo(r4.y), bf16_hi(r4.y));
         fadd2(v[8 * j + 4], v[8 * j + 5], v[8 * j + 4], v[8 * j + 5], bf16_lo(r4.z), bf16_hi(r4.z));
         fadd2(v[8 * j + 6], v[8 * j + 7], v[8 * j + 6], v[8 * j + 7], bf16_lo(r4.w), bf16_hi(r4.w));
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rq[j] = rn[j];
       if (ln) {
         rs.add(v);
         to_raw(raw, v);
@@ -464,7 +553,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     if (ln) {
       // row statistics of the four warps sharing this lane quarter
-      float4* xch = reinterpret_cast<float4*>(part2);  // [4 q][4 c][32] (aliases the column sums: dead since barrier #2)
+      float4* xch = reinterpret_cast<float4*>(part2);  // [4 q][4 c][32] (aliases the tap staging area: dead after the last round)
       tmem_st_wait();
       xch[(q * 4 + c) * 32 + lane] = make_float4(rs.s0, rs.s1, rs.q0, rs.q1);
       named_bar_sync(4 + q, 128);
@@ -486,7 +575,19 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tmem_ld32(tmem_base + lane_addr + col, raw);
         tmem_ld_wait();
         to_float(v, raw);
-        epi_layernorm(v, pr.ln_g, pr.ln_b, m, rstd, col);
+        {  // ((v - mean) * rstd) * gamma + beta, gamma / beta from shared memory
+          const float nm = -m * rstd;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 gg = *reinterpret_cast<const float4*>(cvec + 256 + col + 4 * j);
+            const float4 bb = *reinterpret_cast<const float4*>(cvec + 512 + col + 4 * j);
+            float x0, x1, x2, x3;
+            ffma2(x0, x1, v[4 * j + 0], v[4 * j + 1], rstd, rstd, nm, nm);
+            ffma2(x2, x3, v[4 * j + 2], v[4 * j + 3], rstd, rstd, nm, nm);
+            ffma2(v[4 * j + 0], v[4 * j + 1], x0, x1, gg.x, gg.y, bb.x, bb.y);
+            ffma2(v[4 * j + 2], v[4 * j + 3], x2, x3, gg.z, gg.w, bb.z, bb.w);
+          }
+        }
         stage_write<false>(stg1, lane, sub, v);
       }
       fence_proxy_async_smem();
@@ -556,7 +657,7 @@ int launch_k(const Conv1dBlockPlan& p, cudaStream_t stream) {
             K, p.B, pr.trace_b, p.ln_g != nullptr);
     for (int r = 0; r < p.T / kBM; ++r) {
       fprintf(stderr, "  rank %d:", r);
-      const int order[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 20, 21, 18, 19, 22};
+      const int order[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 20, 23, 21, 24, 18, 19, 22};
       for (int e : order) fprintf(stderr, " %d:%lld", e, h[r * 32 + e] ? h[r * 32 + e] - h[r * 32] : -1);
       fprintf(stderr, "\n");
     }

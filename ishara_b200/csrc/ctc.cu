@@ -17,6 +17,10 @@
 namespace ishara {
 namespace {
 
+// labels outside [0, V) would index the staged logits row and the occupancy table out of bounds: clamp for memory safety
+// (host entry points that see the labels reject them with ISHARA_ERR_INVALID before any launch)
+__device__ __forceinline__ int ctc_label(const int32_t* lab, int i, int V) { return min(max(lab[i], 0), V - 1); }
+
 constexpr float kLogZero = -1.0e30f;
 constexpr int kCtcBlk = 32;  // frames staged per shared-memory block
 
@@ -94,7 +98,7 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
 
   // label length = number of non-blank entries (reference: reduce_sum(labels != pad))
   int cnt = 0;
-  for (int i = lane; i < L; i += 32) cnt += (lab[i] != blank) ? 1 : 0;
+  for (int i = lane; i < L; i += 32) cnt += (ctc_label(lab, i, V) != blank) ? 1 : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   const int Lb = cnt;
@@ -108,10 +112,10 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
   for (int i = 0; i < SPL; ++i) {
     const int s = lane * SPL + i;
     int e = blank;
-    if (s < S && (s & 1)) e = lab[s >> 1];
+    if (s < S && (s & 1)) e = ctc_label(lab, s >> 1, V);
     ext[i] = e;
-    skip_fwd[i] = (s < S) && (s & 1) && (s >= 3) && (lab[s >> 1] != lab[(s >> 1) - 1]);
-    skip_bwd[i] = (s + 2 < S) && (s & 1) && (lab[(s >> 1) + 1] != lab[s >> 1]);
+    skip_fwd[i] = (s < S) && (s & 1) && (s >= 3) && (ctc_label(lab, s >> 1, V) != ctc_label(lab, (s >> 1) - 1, V));
+    skip_bwd[i] = (s + 2 < S) && (s & 1) && (ctc_label(lab, (s >> 1) + 1, V) != ctc_label(lab, s >> 1, V));
   }
 
   // log-sum-exp of frame (tb*32 + lane) from the staged block; lanes walk the classes in rotated order (bank spread)
@@ -277,7 +281,7 @@ ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ la
   __syncwarp();
   if (feasible) {
     int cnt = 0;
-    for (int i = lane; i < L; i += 32) cnt += (lab[i] != blank) ? 1 : 0;
+    for (int i = lane; i < L; i += 32) cnt += (ctc_label(lab, i, V) != blank) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     const int S = 2 * cnt + 1;
@@ -289,7 +293,7 @@ ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ la
     for (int i = 0; i < SPL; ++i) {
       const int s = lane * SPL + i;
       int ex = blank;
-      if (s < S && (s & 1)) ex = lab[s >> 1];
+      if (s < S && (s & 1)) ex = ctc_label(lab, s >> 1, V);
       ext[i] = ex;
       const float em = (row[ex] - lt) * kLog2e;
       e[i] = (s < S) ? alpha_ws[off + i] + beta_ws[off + i] - em : kLogZero;
@@ -371,13 +375,18 @@ greedy_decode_kernel(const float* __restrict__ logits, int B, int T, int V, int 
   if (lane == 0) lens[b] = total;
 }
 
-float* g_alpha_ws = nullptr;
-size_t g_alpha_ws_bytes = 0;
-
 }  // namespace
 
+// alphas | betas of the gradient pass: caller-owned (per handle / per call), so two handles, devices or streams never
+// share it and nothing is allocated inside a launcher that may run under stream capture
+size_t ctc_workspace_bytes(int B, int T, int L) {
+  const int spl = (2 * L + 1 + 31) / 32;
+  const int SPL = spl <= 5 ? 5 : 9;
+  return 2 * static_cast<size_t>(B) * T * 32 * SPL * sizeof(float);
+}
+
 int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, int V, int L, int blank, float* nll,
-                    float* grad, cudaStream_t stream) {
+                    float* grad, float* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (B <= 0 || T <= 0 || V <= 0 || L < 0 || blank < 0 || blank >= V) {
     set_last_error("ctc_loss: bad shape");
     return 2;
@@ -396,15 +405,12 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
   }
   float* ws = nullptr;
   if (grad != nullptr) {
-    const size_t need = 2 * static_cast<size_t>(B) * T * 32 * SPL * sizeof(float);  // alphas | betas
-    if (need > g_alpha_ws_bytes) {
-      if (g_alpha_ws != nullptr) ISHARA_CUDA_OK(cudaFree(g_alpha_ws));
-      g_alpha_ws = nullptr;
-      g_alpha_ws_bytes = 0;
-      ISHARA_CUDA_OK(cudaMalloc(&g_alpha_ws, need));
-      g_alpha_ws_bytes = need;
+    const size_t need = ctc_workspace_bytes(B, T, L);  // alphas | betas
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_last_error("ctc_loss: the gradient pass needs a caller-owned workspace of ctc_workspace_bytes(B, T, L) bytes");
+      return 2;
     }
-    ws = g_alpha_ws;
+    ws = workspace;
   }
   if (SPL == 5) {
     auto kern = ctc_kernel<5>;

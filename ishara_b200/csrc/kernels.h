@@ -214,8 +214,10 @@ int preprocess_launch(const float* frames, const int32_t* offsets, int B, int ma
 // ---- CTC + greedy decode ----------------------------------------------------------------------
 // logits fp32 [B,T,V]; labels int32 [B,L] padded with `blank`; nll [B]; grad [B,T,V] or null
 // (grad = d nll_b / d logits, unreduced).
+// The gradient pass (grad != null) needs a caller-owned workspace of ctc_workspace_bytes(B, T, L) bytes.
+size_t ctc_workspace_bytes(int B, int T, int L);
 int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, int V, int L, int blank, float* nll,
-                    float* grad, cudaStream_t stream);
+                    float* grad, float* workspace, size_t workspace_bytes, cudaStream_t stream);
 // ids_out int32 [B, T] (first lens[b] valid), lens int32 [B]; reproduces the reference decode_phrase quirk.
 int greedy_decode_launch(const float* logits, int B, int T, int V, int blank, int32_t* ids_out, int32_t* lens,
                          cudaStream_t stream);

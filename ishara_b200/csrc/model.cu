@@ -1011,7 +1011,7 @@ int model_infer_submit(ishara_model* m, const float* x_host, int batch, const in
   const int blank = c.num_classes - 1;
   if ((rc = greedy_decode_launch(m->logits_own, batch, c.frames, c.num_classes, blank, m->ids_dev, m->lens_dev, s))) return rc;
   if (nlab) {
-    if ((rc = ctc_loss_launch(m->logits_own, sl.labels, batch, c.frames, c.num_classes, max_label_len, blank, m->nll_dev, nullptr, s))) return rc;
+    if ((rc = ctc_loss_launch(m->logits_own, sl.labels, batch, c.frames, c.num_classes, max_label_len, blank, m->nll_dev, nullptr, nullptr, 0, s))) return rc;
     ISHARA_CUDA_OK(cudaMemcpyAsync(nll_host, m->nll_dev, batch * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   ISHARA_CUDA_OK(cudaEventRecord(sl.x_free, s));  // every reader of this slot's x AND labels has been enqueued before this point

@@ -97,6 +97,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// cp.async (LDGSTS): 16-byte global -> shared copies that bypass registers
+__device__ __forceinline__ void cpa_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, ld/st
 // ---------------------------------------------------------------------------------------------
@@ -188,6 +195,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16-column variant (epilogues that double-buffer the TMEM read under their math)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// wait::ld that makes every later use of r[] data-dependent on the wait (the load was issued earlier, under other work)
+__device__ __forceinline__ void tmem_ld_fence16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 // wait::ld that also makes every consumer of r[] data-dependent on the wait, so the compiler cannot hoist arithmetic
 // on registers of an in-flight tcgen05.ld above it (needed when a load is issued early to overlap with other work).
 __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
@@ -343,6 +368,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+// same value through PRMT (ALU pipe): the shift form compiles to IMAD.U32 x, 0x10000 on the FMA pipe, which the
+// FFMA-bound stencils cannot spare
+__device__ __forceinline__ float bf16_lo_prmt(uint32_t v) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(r) : "r"(v));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {

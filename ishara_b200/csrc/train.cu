@@ -62,6 +62,9 @@ struct TrainState {
   float* x_dev = nullptr;
   int32_t* labels_dev = nullptr;
   float *logits = nullptr, *dlogits = nullptr, *nll = nullptr, *loss_dev = nullptr;
+  float* ctc_ws = nullptr;    // alphas | betas of the CTC gradient pass: owned by this handle's program (ctc.cu)
+  size_t ctc_ws_bytes = 0;
+  int* skipped_dev = nullptr; // optimiser steps skipped because the gradient norm was not finite
   float* loss_pinned = nullptr;
   std::shared_ptr<void> builder;  // closures may refer to builder members: it lives as long as the program
 };
@@ -812,6 +815,8 @@ int build_train_program(ishara_model* m, TrainState* ts, int batch, int labels_l
   ts->dlogits = b.f32(static_cast<size_t>(M) * c.num_classes);
   ts->nll = b.f32(batch);
   ts->loss_dev = b.f32(4);
+  ts->ctc_ws_bytes = ctc_workspace_bytes(batch, c.frames, labels_len);
+  ts->ctc_ws = b.f32(ts->ctc_ws_bytes / sizeof(float));
   ts->labels_dev = b.alloc<int32_t>(static_cast<size_t>(batch) * labels_len);
   if (b.rc) return b.rc;
 
@@ -953,7 +958,7 @@ int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* l
   ISHARA_CUDA_OK(cudaMemsetAsync(ts->stats, 0, ts->stats_count * sizeof(double), stream));
   for (auto& st : ts->fwd)
     if ((rc = st(stream))) { set_last_error(std::string("train forward: ") + get_last_error()); return rc; }
-  if ((rc = ctc_loss_launch(ts->logits, ts->labels_dev, batch, c.frames, c.num_classes, labels_len, c.num_classes - 1, ts->nll, ts->dlogits, stream)))
+  if ((rc = ctc_loss_launch(ts->logits, ts->labels_dev, batch, c.frames, c.num_classes, labels_len, c.num_classes - 1, ts->nll, ts->dlogits, ts->ctc_ws, ts->ctc_ws_bytes, stream)))
     return rc;
   mean_kernel<<<1, 32, 0, stream>>>(ts->nll, batch, ts->loss_dev);
   ISHARA_CUDA_OK(cudaGetLastError());
