@@ -41,7 +41,7 @@ constexpr int kHRegion = 8 * kBoxStride;      // 144 KB
 constexpr int kWSlot = 32 * 1024;             // one [256 x 64] k-slice of Wp^T
 constexpr int kWRing = 2 * kWSlot;
 constexpr int kXSlot = 48 * 1024;             // expand slot: S chunk [128 x 64] + We chunk [256 x 64]
-constexpr int kFloatBytes = 16 * 1024;        // part2 | corr2 (later: tap staging, LN exchange) | mean (first: expand bias) | scale | constants
+constexpr int kFloatBytes = 16 * 1024;        // part | corr | tapbuf (overlaps mean, which first holds the expand bias) | scale | constants; LN exchange over the first 8 KB
 constexpr int kCbSmem = kHRegion + kWRing + kFloatBytes + 256 + 1024;
 constexpr int kWorkers = 16;
 constexpr int kCbThreads = 128 + 32 * kWorkers;
@@ -62,6 +62,7 @@ struct CbBars {
   uint64_t wfull[2], wempty[2]; // Wp ring
   uint64_t boxr[8];             // stencil finished box b (8 warps each)
   uint64_t acc2f;               // project accumulator ready
+  uint64_t taps_full, taps_empty;  // tap staging buffer: filled by warps 2-3, drained by the 16 worker warps
   uint32_t tmem_slot;
 };
 
@@ -89,12 +90,12 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* part2 = reinterpret_cast<float*>(smem + kHRegion + kWRing);  // [2][512] column sums (valid frames) of the row halves
-  float* corr2 = part2 + 2 * kKC;                                     // [2][512] tail-correction shares
-  float* mean = corr2 + 2 * kKC;                                      // [512] (holds the expand bias until the drain is over)
-  float* scale = mean + kKC;                                          // [512]
-  float* cvec = scale + kKC;                                          // bias_p[256] | ln_g[256] | ln_b[256] | eca_w[5]
-  float* tapbuf = part2;                                              // [(K+1)][128] taps + offset of the NEXT stencil round
+  float* part = reinterpret_cast<float*>(smem + kHRegion + kWRing);   // [512] column sums of H over this tile's valid frames
+  float* corr = part + kKC;                                           // [512] this tile's share of the tail correction
+  float* tapbuf = corr + kKC;                                         // [(K+1)][128] taps + offset of the NEXT stencil round (6 KB)
+  float* mean = part + 4 * kKC;                                       // [512] (holds the expand bias until the drain is over)
+  float* scale = part + 5 * kKC;                                      // [512]
+  float* cvec = part + 6 * kKC;                                          // bias_p[256] | ln_g[256] | ln_b[256] | eca_w[5]
   CbBars* bars = reinterpret_cast<CbBars*>(smem + kHRegion + kWRing + kFloatBytes);
 
   const int rank = blockIdx.x, nrank = gridDim.x;   // tile index inside the sequence == rank in the cluster
@@ -116,6 +117,8 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(&bars->accf[s], 1); mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
     for (int s = 0; s < 8; ++s) mbar_init(&bars->boxr[s], 8);
     mbar_init(&bars->acc2f, 1);
+    mbar_init(&bars->taps_full, 2);
+    mbar_init(&bars->taps_empty, kWorkers);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_slot, 512);
@@ -191,6 +194,8 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (pr.ln_g != nullptr) reinterpret_cast<float4*>(cvec)[wt - 128] = __ldg(reinterpret_cast<const float4*>(pr.ln_b) + (wt - 256));
       } else if (wt < 325) {
         cvec[768 + (wt - 320)] = __ldg(pr.eca_w + (wt - 320));
+      } else if (wt >= 384) {
+        reinterpret_cast<float4*>(part)[wt - 384] = make_float4(0.f, 0.f, 0.f, 0.f);  // 128 threads x 4 floats
       }
       named_bar_sync(3, 32 * kWorkers);
     }
@@ -199,6 +204,8 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int q = warp & 3, c = ww >> 2;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float* bias_s = mean;
+    const int Lseq = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
+    const float rowvalid = (rank * kBM + q * 32 + lane) < Lseq ? 1.f : 0.f;  // frame counted by the ECA mean
 #pragma unroll 1
     for (int nh = 0; nh < 2; ++nh) {
       mbar_wait(&bars->accf[nh], 0);
@@ -235,6 +242,25 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           st_shared_v4(rowbase + ((static_cast<uint32_t>(2 * i + j) ^ xr) << 4), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
                        pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
                        pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        // column sums of these 16 columns over the warp's 32 frames: transpose-reduce butterfly (16 shuffles), then one
+        // conflict-free shared-memory atomic from the 16 even lanes (lane 2c holds column c)
+        {
+          float r8[8], r4[4], r2[2];
+          const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0, up2 = (lane & 2) != 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float mine = (up16 ? v[8 + j] : v[j]) * rowvalid, send = (up16 ? v[j] : v[8 + j]) * rowvalid;
+            r8[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r4[j] = (up8 ? r8[4 + j] : r8[j]) + __shfl_xor_sync(0xffffffffu, up8 ? r8[j] : r8[4 + j], 8);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) r2[j] = (up4 ? r4[2 + j] : r4[j]) + __shfl_xor_sync(0xffffffffu, up4 ? r4[j] : r4[2 + j], 4);
+          float r1 = (up2 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, up2 ? r2[0] : r2[1], 2);
+          r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+          // lane bits (16, 8, 4, 2) select column 8*b16 + 4*b8 + 2*b4 + b2
+          if ((lane & 1) == 0) atomicAdd(part + col0 + 16 * i + (lane >> 1), r1);
+        }
       }
       if (warp == 4 && lane == 0) CB_TRACE(5 + 2 * nh);
     }
@@ -242,36 +268,16 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     named_bar_sync(3, 32 * kWorkers);  // the whole H tile is in shared memory
     if (warp == 4 && lane == 0) CB_TRACE(8);
 
-    // ---- column sums over the valid frames of this tile + this tile's share of the tail correction ----
+    // ---- this tile's share of the tail correction (the column sums were accumulated by the drain) ----
     //   sum_{t<L} y[t] = L*b + sum_j w_j * (S_L - [last K-1-j valid frames]),  S_L = sum_{u<L} h[u]
     //                  = L*b + wsum*S_L - sum_{i=1..K-1} cw_i * h[L-i],         cw_i = w_0 + ... + w_{K-1-i}
-    {
-      const int box = ww >> 1, rh = ww & 1;
-      const int L = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
-      const int lloc = L - rank * kBM;  // valid frames of the sequence that end inside / before / after this tile
-      const int lo = rh * 64, hi = min(lo + 64, lloc);
+    if (ww < 8) {
+      const int box = ww;
+      const int lloc = Lseq - rank * kBM;  // valid frames of the sequence that end inside / before / after this tile
       const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
       const uint32_t lsw = static_cast<uint32_t>(lane >> 2), lw = static_cast<uint32_t>(lane & 3) << 2;
-      float2 s = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
-      int r = lo;
-      for (; r + 8 <= hi; r += 8) {  // lo is a multiple of 8: frame r + i has swizzle phase i; eight loads in flight
-        uint32_t u[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          u[i] = ld_shared_u32(bx + static_cast<uint32_t>(r + i) * 128u + (((lsw ^ static_cast<uint32_t>(i)) << 4) | lw));
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          fadd2(s.x, s.y, s.x, s.y, bf16_lo(u[i]), bf16_hi(u[i]));
-          fadd2(s2.x, s2.y, s2.x, s2.y, bf16_lo(u[i + 1]), bf16_hi(u[i + 1]));
-        }
-      }
-      for (; r < hi; ++r) {
-        const uint32_t u = ld_shared_u32(bx + static_cast<uint32_t>(r) * 128u + (((lsw ^ static_cast<uint32_t>(r & 7)) << 4) | lw));
-        fadd2(s.x, s.y, s.x, s.y, bf16_lo(u), bf16_hi(u));
-      }
-      s.x += s2.x; s.y += s2.y;
       float2 cr = make_float2(0.f, 0.f);
-      if (lloc >= 1 && lloc - (K - 1) < lo + 64 && lloc > lo) {  // some of the frames L-1 .. L-(K-1) fall into this row half
+      if (lloc >= 1 && lloc - (K - 1) < kBM) {  // some of the frames L-1 .. L-(K-1) fall into this tile
         const int ch = box * 64 + 2 * lane;
         float2 cw = make_float2(0.f, 0.f);  // running prefix sum of the taps: after adding tap j it equals cw_{K-1-j}
 #pragma unroll
@@ -280,20 +286,24 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           cw.x += wj.x; cw.y += wj.y;
           const int i = K - 1 - j;     // cw now = cw_i, pairs with frame L - i
           const int r = lloc - i;
-          if (r >= lo && r < lo + 64 && r < kBM) {
+          if (r >= 0 && r < kBM) {
             const uint32_t u = ld_shared_u32(bx + static_cast<uint32_t>(r) * 128u + (((lsw ^ static_cast<uint32_t>(r & 7)) << 4) | lw));
             cr.x = fmaf(cw.x, bf16_lo(u), cr.x);
             cr.y = fmaf(cw.y, bf16_hi(u), cr.y);
           }
         }
       }
-      *reinterpret_cast<float2*>(part2 + rh * kKC + box * 64 + 2 * lane) = s;
-      *reinterpret_cast<float2*>(corr2 + rh * kKC + box * 64 + 2 * lane) = cr;
+      *reinterpret_cast<float2*>(corr + box * 64 + 2 * lane) = cr;
     }
+    named_bar_sync(3, 32 * kWorkers);  // every worker's shared-memory writes are ordered before the one fence below
+    if (warp == 4 && lane == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
   }
   __syncwarp();
   if (warp == 4 && lane == 0) CB_TRACE(9);
-  cluster_arrive();   // #1: every CTA of the sequence has its H tile and its partial sums in shared memory
+  // #1: every CTA of the sequence has its H tile and its partial sums in shared memory. A release-arrive by all 640
+  // threads cost ~2k cycles of MEMBAR per barrier (ncu: ERRBAR / UCGABAR_ARV membar stalls); here the workers order their
+  // writes with a CTA barrier, ONE thread issues the cluster-scope fence and everybody arrives relaxed.
+  cluster_arrive_relaxed();
   cluster_wait();
   if (warp == 4 && lane == 0) CB_TRACE(10);
 
@@ -329,26 +339,22 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
       for (int j = 0; j < K; ++j) wj[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
       const float2 bdw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
-      for (int r0 = 0; r0 < nrank; r0 += 4) {  // four CTAs' partial sums in flight at a time
-        float2 a[4][2], c2[4][2];
+      {  // every CTA's partial sums in flight at once (<= 8 ranks)
+        float2 a[8], c2[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int rh = 0; rh < 2; ++rh) {
-            a[i][rh] = make_float2(0.f, 0.f);
-            c2[i][rh] = make_float2(0.f, 0.f);
-            if (r0 + i < nrank) {
-              a[i][rh] = ld_dsmem_f32x2(mapa_shared(smem_u32(part2 + rh * kKC + ch), r0 + i));
-              c2[i][rh] = ld_dsmem_f32x2(mapa_shared(smem_u32(corr2 + rh * kKC + ch), r0 + i));
-            }
+        for (int i = 0; i < 8; ++i) {
+          a[i] = make_float2(0.f, 0.f);
+          c2[i] = make_float2(0.f, 0.f);
+          if (i < nrank) {
+            a[i] = ld_dsmem_f32x2(mapa_shared(smem_u32(part + ch), i));
+            c2[i] = ld_dsmem_f32x2(mapa_shared(smem_u32(corr + ch), i));
           }
+        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int rh = 0; rh < 2; ++rh) {
-            S.x += a[i][rh].x; S.y += a[i][rh].y;
-            C.x += c2[i][rh].x; C.y += c2[i][rh].y;
-          }
+        for (int i = 0; i < 8; ++i) {
+          S.x += a[i].x; S.y += a[i].y;
+          C.x += c2[i].x; C.y += c2[i].y;
+        }
       }
 #pragma unroll
       for (int j = 0; j < K; ++j) { wsum.x += wj[j].x; wsum.y += wj[j].y; }
@@ -361,14 +367,14 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __syncwarp();
   if (warp == 4 && lane == 0) CB_TRACE(11);
   cluster_arrive();   // #2 (arrive): this CTA no longer reads its neighbours' shared memory
-  float2 wraw[K];                  // taps (BatchNorm folded) of this thread's channel pair in the CURRENT stencil round
-  float2 braw = make_float2(0.f, 0.f);
+  float2 wt[K];                    // taps (BatchNorm folded, then ECA-scaled) of this thread's channel pair in the current round
+  float2 bs = make_float2(0.f, 0.f);
   if (warp >= 4) {
     {  // round 0 straight from global memory, requested now so the L2 latency hides under the barriers below
       const int ch0 = ((warp - 4) >> 3) * 64 + 2 * lane;
 #pragma unroll
-      for (int j = 0; j < K; ++j) wraw[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch0));
-      braw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch0));
+      for (int j = 0; j < K; ++j) wt[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch0));
+      bs = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch0));
     }
     named_bar_sync(3, 32 * kWorkers);  // mean[] complete
     const int wt = threadIdx.x - 128;  // one channel per worker thread
@@ -380,6 +386,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     scale[wt] = sigmoid_exact(z);
     named_bar_sync(3, 32 * kWorkers);  // scale[] complete, halo rows written
+    asm volatile("bar.arrive 8, %0;" ::"r"(32 * kWorkers + 64) : "memory");  // mean[] is dead: warps 2-3 may overwrite it with taps
   }
   if (warp == 4 && lane == 0) CB_TRACE(12);
   cluster_wait();     // #2 (wait): the neighbour has copied its halo, this CTA's H tile may now be overwritten in place
@@ -415,6 +422,23 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       umma_commit(&bars->acc2f);
       CB_TRACE(24);
     }
+  } else if (warp == 2 || warp == 3) {
+    // ---- tap staging: taps + offsets of stencil round r+1 (128 channels) go global -> tapbuf while round r computes ----
+    const int t64 = (warp - 2) * 32 + lane;
+    named_bar_sync(8, 32 * kWorkers + 64);  // tapbuf overlaps mean[]: wait until the workers have derived the ECA scales
+#pragma unroll 1
+    for (int round = 1; round < 4; ++round) {
+      if (round > 1) mbar_wait(&bars->taps_empty, static_cast<uint32_t>(round & 1));  // completion index round-2
+      for (int i = t64; i < (K + 1) * 32; i += 64) {
+        const int j = i >> 5, piece = i & 31;  // row j of the tap table (row K = offsets), 16-byte piece of 128 channels
+        const float* src = (j < K ? pr.dw_w + static_cast<size_t>(j) * kKC : pr.dw_b) + round * 128 + piece * 4;
+        cpa_16(smem_u32(tapbuf + j * 128 + piece * 4), src);
+      }
+      cpa_commit();
+      cpa_wait_all();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->taps_full);
+    }
   } else if (warp >= 4) {
     const int ww = warp - 4;
     // ---- stencil, in place: 4 rounds of two boxes; warp = (box of the round, 16-frame group), lane = channel pair ----
@@ -425,17 +449,6 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       uint32_t sw[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) sw[e] = ((lsw ^ static_cast<uint32_t>(e)) << 4) | lw;
-      // taps of round r+1 are copied global -> tapbuf (the dead column-sum area) by cp.async while round r computes
-      const int wtid = threadIdx.x - 128;
-      auto stage_taps = [&](int round) {
-        if (wtid < (K + 1) * 32) {
-          const int j = wtid >> 5, part = wtid & 31;  // row j of the tap table (row K = offsets), 16-byte piece `part` of 128 channels
-          const float* src = (j < K ? pr.dw_w + static_cast<size_t>(j) * kKC : pr.dw_b) + round * 128 + part * 4;
-          cpa_16(smem_u32(tapbuf + j * 128 + part * 4), src);
-        }
-        cpa_commit();
-      };
-      stage_taps(1);
 #pragma unroll 1
       for (int round = 0; round < 4; ++round) {
         const int box = 2 * round + bi;
@@ -449,22 +462,21 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const int r = j - (K - 1);  // -(K-1) .. -1
           hw[j] = ld_shared_u32(base + static_cast<uint32_t>(r * 128) + sw[r & 7]);
         }
-        if (round > 0) cpa_wait_all();
-        named_bar_sync(3, 32 * kWorkers);  // halo frames read by everybody; this round's taps have landed
+        named_bar_sync(1 + bi, 256);  // the 8 warps of this box have read their halo frames
         if (round > 0) {
+          mbar_wait(&bars->taps_full, static_cast<uint32_t>((round - 1) & 1));
 #pragma unroll
-          for (int j = 0; j < K; ++j) wraw[j] = *reinterpret_cast<const float2*>(tapbuf + j * 128 + bi * 64 + 2 * lane);
-          braw = *reinterpret_cast<const float2*>(tapbuf + K * 128 + bi * 64 + 2 * lane);
-          if (round < 3) {
-            named_bar_sync(3, 32 * kWorkers);  // everybody holds this round's taps in registers: tapbuf may be refilled
-            stage_taps(round + 1);
-          }
+          for (int j = 0; j < K; ++j) wt[j] = *reinterpret_cast<const float2*>(tapbuf + j * 128 + bi * 64 + 2 * lane);
+          bs = *reinterpret_cast<const float2*>(tapbuf + K * 128 + bi * 64 + 2 * lane);
+          __syncwarp();
+          if (lane == 0 && round < 3) mbar_arrive(&bars->taps_empty);  // this warp holds the round's taps in registers
         }
-        const float2 sc = *reinterpret_cast<const float2*>(scale + ch);
-        float2 wt[K];
+        {
+          const float2 sc = *reinterpret_cast<const float2*>(scale + ch);
 #pragma unroll
-        for (int j = 0; j < K; ++j) wt[j] = make_float2(wraw[j].x * sc.x, wraw[j].y * sc.y);
-        const float2 bs = make_float2(braw.x * sc.x, braw.y * sc.y);
+          for (int j = 0; j < K; ++j) { wt[j].x *= sc.x; wt[j].y *= sc.y; }
+          bs.x *= sc.x; bs.y *= sc.y;
+        }
         float2 x[TB + K - 1];
 #pragma unroll
         for (int blk = 16 / TB - 1; blk >= 0; --blk) {
@@ -553,7 +565,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     if (ln) {
       // row statistics of the four warps sharing this lane quarter
-      float4* xch = reinterpret_cast<float4*>(part2);  // [4 q][4 c][32] (aliases the tap staging area: dead after the last round)
+      float4* xch = reinterpret_cast<float4*>(part);  // [4 q][4 c][32] = 8 KB (aliases sums / tap staging: dead after the last round)
       tmem_st_wait();
       xch[(q * 4 + c) * 32 + lane] = make_float4(rs.s0, rs.s1, rs.q0, rs.q1);
       named_bar_sync(4 + q, 128);

@@ -262,6 +262,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
 }
 // split-phase cluster barrier (every thread of every CTA of the cluster executes both halves, warp-convergent)
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_nctarank() {
   uint32_t r;
