@@ -90,9 +90,9 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* part = reinterpret_cast<float*>(smem + kHRegion + kWRing);   // [512] column sums of H over this tile's valid frames
-  float* corr = part + kKC;                                           // [512] this tile's share of the tail correction
-  float* tapbuf = corr + kKC;                                         // [(K+1)][128] taps + offset of the NEXT stencil round (6 KB)
+  float* part = reinterpret_cast<float*>(smem + kHRegion + kWRing);   // [2 row halves][512] column sums of H over this tile's valid frames
+  float* corr = part + 2 * kKC;                                       // [512] this tile's share of the tail correction
+  float* tapbuf = part;                                               // [(K+1)][128] taps + offset of the NEXT stencil round (6 KB; part/corr are dead by then)
   float* mean = part + 4 * kKC;                                       // [512] (holds the expand bias until the drain is over)
   float* scale = part + 5 * kKC;                                      // [512]
   float* cvec = part + 6 * kKC;                                          // bias_p[256] | ln_g[256] | ln_b[256] | eca_w[5]
@@ -194,8 +194,6 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (pr.ln_g != nullptr) reinterpret_cast<float4*>(cvec)[wt - 128] = __ldg(reinterpret_cast<const float4*>(pr.ln_b) + (wt - 256));
       } else if (wt < 325) {
         cvec[768 + (wt - 320)] = __ldg(pr.eca_w + (wt - 320));
-      } else if (wt >= 384) {
-        reinterpret_cast<float4*>(part)[wt - 384] = make_float4(0.f, 0.f, 0.f, 0.f);  // 128 threads x 4 floats
       }
       named_bar_sync(3, 32 * kWorkers);
     }
@@ -205,7 +203,6 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float* bias_s = mean;
     const int Lseq = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
-    const float rowvalid = (rank * kBM + q * 32 + lane) < Lseq ? 1.f : 0.f;  // frame counted by the ECA mean
 #pragma unroll 1
     for (int nh = 0; nh < 2; ++nh) {
       mbar_wait(&bars->accf[nh], 0);
@@ -242,25 +239,6 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           st_shared_v4(rowbase + ((static_cast<uint32_t>(2 * i + j) ^ xr) << 4), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
                        pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
                        pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        // column sums of these 16 columns over the warp's 32 frames: transpose-reduce butterfly (16 shuffles), then one
-        // conflict-free shared-memory atomic from the 16 even lanes (lane 2c holds column c)
-        {
-          float r8[8], r4[4], r2[2];
-          const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0, up2 = (lane & 2) != 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float mine = (up16 ? v[8 + j] : v[j]) * rowvalid, send = (up16 ? v[j] : v[8 + j]) * rowvalid;
-            r8[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) r4[j] = (up8 ? r8[4 + j] : r8[j]) + __shfl_xor_sync(0xffffffffu, up8 ? r8[j] : r8[4 + j], 8);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) r2[j] = (up4 ? r4[2 + j] : r4[j]) + __shfl_xor_sync(0xffffffffu, up4 ? r4[j] : r4[2 + j], 4);
-          float r1 = (up2 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, up2 ? r2[0] : r2[1], 2);
-          r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
-          // lane bits (16, 8, 4, 2) select column 8*b16 + 4*b8 + 2*b4 + b2
-          if ((lane & 1) == 0) atomicAdd(part + col0 + 16 * i + (lane >> 1), r1);
-        }
       }
       if (warp == 4 && lane == 0) CB_TRACE(5 + 2 * nh);
     }
@@ -268,7 +246,43 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     named_bar_sync(3, 32 * kWorkers);  // the whole H tile is in shared memory
     if (warp == 4 && lane == 0) CB_TRACE(8);
 
-    // ---- this tile's share of the tail correction (the column sums were accumulated by the drain) ----
+    // ---- column sums of H over this tile's valid frames. Warp = (box, 64-frame half); lane = (16-byte chunk c8 of the
+    //      128-byte row, frame phase sub): the 8 lanes of a quarter warp read one whole swizzled row (conflict-free
+    //      LDS.128), every thread keeps 8 channel accumulators, the 4 frame phases are folded with two shuffles ----
+    {
+      const int box = ww >> 1, rh = ww & 1;
+      const int c8 = lane & 7, sub = lane >> 3;
+      const int lloc = Lseq - rank * kBM;
+      const int hi = min(rh * 64 + 64, lloc);
+      const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int r = rh * 64 + 4 * i + sub;
+        if (r < hi) {
+          uint4 v;
+          const uint32_t addr = bx + static_cast<uint32_t>(r) * 128u + ((static_cast<uint32_t>(c8) ^ static_cast<uint32_t>(r & 7)) << 4);
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+          fadd2(acc[0], acc[1], acc[0], acc[1], bf16_lo(v.x), bf16_hi(v.x));
+          fadd2(acc[2], acc[3], acc[2], acc[3], bf16_lo(v.y), bf16_hi(v.y));
+          fadd2(acc[4], acc[5], acc[4], acc[5], bf16_lo(v.z), bf16_hi(v.z));
+          fadd2(acc[6], acc[7], acc[6], acc[7], bf16_lo(v.w), bf16_hi(v.w));
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+      }
+      if (sub == 0) {
+        float4* dst = reinterpret_cast<float4*>(part + rh * kKC + box * 64 + c8 * 8);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+    // ---- this tile's share of the tail correction ----
     //   sum_{t<L} y[t] = L*b + sum_j w_j * (S_L - [last K-1-j valid frames]),  S_L = sum_{u<L} h[u]
     //                  = L*b + wsum*S_L - sum_{i=1..K-1} cw_i * h[L-i],         cw_i = w_0 + ... + w_{K-1-i}
     if (ww < 8) {
@@ -339,20 +353,20 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
       for (int j = 0; j < K; ++j) wj[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
       const float2 bdw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
-      {  // every CTA's partial sums in flight at once (<= 8 ranks)
-        float2 a[8], c2[8];
+      for (int r0 = 0; r0 < nrank; r0 += 4) {  // four CTAs' partial sums in flight at a time
+        float2 a[4][2], c2[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          a[i] = make_float2(0.f, 0.f);
-          c2[i] = make_float2(0.f, 0.f);
-          if (i < nrank) {
-            a[i] = ld_dsmem_f32x2(mapa_shared(smem_u32(part + ch), i));
-            c2[i] = ld_dsmem_f32x2(mapa_shared(smem_u32(corr + ch), i));
+        for (int i = 0; i < 4; ++i) {
+          a[i][0] = a[i][1] = c2[i] = make_float2(0.f, 0.f);
+          if (r0 + i < nrank) {
+            a[i][0] = ld_dsmem_f32x2(mapa_shared(smem_u32(part + ch), r0 + i));
+            a[i][1] = ld_dsmem_f32x2(mapa_shared(smem_u32(part + kKC + ch), r0 + i));
+            c2[i] = ld_dsmem_f32x2(mapa_shared(smem_u32(corr + ch), r0 + i));
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          S.x += a[i].x; S.y += a[i].y;
+        for (int i = 0; i < 4; ++i) {
+          S.x += a[i][0].x + a[i][1].x; S.y += a[i][0].y + a[i][1].y;
           C.x += c2[i].x; C.y += c2[i].y;
         }
       }
@@ -366,7 +380,9 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   }
   __syncwarp();
   if (warp == 4 && lane == 0) CB_TRACE(11);
-  cluster_arrive();   // #2 (arrive): this CTA no longer reads its neighbours' shared memory
+  // #2 (arrive): this CTA no longer reads its neighbours' shared memory. Relaxed: the remote loads above have completed
+  // (their values were consumed), which is all the write-after-read hazard needs; a release-arrive costs a MEMBAR per warp
+  cluster_arrive_relaxed();
   float2 wt[K];                    // taps (BatchNorm folded, then ECA-scaled) of this thread's channel pair in the current round
   float2 bs = make_float2(0.f, 0.f);
   if (warp >= 4) {
@@ -565,7 +581,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     if (ln) {
       // row statistics of the four warps sharing this lane quarter
-      float4* xch = reinterpret_cast<float4*>(part);  // [4 q][4 c][32] = 8 KB (aliases sums / tap staging: dead after the last round)
+      float4* xch = reinterpret_cast<float4*>(part);  // [4 q][4 c][32] = 8 KB (aliases sums / tap staging / the dead mean: all consumed by now)
       tmem_st_wait();
       xch[(q * 4 + c) * 32 + lane] = make_float4(rs.s0, rs.s1, rs.q0, rs.q1);
       named_bar_sync(4 + q, 128);
