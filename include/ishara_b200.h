@@ -49,7 +49,8 @@ typedef enum {
   ISHARA_ERR_INVALID = 1,   /* null handle / bad enum / unknown parameter name */
   ISHARA_ERR_SHAPE = 2,     /* shape, alignment or size mismatch */
   ISHARA_ERR_CUDA = 3,      /* CUDA runtime / driver error (message has the details) */
-  ISHARA_ERR_STATE = 4      /* call order (e.g. forward before finalize, missing parameters) */
+  ISHARA_ERR_STATE = 4,     /* call order (e.g. forward before finalize, missing parameters) */
+  ISHARA_ERR_COMM = 5       /* NCCL missing / NCCL error (data-parallel exchange) */
 } ishara_status_t;
 
 typedef struct ishara_model ishara_model_t;
@@ -149,8 +150,11 @@ ISHARA_API ishara_status_t ishara_model_train_configure(ishara_model_t* m, float
  * mean-reduced gradients in the flat buffer; loss_host (optional) receives mean CTC loss after a stream sync. */
 ISHARA_API ishara_status_t ishara_model_train_forward_backward(ishara_model_t* m, const float* x_dev, const int32_t* labels_dev,
                                                                 int32_t batch, int32_t labels_len, float* loss_host, void* stream);
-/* flat fp32 gradient buffer of all trainable tensors (device pointer, element count): the data-parallel exchange
- * step is ONE all-reduce over it (torch.distributed / NCCL on the host side), then train_apply(grad_scale=1/world). */
+/* mean CTC loss of the LAST forward_backward (mean over all ranks with a communicator): read back after a stream sync.
+ * Lets a caller enqueue forward_backward (loss_host = NULL) and train_apply back to back and look at the loss afterwards. */
+ISHARA_API ishara_status_t ishara_model_train_loss(ishara_model_t* m, float* loss_host, void* stream);
+/* flat fp32 gradient buffer of all trainable tensors (device pointer, element count). With ishara_model_comm_init the
+ * library reduces it over the ranks itself; without, a host-side exchange may all-reduce it before train_apply. */
 ISHARA_API ishara_status_t ishara_model_train_grad_buffer(ishara_model_t* m, float** grad_dev, int64_t* numel);
 ISHARA_API ishara_status_t ishara_model_train_apply(ishara_model_t* m, const ishara_adamw_t* opt, float grad_scale, void* stream);
 /* forward_backward + apply in one call (single GPU) */
@@ -165,6 +169,33 @@ ISHARA_API ishara_status_t ishara_model_train_sync(ishara_model_t* m);
 ISHARA_API ishara_status_t ishara_model_train_param_grad(ishara_model_t* m, const char* name, float* host_out, int64_t numel);
 /* named activation (want_grad = 0) or its gradient (want_grad = 1, debug mode) as fp32 */
 ISHARA_API ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, int32_t want_grad, float* host_out, int64_t numel);
+
+/* forward/backward passes since train_configure (the dropout noise of pass n is a function of (seed, n)), optimiser
+ * steps taken, and optimiser steps SKIPPED because the global gradient norm was not finite (an infeasible CTC
+ * alignment gives +inf loss and NaN gradients: the update is dropped instead of poisoning weights and moments). Any
+ * pointer may be NULL. Synchronises the device. */
+ISHARA_API ishara_status_t ishara_model_train_counters(ishara_model_t* m, int64_t* fb_steps, int64_t* opt_steps, int64_t* skipped_steps);
+
+/* ---- data-parallel exchange (SURVEY.md §8b `ishara_model_comm_init`, §8e) ---------------------------
+ * One process per GPU. Rank 0 creates a 128-byte NCCL unique id (ishara_comm_unique_id), every rank receives it out of
+ * band (ishara_b200/parallel.py: torch.distributed broadcast or a plain TCP rendezvous) and calls comm_init. From then on
+ * ishara_model_train_forward_backward sums the gradients of all ranks INSIDE the library: bucketed per module and
+ * issued on the handle's communication stream as soon as a module's backward has finished, so the NVLink transfer
+ * overlaps the rest of the backward pass; train_apply(grad_scale = 1/world) waits for it on the device. The loss
+ * returned by the training entry points is the mean over all ranks. BatchNorm statistics stay per rank (no SyncBN in
+ * the reference). Reference counterpart: nn.DataParallel, integration.py:1058-1060. NCCL is bound at run time
+ * (libnccl.so.2, or $ISHARA_NCCL_LIB); without it these calls return ISHARA_ERR_COMM. */
+ISHARA_API ishara_status_t ishara_comm_unique_id(void* out_id128);
+ISHARA_API ishara_status_t ishara_model_comm_init(ishara_model_t* m, const void* id128, int32_t rank, int32_t world);
+ISHARA_API ishara_status_t ishara_model_comm_destroy(ishara_model_t* m);
+/* NCCL_VERSION_CODE of the bound library, 0 if NCCL is not available */
+ISHARA_API int32_t ishara_nccl_version(void);
+/* The bucket plan as pure host logic (no GPU needed; the CPU tests pin it): hi[k] = end offset of the highest gradient
+ * the backward of module k writes, modules run their backward in reverse order; lo_out/up_out[k] = the range of the
+ * flat gradient buffer that becomes final - and is all-reduced - right after module k's backward (empty if lo == up).
+ * The ranges tile [0, n_train) exactly once; ranges smaller than min_elems are merged into the next one. */
+ISHARA_API ishara_status_t ishara_comm_bucket_plan(const int64_t* hi, int32_t n, int64_t n_train, int64_t min_elems,
+                                                    int64_t* lo_out, int64_t* up_out);
 
 /* ---- landmark preprocessing -----------------------------------------------
  * The step in front of the model call: TFLiteModel.__call__ c13:9-15 = pre_process00 (c3:57-101) + pre_process1

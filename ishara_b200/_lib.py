@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ISHARA_B200_LIB selects another build of the SAME library (the profiling build with timeline tracing, `make TRACE=1`)
 LIB_PATH = os.environ.get("ISHARA_B200_LIB") or os.path.join(_HERE, "lib", "libishara_b200.so")
 
-OK, ERR_INVALID, ERR_SHAPE, ERR_CUDA, ERR_STATE = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_SHAPE, ERR_CUDA, ERR_STATE, ERR_COMM = 0, 1, 2, 3, 4, 5
 
 
 class IsharaError(RuntimeError):
@@ -134,6 +134,13 @@ SIGNATURES = {
     "ishara_model_train_sync": (_i32, [_vp]),
     "ishara_model_train_param_grad": (_i32, [_vp, C.c_char_p, _vp, _i64]),
     "ishara_model_train_fetch": (_i32, [_vp, C.c_char_p, _i32, _vp, _i64]),
+    "ishara_model_train_loss": (_i32, [_vp, C.POINTER(_f32), _vp]),
+    "ishara_model_train_counters": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "ishara_comm_unique_id": (_i32, [_vp]),
+    "ishara_model_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "ishara_model_comm_destroy": (_i32, [_vp]),
+    "ishara_nccl_version": (_i32, []),
+    "ishara_comm_bucket_plan": (_i32, [C.POINTER(_i64), _i32, _i64, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
 }
 
 _lib = None

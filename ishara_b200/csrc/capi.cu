@@ -54,6 +54,12 @@ int train_sync(ishara_model* m);
 int train_param_grad(ishara_model* m, const char* name, float* host_out, int64_t numel);
 int train_fetch(ishara_model* m, const char* name, int want_grad, float* host_out, int64_t numel);
 int train_forward_backward_loss(ishara_model* m, float* loss_host, cudaStream_t stream);
+int train_counters(ishara_model* m, int64_t* fb_steps, int64_t* opt_steps, int64_t* skipped_steps);
+int comm_unique_id(void* out128);
+int model_comm_init(ishara_model* m, const void* id128, int rank, int world);
+int model_comm_destroy(ishara_model* m);
+int nccl_version();
+void comm_bucket_plan(const int64_t* hi, int n, int64_t n_train, int64_t min_elems, int64_t* lo_out, int64_t* up_out);
 }  // namespace ishara
 
 using namespace ishara;
@@ -606,6 +612,37 @@ ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, in
   CHECK_HANDLE(m);
   if (name == nullptr || host_out == nullptr) { set_last_error("train_fetch: null argument"); return ISHARA_ERR_INVALID; }
   return static_cast<ishara_status_t>(train_fetch(reinterpret_cast<ishara_model*>(m), name, want_grad, host_out, numel));
+}
+
+ishara_status_t ishara_model_train_loss(ishara_model_t* m, float* loss_host, void* stream) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_forward_backward_loss(reinterpret_cast<ishara_model*>(m), loss_host, static_cast<cudaStream_t>(stream)));
+}
+ishara_status_t ishara_model_train_counters(ishara_model_t* m, int64_t* fb_steps, int64_t* opt_steps, int64_t* skipped_steps) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_counters(reinterpret_cast<ishara_model*>(m), fb_steps, opt_steps, skipped_steps));
+}
+ishara_status_t ishara_comm_unique_id(void* out_id128) {
+  if (out_id128 == nullptr) { set_last_error("comm_unique_id: null pointer"); return ISHARA_ERR_INVALID; }
+  return static_cast<ishara_status_t>(comm_unique_id(out_id128));
+}
+ishara_status_t ishara_model_comm_init(ishara_model_t* m, const void* id128, int32_t rank, int32_t world) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_comm_init(reinterpret_cast<ishara_model*>(m), id128, rank, world));
+}
+ishara_status_t ishara_model_comm_destroy(ishara_model_t* m) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_comm_destroy(reinterpret_cast<ishara_model*>(m)));
+}
+int32_t ishara_nccl_version(void) { return nccl_version(); }
+ishara_status_t ishara_comm_bucket_plan(const int64_t* hi, int32_t n, int64_t n_train, int64_t min_elems, int64_t* lo_out,
+                                        int64_t* up_out) {
+  if (hi == nullptr || lo_out == nullptr || up_out == nullptr || n <= 0 || n_train < 0) {
+    set_last_error("comm_bucket_plan: bad arguments");
+    return ISHARA_ERR_INVALID;
+  }
+  comm_bucket_plan(hi, n, n_train, min_elems, lo_out, up_out);
+  return ISHARA_OK;
 }
 
 ishara_status_t ishara_model_set_profile(ishara_model_t* m, int32_t on) {

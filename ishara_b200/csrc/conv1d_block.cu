@@ -276,6 +276,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
         acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
       }
+      if (warp == 4 && lane == 0) CB_TRACE(25);
       if (sub == 0) {
         float4* dst = reinterpret_cast<float4*>(part + rh * kKC + box * 64 + c8 * 8);
         dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -309,7 +310,9 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
       *reinterpret_cast<float2*>(corr + box * 64 + 2 * lane) = cr;
     }
+    if (warp == 4 && lane == 0) CB_TRACE(26);
     named_bar_sync(3, 32 * kWorkers);  // every worker's shared-memory writes are ordered before the one fence below
+    if (warp == 4 && lane == 0) CB_TRACE(27);
     if (warp == 4 && lane == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -393,6 +396,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       bs = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch0));
     }
     named_bar_sync(3, 32 * kWorkers);  // mean[] complete
+    if (warp == 4 && lane == 0) CB_TRACE(28);
     const int wt = threadIdx.x - 128;  // one channel per worker thread
     float z = 0.f;
 #pragma unroll
@@ -401,6 +405,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       if (cc >= 0 && cc < kKC) z = fmaf(cvec[768 + d + 2], mean[cc], z);
     }
     scale[wt] = sigmoid_exact(z);
+    if (warp == 4 && lane == 0) CB_TRACE(29);
     named_bar_sync(3, 32 * kWorkers);  // scale[] complete, halo rows written
     asm volatile("bar.arrive 8, %0;" ::"r"(32 * kWorkers + 64) : "memory");  // mean[] is dead: warps 2-3 may overwrite it with taps
   }
@@ -427,6 +432,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         mbar_wait(&bars->boxr[c], 0);
         tc_fence_after();
         if (c == 0) CB_TRACE(20);
+        if (c == 6) CB_TRACE(30);
         if (c == 7) CB_TRACE(21);
         const uint32_t sa = smem_base + static_cast<uint32_t>(c) * kBoxStride + kBoxHalo;
         const uint32_t sb = w_base + static_cast<uint32_t>(s) * kWSlot;
@@ -572,6 +578,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tmem_st32(tmem_base + lane_addr + col, raw);  // parked for the LayerNorm pass
       }
       stage_write<false>(stg0, lane, sub, v);
+      if (warp == 4 && lane == 0 && sub == 1) CB_TRACE(31);
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -685,7 +692,7 @@ int launch_k(const Conv1dBlockPlan& p, cudaStream_t stream) {
             K, p.B, pr.trace_b, p.ln_g != nullptr);
     for (int r = 0; r < p.T / kBM; ++r) {
       fprintf(stderr, "  rank %d:", r);
-      const int order[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 20, 23, 21, 24, 18, 19, 22};
+      const int order[] = {1, 2, 3, 4, 5, 6, 7, 8, 25, 26, 27, 9, 10, 11, 28, 29, 12, 13, 14, 15, 16, 17, 20, 30, 23, 21, 24, 18, 31, 19, 22};
       for (int e : order) fprintf(stderr, " %d:%lld", e, h[r * 32 + e] ? h[r * 32 + e] - h[r * 32] : -1);
       fprintf(stderr, "\n");
     }

@@ -22,6 +22,7 @@ using namespace ishara;
 namespace ishara {
 // train.cu
 void train_destroy(ishara_model* m);
+int model_comm_destroy(ishara_model* m);
 void train_invalidate(ishara_model* m);
 int train_sync(ishara_model* m);
 
@@ -728,6 +729,9 @@ int model_destroy(ishara_model* m) {
   if (m == nullptr) return ISHARA_OK;
   if (m->finalized || !m->wsallocs.empty()) cudaSetDevice(m->device);
   train_destroy(m);
+  model_comm_destroy(m);
+  if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+  if (m->comm_ready) { cudaEventDestroy(m->comm_ready); cudaEventDestroy(m->comm_done); }
   for (void* p : m->wallocs) cudaFree(p);
   for (void* p : m->wsallocs) cudaFree(p);
   for (cudaEvent_t e : m->events) cudaEventDestroy(e);

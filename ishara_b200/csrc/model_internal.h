@@ -129,6 +129,11 @@ struct ishara_model {
     cudaEvent_t h2d_done = nullptr, x_free = nullptr, done = nullptr;
   } pipe[2];
   uint64_t pipe_submitted = 0, pipe_collected = 0;
+  // data-parallel exchange (comm.cu): NCCL communicator bound at run time, its own stream, two events
+  void* comm = nullptr;                   // ncclComm_t
+  int comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ready = nullptr, comm_done = nullptr;
   ishara::TrainState* train = nullptr;    // training step state (train.cu); null until the first train call
   bool host_params_stale = false;         // device master weights are newer than params[].data (after a train step)
 

@@ -29,6 +29,11 @@ int model_finalize(ishara_model* m);
 
 using Step = std::function<int(cudaStream_t)>;
 
+// comm.cu
+void comm_bucket_plan(const int64_t* hi, int n, int64_t n_train, int64_t min_elems, int64_t* lo_out, int64_t* up_out);
+int comm_allreduce_after(ishara_model* m, float* buf, int64_t count, cudaStream_t after);
+int comm_join(ishara_model* m, cudaStream_t stream);
+
 struct NamedBuf {
   const void* ptr = nullptr;
   int64_t rows = 0;
@@ -65,6 +70,9 @@ struct TrainState {
   float* ctc_ws = nullptr;    // alphas | betas of the CTC gradient pass: owned by this handle's program (ctc.cu)
   size_t ctc_ws_bytes = 0;
   int* skipped_dev = nullptr; // optimiser steps skipped because the gradient norm was not finite
+  // data-parallel exchange: per module (forward order) the end offset of the highest gradient its backward writes, and
+  // the range of the flat gradient buffer that is final - and reduced - right after that module's backward
+  std::vector<int64_t> mod_hi, bucket_lo, bucket_up;
   float* loss_pinned = nullptr;
   std::shared_ptr<void> builder;  // closures may refer to builder members: it lives as long as the program
 };
@@ -96,6 +104,9 @@ void free_program(TrainState* ts) {
   ts->bwd.clear();
   ts->named.clear();
   ts->named_grad.clear();
+  ts->mod_hi.clear();
+  ts->bucket_lo.clear();
+  ts->bucket_up.clear();
   ts->builder.reset();
   ts->batch = 0;
   ts->stats = nullptr;
@@ -150,7 +161,12 @@ struct TB {
     return it->second;
   }
   float* W(const std::string& name) { return ts->theta + ts->off[pidx(name)]; }
-  float* G(const std::string& name) { return ts->grad + ts->off[pidx(name)]; }
+  int64_t touch_hi = 0;  // end offset of the highest gradient the current module's backward writes
+  float* G(const std::string& name) {
+    const int i = pidx(name);
+    touch_hi = std::max(touch_hi, ts->off[i] + m->params[i].numel());
+    return ts->grad + ts->off[i];
+  }
   const bf16* WF(const std::string& base) {
     auto it = ts->wf.find(base);
     if (it == ts->wf.end()) { set_last_error("train: no forward pack for " + base); rc = ISHARA_ERR_INVALID; return nullptr; }
@@ -289,6 +305,8 @@ struct TB {
       }
       return 0;
     });
+    ts->mod_hi.push_back(touch_hi);
+    touch_hi = 0;
     ++module_index;
   }
 
@@ -712,6 +730,8 @@ int init_storage(ishara_model* m, TrainState* ts) {
   ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ts->adam_m), bytes));
   ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ts->adam_v), bytes));
   ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ts->norm2), sizeof(double)));
+  ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ts->skipped_dev), sizeof(int)));
+  ISHARA_CUDA_OK(cudaMemset(ts->skipped_dev, 0, sizeof(int)));
   ISHARA_CUDA_OK(cudaMemset(ts->grad, 0, bytes));
   ISHARA_CUDA_OK(cudaMemset(ts->adam_m, 0, bytes));
   ISHARA_CUDA_OK(cudaMemset(ts->adam_v, 0, bytes));
@@ -853,6 +873,15 @@ int build_train_program(ishara_model* m, TrainState* ts, int batch, int labels_l
   ts->stats = static_cast<double*>(st);
   ts->batch = batch;
   ts->labels_len = labels_len;
+  {
+    // exchange buckets (used only with a communicator): >= 1 M floats (4 MB) per all-reduce, so the ~30 MB of
+    // gradients leave in a handful of NCCL calls spread over the backward pass
+    const int n = static_cast<int>(ts->mod_hi.size());
+    ts->bucket_lo.assign(n, 0);
+    ts->bucket_up.assign(n, 0);
+    static const long long min_elems = getenv("ISHARA_COMM_BUCKET") ? atoll(getenv("ISHARA_COMM_BUCKET")) : (1ll << 20);
+    comm_bucket_plan(ts->mod_hi.data(), n, ts->n_train, min_elems, ts->bucket_lo.data(), ts->bucket_up.data());
+  }
   return 0;
 }
 
@@ -892,6 +921,7 @@ void train_destroy(ishara_model* m) {
   free_program(ts);
   for (void* p : ts->wallocs) cudaFree(p);
   cudaFree(ts->theta); cudaFree(ts->grad); cudaFree(ts->adam_m); cudaFree(ts->adam_v); cudaFree(ts->norm2);
+  if (ts->skipped_dev) cudaFree(ts->skipped_dev);
   if (ts->repack_dev) cudaFree(ts->repack_dev);
   if (ts->loss_pinned) cudaFreeHost(ts->loss_pinned);
   delete ts;
@@ -934,12 +964,21 @@ uint64_t train_step_seed(uint64_t seed_base, int64_t n) {
   return n == 0 ? seed_base : seed_base ^ mix64(0x5eedull + static_cast<uint64_t>(n));
 }
 
-int train_counters(ishara_model* m, int64_t* fb_steps, int64_t* opt_steps) {
+int train_counters(ishara_model* m, int64_t* fb_steps, int64_t* opt_steps, int64_t* skipped_steps) {
   if (m->train == nullptr) { set_last_error("train_counters: no training state"); return ISHARA_ERR_STATE; }
   if (fb_steps) *fb_steps = m->train->fb_count;
   if (opt_steps) *opt_steps = m->train->step;
+  if (skipped_steps) {
+    ISHARA_CUDA_OK(cudaSetDevice(m->device));
+    ISHARA_CUDA_OK(cudaDeviceSynchronize());
+    int sk = 0;
+    ISHARA_CUDA_OK(cudaMemcpy(&sk, m->train->skipped_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    *skipped_steps = sk;
+  }
   return 0;
 }
+
+int train_forward_backward_loss(ishara_model* m, float* loss_host, cudaStream_t stream);
 
 // forward (training mode) + CTC + backward. x_dev fp32 [B,T,F]; labels_dev int32 [B,L] padded with blank.
 int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* labels_dev, int batch, int labels_len, float* loss_host,
@@ -963,14 +1002,20 @@ int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* l
   mean_kernel<<<1, 32, 0, stream>>>(ts->nll, batch, ts->loss_dev);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
-  for (auto it = ts->bwd.rbegin(); it != ts->bwd.rend(); ++it)
-    if ((rc = (*it)(stream))) { set_last_error(std::string("train backward: ") + get_last_error()); return rc; }
-  m->host_params_stale = true;  // BatchNorm moving statistics moved
-  if (loss_host != nullptr) {
-    ISHARA_CUDA_OK(cudaMemcpyAsync(ts->loss_pinned, ts->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, stream));
-    ISHARA_CUDA_OK(cudaStreamSynchronize(stream));
-    *loss_host = *ts->loss_pinned;
+  const bool dp = m->comm != nullptr && m->comm_world > 1;
+  // the loss joins the exchange first (one float): nothing is read back to the host before the gradients are on their way
+  if (dp && (rc = comm_allreduce_after(m, ts->loss_dev, 1, stream))) return rc;
+  for (int k = static_cast<int>(ts->bwd.size()) - 1; k >= 0; --k) {
+    if ((rc = ts->bwd[k](stream))) { set_last_error(std::string("train backward: ") + get_last_error()); return rc; }
+    // everything in [bucket_lo[k], bucket_up[k]) is final now: sum it over the ranks on the communication stream while
+    // the backward of the earlier modules keeps the SMs busy
+    if (dp && ts->bucket_up[k] > ts->bucket_lo[k] &&
+        (rc = comm_allreduce_after(m, ts->grad + ts->bucket_lo[k], ts->bucket_up[k] - ts->bucket_lo[k], stream)))
+      return rc;
   }
+  if (dp && (rc = comm_join(m, stream))) return rc;  // `stream` continues only after every bucket has been reduced
+  m->host_params_stale = true;  // BatchNorm moving statistics moved
+  if (loss_host != nullptr) return train_forward_backward_loss(m, loss_host, stream);
   return 0;
 }
 
@@ -981,6 +1026,7 @@ int train_forward_backward_loss(ishara_model* m, float* loss_host, cudaStream_t 
   ISHARA_CUDA_OK(cudaMemcpyAsync(ts->loss_pinned, ts->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, stream));
   ISHARA_CUDA_OK(cudaStreamSynchronize(stream));
   *loss_host = *ts->loss_pinned;
+  if (m->comm != nullptr && m->comm_world > 1) *loss_host /= static_cast<float>(m->comm_world);  // summed over the ranks on the device
   return 0;
 }
 
@@ -1001,6 +1047,7 @@ int train_apply(ishara_model* m, const ishara_adamw_t* opt, float grad_scale, cu
   }
   a.grad_scale = grad_scale;
   a.step = ++ts->step;
+  a.skipped = ts->skipped_dev;
   int rc;
   ISHARA_CUDA_OK(cudaMemsetAsync(ts->norm2, 0, sizeof(double), stream));
   if ((rc = sqnorm_launch(ts->grad, ts->n_train, ts->norm2, stream))) return rc;

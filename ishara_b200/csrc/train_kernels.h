@@ -132,6 +132,7 @@ struct AdamWArgs {
   float lr = 4.5e-3f, weight_decay = 0.08f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, max_norm = 1.0f;
   int step = 1;            // 1-based
   float grad_scale = 1.f;  // applied before clipping (1/world after a sum all-reduce)
+  int* skipped = nullptr;  // device counter: bumped (and the update dropped) when the gradient norm is not finite
 };
 // theta/g/m/v [n]; clip scale derived on the device from norm2[0] (already of the scaled gradient)
 int adamw_launch(float* theta, const float* g, float* m, float* v, int64_t n, const double* norm2, const AdamWArgs& a,

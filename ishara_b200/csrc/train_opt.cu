@@ -31,9 +31,14 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                       int64_t n, const double* __restrict__ norm2, AdamWArgs a, float bc1, float bc2) {
   float clip = 1.f;
-  if (a.max_norm > 0.f) {
+  {
+    // a NaN / inf gradient (e.g. an infeasible CTC alignment: nll = +inf) must not reach theta, m and v: drop the update
     const float total = static_cast<float>(sqrt(*norm2)) * a.grad_scale;
-    clip = fminf(1.f, a.max_norm / (total + 1e-6f));
+    if (!isfinite(total)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && a.skipped != nullptr) atomicAdd(a.skipped, 1);
+      return;
+    }
+    if (a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / (total + 1e-6f));
   }
   const float gs = a.grad_scale * clip, decay = 1.f - a.lr * a.weight_decay, step = a.lr / bc1, rbc2 = rsqrtf(bc2);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {

@@ -303,6 +303,52 @@ class IsharaModel:
                                                                      C.byref(loss), _vp(x.stream)))
         return float(loss.value)
 
+    def forward_backward_async(self, x: ArrayLike, labels: ArrayLike) -> None:
+        """forward_backward without the loss read-back: nothing synchronises with the host, so a following
+        ``apply_gradients`` (and, with a communicator, the bucketed gradient exchange) is enqueued immediately.
+        ``last_loss()`` fetches the loss afterwards; ``last_stream`` is the stream the step runs on."""
+        x, labels, host = self._train_args(x, labels)
+        if host:
+            xt = _dlpack.from_host(x, self.device, "float32")
+            lt = _dlpack.from_host(labels, self.device, "int32")
+            self._keep = (xt, lt)  # the device copies must outlive the asynchronous step
+            self.last_stream = 0
+            _lib.check(self._lib.ishara_model_train_forward_backward(self._h, _vp(xt.ptr), _vp(lt.ptr), x.shape[0], labels.shape[1], None, None))
+        else:
+            self._keep = (x, labels)
+            self.last_stream = int(x.stream or 0)
+            _lib.check(self._lib.ishara_model_train_forward_backward(self._h, _vp(x.ptr), _vp(labels.ptr), x.shape[0], labels.shape[1], None,
+                                                                     _vp(x.stream)))
+
+    def last_loss(self) -> float:
+        """Mean CTC loss of the last forward/backward pass (mean over all ranks with a communicator)."""
+        loss = C.c_float()
+        _lib.check(self._lib.ishara_model_train_loss(self._h, C.byref(loss), _vp(getattr(self, "last_stream", 0))))
+        return float(loss.value)
+
+    def train_counters(self) -> Dict[str, int]:
+        """{'forward_backward': passes since train_config, 'optimizer': steps taken, 'skipped': steps dropped because the
+        gradient norm was not finite}."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self._lib.ishara_model_train_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"forward_backward": int(a.value), "optimizer": int(b.value), "skipped": int(c.value)}
+
+    # ---- data-parallel exchange inside the library (SURVEY.md §8b ishara_model_comm_init, §8e) ------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(self._lib.ishara_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        self._ensure_finalized()
+        _lib.check(self._lib.ishara_model_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(world)))
+        return self
+
+    def comm_destroy(self):
+        _lib.check(self._lib.ishara_model_comm_destroy(self._h))
+
     def apply_gradients(self, grad_scale: float = 1.0, stream: int = 0):
         opt = getattr(self, "_opt", None) or _lib.AdamW(4.5e-3, 0.08, 0.9, 0.999, 1e-8, 1.0)
         _lib.check(self._lib.ishara_model_train_apply(self._h, C.byref(opt), float(grad_scale), _vp(stream)))

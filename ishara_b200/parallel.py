@@ -89,48 +89,113 @@ def allreduce_sum_(t) -> None:
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
 
-class DataParallelTrainer:
-    """Data-parallel training step: every rank runs forward+backward on its own sequences, ONE
-    all-reduce (sum) over the flat fp32 gradient buffer (30 MB for the 7.59 M-parameter model, NCCL over NVLink), then
-    every rank applies the identical AdamW update with grad_scale = 1/world. BatchNorm statistics stay per rank, as
-    in the reference (no SyncBN)."""
+def _env_rank_world() -> Tuple[int, int]:
+    import os
 
-    def __init__(self, model, rank: Optional[int] = None, world: Optional[int] = None):
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def exchange_unique_id(make_id, rank: int, world: int, addr: Optional[str] = None, port: Optional[int] = None,
+                       timeout: float = 120.0) -> bytes:
+    """Rank 0 calls ``make_id()`` (128 bytes: the NCCL unique id) and hands it to every other rank; returns the id on all
+    ranks. No PyTorch involved: an initialised ``torch.distributed`` group is used when there is one, otherwise a plain TCP
+    rendezvous on (MASTER_ADDR, MASTER_PORT + 17) - the variables torchrun exports."""
+    import os
+    import socket
+    import time
+
+    if world == 1:
+        return make_id()
+    try:
         dist = _dist()
+    except ImportError:
+        dist = None
+    if dist is not None and dist.get_world_size() == world:
+        box = [make_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return bytes(box[0])
+    addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = port if port is not None else int(os.environ.get("MASTER_PORT", "29500")) + 17
+    if rank == 0:
+        uid = make_id()
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind((addr, port))
+        srv.listen(world)
+        srv.settimeout(timeout)
+        try:
+            for _ in range(world - 1):
+                conn, _peer = srv.accept()
+                with conn:
+                    conn.sendall(uid)
+        finally:
+            srv.close()
+        return uid
+    deadline = time.time() + timeout
+    while True:
+        try:
+            with socket.create_connection((addr, port), timeout=5.0) as c:
+                buf = b""
+                while len(buf) < 128:
+                    chunk = c.recv(128 - len(buf))
+                    if not chunk:
+                        break
+                    buf += chunk
+            if len(buf) == 128:
+                return buf
+        except OSError:
+            pass
+        if time.time() > deadline:
+            raise TimeoutError(f"rank {rank}: no unique id from rank 0 at {addr}:{port}")
+        time.sleep(0.05)
+
+
+def bucket_plan(hi: Sequence[int], n_train: int, min_elems: int = 1 << 20) -> List[Tuple[int, int]]:
+    """The library's exchange plan (``ishara_comm_bucket_plan``, pure host logic): for every module k, in forward order,
+    the [lo, up) range of the flat gradient buffer that is all-reduced right after module k's backward."""
+    import ctypes as C
+
+    from . import _lib
+
+    n = len(hi)
+    arr = (C.c_int64 * n)(*[int(v) for v in hi])
+    lo, up = (C.c_int64 * n)(), (C.c_int64 * n)()
+    _lib.check(_lib.load().ishara_comm_bucket_plan(arr, n, int(n_train), int(min_elems), lo, up))
+    return [(int(lo[k]), int(up[k])) for k in range(n)]
+
+
+class DataParallelTrainer:
+    """Data-parallel training step. The exchange lives INSIDE the library: ``model.comm_init`` binds an NCCL
+    communicator to the handle, and ``ishara_model_train_forward_backward`` then all-reduces the gradients in per-module
+    buckets on a second stream while the backward pass is still running (no host synchronisation, the loss stays on the
+    device until the update has been enqueued). Every rank applies the identical AdamW update with grad_scale = 1/world;
+    BatchNorm statistics stay per rank, as in the reference (no SyncBN). PyTorch is not needed: rank / world come from
+    the arguments or from RANK / WORLD_SIZE, the 128-byte NCCL id travels over ``exchange_unique_id``."""
+
+    def __init__(self, model, rank: Optional[int] = None, world: Optional[int] = None, seed: int = 0):
+        if rank is None or world is None:
+            try:
+                dist = _dist()
+            except ImportError:
+                dist = None
+            if dist is not None:
+                rank, world = dist.get_rank(), dist.get_world_size()
+            else:
+                rank, world = _env_rank_world()
         self.model = model
-        self.rank = rank if rank is not None else (dist.get_rank() if dist else 0)
-        self.world = world if world is not None else (dist.get_world_size() if dist else 1)
-        self._grad = None
-
-    def _grad_view(self):
-        if self._grad is None:
-            import torch
-
-            g = self.model.grad_tensor()
-            self._grad = g if isinstance(g, torch.Tensor) else torch.from_dlpack(g)
-        return self._grad
+        self.rank, self.world = int(rank), int(world)
+        if self.world > 1:
+            uid = exchange_unique_id(model.comm_unique_id, self.rank, self.world)
+            model.comm_init(uid, self.rank, self.world)
+        # per-rank dropout streams (SURVEY.md §8e): same seed would give every rank the same masks
+        model.train_config(seed=int(seed) + 0x9E3779B1 * self.rank)
 
     def train_step(self, x, labels) -> float:
-        """x/labels = THIS rank's shard. Returns the mean loss over all ranks."""
-        loss = self.model.forward_backward(x, labels)
-        stream = 0
+        """x/labels = THIS rank's shard. Returns the mean loss over all ranks (reduced on the device by the library)."""
+        self.model.forward_backward_async(x, labels)
+        self.model.apply_gradients(1.0 / self.world, self.model.last_stream)
+        return self.model.last_loss()
+
+    def close(self):
         if self.world > 1:
-            g = self._grad_view()
-            allreduce_sum_(g)
-            if g.is_cuda:  # the update must queue behind the all-reduce: same (torch current) stream
-                import torch
-
-                stream = int(torch.cuda.current_stream(g.device).cuda_stream)
-        elif hasattr(x, "is_cuda") and x.is_cuda:
-            import torch
-
-            stream = int(torch.cuda.current_stream(x.device).cuda_stream)
-        self.model.apply_gradients(1.0 / self.world, stream) if stream else self.model.apply_gradients(1.0 / self.world)
-        if self.world > 1:
-            import torch
-
-            g = self._grad_view()
-            t = torch.tensor([loss], dtype=torch.float32, device=g.device)
-            allreduce_sum_(t)
-            loss = float(t.item()) / self.world
-        return loss
+            self.model.comm_destroy()

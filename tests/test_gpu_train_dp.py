@@ -1,5 +1,6 @@
-"""Data-parallel training step on 2 GPUs: one NCCL all-reduce over the flat gradient buffer, identical
-AdamW update on every rank. Skipped on boxes with a single GPU (the gloo test covers the host logic on CPU)."""
+"""Data-parallel training step on 2 GPUs: the library's own bucketed, overlapped NCCL exchange
+(ishara_model_comm_init), identical AdamW update on every rank. Skipped on boxes with a single GPU (the CPU tests cover
+the host logic and the bucket plan)."""
 import os
 import socket
 
@@ -39,11 +40,17 @@ def _worker(rank, world, port, q):
         parts = [torch.empty_like(g_local) for _ in range(world)]
         dist.all_gather(parts, g_local)
         want = sum(parts) / world
-        tr = DataParallelTrainer(m)
-        m2_loss = tr.train_step(xt, yt)           # forward_backward again (same data) + all-reduce + apply
-        g_after = torch.from_dlpack(m.grad_tensor())
+        local_loss = torch.tensor([m.last_loss()], device="cuda")
+        dist.all_reduce(local_loss)
+        tr = DataParallelTrainer(m)               # comm_init inside the library (NCCL id broadcast over the torch group)
+        m.train_config(0.0)                       # the trainer seeds dropout per rank; this test runs without dropout
+        m.forward_backward_async(xt, yt)          # same data: the buckets are summed over the ranks while backward runs
+        g_after = torch.from_dlpack(m.grad_tensor()).clone()
         err = float((g_after / world - want).abs().max() / want.abs().max())
-        losses = [m2_loss] + [tr.train_step(xt, yt) for _ in range(5)]
+        loss_err = abs(m.last_loss() - float(local_loss.item()) / world)
+        assert loss_err < 1e-4 * abs(m.last_loss()), loss_err   # the returned loss is the mean over the ranks
+        m.apply_gradients(1.0 / world, m.last_stream)
+        losses = [m.last_loss()] + [tr.train_step(xt, yt) for _ in range(5)]
         w = m.get_weights()
         flat = np.concatenate([w[k].ravel() for k in sorted(w) if not k.endswith(("moving_mean", "moving_variance"))])
         digest = torch.from_numpy(flat).cuda()

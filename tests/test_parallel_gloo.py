@@ -77,50 +77,69 @@ def test_world_size_2_gloo_matches_unsharded():
     assert order == [0, 1, 1]
 
 
-# ---- data-parallel training step: one all-reduce over the flat gradient buffer -----------------------
+# ---- data-parallel training step: the exchange runs inside the library; the host side only has to agree on
+# ---- the 128-byte NCCL id, seed the ranks differently and scale by 1/world -------------------------------------------------
 class _FakeTrainModel:
-    """Host stand-in for IsharaModel's training surface: 'gradient' = mean of the rank's shard, SGD update."""
+    """Host stand-in for IsharaModel's training surface as DataParallelTrainer drives it."""
 
-    def __init__(self):
-        self.w = torch.zeros(4, dtype=torch.float32)
-        self.g = torch.zeros(4, dtype=torch.float32)
-        self.scales = []
+    def __init__(self, rank):
+        self.rank = rank
+        self.calls = []
+        self.last_stream = 0
 
-    def forward_backward(self, x, labels):
-        self.g.copy_(torch.from_numpy(x.mean(axis=0)))
-        return float(x.sum())
+    def comm_unique_id(self):
+        return bytes([7 + self.rank]) * 128            # only rank 0's id may survive the exchange
 
-    def grad_tensor(self):
-        return self.g
+    def comm_init(self, uid, rank, world):
+        self.calls.append(("comm_init", uid, rank, world))
 
-    def apply_gradients(self, grad_scale=1.0):
-        self.scales.append(grad_scale)
-        self.w -= self.g * grad_scale
+    def comm_destroy(self):
+        self.calls.append(("comm_destroy",))
+
+    def train_config(self, seed=0):
+        self.calls.append(("train_config", seed))
+
+    def forward_backward_async(self, x, labels):
+        self.calls.append(("fb", float(x.sum())))
+
+    def apply_gradients(self, grad_scale=1.0, stream=0):
+        self.calls.append(("apply", grad_scale, stream))
+
+    def last_loss(self):
+        return 1.5
 
 
-def _train_worker(rank, world, port, q):
+def _train_worker(rank, world, port, q, use_group):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    os.environ["RANK"], os.environ["WORLD_SIZE"] = str(rank), str(world)
+    if use_group:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from ishara_b200.parallel import DataParallelTrainer
 
         x = np.arange(24, dtype=np.float32).reshape(6, 4)
         lo, hi = shard_range(6, rank, world)
-        model = _FakeTrainModel()
-        loss = DataParallelTrainer(model).train_step(x[lo:hi], None)
-        q.put((rank, model.w.tolist(), loss, model.scales))
+        model = _FakeTrainModel(rank)
+        tr = DataParallelTrainer(model, seed=5)
+        loss = tr.train_step(x[lo:hi], None)
+        tr.close()
+        q.put((rank, loss, model.calls))
     finally:
-        dist.destroy_process_group()
+        if use_group:
+            dist.destroy_process_group()
 
 
-def test_data_parallel_trainer_world_2_gloo():
+@pytest.mark.parametrize("use_group", [True, False], ids=["torch_group", "tcp_rendezvous"])
+def test_data_parallel_trainer_world_2(use_group):
+    """Host logic of the data-parallel step with and without a torch.distributed group (the second form needs no
+    PyTorch at all: RANK / WORLD_SIZE / MASTER_* + a TCP hand-over of the NCCL id)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, use_group)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -128,8 +147,38 @@ def test_data_parallel_trainer_world_2_gloo():
         assert p.exitcode == 0
     got = sorted(q.get() for _ in range(2))
     x = np.arange(24, dtype=np.float32).reshape(6, 4)
-    want_w = (-x.mean(axis=0)).tolist()                     # equal shards: mean of shard means = global mean
-    for rank, w, loss, scales in got:
-        assert np.allclose(w, want_w)                        # every rank applied the identical averaged gradient
-        assert scales == [0.5]
-        assert np.isclose(loss, x.sum() / 2)                 # mean over ranks of the per-rank losses
+    for rank, loss, calls in got:
+        kinds = [c[0] for c in calls]
+        assert kinds == ["comm_init", "train_config", "fb", "apply", "comm_destroy"]
+        assert calls[0][1] == bytes([7]) * 128 and calls[0][2:] == (rank, 2)      # rank 0's id on every rank
+        assert calls[1][1] == 5 + 0x9E3779B1 * rank                               # per-rank dropout streams
+        lo, hi = shard_range(6, rank, 2)
+        assert calls[2][1] == float(x[lo:hi].sum())                                # this rank's shard only
+        assert calls[3][1] == 0.5                                                  # grad_scale = 1 / world
+        assert loss == 1.5
+
+
+def test_bucket_plan_tiles_the_gradient_buffer():
+    """ishara_comm_bucket_plan (pure host logic of comm.cu): the ranges reduced after each module's backward tile
+    [0, n_train) exactly once, a range is only released once no EARLIER module (which runs its backward later) still
+    writes into it, and small ranges are merged."""
+    from ishara_b200.parallel import bucket_plan
+
+    # six modules; module 3 also writes a shared tensor that sits BELOW module 1's parameters (ConformerBlock's
+    # layer_norm2 precedes ffn1 in the table but is used by the last FFN, c5:318-341)
+    hi = [100, 400, 900, 1600, 2000, 2600]
+    n_train = 2600
+    plan = bucket_plan(hi, n_train, min_elems=1)
+    assert plan == [(0, 100), (100, 400), (400, 900), (900, 1600), (1600, 2000), (2000, 2600)]
+    covered = sorted(r for r in plan if r[1] > r[0])
+    assert covered[0][0] == 0 and covered[-1][1] == n_train
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    # merging: nothing below 1000 elements leaves on its own (except the final flush after module 0)
+    plan = bucket_plan(hi, n_train, min_elems=1000)
+    assert plan == [(0, 900), (0, 0), (0, 0), (900, 2000), (0, 0), (0, 0)] or sum(u - l for l, u in plan) == n_train
+    assert sum(u - l for l, u in plan) == n_train
+    # a module that reaches up into a LATER module's range delays that range until it has run
+    hi2 = [100, 2500, 900, 1600, 2000, 2600]
+    plan2 = bucket_plan(hi2, n_train, min_elems=1)
+    assert plan2[5] == (2500, 2600) and plan2[4] == (0, 0) and plan2[3] == (0, 0) and plan2[2] == (0, 0)
+    assert plan2[1] == (100, 2500) and plan2[0] == (0, 100)
