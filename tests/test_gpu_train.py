@@ -166,7 +166,18 @@ def test_dropout_masks_reproduce_on_the_host():
     names = sorted(ref["grads"])
     a, b = _flat(m.gradients(), names), _flat(ref["grads"], names)
     assert float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b))) >= 0.97
-    # determinism: same seed -> same loss (up to the order of fp64 atomics); another seed -> another loss
+    # every pass draws fresh noise, like Keras Dropout: the second pass since train_config uses other masks ...
+    loss1 = m.forward_backward(x, y)
+    assert abs(loss1 - loss) > 1e-4 * abs(loss)
+    assert m.train_counters()["forward_backward"] == 2
+    # ... which the host reproduces from (seed, step) as well
+    masks1 = m.dropout_masks(B, 1234, 0.2, step=1)
+    assert not np.array_equal(masks1["head.drop"], masks["head.drop"])
+    ref1 = TO.forward_train(p, x, y, cfg, dropout_masks=masks1)
+    assert abs(loss1 - ref1["loss"]) <= 2e-3 * abs(ref1["loss"]), (loss1, ref1["loss"])
+    # determinism: reconfiguring with the same seed restarts the sequence (up to the order of fp64 atomics);
+    # another seed -> another loss
+    m.train_config(0.2, seed=1234, debug=True)
     assert abs(m.forward_backward(x, y) - loss) <= 1e-5 * abs(loss)
     m.train_config(0.2, seed=99)
     assert abs(m.forward_backward(x, y) - loss) > 1e-4 * abs(loss)
