@@ -99,6 +99,16 @@ ISHARA_API ishara_status_t ishara_model_finalize(ishara_model_t* m);
  * statistics, dropout off). Device pointers. */
 ISHARA_API ishara_status_t ishara_model_forward(ishara_model_t* m, const float* x_dev, int32_t batch, float* logits_dev,
                                      void* stream);
+/* mask_mode: 0 = "dropped" (default; the reference AS EXECUTED: the Keras mask of Masking(0.0), c7:13, is lost at the
+ * TFOpLambda `x + pe`, c7:16, so ECA / SqueezeExcite average over all T frames and the softmax is unmasked), 1 =
+ * "propagated" (the authors' apparent intent: mask_t = any(x[t,:] != 0) reaches ECA's and SqueezeExcite's
+ * GlobalAveragePooling1D(mask), c5:8-9,129-130, and Softmax(mask) of the SqueezeformerBlock MHSA, c5:109-112; the first
+ * ConformerBlock ends it because ConformerBlock has no supports_masking, c5:311-343). Inference only. */
+ISHARA_API ishara_status_t ishara_model_set_mask_mode(ishara_model_t* m, int32_t mode);
+/* forward with an explicit frame mask: mask_dev uint8 [B,T], 1 = the frame carries data, or NULL = derive it from x
+ * like Masking(0.0). A non-NULL mask needs mask_mode = 1. (SURVEY.md §8b `..._forward(model, x, mask_or_null, ...)`.) */
+ISHARA_API ishara_status_t ishara_model_forward_masked(ishara_model_t* m, const float* x_dev, const uint8_t* mask_dev, int32_t batch,
+                                                       float* logits_dev, void* stream);
 /* Same through host buffers: H2D copy, forward, D2H copy, stream sync (the reference-facing call). */
 ISHARA_API ishara_status_t ishara_model_forward_host(ishara_model_t* m, const float* x_host, int32_t batch, float* logits_host);
 /* Whole inference step through host buffers: forward + greedy decode (+ CTC loss when labels != NULL).

@@ -134,6 +134,8 @@ SIGNATURES = {
     "ishara_model_train_sync": (_i32, [_vp]),
     "ishara_model_train_param_grad": (_i32, [_vp, C.c_char_p, _vp, _i64]),
     "ishara_model_train_fetch": (_i32, [_vp, C.c_char_p, _i32, _vp, _i64]),
+    "ishara_model_set_mask_mode": (_i32, [_vp, _i32]),
+    "ishara_model_forward_masked": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "ishara_model_train_loss": (_i32, [_vp, C.POINTER(_f32), _vp]),
     "ishara_model_train_counters": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "ishara_comm_unique_id": (_i32, [_vp]),

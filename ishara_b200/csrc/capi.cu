@@ -54,6 +54,8 @@ int train_sync(ishara_model* m);
 int train_param_grad(ishara_model* m, const char* name, float* host_out, int64_t numel);
 int train_fetch(ishara_model* m, const char* name, int want_grad, float* host_out, int64_t numel);
 int train_forward_backward_loss(ishara_model* m, float* loss_host, cudaStream_t stream);
+int model_set_mask_mode(ishara_model* m, int mode);
+int model_forward_masked(ishara_model* m, const float* x_dev, const uint8_t* mask_dev, int batch, float* logits_dev, cudaStream_t stream);
 int train_counters(ishara_model* m, int64_t* fb_steps, int64_t* opt_steps, int64_t* skipped_steps);
 int comm_unique_id(void* out128);
 int model_comm_init(ishara_model* m, const void* id128, int rank, int world);
@@ -614,6 +616,17 @@ ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, in
   return static_cast<ishara_status_t>(train_fetch(reinterpret_cast<ishara_model*>(m), name, want_grad, host_out, numel));
 }
 
+ishara_status_t ishara_model_set_mask_mode(ishara_model_t* m, int32_t mode) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(model_set_mask_mode(reinterpret_cast<ishara_model*>(m), mode));
+}
+ishara_status_t ishara_model_forward_masked(ishara_model_t* m, const float* x_dev, const uint8_t* mask_dev, int32_t batch, float* logits_dev,
+                                            void* stream) {
+  CHECK_HANDLE(m);
+  if (x_dev == nullptr || logits_dev == nullptr || batch <= 0) { set_last_error("forward_masked: bad arguments"); return ISHARA_ERR_INVALID; }
+  return static_cast<ishara_status_t>(
+      model_forward_masked(reinterpret_cast<ishara_model*>(m), x_dev, mask_dev, batch, logits_dev, static_cast<cudaStream_t>(stream)));
+}
 ishara_status_t ishara_model_train_loss(ishara_model_t* m, float* loss_host, void* stream) {
   CHECK_HANDLE(m);
   return static_cast<ishara_status_t>(train_forward_backward_loss(reinterpret_cast<ishara_model*>(m), loss_host, static_cast<cudaStream_t>(stream)));

@@ -42,7 +42,7 @@ constexpr int kWSlot = 32 * 1024;             // one [256 x 64] k-slice of Wp^T
 constexpr int kWRing = 2 * kWSlot;
 constexpr int kXSlot = 48 * 1024;             // expand slot: S chunk [128 x 64] + We chunk [256 x 64]
 constexpr int kFloatBytes = 16 * 1024;        // part | corr | tapbuf (overlaps mean, which first holds the expand bias) | scale | constants; LN exchange over the first 8 KB
-constexpr int kCbSmem = kHRegion + kWRing + kFloatBytes + 256 + 1024;
+constexpr int kCbSmem = kHRegion + kWRing + kFloatBytes + 384 + 1024;
 constexpr int kWorkers = 16;
 constexpr int kCbThreads = 128 + 32 * kWorkers;
 
@@ -63,6 +63,8 @@ struct CbBars {
   uint64_t boxr[8];             // stencil finished box b (8 warps each)
   uint64_t acc2f;               // project accumulator ready
   uint64_t taps_full, taps_empty;  // tap staging buffer: filled by warps 2-3, drained by the 16 worker warps
+  uint64_t stg_free;            // boxes 0-3 are dead (project MMAs of chunks 0-3 retired): the epilogue staging may be filled
+  uint64_t resid_full[kWorkers];  // residual box of each epilogue warp has landed in its staging box
   uint32_t tmem_slot;
 };
 
@@ -76,7 +78,9 @@ struct CbParams {
   const float* ln_g;     // LayerNorm of the NEXT module (null: none)
   const float* ln_b;
   float ln_eps;
-  const int32_t* seq_len;  // [B] valid frames per sequence for the ECA mean (mask_mode="propagated"), null = all T
+  const float* dw_wsum;    // [512] sum over the k taps (per channel)
+  const uint16_t* wbits;   // [B*T] window validity bits (mask_mode="propagated": ECA averages over valid frames), null = all valid
+  const int32_t* valid_cnt;  // [B] valid frames per sequence (with wbits)
   int T;
   long long* trace;        // ISHARA_C1B_TRACE builds only
   int trace_b;
@@ -97,6 +101,9 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   float* scale = part + 5 * kKC;                                      // [512]
   float* cvec = part + 6 * kKC;                                          // bias_p[256] | ln_g[256] | ln_b[256] | eca_w[5]
   CbBars* bars = reinterpret_cast<CbBars*>(smem + kHRegion + kWRing + kFloatBytes);
+  static_assert(sizeof(CbBars) <= 384, "barrier block");
+  uint16_t* wb_s = reinterpret_cast<uint16_t*>(cvec + 800);           // [128] window bits of this tile's frames
+  uint32_t* mixed_s = reinterpret_cast<uint32_t*>(cvec + 800 + 64);   // [4] ballots: frames whose k-window is partly valid
 
   const int rank = blockIdx.x, nrank = gridDim.x;   // tile index inside the sequence == rank in the cluster
   const int b = blockIdx.y;
@@ -119,6 +126,8 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     mbar_init(&bars->acc2f, 1);
     mbar_init(&bars->taps_full, 2);
     mbar_init(&bars->taps_empty, kWorkers);
+    mbar_init(&bars->stg_free, 1);
+    for (int s = 0; s < kWorkers; ++s) mbar_init(&bars->resid_full[s], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_slot, 512);
@@ -194,6 +203,15 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (pr.ln_g != nullptr) reinterpret_cast<float4*>(cvec)[wt - 128] = __ldg(reinterpret_cast<const float4*>(pr.ln_b) + (wt - 256));
       } else if (wt < 325) {
         cvec[768 + (wt - 320)] = __ldg(pr.eca_w + (wt - 320));
+      } else if (wt >= 384) {
+        // window validity of this tile's 128 frames, cut to the k taps of this block: bit d = frame t+d counts in the ECA mean
+        const int r = wt - 384, t = rank * kBM + r;
+        constexpr uint32_t KM = (1u << K) - 1u;
+        uint32_t bits = pr.wbits != nullptr ? pr.wbits[static_cast<size_t>(b) * T + t] : (T - t >= 16 ? 0xFFFFu : ((1u << (T - t)) - 1u));
+        bits &= KM;
+        wb_s[r] = static_cast<uint16_t>(bits);
+        const uint32_t mixed = __ballot_sync(0xffffffffu, bits != 0u && bits != KM);
+        if (lane == 0) mixed_s[r >> 5] = mixed;
       }
       named_bar_sync(3, 32 * kWorkers);
     }
@@ -202,7 +220,6 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int q = warp & 3, c = ww >> 2;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const float* bias_s = mean;
-    const int Lseq = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
 #pragma unroll 1
     for (int nh = 0; nh < 2; ++nh) {
       mbar_wait(&bars->accf[nh], 0);
@@ -246,14 +263,17 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     named_bar_sync(3, 32 * kWorkers);  // the whole H tile is in shared memory
     if (warp == 4 && lane == 0) CB_TRACE(8);
 
-    // ---- column sums of H over this tile's valid frames. Warp = (box, 64-frame half); lane = (16-byte chunk c8 of the
-    //      128-byte row, frame phase sub): the 8 lanes of a quarter warp read one whole swizzled row (conflict-free
-    //      LDS.128), every thread keeps 8 channel accumulators, the 4 frame phases are folded with two shuffles ----
+    // ---- ECA mean without a second conv pass. With m = frame validity (all ones unless mask_mode="propagated"):
+    //   sum_t m_t y_t = b * sum_t m_t + sum_u h[u] * (sum_d w_{K-1-d} m_{u+d})
+    // i.e. wsum * h[u] for every frame whose k-frame window [u, u+K) is entirely valid ("full"), an explicit weight for
+    // the few frames next to a validity edge or the end of the sequence ("mixed"), nothing for the others.
+    // Full frames: warp = (box, 64-frame half); lane = (16-byte chunk c8 of the 128-byte row, frame phase sub): the 8
+    // lanes of a quarter warp read one whole swizzled row (conflict-free LDS.128), 8 channel accumulators per thread,
+    // the 4 frame phases are folded with two shuffles ----
     {
+      constexpr uint32_t KM = (1u << K) - 1u;
       const int box = ww >> 1, rh = ww & 1;
       const int c8 = lane & 7, sub = lane >> 3;
-      const int lloc = Lseq - rank * kBM;
-      const int hi = min(rh * 64 + 64, lloc);
       const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
       float acc[8];
 #pragma unroll
@@ -261,7 +281,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll 4
       for (int i = 0; i < 16; ++i) {
         const int r = rh * 64 + 4 * i + sub;
-        if (r < hi) {
+        if (wb_s[r] == KM) {
           uint4 v;
           const uint32_t addr = bx + static_cast<uint32_t>(r) * 128u + ((static_cast<uint32_t>(c8) ^ static_cast<uint32_t>(r & 7)) << 4);
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -283,28 +303,32 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
     }
-    // ---- this tile's share of the tail correction ----
-    //   sum_{t<L} y[t] = L*b + sum_j w_j * (S_L - [last K-1-j valid frames]),  S_L = sum_{u<L} h[u]
-    //                  = L*b + wsum*S_L - sum_{i=1..K-1} cw_i * h[L-i],         cw_i = w_0 + ... + w_{K-1-i}
+    // mixed frames (warp = box, lane = channel pair): the last k-1 frames of the sequence, plus the frames next to every
+    // validity edge in propagated mode
     if (ww < 8) {
       const int box = ww;
-      const int lloc = Lseq - rank * kBM;  // valid frames of the sequence that end inside / before / after this tile
       const uint32_t bx = smem_base + static_cast<uint32_t>(box) * kBoxStride + kBoxHalo;
       const uint32_t lsw = static_cast<uint32_t>(lane >> 2), lw = static_cast<uint32_t>(lane & 3) << 2;
       float2 cr = make_float2(0.f, 0.f);
-      if (lloc >= 1 && lloc - (K - 1) < kBM) {  // some of the frames L-1 .. L-(K-1) fall into this tile
+      if ((mixed_s[0] | mixed_s[1] | mixed_s[2] | mixed_s[3]) != 0u) {
         const int ch = box * 64 + 2 * lane;
-        float2 cw = make_float2(0.f, 0.f);  // running prefix sum of the taps: after adding tap j it equals cw_{K-1-j}
+        float2 wj[K];
 #pragma unroll
-        for (int j = 0; j < K - 1; ++j) {
-          const float2 wj = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
-          cw.x += wj.x; cw.y += wj.y;
-          const int i = K - 1 - j;     // cw now = cw_i, pairs with frame L - i
-          const int r = lloc - i;
-          if (r >= 0 && r < kBM) {
+        for (int j = 0; j < K; ++j) wj[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
+#pragma unroll 1
+        for (int g32 = 0; g32 < 4; ++g32) {
+          uint32_t mm = mixed_s[g32];
+          while (mm != 0u) {
+            const int r = g32 * 32 + __ffs(static_cast<int>(mm)) - 1;
+            mm &= mm - 1u;
+            const uint32_t bits = wb_s[r];
+            float2 w = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < K; ++d)
+              if ((bits >> d) & 1u) { w.x += wj[K - 1 - d].x; w.y += wj[K - 1 - d].y; }
             const uint32_t u = ld_shared_u32(bx + static_cast<uint32_t>(r) * 128u + (((lsw ^ static_cast<uint32_t>(r & 7)) << 4) | lw));
-            cr.x = fmaf(cw.x, bf16_lo(u), cr.x);
-            cr.y = fmaf(cw.y, bf16_hi(u), cr.y);
+            cr.x = fmaf(w.x, bf16_lo(u), cr.x);
+            cr.y = fmaf(w.y, bf16_hi(u), cr.y);
           }
         }
       }
@@ -351,11 +375,10 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (wt < kKC / 2) {
       const int ch = 2 * wt;
       float2 S = make_float2(0.f, 0.f), C = make_float2(0.f, 0.f);
-      float2 wsum = make_float2(0.f, 0.f);
-      float2 wj[K];
-#pragma unroll
-      for (int j = 0; j < K; ++j) wj[j] = __ldg(reinterpret_cast<const float2*>(pr.dw_w + static_cast<size_t>(j) * kKC + ch));
+      const float2 wsum = __ldg(reinterpret_cast<const float2*>(pr.dw_wsum + ch));
       const float2 bdw = __ldg(reinterpret_cast<const float2*>(pr.dw_b + ch));
+      // GlobalAveragePooling1D(mask) divides by the number of valid frames (0 valid frames: 0/0 = NaN, as in Keras)
+      const float invL = 1.f / static_cast<float>(pr.valid_cnt != nullptr ? pr.valid_cnt[b] : T);
       for (int r0 = 0; r0 < nrank; r0 += 4) {  // four CTAs' partial sums in flight at a time
         float2 a[4][2], c2[4];
 #pragma unroll
@@ -373,12 +396,8 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           C.x += c2[i].x; C.y += c2[i].y;
         }
       }
-#pragma unroll
-      for (int j = 0; j < K; ++j) { wsum.x += wj[j].x; wsum.y += wj[j].y; }
-      const int L = pr.seq_len != nullptr ? min(max(pr.seq_len[b], 0), T) : T;
-      const float invL = L > 0 ? 1.f / static_cast<float>(L) : 0.f;
-      mean[ch] = fmaf(fmaf(wsum.x, S.x, -C.x), invL, bdw.x);
-      mean[ch + 1] = fmaf(fmaf(wsum.y, S.y, -C.y), invL, bdw.y);
+      mean[ch] = fmaf(fmaf(wsum.x, S.x, C.x), invL, bdw.x);
+      mean[ch + 1] = fmaf(fmaf(wsum.y, S.y, C.y), invL, bdw.y);
     }
   }
   __syncwarp();
@@ -440,6 +459,7 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int k = 0; k < kBK / 16; ++k)
           umma_bf16(tmem_base, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC, (c | k) != 0 ? 1u : 0u);
         umma_commit(&bars->wempty[s]);
+        if (c == 3) umma_commit(&bars->stg_free);  // boxes 0-3 are no longer read: the epilogue staging (same bytes) may be filled
       }
       umma_commit(&bars->acc2f);
       CB_TRACE(24);
@@ -542,14 +562,29 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const bool ln = pr.ln_g != nullptr;
     const uint32_t stg0 = smem_base + static_cast<uint32_t>(ww) * kWarpStgBytes;             // H region is dead once acc2f fires
     const uint32_t stg1 = smem_base + static_cast<uint32_t>(kWorkers + ww) * kWarpStgBytes;
-    const bf16* rrow = pr.resid + static_cast<size_t>(row) * kKD + c * 64;
-    uint4 rq[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rq[j] = __ldg(reinterpret_cast<const uint4*>(rrow) + j);  // in flight while the MMAs finish
+    // residual: this warp's [32 x 64] box of S goes straight into its staging box by TMA (one bulk copy instead of 8
+    // loads per thread that each touch 32 different lines: ~4k cycles of L1 wavefronts per tile, ncu/trace r2g)
+    if (lane == 0) {
+      mbar_wait(&bars->stg_free, 0);
+      mbar_arrive_expect_tx(&bars->resid_full[ww], kWarpStgBytes);
+      tma_load_2d(smem + static_cast<uint32_t>(ww) * kWarpStgBytes, &tmO0, &bars->resid_full[ww], c * 64, row_g0 + q * 32);
+    }
+    (void)row;
     mbar_wait(&bars->acc2f, 0);
     tc_fence_after();
     if (warp == 4 && lane == 0) CB_TRACE(18);
     RowStats rs;
+    uint4 rq[8];
+    mbar_wait(&bars->resid_full[ww], 0);
+    {
+      const uint32_t rb = stg0 + static_cast<uint32_t>(lane) * 128u, xr = static_cast<uint32_t>(lane & 7);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rq[j].x), "=r"(rq[j].y), "=r"(rq[j].z), "=r"(rq[j].w)
+                     : "r"(rb + ((static_cast<uint32_t>(j) ^ xr) << 4))
+                     : "memory");
+    }
 #pragma unroll
     for (int sub = 0; sub < 2; ++sub) {
       const int col = c * 64 + sub * 32;
@@ -652,7 +687,8 @@ int launch_k(const Conv1dBlockPlan& p, cudaStream_t stream) {
   }
   CbParams pr;
   pr.bias_e = p.bias_e; pr.dw_w = p.dw_w; pr.dw_b = p.dw_b; pr.eca_w = p.eca_w; pr.bias_p = p.bias_p;
-  pr.resid = p.resid; pr.ln_g = p.ln_g; pr.ln_b = p.ln_b; pr.ln_eps = p.ln_eps; pr.seq_len = p.seq_len; pr.T = p.T;
+  pr.resid = p.resid; pr.ln_g = p.ln_g; pr.ln_b = p.ln_b; pr.ln_eps = p.ln_eps; pr.T = p.T;
+  pr.dw_wsum = p.dw_wsum; pr.wbits = p.wbits; pr.valid_cnt = p.valid_cnt;
   pr.trace = nullptr; pr.trace_b = 0;
 #ifdef ISHARA_C1B_TRACE
   static long long* tbuf = nullptr;

@@ -37,7 +37,7 @@ template <int K, int POST>
 __global__ void __launch_bounds__(kThreads, (K <= 11 ? 4 : (K <= 15 ? 3 : 1)))
 dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ w,
               const float* __restrict__ bias, const float* __restrict__ eca_w, float* __restrict__ colsum, int T,
-              int C, int pad_left, int rows_alloc) {
+              int C, int pad_left, int rows_alloc, const uint8_t* __restrict__ key_mask, const int32_t* __restrict__ valid_cnt) {
   constexpr int kTB = dw_tb<K>();
   extern __shared__ __align__(16) uint8_t smem_dw[];
   uint32_t* tile = reinterpret_cast<uint32_t*>(smem_dw);           // [rows_alloc][32] bf16x2
@@ -72,7 +72,38 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
 
   float2 scale = make_float2(1.f, 1.f);
   cg::cluster_group cluster = cg::this_cluster();
+  const uint8_t* mrow = key_mask != nullptr ? key_mask + static_cast<size_t>(b) * T : nullptr;  // 1 = frame counts (propagated mask)
   if constexpr (POST == 2) {
+    if (mrow != nullptr) {
+      // ---- ECA with a propagated Keras mask (c5:8-9): GlobalAveragePooling1D(mask) = mean of y over the VALID frames.
+      //      Arbitrary masks: one explicit conv pass over the valid frames (this is the non-default mode; the dense
+      //      case below needs no conv pass at all) ----
+      float2 s = make_float2(0.f, 0.f);
+      for (int t = t_begin; t < t_end; ++t) {
+        if (mrow[t] == 0) continue;
+        float2 a = bs;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const uint32_t u = tile[(t + j) * 32 + lane];
+          ffma2(a.x, a.y, wt[j].x, wt[j].y, bf16_lo(u), bf16_hi(u), a.x, a.y);
+        }
+        s.x += a.x; s.y += a.y;
+      }
+      red[warp * kSlab + 2 * lane] = s.x;
+      red[warp * kSlab + 2 * lane + 1] = s.y;
+      __syncthreads();
+      if (warp == 0) {
+        float2 S = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int wv = 0; wv < kWarps; ++wv) {
+          S.x += red[wv * kSlab + 2 * lane];
+          S.y += red[wv * kSlab + 2 * lane + 1];
+        }
+        const float invn = 1.f / static_cast<float>(valid_cnt[b]);  // 0 valid frames: 0/0 = NaN, as in Keras
+        mean_s[2 * lane] = S.x * invn;
+        mean_s[2 * lane + 1] = S.y * invn;
+      }
+    } else {
     // ---- ECA: mean over T of y = conv + bias, then 5-tap conv over channels, sigmoid ----
     // The convolution is linear in time, so its mean needs no convolution pass: with S = sum_t x[t],
     //   sum_t y[t] = T*bias + sum_j w[j] * (S - [rows that tap j shifts out of the window]),
@@ -116,6 +147,7 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
       const float invT = 1.f / static_cast<float>(T);
       mean_s[2 * lane] = fmaf(acc.x, invT, bs.x);
       mean_s[2 * lane + 1] = fmaf(acc.y, invT, bs.y);
+    }
     }
     // exchange slab-edge means with the neighbouring slabs of the same sequence (DSMEM)
     cluster.sync();
@@ -172,7 +204,7 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
         const uint32_t packed = pack_bf16x2(a.x, a.y);
         *drow = packed;
         drow += cw;
-        if (colsum != nullptr) { cs.x += bf16_lo(packed); cs.y += bf16_hi(packed); }
+        if (colsum != nullptr && (mrow == nullptr || mrow[t_begin + blk * kTB + i] != 0)) { cs.x += bf16_lo(packed); cs.y += bf16_hi(packed); }
       }
       trow += kTB * 32;
     }
@@ -188,7 +220,7 @@ dwconv_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* 
       const uint32_t packed = pack_bf16x2(a.x, a.y);
       *drow = packed;
       drow += cw;
-      if (colsum != nullptr) { cs.x += bf16_lo(packed); cs.y += bf16_hi(packed); }
+      if (colsum != nullptr && (mrow == nullptr || mrow[t_begin + i] != 0)) { cs.x += bf16_lo(packed); cs.y += bf16_hi(packed); }
       trow += 32;
     }
   }
@@ -242,7 +274,7 @@ int launch_inst(const DwConvArgs& a, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
   ISHARA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a.in, a.out, a.w, a.bias, a.eca_w, a.colsum, a.T, a.C, a.pad_left,
-                                    rows_alloc));
+                                    rows_alloc, a.key_mask, a.valid_cnt));
   note_launch();
   return 0;
 }

@@ -110,13 +110,16 @@ struct Conv1dBlockPlan {
   const float* bias_e = nullptr;  // [512] expand bias
   const float* dw_w = nullptr;    // [k, 512] depthwise taps with BatchNorm folded in
   const float* dw_b = nullptr;    // [512] BatchNorm offset
+  const float* dw_wsum = nullptr; // [512] sum of the k taps per channel
   const float* eca_w = nullptr;   // [5]
   const float* bias_p = nullptr;  // [256] project bias
   const bf16* resid = nullptr;    // = S (set by plan_init)
   const float* ln_g = nullptr;    // LayerNorm of the next module: XN = LN(S) (null: none)
   const float* ln_b = nullptr;
   float ln_eps = 0.f;
-  const int32_t* seq_len = nullptr;  // [B] valid frames for the ECA mean (mask_mode="propagated") or null
+  // mask_mode="propagated": ECA averages over the valid frames only (c5:8-9). Null = every frame counts.
+  const uint16_t* wbits = nullptr;     // [B*T] window validity bits (mask_prep_launch)
+  const int32_t* valid_cnt = nullptr;  // [B]
   int B = 0, T = 0, k = 0;
 };
 bool conv1d_block_applicable(int D, int T, int k);
@@ -136,6 +139,9 @@ struct DwConvArgs {
   const float* eca_w = nullptr; // [5] fp32 (post == 2)
   float* colsum = nullptr;      // [B, C] or null
   int B = 0, T = 0, C = 0, k = 0, pad_left = 0, post = 0;
+  // mask_mode="propagated": frames with key_mask == 0 do not count in the ECA mean (post 2) / the column sums (SE)
+  const uint8_t* key_mask = nullptr;   // [B, T], 1 = valid
+  const int32_t* valid_cnt = nullptr;  // [B]
 };
 int dwconv_launch(const DwConvArgs& a, cudaStream_t stream);
 
@@ -177,7 +183,12 @@ struct SeGateArgs {
   float* gate = nullptr;          // [B, D]
   int B = 0, C = 0, D = 0, R = 0;
   float inv_T = 1.f;
+  const int32_t* valid_cnt = nullptr;  // [B] valid frames per sequence (mask_mode="propagated"): mean = colsum / valid_cnt
 };
+// Keras Masking(0.0) for mask_mode="propagated": mask_out[B*T] (1 = frame carries data) from x fp32 [B,T,F] (or from
+// user_mask when given and *use_user != 0), wbits[B*T] (bit d = frame t+d valid, d < 16), valid_cnt[B]
+int mask_prep_launch(const float* x, const uint8_t* user_mask, const int* use_user, int B, int T, int F, uint8_t* mask_out,
+                     uint16_t* wbits, int32_t* valid_cnt, cudaStream_t stream);
 int se_gate_launch(const SeGateArgs& a, cudaStream_t stream);
 // standalone LayerNorm (fallback / operator-level use): x bf16 [M, D] -> bf16
 int layernorm_launch(const bf16* x, bf16* out, const float* g, const float* b, float eps, int64_t M, int D,

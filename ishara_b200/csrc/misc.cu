@@ -42,6 +42,49 @@ __global__ void cast_pad_kernel(const float* __restrict__ x, bf16* __restrict__ 
   }
 }
 
+// Keras Masking(0.0) (nb:conv-hybrid-model c7:13) for mask_mode="propagated": mask[t] = any(x[t, :] != 0) (or the caller's
+// mask), plus what the mask consumers need: the number of valid frames per sequence and, per frame, the validity of the
+// 16 frames starting at it (bit d = frame t+d is inside the sequence and valid). The depthwise kernels use the window
+// bits to evaluate GlobalAveragePooling1D(mask) of the conv OUTPUT from column sums of its INPUT:
+//   sum_t m_t y_t = sum_u h[u] * (sum_d w_{K-1-d} m_{u+d}),  i.e. wsum * h[u] wherever the K-frame window is all valid.
+// One CTA per sequence.
+__global__ void __launch_bounds__(256)
+mask_prep_kernel(const float* __restrict__ x, const uint8_t* __restrict__ user_mask, const int* __restrict__ use_user, int T, int F,
+                 uint8_t* __restrict__ mask_out, uint16_t* __restrict__ wbits, int32_t* __restrict__ valid_cnt) {
+  extern __shared__ uint8_t msk[];  // [T + 16]
+  __shared__ int cnt_s;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) cnt_s = 0;
+  const bool from_user = user_mask != nullptr && (use_user == nullptr || *use_user != 0);
+  if (from_user) {
+    for (int t = tid; t < T; t += 256) msk[t] = user_mask[static_cast<size_t>(b) * T + t] != 0 ? 1 : 0;
+  } else {
+    for (int t = warp; t < T; t += 8) {
+      const float* row = x + (static_cast<size_t>(b) * T + t) * F;
+      bool nz = false;
+      for (int c = lane; c < F; c += 32) nz |= (row[c] != 0.f);
+      nz = __any_sync(0xffffffffu, nz);
+      if (lane == 0) msk[t] = nz ? 1 : 0;
+    }
+  }
+  for (int t = T + tid; t < T + 16; t += 256) msk[t] = 0;
+  __syncthreads();
+  int local = 0;
+  for (int t = tid; t < T; t += 256) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) bits |= static_cast<uint32_t>(msk[t + d]) << d;
+    wbits[static_cast<size_t>(b) * T + t] = static_cast<uint16_t>(bits);
+    mask_out[static_cast<size_t>(b) * T + t] = msk[t];
+    local += msk[t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if (lane == 0) atomicAdd(&cnt_s, local);  // integer: order-independent
+  __syncthreads();
+  if (tid == 0) valid_cnt[b] = cnt_s;
+}
+
 // SqueezeExcite gate (nb:conv-hybrid-model c5:120-133) computed from the column sums of the conv3 INPUT:
 // mean_t(conv3(h)) = mean_t(h) @ W3 + b3 (1x1 conv is linear), so no pass over the [T, D] output is needed.
 __global__ void __launch_bounds__(256)
@@ -52,7 +95,9 @@ se_gate_kernel(SeGateArgs a) {
   float* part = z + a.D;       // [8][R] partial sums of fc1
   float* hid = part + 8 * a.R; // [R]
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int c = tid; c < a.C; c += 256) mean[c] = a.colsum[static_cast<size_t>(b) * a.C + c] * a.inv_T;
+  // GlobalAveragePooling1D(mask): the column sums already cover the valid frames only; 0 valid frames -> 0/0 = NaN as in Keras
+  const float inv_n = a.valid_cnt != nullptr ? 1.f / static_cast<float>(a.valid_cnt[b]) : a.inv_T;
+  for (int c = tid; c < a.C; c += 256) mean[c] = a.colsum[static_cast<size_t>(b) * a.C + c] * inv_n;
   __syncthreads();
   // z = mean @ W3 + b3: four output channels per warp iteration (independent load streams), 16-byte weight loads
   for (int d0 = warp * 4; d0 < a.D; d0 += 32) {
@@ -148,6 +193,15 @@ int cast_pad_launch(const float* x, bf16* out, int64_t M, int F, int Fpad, cudaS
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   cast_pad_kernel<<<grid, 256, 0, stream>>>(x, out, M, F, Fpad);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int mask_prep_launch(const float* x, const uint8_t* user_mask, const int* use_user, int B, int T, int F, uint8_t* mask_out,
+                     uint16_t* wbits, int32_t* valid_cnt, cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || T > 16384) { set_last_error("mask_prep: bad shape"); return 2; }
+  mask_prep_kernel<<<B, 256, T + 16, stream>>>(x, user_mask, use_user, T, F, mask_out, wbits, valid_cnt);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

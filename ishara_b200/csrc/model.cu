@@ -211,6 +211,15 @@ int pack_conv_blocks(ishara_model* m, const std::string& tag, int i) {
     float* d;
     if ((rc = pack_f32(m, n + "_dw.w", w, &d))) return rc;
     if ((rc = pack_f32(m, n + "_dw.b", o, &d))) return rc;
+    {
+      std::vector<float> ws(2 * D, 0.f);
+      for (int ch = 0; ch < 2 * D; ++ch) {
+        double acc = 0.0;
+        for (int t = 0; t < k; ++t) acc += w[static_cast<size_t>(t) * 2 * D + ch];
+        ws[ch] = static_cast<float>(acc);
+      }
+      if ((rc = pack_f32(m, n + "_dw.wsum", ws, &d))) return rc;
+    }
     if ((rc = pack_f32(m, n + "_eca.w", P(m, n + "_eca.kernel"), &d))) return rc;
     if ((rc = pack_dense(m, n + "_project_conv", 2 * D, D, true))) return rc;
   }
@@ -369,6 +378,12 @@ int ensure_workspace(ishara_model* m, int batch) {
   if ((rc = ws_alloc(m, &m->ids_dev, M))) return rc;
   if ((rc = ws_alloc(m, &m->lens_dev, static_cast<size_t>(batch)))) return rc;
   if ((rc = ws_alloc(m, &m->nll_dev, static_cast<size_t>(batch)))) return rc;
+  if ((rc = ws_alloc(m, &m->mask_dev, M))) return rc;
+  if ((rc = ws_alloc(m, &m->wbits_dev, M))) return rc;
+  if ((rc = ws_alloc(m, &m->valid_dev, static_cast<size_t>(batch)))) return rc;
+  if ((rc = ws_alloc(m, &m->user_mask_dev, M))) return rc;
+  if ((rc = ws_alloc(m, &m->use_user_mask_dev, 4))) return rc;
+  ISHARA_CUDA_OK(cudaMemset(m->use_user_mask_dev, 0, 4 * sizeof(int)));
   m->labels_dev = nullptr;
   m->labels_cap = 0;
   m->cap_batch = batch;
@@ -381,6 +396,9 @@ struct Builder {
   std::vector<Op>& ops;
   Packed pk;
   int rc = 0;
+  // mask_mode="propagated": true while the Keras mask is alive, i.e. up to and including the Conv1DBlocks in front of
+  // the first ConformerBlock (ConformerBlock neither consumes nor forwards a mask: no supports_masking, c5:311-343)
+  bool masked = false;
 
   void wide_gemm(const char* label, const bf16* A, int K, const std::string& wkey, const std::string& bkey, int N,
                  int act, bf16* out) {
@@ -476,6 +494,10 @@ struct Builder {
     op.dw.bias = bkey.empty() ? nullptr : pk.get<float>(bkey);
     op.dw.eca_w = ecakey.empty() ? nullptr : pk.get<float>(ecakey);
     op.dw.colsum = colsum;
+    if (masked && (post == 2 || colsum != nullptr)) {  // ECA mean / SqueezeExcite pooling over the valid frames only
+      op.dw.key_mask = m->mask_dev;
+      op.dw.valid_cnt = m->valid_dev;
+    }
     op.dw.B = B; op.dw.T = T; op.dw.C = C; op.dw.k = k; op.dw.pad_left = pad_left; op.dw.post = post;
     op.flops = 2.0 * M * C * k;
     op.bytes = 4.0 * M * C;  // bf16 in + bf16 out
@@ -486,7 +508,8 @@ struct Builder {
     Op op;
     op.kind = OP_ATTN;
     op.label = "attention";
-    op.at.qkv = qkv; op.at.out = out; op.at.key_mask = nullptr;
+    op.at.qkv = qkv; op.at.out = out;
+    op.at.key_mask = masked ? m->mask_dev : nullptr;  // Softmax(mask): scores of padded keys += -1e9 (c5:109-112)
     op.at.B = B; op.at.T = T; op.at.H = m->cfg.num_heads; op.at.dh = D / m->cfg.num_heads;
     op.at.scale = 1.f / std::sqrt(static_cast<float>(D));  // self.scale = dim ** -0.5 (c5:95), NOT dh ** -0.5
     op.flops = 4.0 * M * T * D;             // QK^T and PV: 2 * (2 * T * T * D) per sequence
@@ -531,11 +554,13 @@ struct Builder {
         p.bias_e = pk.get<float>(n + "_expand_conv.b");
         p.dw_w = pk.get<float>(n + "_dw.w");
         p.dw_b = pk.get<float>(n + "_dw.b");
+        p.dw_wsum = pk.get<float>(n + "_dw.wsum");
         p.eca_w = pk.get<float>(n + "_eca.w");
         p.bias_p = pk.get<float>(n + "_project_conv.b");
         const LnRef nl = last_blk ? next_ln : LnRef();
         p.ln_g = nl.g; p.ln_b = nl.b; p.ln_eps = nl.eps;
-        p.seq_len = m->seq_len_active;
+        p.wbits = masked ? m->wbits_dev : nullptr;
+        p.valid_cnt = masked ? m->valid_dev : nullptr;
         rc = conv1d_block_plan_init(&p, m->S, pk.get<bf16>(n + "_expand_conv.w"), pk.get<bf16>(n + "_project_conv.w"),
                                     nl.g ? m->XN : nullptr);
         op.flops = 2.0 * M * D * 2 * D * 2 + 2.0 * M * 2 * D * k;
@@ -616,6 +641,7 @@ int build_program(ishara_model* m, int batch, float* logits) {
     return LnRef();
   };
   const bool has_conv = c.num_conv_per_block > 0;
+  b.masked = m->mask_mode == 1;
 
   {
     // stem
@@ -648,6 +674,7 @@ int build_program(ishara_model* m, int batch, float* logits) {
       op.se.gate = m->gate;
       op.se.B = batch; op.se.C = E; op.se.D = D; op.se.R = std::max(1, D / 8);
       op.se.inv_T = 1.f / static_cast<float>(c.frames);
+      op.se.valid_cnt = b.masked ? m->valid_dev : nullptr;
       op.flops = 2.0 * batch * (static_cast<double>(E) * D + 2.0 * D * op.se.R);
       op.bytes = 4.0 * batch * (E + D) + 2.0 * E * D;
       m->program.push_back(op);
@@ -661,6 +688,7 @@ int build_program(ishara_model* m, int batch, float* logits) {
     const std::string n = "conformer_" + std::to_string(i);
     const LnRef ln1 = b.ln(n + ".layer_norm1", 1e-6f);
     b.conv_blocks("conform", i, ln1);
+    b.masked = false;  // the mask dies at the first ConformerBlock
     LnRef after = has_conv ? LnRef() : first_ln_of(c.num_conv_squeeze_blocks, i + 1);
     b.ffn(n + ".ffn1", ln1);            // layer_norm1 is reused for the MHSA input (c5:324,330)
     b.mhsa(n + ".mha", LnRef());        // conv module consumes the raw stream
@@ -783,7 +811,13 @@ static void drop_graphs(ishara_model* m) {
   m->graphs.clear();
 }
 
+int model_forward_impl(ishara_model* m, const float* x_dev, int batch, float* logits_dev, cudaStream_t stream);
 int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_dev, cudaStream_t stream) {
+  // propagated masks come from x itself (Masking(0.0)) unless forward_masked supplied one for this call
+  if (m->mask_mode == 1 && m->use_user_mask_dev != nullptr) ISHARA_CUDA_OK(cudaMemsetAsync(m->use_user_mask_dev, 0, sizeof(int), stream));
+  return model_forward_impl(m, x_dev, batch, logits_dev, stream);
+}
+int model_forward_impl(ishara_model* m, const float* x_dev, int batch, float* logits_dev, cudaStream_t stream) {
   if (!m->finalized) { set_last_error("forward before finalize"); return ISHARA_ERR_STATE; }
   if (m->host_params_stale) { int rcs = train_sync(m); if (rcs) return rcs; }  // weights moved by a training step
   if (batch <= 0 || x_dev == nullptr || logits_dev == nullptr) { set_last_error("forward: bad arguments"); return ISHARA_ERR_INVALID; }
@@ -855,6 +889,37 @@ int model_forward(ishara_model* m, const float* x_dev, int batch, float* logits_
   return launch_program(m, x_dev, batch, stream, prof);
 }
 
+int model_set_mask_mode(ishara_model* m, int mode) {
+  if (mode != 0 && mode != 1) { set_last_error("mask_mode: 0 (dropped) or 1 (propagated)"); return ISHARA_ERR_INVALID; }
+  if (m->mask_mode != mode) {
+    m->mask_mode = mode;
+    m->program.clear();
+    m->program_cache.clear();
+    drop_graphs(m);
+    m->program_batch = 0;
+  }
+  return 0;
+}
+
+// forward with an explicit frame mask (uint8 [B, T], 1 = frame carries data) instead of Masking(0.0)'s any(x != 0); only
+// meaningful with mask_mode = propagated. mask_dev == null: derive it from x.
+int model_forward_masked(ishara_model* m, const float* x_dev, const uint8_t* mask_dev, int batch, float* logits_dev, cudaStream_t stream) {
+  if (mask_dev != nullptr && m->mask_mode != 1) { set_last_error("forward_masked: a mask needs mask_mode = propagated (ishara_model_set_mask_mode)"); return ISHARA_ERR_STATE; }
+  if (m->mask_mode == 1) {
+    ISHARA_CUDA_OK(cudaSetDevice(m->device));
+    int rc = ensure_workspace(m, batch);
+    if (rc) return rc;
+    const int flag = mask_dev != nullptr ? 1 : 0;
+    // the flag and the mask copy are stream-ordered in front of the (possibly graph-replayed) program that reads them
+    ISHARA_CUDA_OK(cudaMemsetAsync(m->use_user_mask_dev, 0, sizeof(int), stream));
+    if (flag) {
+      ISHARA_CUDA_OK(cudaMemcpyAsync(m->user_mask_dev, mask_dev, static_cast<size_t>(batch) * m->cfg.frames, cudaMemcpyDeviceToDevice, stream));
+      ISHARA_CUDA_OK(cudaMemsetAsync(m->use_user_mask_dev, 1, 1, stream));  // little-endian int 1
+    }
+  }
+  return model_forward_impl(m, x_dev, batch, logits_dev, stream);
+}
+
 int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t stream, bool prof) {
   const ishara_config_t& c = m->cfg;
   const int64_t M = static_cast<int64_t>(batch) * c.frames;
@@ -867,6 +932,10 @@ int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t 
     }
     ISHARA_CUDA_OK(cudaEventRecord(m->events[0], stream));
   }
+  if (m->mask_mode == 1 &&
+      (rc = mask_prep_launch(x_dev, m->user_mask_dev, m->use_user_mask_dev, batch, c.frames, c.features, m->mask_dev, m->wbits_dev,
+                             m->valid_dev, stream)))
+    return rc;
   if ((rc = cast_pad_launch(x_dev, m->XIN, M, c.features, m->fpad(), stream))) return rc;
   if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[1], stream));
   size_t op_index = 0;

@@ -97,9 +97,13 @@ struct ishara_model {
   std::vector<void*> wsallocs;
   bf16 *XIN = nullptr, *S = nullptr, *XN = nullptr, *H1 = nullptr, *H2 = nullptr, *O = nullptr, *HEAD = nullptr;
   float *colsum = nullptr, *gate = nullptr;
-  int32_t* seq_len_dev = nullptr;      // [cap_batch] valid frames per sequence (mask_mode="propagated")
-  uint8_t* key_mask_dev = nullptr;     // [cap_batch * frames] 1 = frame carries data
-  const int32_t* seq_len_active = nullptr;  // = seq_len_dev while a propagated-mask program is being built, else null
+  // mask_mode="propagated" (Keras Masking reaching ECA / SE / Softmax, c5:8-9,109-112,129-130): written by mask_prep_launch
+  int mask_mode = 0;                   // 0 = dropped (the reference as executed), 1 = propagated
+  uint8_t* mask_dev = nullptr;         // [cap_batch * frames] 1 = frame carries data
+  uint16_t* wbits_dev = nullptr;       // [cap_batch * frames] validity of the 16 frames starting at each frame
+  int32_t* valid_dev = nullptr;        // [cap_batch] valid frames per sequence
+  uint8_t* user_mask_dev = nullptr;    // [cap_batch * frames] copy of the caller's mask (forward_masked)
+  int* use_user_mask_dev = nullptr;    // device flag read by mask_prep: 1 = take user_mask_dev, 0 = derive the mask from x
   float* logits_own = nullptr;
   int32_t *ids_dev = nullptr, *lens_dev = nullptr, *labels_dev = nullptr;
   float* nll_dev = nullptr;

@@ -101,9 +101,10 @@ class IsharaModel:
     def __init__(self, dim=256, num_conv_squeeze_blocks=2, num_conv_conform_blocks=2, kernel_sizes=(11, 5, 3),
                  num_conv_per_block=3, dropout_rate=0.2, num_heads=8, expansion_factor=2, transformer_kernel_size=15,
                  *, input_shape=(384, 276), num_classes=60, device=0, mask_mode="dropped", seed=0):
-        if mask_mode != "dropped":
-            # "dropped" is the reference as executed (the Keras mask dies at `x + pe`)
-            raise NotImplementedError("mask_mode='propagated' is not built yet; the reference as executed is 'dropped'")
+        if mask_mode not in ("dropped", "propagated"):
+            # "dropped" = the reference as executed (the Keras mask dies at `x + pe`); "propagated" = the
+            # authors' apparent intent (mask reaches ECA / SqueezeExcite / Softmax, c5:8-9,109-112,129-130)
+            raise ValueError("mask_mode must be 'dropped' or 'propagated'")
         self._lib = _lib.load()
         self.device = int(device)
         self.dropout_rate = float(dropout_rate)
@@ -127,6 +128,8 @@ class IsharaModel:
         _lib.check(self._lib.ishara_model_create(C.byref(cfg), self.device, C.byref(h)))
         self._h = h
         self._finalized = False
+        if mask_mode == "propagated":
+            _lib.check(self._lib.ishara_model_set_mask_mode(self._h, 1))
         self._specs = self._read_specs()
         self._init_weights(seed)
 
@@ -232,10 +235,32 @@ class IsharaModel:
         if len(shape) != 3 or shape[1] != self.frames or shape[2] != self.features:
             raise ValueError(f"expected x of shape [B,{self.frames},{self.features}], got {tuple(shape)}")
 
-    def __call__(self, x: ArrayLike, training: bool = False):
-        """logits [B,T,num_classes] float32 = model(x). numpy in -> numpy out; CUDA DLPack in -> device out."""
+    def __call__(self, x: ArrayLike, training: bool = False, mask: Optional[ArrayLike] = None):
+        """logits [B,T,num_classes] float32 = model(x). numpy in -> numpy out; CUDA DLPack in -> device out.
+        ``mask`` (bool / uint8 [B,T], True = frame carries data; ``mask_mode="propagated"`` only) replaces the mask that
+        ``Masking(0.0)`` derives from x (c7:13)."""
         if training:
             raise NotImplementedError("training=True forward (batch statistics, dropout) goes through train_step")
+        if mask is not None:
+            if self.mask_mode != "propagated":
+                raise ValueError("a mask needs get_model(..., mask_mode='propagated')")
+            host = isinstance(x, np.ndarray)
+            if host:
+                x = np.ascontiguousarray(x, dtype=np.float32)
+                self._check_x(x.shape)
+                xd_t = _dlpack.from_host(x, self.device, "float32")
+                md_t = _dlpack.from_host(np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8), self.device, "uint8")
+                self._ensure_finalized()
+                out = DeviceTensor((x.shape[0], self.frames, self.num_classes), "float32", self.device)
+                _lib.check(self._lib.ishara_model_forward_masked(self._h, _vp(xd_t.ptr), _vp(md_t.ptr), x.shape[0], _vp(out.ptr), None))
+                return out.numpy(0)
+            xd = _Dev(x, "float32", self.device)
+            md = _Dev(mask, "uint8", self.device)
+            self._check_x(xd.shape)
+            self._ensure_finalized()
+            out, optr = _new_like(xd, (xd.shape[0], self.frames, self.num_classes), "float32", self.device)
+            _lib.check(self._lib.ishara_model_forward_masked(self._h, _vp(xd.ptr), _vp(md.ptr), xd.shape[0], _vp(optr), _vp(xd.stream)))
+            return out
         if isinstance(x, np.ndarray):
             x = np.ascontiguousarray(x, dtype=np.float32)
             self._check_x(x.shape)

@@ -294,3 +294,57 @@ def test_pipelined_inference_matches_blocking_calls():
     g2 = list(m.infer_pipelined([x for x, _ in batches[:3]]))
     assert [r["text"] for r in g2] == [w["text"] for w in want[:3]] and g2[0]["nll"] is None
     m.close()
+
+
+# ---- mask_mode="propagated" (c7:13, c5:8-9, c5:109-112, c5:129-130) ----------------------------------
+def _masked_model(cfg, params):
+    m = ib.get_model(cfg.dim, cfg.num_conv_squeeze_blocks, cfg.num_conv_conform_blocks, cfg.kernel_sizes,
+                     cfg.num_conv_per_block, cfg.dropout_rate, cfg.num_heads, cfg.expansion_factor,
+                     cfg.transformer_kernel_size, input_shape=(cfg.frames, cfg.features), num_classes=cfg.num_classes,
+                     mask_mode="propagated")
+    return m.load_weights(params)
+
+
+@pytest.mark.parametrize("frames", [384, 176], ids=["T384_fused_conv1d_block", "T176_three_kernel_path"])
+def test_propagated_mask_matches_oracle(frames):
+    """Ragged (zero-padded) sequences with the Keras mask PROPAGATED: ECA and SqueezeExcite average over the valid frames,
+    the SqueezeformerBlock softmax ignores padded keys, the mask ends at the first ConformerBlock. T=384 runs the fused
+    Conv1DBlock kernel, T=176 (the reference's own FRAME_LEN, c1:27) the three-kernel path."""
+    cfg = O.Config(frames=frames)
+    params = O.init_params(cfg, seed=42)
+    m = _masked_model(cfg, params)
+    x = O.make_inputs(cfg, 4, seed=11, ragged=True)
+    x[1, 40:43] = 0.0                     # an all-zero frame run in the MIDDLE of a sequence (non-prefix mask)
+    x[2, 0:2] = 0.0                       # and at the very start
+    x[3, frames - 1] = 0.0                # one masked frame at the end (inside every k-tap window of the last frames)
+    ref = O.forward(params, x, cfg, "float64", mask_mode="propagated")
+    got = m(x)
+    _check_logits(got, ref, f"propagated mask T={frames}")
+    # the two modes really differ on padded input (otherwise this test proves nothing) ...
+    ref_dropped = O.forward(params, x, cfg, "float64", mask_mode="dropped")
+    assert np.abs(got - ref).max() < 0.5 * np.abs(got - ref_dropped).max()
+    # ... and agree on dense input, where the mask is all ones
+    xd = O.make_inputs(cfg, 2, seed=3)
+    m0 = _model_for(cfg, params)
+    assert np.array_equal(m(xd), m0(xd))
+    m0.close()
+    m.close()
+
+
+def test_explicit_mask_argument():
+    """model(x, mask=...) (SURVEY.md §8b forward(model, x, mask_or_null, ...)) overrides Masking(0.0)'s any(x != 0)."""
+    cfg = O.Config()
+    params = O.init_params(cfg, seed=42)
+    m = _masked_model(cfg, params)
+    x = O.make_inputs(cfg, 3, seed=5, ragged=True)
+    auto = m(x)
+    mask = (x != 0).any(-1)
+    assert np.array_equal(m(x, mask=mask), auto)                  # the same mask, handed over explicitly
+    full = m(x, mask=np.ones_like(mask))                          # all frames declared valid = the dropped-mask result
+    m0 = _model_for(cfg, params)
+    assert np.array_equal(full, m0(x))
+    assert not np.array_equal(full, auto)
+    with pytest.raises(ValueError):
+        m0(x, mask=mask)                                          # a mask needs mask_mode="propagated"
+    m0.close()
+    m.close()
