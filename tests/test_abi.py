@@ -123,8 +123,14 @@ def test_error_reporting_without_gpu():
     assert st == _lib.ERR_STATE
     with pytest.raises(ValueError):
         m(np.zeros((1, 31, 20), np.float32))
-    with pytest.raises(NotImplementedError):
-        ib.get_model(mask_mode="propagated")
+    with pytest.raises(ValueError):
+        ib.get_model(mask_mode="something-else")
+    mp = ib.get_model(dim=64, num_conv_squeeze_blocks=0, num_conv_conform_blocks=1, num_heads=4, input_shape=(32, 20),
+                      num_classes=12, mask_mode="propagated")       # accepted; the mode is a host-side switch until forward
+    assert lib.ishara_model_set_mask_mode(mp._h, 7) == _lib.ERR_INVALID
+    assert lib.ishara_model_comm_init(mp._h, None, 0, 2) == _lib.ERR_INVALID   # null unique id
+    assert lib.ishara_model_train_counters(mp._h, None, None, None) == _lib.ERR_STATE  # no training state yet
+    mp.close()
     bad = _lib.Config()
     h = C.c_void_p()
     assert lib.ishara_model_create(C.byref(bad), 0, C.byref(h)) == _lib.ERR_SHAPE
