@@ -173,6 +173,36 @@ ISHARA_API ishara_status_t ishara_model_train_step(ishara_model_t* m, const floa
 /* same with host buffers (H2D inside), on the handle's stream; returns after a sync */
 ISHARA_API ishara_status_t ishara_model_train_step_host(ishara_model_t* m, const float* x_host, const int32_t* labels_host,
                                                          int32_t batch, int32_t labels_len, const ishara_adamw_t* opt, float* loss_host);
+/* The optimiser the reference itself compiles the model with (nb:conv-hybrid-model c7:68-69):
+ * tfa.optimizers.Lookahead(tfa.optimizers.RectifiedAdam(sma_threshold=4), sync_period=5). tensorflow_addons is a
+ * third-party dependency that is neither vendored nor pinned (Dockerfile:20-21); the arithmetic restated here is its
+ * published algorithm (rectified_adam.py with total_steps = 0, lookahead.py with slow_step_size = 0.5). Same role as
+ * train_apply; the two must not be mixed on one handle (they share the moment buffers and the step counter).
+ * Note: WeightDecayCallback (c11:58-65) assigns `weight_decay` on the Lookahead wrapper, which does not reach the
+ * wrapped RectifiedAdam (built with weight_decay = 0): the reference as executed decays nothing, hence the default 0. */
+typedef struct {
+  float lr;             /* 1e-3 (tfa default; the per-epoch value comes from the LR schedule c11:51-55) */
+  float weight_decay;   /* 0 */
+  float beta1;          /* 0.9 */
+  float beta2;          /* 0.999 */
+  float eps;            /* 1e-7 */
+  float max_norm;       /* global-norm clip; <= 0 disables (Keras default: none) */
+  float sma_threshold;  /* 4 (c7:68) */
+  int32_t sync_period;  /* 5 (c7:69) */
+  float slow_step_size; /* 0.5 */
+} ishara_radam_lookahead_t;
+ISHARA_API ishara_status_t ishara_model_train_apply_radam(ishara_model_t* m, const ishara_radam_lookahead_t* opt, float grad_scale,
+                                                          void* stream);
+/* ---- optimiser-state checkpoint (model.save_weights c9:10, integration.py:912-958) --------
+ * Flat fp32 slots in the order of the parameter table (ishara_model_param_info gives names and sizes; every slot has
+ * `numel` = the sum of all parameter sizes): which = 0 Adam m, 1 Adam v, 2 Lookahead slow weights (only after a RAdam
+ * step), 3 master weights (read only; weights are restored through set_param). Counters: optimiser steps (bias
+ * correction, Lookahead phase) and forward/backward passes (dropout stream). Host buffers; synchronises the device. */
+ISHARA_API ishara_status_t ishara_model_train_state_info(ishara_model_t* m, int64_t* numel, int64_t* opt_steps, int64_t* fb_steps,
+                                                         int32_t* has_slow);
+ISHARA_API ishara_status_t ishara_model_train_state_get(ishara_model_t* m, int32_t which, float* host_out, int64_t numel);
+ISHARA_API ishara_status_t ishara_model_train_state_set(ishara_model_t* m, int32_t which, const float* host_in, int64_t numel);
+ISHARA_API ishara_status_t ishara_model_train_state_set_counters(ishara_model_t* m, int64_t opt_steps, int64_t fb_steps);
 /* device masters -> parameter table (get_param) -> inference packs */
 ISHARA_API ishara_status_t ishara_model_train_sync(ishara_model_t* m);
 /* gradient of one named parameter (Keras layout) after train_forward_backward */

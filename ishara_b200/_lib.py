@@ -48,6 +48,13 @@ class AdamW(C.Structure):
                 ("eps", C.c_float), ("max_norm", C.c_float)]
 
 
+class RAdamLookahead(C.Structure):
+    """ishara_radam_lookahead_t — the reference's optimiser (c7:68-69), tensorflow_addons defaults."""
+
+    _fields_ = [("lr", C.c_float), ("weight_decay", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("max_norm", C.c_float), ("sma_threshold", C.c_float), ("sync_period", C.c_int32), ("slow_step_size", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     """ishara_gemm_args_t"""
 
@@ -134,6 +141,11 @@ SIGNATURES = {
     "ishara_model_train_sync": (_i32, [_vp]),
     "ishara_model_train_param_grad": (_i32, [_vp, C.c_char_p, _vp, _i64]),
     "ishara_model_train_fetch": (_i32, [_vp, C.c_char_p, _i32, _vp, _i64]),
+    "ishara_model_train_apply_radam": (_i32, [_vp, _vp, _f32, _vp]),
+    "ishara_model_train_state_info": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
+    "ishara_model_train_state_get": (_i32, [_vp, _i32, _vp, _i64]),
+    "ishara_model_train_state_set": (_i32, [_vp, _i32, _vp, _i64]),
+    "ishara_model_train_state_set_counters": (_i32, [_vp, _i64, _i64]),
     "ishara_model_set_mask_mode": (_i32, [_vp, _i32]),
     "ishara_model_forward_masked": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "ishara_model_train_loss": (_i32, [_vp, C.POINTER(_f32), _vp]),

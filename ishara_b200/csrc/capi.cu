@@ -54,6 +54,11 @@ int train_sync(ishara_model* m);
 int train_param_grad(ishara_model* m, const char* name, float* host_out, int64_t numel);
 int train_fetch(ishara_model* m, const char* name, int want_grad, float* host_out, int64_t numel);
 int train_forward_backward_loss(ishara_model* m, float* loss_host, cudaStream_t stream);
+int train_apply_radam(ishara_model* m, const ishara_radam_lookahead_t* opt, float grad_scale, cudaStream_t stream);
+int train_state_info(ishara_model* m, int64_t* numel, int64_t* opt_steps, int64_t* fb_steps, int32_t* has_slow);
+int train_state_get(ishara_model* m, int which, float* host_out, int64_t numel);
+int train_state_set(ishara_model* m, int which, const float* host_in, int64_t numel);
+int train_state_set_counters(ishara_model* m, int64_t opt_steps, int64_t fb_steps);
 int model_set_mask_mode(ishara_model* m, int mode);
 int model_forward_masked(ishara_model* m, const float* x_dev, const uint8_t* mask_dev, int batch, float* logits_dev, cudaStream_t stream);
 int train_counters(ishara_model* m, int64_t* fb_steps, int64_t* opt_steps, int64_t* skipped_steps);
@@ -616,6 +621,26 @@ ishara_status_t ishara_model_train_fetch(ishara_model_t* m, const char* name, in
   return static_cast<ishara_status_t>(train_fetch(reinterpret_cast<ishara_model*>(m), name, want_grad, host_out, numel));
 }
 
+ishara_status_t ishara_model_train_apply_radam(ishara_model_t* m, const ishara_radam_lookahead_t* opt, float grad_scale, void* stream) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_apply_radam(reinterpret_cast<ishara_model*>(m), opt, grad_scale, static_cast<cudaStream_t>(stream)));
+}
+ishara_status_t ishara_model_train_state_info(ishara_model_t* m, int64_t* numel, int64_t* opt_steps, int64_t* fb_steps, int32_t* has_slow) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_state_info(reinterpret_cast<ishara_model*>(m), numel, opt_steps, fb_steps, has_slow));
+}
+ishara_status_t ishara_model_train_state_get(ishara_model_t* m, int32_t which, float* host_out, int64_t numel) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_state_get(reinterpret_cast<ishara_model*>(m), which, host_out, numel));
+}
+ishara_status_t ishara_model_train_state_set(ishara_model_t* m, int32_t which, const float* host_in, int64_t numel) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_state_set(reinterpret_cast<ishara_model*>(m), which, host_in, numel));
+}
+ishara_status_t ishara_model_train_state_set_counters(ishara_model_t* m, int64_t opt_steps, int64_t fb_steps) {
+  CHECK_HANDLE(m);
+  return static_cast<ishara_status_t>(train_state_set_counters(reinterpret_cast<ishara_model*>(m), opt_steps, fb_steps));
+}
 ishara_status_t ishara_model_set_mask_mode(ishara_model_t* m, int32_t mode) {
   CHECK_HANDLE(m);
   return static_cast<ishara_status_t>(model_set_mask_mode(reinterpret_cast<ishara_model*>(m), mode));

@@ -46,6 +46,7 @@ struct TrainState {
   std::vector<int64_t> off;  // per parameter index: offset in floats
   int64_t n_train = 0, n_total = 0;
   float *theta = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  float* slow = nullptr;  // Lookahead slow weights (allocated with the first RAdam + Lookahead step, = the weights at that time)
   double* norm2 = nullptr;
   int step = 0;
   std::unordered_map<std::string, bf16*> wf, wb;
@@ -922,6 +923,7 @@ void train_destroy(ishara_model* m) {
   for (void* p : ts->wallocs) cudaFree(p);
   cudaFree(ts->theta); cudaFree(ts->grad); cudaFree(ts->adam_m); cudaFree(ts->adam_v); cudaFree(ts->norm2);
   if (ts->skipped_dev) cudaFree(ts->skipped_dev);
+  if (ts->slow) cudaFree(ts->slow);
   if (ts->repack_dev) cudaFree(ts->repack_dev);
   if (ts->loss_pinned) cudaFreeHost(ts->loss_pinned);
   delete ts;
@@ -1054,6 +1056,82 @@ int train_apply(ishara_model* m, const ishara_adamw_t* opt, float grad_scale, cu
   if ((rc = adamw_launch(ts->theta, ts->grad, ts->adam_m, ts->adam_v, ts->n_train, ts->norm2, a, stream))) return rc;
   if ((rc = repack_launch(ts->repack_dev, ts->repack_n, ts->repack_max_tiles, stream))) return rc;
   m->host_params_stale = true;
+  return 0;
+}
+
+// the reference's own optimiser (c7:68-69): RectifiedAdam(sma_threshold=4) wrapped in Lookahead(sync_period=5)
+int train_apply_radam(ishara_model* m, const ishara_radam_lookahead_t* opt, float grad_scale, cudaStream_t stream) {
+  if (m->train == nullptr) { set_last_error("train_apply_radam: no training state"); return ISHARA_ERR_STATE; }
+  TrainState* ts = m->train;
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  RAdamArgs a;
+  if (opt != nullptr) {
+    a.lr = opt->lr; a.weight_decay = opt->weight_decay; a.beta1 = opt->beta1; a.beta2 = opt->beta2; a.eps = opt->eps;
+    a.max_norm = opt->max_norm; a.sma_threshold = opt->sma_threshold; a.sync_period = opt->sync_period; a.slow_step = opt->slow_step_size;
+  }
+  if (ts->slow == nullptr) {
+    // Lookahead's slow slot starts as a copy of the variables at the first step
+    ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ts->slow), static_cast<size_t>(ts->n_total) * sizeof(float)));
+    ISHARA_CUDA_OK(cudaMemcpyAsync(ts->slow, ts->theta, static_cast<size_t>(ts->n_total) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  }
+  a.grad_scale = grad_scale;
+  a.step = ++ts->step;
+  a.skipped = ts->skipped_dev;
+  int rc;
+  ISHARA_CUDA_OK(cudaMemsetAsync(ts->norm2, 0, sizeof(double), stream));
+  if ((rc = sqnorm_launch(ts->grad, ts->n_train, ts->norm2, stream))) return rc;
+  if ((rc = radam_lookahead_launch(ts->theta, ts->grad, ts->adam_m, ts->adam_v, ts->slow, ts->n_train, ts->norm2, a, stream))) return rc;
+  if ((rc = repack_launch(ts->repack_dev, ts->repack_n, ts->repack_max_tiles, stream))) return rc;
+  m->host_params_stale = true;
+  return 0;
+}
+
+// ---- optimiser-state checkpoint (the reference saves weights every epoch, c9:10, and
+// integration.py:912-958 saves optimiser state with them): flat fp32 slots in the order of the parameter table ----
+int train_state_info(ishara_model* m, int64_t* numel, int64_t* opt_steps, int64_t* fb_steps, int32_t* has_slow) {
+  if (m->train == nullptr) { set_last_error("train_state: no training state (call train_configure first)"); return ISHARA_ERR_STATE; }
+  if (numel) *numel = m->train->n_total;
+  if (opt_steps) *opt_steps = m->train->step;
+  if (fb_steps) *fb_steps = m->train->fb_count;
+  if (has_slow) *has_slow = m->train->slow != nullptr ? 1 : 0;
+  return 0;
+}
+static float* state_slot(TrainState* ts, int which) {
+  switch (which) {
+    case 0: return ts->adam_m;
+    case 1: return ts->adam_v;
+    case 2: return ts->slow;
+    case 3: return ts->theta;
+  }
+  return nullptr;
+}
+int train_state_get(ishara_model* m, int which, float* host_out, int64_t numel) {
+  if (m->train == nullptr) { set_last_error("train_state_get: no training state"); return ISHARA_ERR_STATE; }
+  TrainState* ts = m->train;
+  float* src = state_slot(ts, which);
+  if (src == nullptr) { set_last_error("train_state_get: slot not present (0 adam_m, 1 adam_v, 2 lookahead slow, 3 weights)"); return ISHARA_ERR_INVALID; }
+  if (host_out == nullptr || numel != ts->n_total) { set_last_error("train_state_get: expected " + std::to_string(ts->n_total) + " elements"); return ISHARA_ERR_SHAPE; }
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  ISHARA_CUDA_OK(cudaDeviceSynchronize());
+  ISHARA_CUDA_OK(cudaMemcpy(host_out, src, static_cast<size_t>(numel) * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int train_state_set(ishara_model* m, int which, const float* host_in, int64_t numel) {
+  if (m->train == nullptr) { set_last_error("train_state_set: no training state"); return ISHARA_ERR_STATE; }
+  TrainState* ts = m->train;
+  if (which < 0 || which > 2) { set_last_error("train_state_set: slot 0 adam_m, 1 adam_v, 2 lookahead slow (weights go through set_param)"); return ISHARA_ERR_INVALID; }
+  if (host_in == nullptr || numel != ts->n_total) { set_last_error("train_state_set: expected " + std::to_string(ts->n_total) + " elements"); return ISHARA_ERR_SHAPE; }
+  ISHARA_CUDA_OK(cudaSetDevice(m->device));
+  if (which == 2 && ts->slow == nullptr) ISHARA_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ts->slow), static_cast<size_t>(ts->n_total) * sizeof(float)));
+  ISHARA_CUDA_OK(cudaDeviceSynchronize());
+  ISHARA_CUDA_OK(cudaMemcpy(state_slot(ts, which), host_in, static_cast<size_t>(numel) * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+int train_state_set_counters(ishara_model* m, int64_t opt_steps, int64_t fb_steps) {
+  if (m->train == nullptr) { set_last_error("train_state_set_counters: no training state"); return ISHARA_ERR_STATE; }
+  if (opt_steps < 0 || fb_steps < 0) { set_last_error("train_state_set_counters: negative counter"); return ISHARA_ERR_INVALID; }
+  m->train->step = static_cast<int>(opt_steps);
+  m->train->fb_count = fb_steps;
   return 0;
 }
 

@@ -134,6 +134,19 @@ struct AdamWArgs {
   float grad_scale = 1.f;  // applied before clipping (1/world after a sum all-reduce)
   int* skipped = nullptr;  // device counter: bumped (and the update dropped) when the gradient norm is not finite
 };
+// tfa.optimizers.Lookahead(tfa.optimizers.RectifiedAdam(sma_threshold=4), sync_period=5) -- the optimiser the reference
+// compiles the model with (nb:conv-hybrid-model c7:68-69). One fused pass over the flat buffers.
+struct RAdamArgs {
+  float lr = 1e-3f, weight_decay = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-7f, max_norm = 0.f;
+  float sma_threshold = 4.f;
+  int sync_period = 5;         // Lookahead k
+  float slow_step = 0.5f;      // Lookahead alpha
+  int step = 1;                // 1-based
+  float grad_scale = 1.f;
+  int* skipped = nullptr;
+};
+int radam_lookahead_launch(float* theta, const float* g, float* m, float* v, float* slow, int64_t n, const double* norm2,
+                           const RAdamArgs& a, cudaStream_t s);
 // theta/g/m/v [n]; clip scale derived on the device from norm2[0] (already of the scaled gradient)
 int adamw_launch(float* theta, const float* g, float* m, float* v, int64_t n, const double* norm2, const AdamWArgs& a,
                  cudaStream_t s);

@@ -51,6 +51,48 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ theta, c
   }
 }
 
+// RectifiedAdam (Liu et al. 2019, as implemented by tensorflow_addons/optimizers/rectified_adam.py, total_steps = 0 so no
+// warm-up schedule) followed by the Lookahead slow-weight step (tensorflow_addons/optimizers/lookahead.py):
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; mhat = m / (1-b1^t) ; vhat = sqrt(v / (1-b2^t))
+//   sma_inf = 2/(1-b2) - 1 ; sma_t = sma_inf - 2 t b2^t / (1-b2^t)
+//   r_t = sqrt((sma_t-4)/(sma_inf-4) * (sma_t-2)/(sma_inf-2) * sma_inf/sma_t)
+//   upd = sma_t >= sma_threshold ? r_t mhat / (vhat + eps) : mhat ;  upd += wd * theta ;  theta -= lr * upd
+//   every sync_period steps: slow += alpha (theta - slow) ; theta = slow     (slow starts as the initial weights)
+// rect / use_rect / sync are step-only quantities computed on the host.
+__global__ void __launch_bounds__(256) radam_lookahead_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
+                                                                float* __restrict__ v, float* __restrict__ slow, int64_t n,
+                                                                const double* __restrict__ norm2, RAdamArgs a, float bc1, float bc2, float rect,
+                                                                int use_rect, int sync) {
+  float clip = 1.f;
+  {
+    const float total = static_cast<float>(sqrt(*norm2)) * a.grad_scale;
+    if (!isfinite(total)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && a.skipped != nullptr) atomicAdd(a.skipped, 1);
+      return;
+    }
+    if (a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / (total + 1e-6f));
+  }
+  const float gs = a.grad_scale * clip, rbc1 = 1.f / bc1, rbc2 = 1.f / bc2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const float gi = g[i] * gs;
+    const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gi;
+    const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float mhat = mi * rbc1;
+    float upd = use_rect ? rect * mhat / (sqrtf(vi * rbc2) + a.eps) : mhat;
+    float th = theta[i];
+    upd += a.weight_decay * th;
+    th -= a.lr * upd;
+    if (sync) {
+      const float sl = slow[i] + a.slow_step * (th - slow[i]);
+      slow[i] = sl;
+      th = sl;
+    }
+    theta[i] = th;
+  }
+}
+
 // one CTA = one 32x32 tile of one dense kernel
 __global__ void __launch_bounds__(256) repack_kernel(const RepackEntry* __restrict__ table) {
   __shared__ float tile[32][33];
@@ -88,6 +130,22 @@ int adamw_launch(float* theta, const float* g, float* m, float* v, int64_t n, co
                  cudaStream_t s) {
   const float bc1 = 1.f - powf(a.beta1, static_cast<float>(a.step)), bc2 = 1.f - powf(a.beta2, static_cast<float>(a.step));
   adamw_kernel<<<148 * 4, 256, 0, s>>>(theta, g, m, v, n, norm2, a, bc1, bc2);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+int radam_lookahead_launch(float* theta, const float* g, float* m, float* v, float* slow, int64_t n, const double* norm2,
+                           const RAdamArgs& a, cudaStream_t s) {
+  const double t = static_cast<double>(a.step), b2 = a.beta2;
+  const double b2t = pow(b2, t);
+  const double sma_inf = 2.0 / (1.0 - b2) - 1.0;
+  const double sma_t = sma_inf - 2.0 * t * b2t / (1.0 - b2t);
+  const int use_rect = sma_t >= static_cast<double>(a.sma_threshold) ? 1 : 0;
+  double rect = 0.0;
+  if (use_rect) rect = sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t);
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(a.beta1), t)), bc2 = static_cast<float>(1.0 - b2t);
+  const int sync = a.sync_period > 0 && (a.step % a.sync_period) == 0 ? 1 : 0;
+  radam_lookahead_kernel<<<148 * 4, 256, 0, s>>>(theta, g, m, v, slow, n, norm2, a, bc1, bc2, static_cast<float>(rect), use_rect, sync);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

@@ -280,10 +280,23 @@ class IsharaModel:
 
 
     # ---- training step (Keras fit's inner step c12:1 with BASELINE's AdamW) -----------------
-    def compile(self, lr: float = 4.5e-3, weight_decay: float = 0.08, beta1: float = 0.9, beta2: float = 0.999,
-                eps: float = 1e-8, clipnorm: float = 1.0):
-        """Optimiser of the training step: AdamW + global-norm clipping (integration.py:675-679,750)."""
-        self._opt = _lib.AdamW(lr, weight_decay, beta1, beta2, eps, clipnorm)
+    def compile(self, lr: Optional[float] = None, weight_decay: Optional[float] = None, beta1: float = 0.9, beta2: float = 0.999,
+                eps: Optional[float] = None, clipnorm: Optional[float] = None, optimizer: str = "adamw",
+                sma_threshold: float = 4.0, sync_period: int = 5, slow_step_size: float = 0.5):
+        """Optimiser of the training step. ``optimizer="adamw"`` (default, BASELINE.json): AdamW + global-norm clipping
+        (integration.py:675-679,750; lr 4.5e-3, weight_decay 0.08, eps 1e-8, clipnorm 1.0). ``optimizer="radam_lookahead"``:
+        what the reference notebook compiles the model with (c7:68-69),
+        ``tfa.optimizers.Lookahead(tfa.optimizers.RectifiedAdam(sma_threshold=4), sync_period=5)`` with tensorflow_addons'
+        defaults (lr 1e-3, weight_decay 0, eps 1e-7, no clipping)."""
+        if optimizer == "adamw":
+            self._opt = _lib.AdamW(4.5e-3 if lr is None else lr, 0.08 if weight_decay is None else weight_decay, beta1, beta2,
+                                   1e-8 if eps is None else eps, 1.0 if clipnorm is None else clipnorm)
+        elif optimizer in ("radam_lookahead", "lookahead_radam"):
+            self._opt = _lib.RAdamLookahead(1e-3 if lr is None else lr, 0.0 if weight_decay is None else weight_decay, beta1, beta2,
+                                            1e-7 if eps is None else eps, 0.0 if clipnorm is None else clipnorm,
+                                            float(sma_threshold), int(sync_period), float(slow_step_size))
+        else:
+            raise ValueError("optimizer must be 'adamw' or 'radam_lookahead'")
         return self
 
     def train_config(self, dropout_rate: Optional[float] = None, seed: int = 0, debug: bool = False):
@@ -376,12 +389,75 @@ class IsharaModel:
 
     def apply_gradients(self, grad_scale: float = 1.0, stream: int = 0):
         opt = getattr(self, "_opt", None) or _lib.AdamW(4.5e-3, 0.08, 0.9, 0.999, 1e-8, 1.0)
-        _lib.check(self._lib.ishara_model_train_apply(self._h, C.byref(opt), float(grad_scale), _vp(stream)))
+        if isinstance(opt, _lib.RAdamLookahead):
+            _lib.check(self._lib.ishara_model_train_apply_radam(self._h, C.byref(opt), float(grad_scale), _vp(stream)))
+        else:
+            _lib.check(self._lib.ishara_model_train_apply(self._h, C.byref(opt), float(grad_scale), _vp(stream)))
+
+    # ---- checkpoint: weights + optimiser state + counters (c9:10 saves weights each epoch; integration.py:912-958 saves the
+    # ---- optimiser with them; there is no resume path in the reference - this adds one) ------------------------------------
+    def _state_info(self):
+        n, so, sf, hs = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(self._lib.ishara_model_train_state_info(self._h, C.byref(n), C.byref(so), C.byref(sf), C.byref(hs)))
+        return int(n.value), int(so.value), int(sf.value), bool(hs.value)
+
+    def optimizer_state(self) -> Dict[str, np.ndarray]:
+        """Per-parameter optimiser slots under Keras-like names: '<param>/m', '<param>/v' (Adam moments) and, after a
+        RAdam + Lookahead step, '<param>/slow'; plus 'opt_steps' / 'fb_steps' counters."""
+        n, so, sf, has_slow = self._state_info()
+        out: Dict[str, np.ndarray] = {"opt_steps": np.asarray(so, np.int64), "fb_steps": np.asarray(sf, np.int64)}
+        for which, tag in ((0, "m"), (1, "v")) + (((2, "slow"),) if has_slow else ()):
+            flat = np.empty(n, np.float32)
+            _lib.check(self._lib.ishara_model_train_state_get(self._h, which, flat.ctypes.data_as(C.c_void_p), n))
+            for name, off, shape in self._flat_layout():
+                out[f"{name}/{tag}"] = flat[off:off + int(np.prod(shape))].reshape(shape).copy()
+        return out
+
+    def _flat_layout(self):
+        """(name, offset, shape) of every parameter in the library's flat training buffers: trainable tensors first
+        (16-byte aligned), BatchNorm moving statistics last (train.cu init_storage)."""
+        out, o = [], 0
+        for frozen in (False, True):
+            for name, shape in self._specs:
+                if name.endswith(("moving_mean", "moving_variance")) != frozen:
+                    continue
+                out.append((name, o, shape))
+                o += (int(np.prod(shape)) + 3) // 4 * 4
+        return out
+
+    def save_checkpoint(self, path):
+        """Weights (Keras names) + optimiser state + counters in one ``.npz``: ``load_checkpoint`` resumes training with
+        the identical trajectory."""
+        data = {f"weights/{k}": v for k, v in self.get_weights().items()}
+        data.update({f"optimizer/{k}": v for k, v in self.optimizer_state().items()})
+        np.savez(path, **data)
+
+    def load_checkpoint(self, path):
+        with np.load(path) as z:
+            weights = {k[len("weights/"):]: z[k] for k in z.files if k.startswith("weights/")}
+            opt = {k[len("optimizer/"):]: z[k] for k in z.files if k.startswith("optimizer/")}
+        self.load_weights(weights)
+        self.train_config(*getattr(self, "_train_cfg", (None, 0, False)))   # (re)creates the training state from the new weights
+        n, _, _, _ = self._state_info()
+        layout = self._flat_layout()
+        for which, tag in ((0, "m"), (1, "v"), (2, "slow")):
+            if not any(k.endswith("/" + tag) for k in opt):
+                continue
+            flat = np.zeros(n, np.float32)
+            for name, off, shape in layout:
+                flat[off:off + int(np.prod(shape))] = opt[f"{name}/{tag}"].ravel()
+            _lib.check(self._lib.ishara_model_train_state_set(self._h, which, flat.ctypes.data_as(C.c_void_p), n))
+        _lib.check(self._lib.ishara_model_train_state_set_counters(self._h, int(opt["opt_steps"]), int(opt["fb_steps"])))
+        return self
 
     def train_step(self, x: ArrayLike, labels: ArrayLike) -> float:
         """One optimisation step on one batch; host arrays go through one C-ABI call (H2D inside)."""
-        x, labels, host = self._train_args(x, labels)
         opt = getattr(self, "_opt", None) or _lib.AdamW(4.5e-3, 0.08, 0.9, 0.999, 1e-8, 1.0)
+        if isinstance(opt, _lib.RAdamLookahead):
+            self.forward_backward_async(x, labels)
+            self.apply_gradients(1.0, self.last_stream)
+            return self.last_loss()
+        x, labels, host = self._train_args(x, labels)
         loss = C.c_float()
         if host:
             _lib.check(self._lib.ishara_model_train_step_host(self._h, x.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),

@@ -202,6 +202,45 @@ def adamw_step(params: Dict[str, np.ndarray], grads: Dict[str, np.ndarray], stat
     return out
 
 
+def radam_lookahead_step(params: Dict[str, np.ndarray], grads: Dict[str, np.ndarray], state: Dict[str, Dict[str, np.ndarray]],
+                         step: int, lr: float = 1e-3, weight_decay: float = 0.0, beta1: float = 0.9, beta2: float = 0.999,
+                         eps: float = 1e-7, sma_threshold: float = 4.0, sync_period: int = 5, slow_step_size: float = 0.5,
+                         max_norm: float = 0.0) -> Dict[str, np.ndarray]:
+    """The optimiser the reference compiles the model with (c7:68-69):
+    ``tfa.optimizers.Lookahead(tfa.optimizers.RectifiedAdam(sma_threshold=4), sync_period=5)``.
+
+    tensorflow_addons is a third-party dependency that is neither vendored nor pinned (``Dockerfile:20-21``) and cannot be
+    imported here, so this restates its published algorithm (``tensorflow_addons/optimizers/rectified_adam.py`` with
+    ``total_steps=0`` -> no warm-up schedule; ``lookahead.py`` with ``slow_step_size=0.5``): bias-corrected Adam moments,
+    the variance-rectification term r_t once the SMA length reaches ``sma_threshold`` (plain momentum SGD before),
+    decoupled weight decay folded into the update, and every ``sync_period`` steps the slow weights move half way to the
+    fast ones and the fast ones are reset to them. The RectifiedAdam part is cross-checked against ``torch.optim.RAdam``
+    (threshold 5) in tests/test_train_oracle.py. ``step`` is 1-based; ``state`` holds m / v / slow per tensor."""
+    _, scale = clip_scale(grads, max_norm) if max_norm and max_norm > 0 else (0.0, 1.0)
+    sma_inf = 2.0 / (1.0 - beta2) - 1.0
+    b2t = beta2 ** step
+    sma_t = sma_inf - 2.0 * step * b2t / (1.0 - b2t)
+    rect = None
+    if sma_t >= sma_threshold:
+        rect = np.sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t)
+    out = dict(params)
+    for k, g in grads.items():
+        g = g.astype(np.float64) * scale
+        p = params[k].astype(np.float64)
+        st = state.setdefault(k, {"m": np.zeros_like(g), "v": np.zeros_like(g), "slow": p.copy()})
+        st["m"] = beta1 * st["m"] + (1 - beta1) * g
+        st["v"] = beta2 * st["v"] + (1 - beta2) * g * g
+        mhat = st["m"] / (1 - beta1 ** step)
+        upd = rect * mhat / (np.sqrt(st["v"] / (1 - b2t)) + eps) if rect is not None else mhat
+        upd = upd + weight_decay * p
+        p = p - lr * upd
+        if sync_period > 0 and step % sync_period == 0:
+            st["slow"] = st["slow"] + slow_step_size * (p - st["slow"])
+            p = st["slow"].copy()
+        out[k] = p.astype(np.float32)
+    return out
+
+
 def train_step(params, x, labels, cfg, state, step, dtype="float32", **adamw):
     r = forward_train(params, x, labels, cfg, dtype=dtype)
     new = adamw_step(params, r["grads"], state, step, **adamw)

@@ -219,3 +219,80 @@ def test_other_widths_train_too():
     assert abs(loss - ref["loss"]) <= 1e-3 * abs(ref["loss"])
     _check_grads(m.gradients(), ref["grads"])
     m.close()
+
+
+def test_radam_lookahead_matches_oracle():
+    """The reference's own optimiser (c7:68-69): Lookahead(RectifiedAdam(sma_threshold=4), sync_period=5). The GPU's gradients
+    drive the oracle restatement of the tensorflow_addons algorithm; 11 steps cross the rectification threshold (step 5)
+    and two Lookahead syncs (steps 5 and 10)."""
+    cfg, B, L = SMALL, 4, 24
+    p = O.init_params(cfg)
+    x = O.make_inputs(cfg, B)
+    y = O.make_labels(cfg, B, max_len=L, min_len=6)
+    m = _model(cfg, p)
+    m.train_config(0.0)
+    m.compile(optimizer="radam_lookahead", lr=2e-3)
+    state, w = {}, {k: v.copy() for k, v in p.items()}
+    for t in range(1, 12):
+        m.forward_backward(x, y)
+        grads = m.gradients()
+        new_ref = TO.radam_lookahead_step(w, grads, state, t, lr=2e-3)
+        m.apply_gradients()
+        got = m.get_weights()
+        for k in grads:
+            assert np.abs(got[k] - new_ref[k]).max() <= 3e-6, (t, k, float(np.abs(got[k] - new_ref[k]).max()))
+        w = {k: got[k] for k in p}          # carry the GPU's weights (and its BatchNorm statistics) into the next step
+    st = m.optimizer_state()
+    assert int(st["opt_steps"]) == 11 and "stem_conv.kernel/slow" in st
+    assert np.abs(st["stem_conv.kernel/slow"] - state["stem_conv.kernel"]["slow"]).max() <= 3e-6
+    m.close()
+
+
+@pytest.mark.parametrize("optimizer", ["adamw", "radam_lookahead"])
+def test_checkpoint_resume_continues_the_same_trajectory(tmp_path, optimizer):
+    """Weights + optimiser state + counters round-trip through save_checkpoint / load_checkpoint:
+    a resumed run produces the losses of the uninterrupted one, dropout stream included."""
+    cfg, B, L = SMALL, 4, 24
+    p = O.init_params(cfg)
+    x = O.make_inputs(cfg, B)
+    y = O.make_labels(cfg, B, max_len=L, min_len=6)
+    m = _model(cfg, p, dropout=0.1)
+    m.train_config(0.1, seed=77)
+    m.compile(optimizer=optimizer, lr=1e-3)
+    for _ in range(6):                      # past the first Lookahead sync
+        m.train_step(x, y)
+    # the flat-slot layout the host assumes is the library's: Adam's m after one more step == b1*m + (1-b1)*clip*g
+    path = tmp_path / "ckpt.npz"
+    m.save_checkpoint(path)
+    want = [m.train_step(x, y) for _ in range(3)]
+    w_want = m.get_weights()
+    m2 = _model(cfg, O.init_params(cfg, seed=999), dropout=0.1)   # different weights: everything must come from the file
+    m2.train_config(0.1, seed=77)
+    m2.compile(optimizer=optimizer, lr=1e-3)
+    m2.load_checkpoint(path)
+    got = [m2.train_step(x, y) for _ in range(3)]
+    assert np.allclose(got, want, rtol=2e-5), (got, want)
+    w_got = m2.get_weights()
+    for k in w_want:
+        assert np.abs(w_got[k] - w_want[k]).max() <= 1e-5 * (np.abs(w_want[k]).max() + 1e-6), k
+    m.close()
+    m2.close()
+
+
+def test_optimizer_state_layout_matches_the_library():
+    """optimizer_state() splits the flat slots with the host's copy of the buffer layout: pin it against the library's own
+    per-parameter view (train_param_grad) through Adam's first moment after one step, m = (1 - b1) * clip * g."""
+    cfg, B, L = SMALL, 4, 24
+    p = O.init_params(cfg)
+    x = O.make_inputs(cfg, B)
+    y = O.make_labels(cfg, B, max_len=L, min_len=6)
+    m = _model(cfg, p)
+    m.train_config(0.0)
+    m.compile(clipnorm=0.0)
+    m.forward_backward(x, y)
+    g = m.gradients()
+    m.apply_gradients()
+    st = m.optimizer_state()
+    for k in ("stem_conv.kernel", "classifier.bias", "squeezeformer_0.mha.qkv.kernel", "convconform_0_3_eca.kernel"):
+        assert np.allclose(st[k + "/m"], 0.1 * g[k], rtol=1e-5, atol=1e-9), k
+    m.close()

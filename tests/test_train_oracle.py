@@ -119,3 +119,44 @@ def test_oracle_against_tf_training_golden_if_present():
             assert np.linalg.norm(r["grads"][k[2:]] - ref) <= 2e-3 * max(np.linalg.norm(ref), 1e-6), k
         if k.startswith("s:"):
             assert np.allclose(r["new_stats"][k[2:]], z[k], rtol=1e-4, atol=1e-6), k
+
+
+def test_radam_matches_torch_and_lookahead_rule():
+    """RectifiedAdam restatement (tfa is absent: third-party, unpinned) vs torch.optim.RAdam on the steps where the two
+    rectification thresholds agree (tfa: sma_t >= threshold, torch: rho_t > 5; with threshold 5 they agree at every step),
+    then the Lookahead rule on top of it."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    p0 = {"w": rng.standard_normal((7, 5)).astype(np.float32), "b": rng.standard_normal(5).astype(np.float32)}
+    grads = [{k: rng.standard_normal(v.shape).astype(np.float32) for k, v in p0.items()} for _ in range(12)]
+    tp = {k: torch.tensor(v.astype(np.float64), requires_grad=True) for k, v in p0.items()}
+    opt = torch.optim.RAdam(list(tp.values()), lr=2e-3, betas=(0.9, 0.999), eps=1e-7, weight_decay=0.0)
+    p, state = dict(p0), {}
+    for t, g in enumerate(grads, 1):
+        for k in tp:
+            tp[k].grad = torch.tensor(g[k].astype(np.float64))
+        opt.step()
+        p = TO.radam_lookahead_step(p, g, state, t, lr=2e-3, eps=1e-7, sma_threshold=5.0, sync_period=0)
+        for k in p:
+            assert np.allclose(p[k], tp[k].detach().numpy(), rtol=2e-6, atol=1e-7), (t, k)
+    # the reference's setting (threshold 4, c7:68): step 5 is already rectified (sma_5 = 4.98), steps 1-4 are momentum SGD
+    p, state = dict(p0), {}
+    prev = None
+    for t, g in enumerate(grads, 1):
+        before = {k: v.copy() for k, v in p.items()}
+        p = TO.radam_lookahead_step(p, g, state, t, lr=2e-3, sma_threshold=4.0, sync_period=5)
+        if t <= 4:   # un-rectified: theta -= lr * mhat
+            mhat = state["w"]["m"] / (1 - 0.9 ** t)
+            assert np.allclose(p["w"], before["w"] - 2e-3 * mhat, atol=1e-7)
+        if t % 5 == 0:  # Lookahead sync: fast == slow afterwards
+            assert np.allclose(p["w"], state["w"]["slow"], atol=0)
+            if prev is not None:
+                pass
+    # slow weights after the first sync = initial + 0.5 * (fast_5 - initial)
+    p, state = dict(p0), {}
+    for t, g in enumerate(grads[:5], 1):
+        fast_before_sync = TO.radam_lookahead_step(p, g, {k: {kk: vv.copy() for kk, vv in v.items()} for k, v in state.items()}, t,
+                                                   lr=2e-3, sync_period=0)
+        p = TO.radam_lookahead_step(p, g, state, t, lr=2e-3, sync_period=5)
+    assert np.allclose(p["w"], p0["w"] + 0.5 * (fast_before_sync["w"] - p0["w"]), atol=1e-7)
