@@ -190,11 +190,12 @@ class DataParallelTrainer:
         # per-rank dropout streams: same seed would give every rank the same masks
         model.train_config(seed=int(seed) + 0x9E3779B1 * self.rank)
 
-    def train_step(self, x, labels) -> float:
-        """x/labels = THIS rank's shard. Returns the mean loss over all ranks (reduced on the device by the library)."""
+    def train_step(self, x, labels, return_loss: bool = True) -> Optional[float]:
+        """x/labels = THIS rank's shard. Returns the mean loss over all ranks (reduced on the device by the library), or
+        None with ``return_loss=False`` - then nothing synchronises with the host and steps can be enqueued back to back."""
         self.model.forward_backward_async(x, labels)
         self.model.apply_gradients(1.0 / self.world, self.model.last_stream)
-        return self.model.last_loss()
+        return self.model.last_loss() if return_loss else None
 
     def close(self):
         if self.world > 1:
