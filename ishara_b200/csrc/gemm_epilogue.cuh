@@ -192,6 +192,16 @@ __device__ __forceinline__ void resid_load(ResidRegs& r, const GemmEpi& ep, cons
     for (int j = 0; j < 4; ++j) r.q[j] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
+// residual segment of this thread's row from a staged [32 rows x 128 B] swizzled box (filled by TMA): 32 bf16 = 64 B
+__device__ __forceinline__ void resid_load_smem(ResidRegs& r, uint32_t box, int lane, int sub) {
+  const uint32_t rb = box + static_cast<uint32_t>(lane) * 128u, x = static_cast<uint32_t>(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.q[j].x), "=r"(r.q[j].y), "=r"(r.q[j].z), "=r"(r.q[j].w)
+                 : "r"(rb + ((static_cast<uint32_t>(sub * 4 + j) ^ x) << 4))
+                 : "memory");
+}
 __device__ __forceinline__ void resid_add(float (&v)[32], const ResidRegs& r) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -220,7 +230,11 @@ __device__ __forceinline__ void exchange_stats(RowStats& rs, float4* slot /*[2][
 template <int BN, bool ROW, bool OUT_F32>
 __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread& th, int n_tile, int N, int row0, int q,
                                               int h, int lane, WarpStore& st, const CUtensorMap* tmO0,
-                                              const CUtensorMap* tmO1, float4* xch, int tile_parity, ResidRegs rr) {
+                                              const CUtensorMap* tmO1, float4* xch, int tile_parity, ResidRegs rr,
+                                              uint32_t resid_smem = 0u) {
+  // resid_smem != 0 (row mode): the residual boxes of this warp were fetched by TMA into its two staging boxes - box k of
+  // the tile sits in staging slot (st.iter + k) & 1, the slot the k-th acquire of this tile hands out. Reading the
+  // residual per thread from global memory touches 32 different lines per load instruction (~8k L1 wavefronts per tile).
   constexpr int CH = OUT_F32 ? 32 : 64;  // output columns per staging box
   constexpr int SUBS = CH / 32;
   if constexpr (!ROW) {
@@ -280,8 +294,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread
     float4* slotA = xch + (tile_parity * 2 + 0) * 256;
     float4* slotB = xch + (tile_parity * 2 + 1) * 256;
     RowStats rs;
+    const uint32_t iter0 = st.iter;
+    int kbox = 0;
     // pass A
-    for (int b = h; b < nbox; b += 2) {
+    for (int b = h; b < nbox; b += 2, ++kbox) {
       uint32_t buf = 0;
       if (!ln0) buf = st.acquire();
 #pragma unroll 1
@@ -291,7 +307,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread
         float v[32];
         tmem_ld32(th.taddr + tc, raw);
         ResidRegs rn;
-        {
+        if (resid_smem != 0u) {
+          resid_load_smem(rr, resid_smem + ((iter0 + static_cast<uint32_t>(kbox)) & 1u) * kWarpStgBytes, lane, sub);
+          rn = rr;
+        } else {
           int nb = b, nsub = sub + 1;
           if (nsub == 2) { nsub = 0; nb = b + 2; }
           if (nb < nbox) {

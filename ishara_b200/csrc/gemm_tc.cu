@@ -45,7 +45,8 @@ template <int BN, bool ROW, bool OUT_F32, bool RESB, int EW>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-               const GemmEpi ep, int M, int N, int K, int num_m_tiles, int num_n_tiles, int num_stages) {
+               const __grid_constant__ CUtensorMap tmR, const GemmEpi ep, int M, int N, int K, int num_m_tiles, int num_n_tiles,
+               int num_stages, int resid_tma) {
   constexpr int B_KB_BYTES = BN * kBK * 2;                              // one k-block of the weight slice
   constexpr int STAGE_BYTES = RESB ? kAStageBytes : gemm_stage_bytes(BN);
   constexpr int NUM_STG = RESB ? 2 : kNumStg;                           // staging tiles (per group: NUM_STG / 2)
@@ -70,6 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint64_t* bfull = bars + 2 * STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  uint64_t* rbar = bars + 2 * STAGES + 6;  // [8] per epilogue warp: residual boxes landed (row mode, resid_tma)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,6 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO0);
     if (ep.ln1_g != nullptr) tma_prefetch_desc(&tmO1);
+    if (resid_tma) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -95,6 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(&tempty[0], EW);  // one arrive per epilogue warp
     mbar_init(&tempty[1], EW);
     mbar_init(bfull, 1);
+    if (ROW && EW == 8) for (int w = 0; w < 8; ++w) mbar_init(&rbar[w], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -187,14 +191,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
       th.taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
       ResidRegs rr;
-      if constexpr (EW != 16) resid_load(rr, ep, th, epilogue_first_col<BN, ROW, OUT_F32>(ep, n_tile, h));  // in flight while the MMAs finish
+      uint32_t rsm = 0u;
+      if constexpr (ROW && EW == 8) {
+        if (resid_tma) {
+          // residual of this warp's output boxes: TMA into its own staging boxes (slot of the k-th acquire of this tile),
+          // once the stores of the previous tile have finished reading them; lands while the MMAs of this tile run
+          rsm = st.base;
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            constexpr int NB = BN / 128;  // boxes per warp per tile
+            mbar_arrive_expect_tx(&rbar[warp - 4], NB * kWarpStgBytes);
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+              tma_load_2d(stg_ptr + static_cast<uint32_t>((warp - 4) * 2) * kWarpStgBytes + ((st.iter + k) & 1u) * kWarpStgBytes, &tmR,
+                          &rbar[warp - 4], (h + 2 * k) * 64, row0);
+          }
+          __syncwarp();
+        }
+      }
+      if constexpr (EW != 16) {
+        if (rsm == 0u) resid_load(rr, ep, th, epilogue_first_col<BN, ROW, OUT_F32>(ep, n_tile, h));  // in flight while the MMAs finish
+      }
 
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
       if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
       if (!(ep.dbg & 2)) {
         if constexpr (EW == 16) epilogue_box16<BN>(ep, th, n_tile, N, row0, h, lane, st, &tmO0);
-        else epilogue_tile<BN, ROW, OUT_F32>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+        else {
+          if constexpr (ROW && EW == 8) {
+            if (rsm != 0u) mbar_wait(&rbar[warp - 4], static_cast<uint32_t>(it & 1));
+          }
+          epilogue_tile<BN, ROW, OUT_F32>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr, rsm);
+        }
       }
       // this warp is done with accumulator buffer `buf`
       tc_fence_before();
@@ -249,7 +278,9 @@ int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   int grid = mt * nt;
   if (grid > num_sms) grid = num_sms;
   if (RESB) grid = grid / nt * nt;  // every CTA owns exactly one n-tile
-  kern<<<grid, 128 + 32 * EW, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.epi, p.M, p.N, p.K, mt, nt, stages);
+  static const int rtma_env = getenv("ISHARA_GEMM_RESID_TMA") ? atoi(getenv("ISHARA_GEMM_RESID_TMA")) : 1;
+  const int rtma = (ROW && EW == 8 && !RESB && p.resid_tma && rtma_env) ? 1 : 0;
+  kern<<<grid, 128 + 32 * EW, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.tmR, p.epi, p.M, p.N, p.K, mt, nt, stages, rtma);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;
@@ -323,6 +354,14 @@ int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* ou
     if ((rc = make_tmap_2d(&p->tmO1, out1, TM_BF16, p->M, nout, ldo1, 32, 64))) return rc;
   } else {
     p->tmO1 = p->tmO0;
+  }
+  p->tmR = p->tmO0;
+  p->resid_tma = false;
+  if (p->row_mode && !p->out_f32 && p->epi.resid != nullptr && p->epi.ld_resid % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(p->epi.resid) & 15) == 0) {
+    // full-row epilogue: the residual tile is fetched by TMA ([32 x 64] boxes) instead of per-thread row reads
+    if ((rc = make_tmap_2d(&p->tmR, p->epi.resid, TM_BF16, p->M, nout, p->epi.ld_resid, 32, 64))) return rc;
+    p->resid_tma = true;
   }
   return 0;
 }

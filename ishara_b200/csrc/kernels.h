@@ -64,6 +64,8 @@ struct GemmEpi {
 
 struct GemmPlan {
   CUtensorMap tmA, tmB, tmBh, tmO0, tmO1;  // tmBh: 128-row B box for the CTA-pair kernel
+  CUtensorMap tmR;                         // residual [M, Nout] with [32 x 64] boxes (row mode: fetched by TMA into the staging boxes)
+  bool resid_tma = false;
   GemmEpi epi;
   int M = 0, N = 0, K = 0;  // N = packed weight rows (MMA N extent), K multiple of 64
   int block_n = 256;        // 64 | 128 | 256
