@@ -175,5 +175,74 @@ def main():
     print("wrote", OUT, f"{os.path.getsize(OUT) / 1e3:.0f} KB,", len(out), "arrays")
 
 
+def bf16_round(t):
+    """Round to bf16-representable fp32 values (stored as uint16 halves in the .npz to keep the fixture small): the CUDA
+    path rounds weights to bf16 anyway, so the reference run and the kernels see IDENTICAL weights."""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def main_t384():
+    """Second set at the BASELINE shape: B=2, T=384, D=256, H=8 (dh=32), k=15 and a key mask that ends in the MIDDLE of a
+    64-key block (284 = 4*64 + 28 valid keys). Only the rows whose kernels change instantiation with the shape: P1/P2
+    (rel-pos attention at dh=32, T=384), P5 (ConvModule k=15, C=512), P7 (time reduction of a [384, 256] plane)."""
+    g = torch.Generator().manual_seed(4321)
+    R = load_reference()
+    B, T, D, H, K = 2, 384, 256, 8, 15
+    out = {"meta": np.array([B, T, D, H, K], np.int64)}
+    x = torch.randn(B, T, D, generator=g)
+    out["x"] = x.numpy()
+
+    def sd16(prefix, module):
+        for k, v in module.state_dict().items():
+            if v.dtype.is_floating_point:
+                out[f"{prefix}.w16.{k}"] = v.detach().to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+    def round_params(module):
+        with torch.no_grad():
+            for p_ in module.parameters():
+                p_.copy_(bf16_round(p_))
+            for b_ in module.buffers():
+                if b_.dtype.is_floating_point:
+                    b_.copy_(bf16_round(b_))
+
+    with torch.no_grad():
+        pe = R["modules"].RelPositionalEncoding(D)
+        pos = pe(x)
+        att = R["attention"].RelativeMultiHeadAttention(D, H, dropout_p=0.0).eval()
+        randomize(att, g)
+        att.u_bias.copy_(torch.randn(H, D // H, generator=g) * 0.3)
+        att.v_bias.copy_(torch.randn(H, D // H, generator=g) * 0.3)
+        round_params(att)
+        sd16("p1", att)
+        mask = torch.zeros(B, 1, T, dtype=torch.bool)
+        mask[1, 0, 284:] = True                                           # True = masked; ends mid-block (284 = 4*64 + 28)
+        mask[0, 0, 383:] = True
+        out["p1.mask"] = mask.numpy()
+        out["p1.out_masked"] = att(x, x, x, pos.repeat(B, 1, 1), mask=mask).numpy()
+        mod = R["attention"].MultiHeadedSelfAttentionModule(D, H, dropout_p=0.0).eval()
+        mod.attention.load_state_dict(att.state_dict())
+        out["p2.out"] = mod(x).numpy()
+
+        conv = R["convolution"].ConvModule(D, kernel_size=K, expansion_factor=2, dropout_p=0.0).eval()
+        randomize(conv, g)
+        round_params(conv)
+        sd16("p5", conv)
+        out["p5.out"] = conv(x).numpy()
+
+        tr = R["convolution"].TimeReductionLayer().eval()
+        randomize(tr, g)
+        sd("p7", tr, out)                                                  # 10 numbers: keep fp32
+        lens = torch.tensor([T, T - 37])
+        red, rl = tr(x, lens.clone())
+        out["p7.reduced"] = red.numpy()
+        out["p7.lengths"] = rl.numpy()
+        out["p7.in_lengths"] = lens.numpy()
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "torch_ops_golden_t384.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, f"{os.path.getsize(path) / 1e3:.0f} KB,", len(out), "arrays")
+
+
 if __name__ == "__main__":
     main()
+    main_t384()

@@ -92,3 +92,42 @@ def test_p9_conformer_block(G, ops):
     close(r["attn"], G["p9.attn"], "P9 MHSA")
     close(r["conv"], G["p9.conv"], "P9 conv")
     close(r["out"], G["p9.out"], "P9 block")
+
+
+# ---- second golden set at the BASELINE shape (B=2, T=384, D=256, H=8 -> dh=32, k=15; key mask ending inside a 64-key
+# ---- block): the instantiations the toy set above never reaches ------------------------------------------------------
+GOLD384 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "torch_ops_golden_t384.npz")
+
+
+@pytest.fixture(scope="module")
+def G384():
+    z = np.load(GOLD384)
+    return {k: z[k] for k in z.files}
+
+
+def sd16(G, prefix):
+    """weights stored as bf16 bit patterns (the reference ran with exactly these bf16-representable values)"""
+    out = {}
+    for k, v in G.items():
+        if k.startswith(prefix + ".w16."):
+            out[k[len(prefix) + 5:]] = (v.astype(np.uint32) << 16).view(np.float32)
+    return out
+
+
+def test_t384_rel_pos_attention_masked_and_module(G384, ops):
+    B, T, D, H, K = (int(v) for v in G384["meta"])
+    assert (T, D, H) == (384, 256, 8)
+    pos = VendoredOps.rel_positional_encoding(T, D)
+    w = sd16(G384, "p1")
+    close(ops.relative_mha(G384["x"], w, pos, H, mask=G384["p1.mask"]), G384["p1.out_masked"], "P1 rel-pos MHA masked, T=384 dh=32")
+    close(ops.mhsa_module(G384["x"], {"attention." + k: v for k, v in w.items()}, H), G384["p2.out"], "P2 MHSA module, T=384")
+
+
+def test_t384_conv_module_k15(G384, ops):
+    close(ops.conv_module(G384["x"], sd16(G384, "p5")), G384["p5.out"], "P5 ConvModule k=15 D=256")
+
+
+def test_t384_time_reduction(G384, ops):
+    red, lens, _ = ops.time_reduction(G384["x"], sd(G384, "p7"), G384["p7.in_lengths"])
+    close(red, G384["p7.reduced"], "P7 TimeReductionLayer [384, 256]")
+    assert list(lens) == list(G384["p7.lengths"])
