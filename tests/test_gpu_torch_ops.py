@@ -128,6 +128,6 @@ def test_t384_conv_module_k15(G384, ops):
 
 
 def test_t384_time_reduction(G384, ops):
-    red, lens, _ = ops.time_reduction(G384["x"], sd(G384, "p7"), G384["p7.in_lengths"])
+    red, lens = ops.time_reduction(G384["x"], sd(G384, "p7"), G384["p7.in_lengths"])
     close(red, G384["p7.reduced"], "P7 TimeReductionLayer [384, 256]")
     assert list(lens) == list(G384["p7.lengths"])
