@@ -164,3 +164,26 @@ def test_untrained_loss_magnitude_matches_reference_logs():
     lg = O.forward(p, O.make_inputs(cfg, 2), cfg)
     loss = O.ctc_loss_mean(O.make_labels(cfg, 2), lg)
     assert 30 < loss < 2000
+
+
+def test_keras_layer_table_covers_every_parameter_once():
+    """ishara_b200/keras_names.py: the explicit Keras-layer -> canonical-name table (used to load model.h5 files, c9:10, and
+    by tools/dump_tf_reference.py) names every tensor of get_model exactly once, for the BASELINE shapes and the notebook's
+    own 4 + 4 call (c7:75-81); the per-layer counts reproduce the recorded model.summary() totals."""
+    from ishara_b200.keras_names import keras_layer_table
+
+    for ns, nc in ((2, 2), (4, 4), (1, 0)):
+        cfg = O.Config(num_conv_squeeze_blocks=ns, num_conv_conform_blocks=nc)
+        specs = dict(O.param_specs(cfg))
+        names = [n for _, tw, ntw in keras_layer_table(ns, nc, cfg.num_conv_per_block) for n in tw + ntw]
+        assert len(names) == len(set(names)) == len(specs) and set(names) == set(specs)
+    table = {l: (tw, ntw) for l, tw, ntw in keras_layer_table()}
+    specs = dict(O.param_specs(O.Config()))
+    count = lambda ns_: sum(int(np.prod(specs[n])) for n in ns_)
+    assert count(table["squeezeformer_0"][0]) == 1_077_280          # nb:conv-squeezeformer-conformer-test c7:out
+    assert count(table["conformer_0"][0]) + count(table["conformer_0"][1]) == 992_000
+    # Keras order inside a SqueezeformerBlock starts with norm1 and ends with ffn2 (c5:161-180); a ConformerBlock lists its
+    # two LayerNorms LAST (c5:314-319)
+    assert table["squeezeformer_0"][0][0] == "squeezeformer_0.norm1.gamma" and table["squeezeformer_0"][0][-1] == "squeezeformer_0.ffn2.2.bias"
+    assert table["conformer_0"][0][-4:] == ["conformer_0.layer_norm1.gamma", "conformer_0.layer_norm1.beta",
+                                            "conformer_0.layer_norm2.gamma", "conformer_0.layer_norm2.beta"]

@@ -47,25 +47,18 @@ def main():
 
     cfg = O.Config(frames=args.frames)
     params = O.init_params(cfg, seed=42)
-    model = ns["get_model"]()
+    model = ns["get_model"](num_conv_squeeze_blocks=cfg.num_conv_squeeze_blocks, num_conv_conform_blocks=cfg.num_conv_conform_blocks,
+                            kernel_sizes=list(cfg.kernel_sizes), num_conv_per_block=cfg.num_conv_per_block, dropout_rate=cfg.dropout_rate)
     x = O.make_inputs(cfg, args.batch, seed=1234)
     y = O.make_labels(cfg, args.batch)
     model(x)  # build
 
-    def keras_name_to_ours(layer, var):
-        return f"{layer}.{var}"
+    # explicit Keras-layer -> canonical-name table (ishara_b200/keras_names.py: order of trainable / non-trainable weights
+    # per layer read off c5 / c7, every assignment shape-checked) instead of guessing from auto-generated variable names
+    from ishara_b200.keras_names import assign_to_keras, keras_layer_table, map_keras_layers
 
-    assigned = 0
-    for v in model.variables:
-        path = v.name.split(":")[0]                      # e.g. 'squeezeformer_0/mha/qkv/kernel' (TF 2.12 naming)
-        cand = path.replace("/", ".")
-        for name in params:
-            if cand.endswith(name) or name.replace("_eca.", ".").endswith(cand):
-                v.assign(params[name].reshape(v.shape))
-                assigned += 1
-                break
-        else:
-            raise SystemExit(f"no oracle parameter for Keras variable {v.name} — extend the name map")
+    table = keras_layer_table(cfg.num_conv_squeeze_blocks, cfg.num_conv_conform_blocks, cfg.num_conv_per_block)
+    assigned = assign_to_keras(model, params, table)
     assert assigned == len(params), (assigned, len(params))
     logits = model(x, training=False).numpy()
     nll = tf.nn.ctc_loss(labels=y, logits=logits, label_length=(y != 59).sum(-1).astype(np.int32),
@@ -80,13 +73,7 @@ def main():
     # be disabled through get_model's kwargs, so every Dropout layer is made the identity for this dump: what is pinned is
     # BatchNormalization on batch statistics + its moving-average update, the loss and the gradients.
     tf.keras.layers.Dropout.call = lambda self, inputs, training=None: inputs
-    name_of = {}
-    for v in model.variables:
-        cand = v.name.split(":")[0].replace("/", ".")
-        for name in params:
-            if cand.endswith(name) or name.replace("_eca.", ".").endswith(cand):
-                name_of[v.ref()] = name
-                break
+    name_of = {var.ref(): name for name, var in map_keras_layers(model.layers, table).items()}
     with tf.GradientTape() as tape:
         lg = model(x, training=True)
         loss = ns["CTCLoss"](tf.constant(y), lg)
