@@ -13,6 +13,8 @@
 //     K-major layout; the epilogue scales by 1/rowsum and writes bf16 straight to the merged-head output.
 // The [H,T,T] score tensor never leaves the SM. The softmax exponentials (T^2 per head) bound this kernel on the MUFU
 // pipe; the legacy mma.sync kernel (attention.cu) stays for other head sizes / longer sequences / relative positions.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -317,6 +319,237 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v4 ("tc2"): two CTAs per SM. The v3 kernel above keeps one (sequence, head) per SM at a time (170 KB of shared memory,
+// 448 TMEM columns), so its per-head fixed costs - TMA latency, the V^T transpose, waiting for the first scores, the last
+// PV and the epilogue - are never hidden: measured 207 us per launch against a 65 us MUFU floor. Here the key axis is
+// streamed in 64-key blocks through a 2-slot ring (S: 2 x 64 TMEM columns, P: 2 x 16 KB), which brings a CTA down to
+// 109 KB / 256 TMEM columns: two heads are resident per SM and one's exponentials run under the other's latencies.
+// The row maximum is EXACT (first sweep of Q K^T over all key blocks: tcgen05 time is free here), so no score bound, no
+// |k| prologue and no fallback path are needed:
+//   MMA thread, per 128-query block:  QK(kb) for kb < nkb   [sweep 0: maxima]
+//                                      QK(kb), PV(kb-1) interleaved, PV(last)   [sweep 1: P = 2^(s c - max), O += P V]
+//   8 softmax warps (lane == row):    sweep 0: tcgen05.ld -> running max;  sweep 1: tcgen05.ld -> ex2 -> bf16 P tile -> PV
+//   epilogue per block: O / rowsum -> bf16 -> global (merged heads); O is double buffered across query blocks.
+constexpr int kP2Bytes = 2 * kQB * 128;  // two [128 x 64-key] P tiles
+__global__ void __launch_bounds__(kThreadsTc, 2)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                const uint8_t* __restrict__ key_mask, int T, int H, float scale_log2, float* __restrict__ lse_out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* qk = smem;                          // [T][128 B] swizzled: cols 0-31 q, 32-63 k
+  uint8_t* vt = qk + kQKBytes;                 // [T/64][32][128 B] swizzled V^T
+  float* mb = reinterpret_cast<float*>(vt + kVtBytes + kP2Bytes);  // [T] additive key bias (log2 domain), only with a mask
+  float* xch = mb + kMaxT;                     // [2 (max | sum)][2 column halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 512);
+  uint64_t* qk_full = bars;        // TMA landed
+  uint64_t* s_full = bars + 1;     // [2] S slot holds Q K_kb^T
+  uint64_t* s_free = bars + 3;     // [2] softmax warps are done reading the S slot
+  uint64_t* p_ready = bars + 5;    // [2] softmax warps wrote the P slot
+  uint64_t* pv_done = bars + 7;    // [2] PV MMAs of that P slot retired
+  uint64_t* o_full = bars + 9;     // [2] O buffer complete
+  uint64_t* o_free = bars + 11;    // [2] epilogue read the O buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nqb = T / kQB, nkb = T / 64;
+  const int ld = 3 * kDH * H;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQK);
+    mbar_init(qk_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 256);
+      mbar_init(&p_ready[i], 256);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 256);
+    }
+    mbar_fence_init();
+    mbar_arrive_expect_tx(qk_full, static_cast<uint32_t>(T) * 128u);
+    for (int r = 0; r < nqb; ++r) tma_load_2d(qk + r * kQB * 128, &tmQK, qk_full, h * 3 * kDH, b * T + r * kQB);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+
+  // ---- V^T into the canonical K-major, 128B-swizzled B-operand layout: element (d, key) ----
+  {
+    const bf16* vbase = qkv + static_cast<size_t>(b) * T * ld + h * 3 * kDH + 2 * kDH;
+    for (int key = tid; key < T; key += kThreadsTc) {
+      const uint4* vp = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(key) * ld);
+      uint4 vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vv[i] = __ldg(vp + i);
+      const int kb = key >> 6, kin = key & 63;
+      uint8_t* blk = vt + kb * 4096;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t w[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
+            const int d = 8 * i + 2 * e + hl;
+            const uint32_t off = static_cast<uint32_t>(d) * 128u + ((static_cast<uint32_t>(kin >> 3) ^ (d & 7)) << 4) + (kin & 7) * 2;
+            *reinterpret_cast<unsigned short*>(blk + off) = static_cast<unsigned short>(hl ? (w[e] >> 16) : (w[e] & 0xFFFFu));
+          }
+        }
+      }
+      if (key_mask != nullptr) mb[key] = key_mask[static_cast<size_t>(b) * T + key] ? 0.f : -1.0e9f * 1.4426950408889634f;
+    }
+  }
+  fence_proxy_async_smem();  // V^T (generic-proxy writes) must be visible to the tensor core's async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 128;     // two 32-column O buffers behind the two 64-column S slots
+  constexpr uint32_t IDESC_S = umma_idesc(128, 64, 1);
+  constexpr uint32_t IDESC_O = umma_idesc(128, 32, 1);
+  const uint32_t qk_addr = smem_base;
+  const uint32_t vt_addr = qk_addr + kQKBytes;
+  const uint32_t p_addr = vt_addr + kVtBytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_wait(qk_full, 0);
+      uint32_t g = 0, pc = 0;  // running use counters of the S slots / P slots
+      for (int blk = 0; blk < nqb; ++blk) {
+        const uint32_t obuf = blk & 1;
+        auto issue_pv = [&](int kb) {
+          const uint32_t ps = pc & 1u;
+          mbar_wait(&p_ready[ps], (pc >> 1) & 1u);
+          if (kb == 0 && blk >= 2) mbar_wait(&o_free[obuf], static_cast<uint32_t>(((blk >> 1) - 1) & 1));  // block blk-2's epilogue read this O buffer
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_O + obuf * 32, umma_desc_sw128(p_addr + ps * (kQB * 128) + k * 32), umma_desc_sw128(vt_addr + kb * 4096 + k * 32),
+                      IDESC_O, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&pv_done[ps]);
+          ++pc;
+        };
+        for (int sweep = 0; sweep < 2; ++sweep) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t slot = g & 1u;
+            if (g >= 2) mbar_wait(&s_free[slot], ((g >> 1) - 1u) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(tmem_base + slot * 64, umma_desc_sw128(qk_addr + blk * kQB * 128 + k * 32),
+                        umma_desc_sw128(qk_addr + kb * 64 * 128 + 64 + k * 32), IDESC_S, k);
+            umma_commit(&s_full[slot]);
+            ++g;
+            if (sweep == 1 && kb >= 1) issue_pv(kb - 1);
+          }
+        }
+        issue_pv(nkb - 1);
+        umma_commit(&o_full[obuf]);
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue =====================
+    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int hh = (warp - 1) >> 2;               // which 32 of the 64 keys of a block / which 16 output columns
+    const int r = q * 32 + lane;                  // row within the 128-query block
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const bool masked = key_mask != nullptr;
+    float* xmax = xch;                            // [2][128]
+    float* xsum = xch + 256;                      // [2][128]
+    uint32_t g = 0, pc = 0;
+    for (int blk = 0; blk < nqb; ++blk) {
+      const uint32_t obuf = blk & 1;
+      // ---- sweep 0: exact row maximum of s * scale_log2 (+ mask bias) ----
+      float mx = -INFINITY;
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const uint32_t slot = g & 1u;
+        mbar_wait(&s_full[slot], (g >> 1) & 1u);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + slot * 64 + hh * 32 + lane_addr, raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[slot]);
+        const int key0 = kb * 64 + hh * 32;
+        if (masked) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(raw[j]), scale_log2, mb[key0 + j]));
+        } else {
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) { m0 = fmaxf(m0, __uint_as_float(raw[j])); m1 = fmaxf(m1, __uint_as_float(raw[j + 1])); }
+          mx = fmaxf(mx, fmaxf(m0, m1) * scale_log2);  // scale_log2 > 0
+        }
+      }
+      xmax[hh * 128 + r] = mx;
+      named_bar_sync(1 + q, 64);
+      mx = fmaxf(mx, xmax[(hh ^ 1) * 128 + r]);
+      const float nb = -mx;
+      // ---- sweep 1: P = 2^(s c - max) as bf16 into the P ring, row sums in fp32 ----
+      float s0 = 0.f, s1 = 0.f;
+      for (int kb = 0; kb < nkb; ++kb, ++g, ++pc) {
+        const uint32_t slot = g & 1u, ps = pc & 1u;
+        mbar_wait(&s_full[slot], (g >> 1) & 1u);
+        if (pc >= 2) mbar_wait(&pv_done[ps], ((pc >> 1) - 1u) & 1u);  // the PV MMAs that last read this P slot have retired
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + slot * 64 + hh * 32 + lane_addr, raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[slot]);
+        const int key0 = kb * 64 + hh * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a0, a1;
+          if (masked) {
+            a0 = fmaf(__uint_as_float(raw[2 * j]), scale_log2, mb[key0 + 2 * j] + nb);
+            a1 = fmaf(__uint_as_float(raw[2 * j + 1]), scale_log2, mb[key0 + 2 * j + 1] + nb);
+          } else {
+            ffma2(a0, a1, __uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]), scale_log2, scale_log2, nb, nb);
+          }
+          const float p0 = ex2f(a0), p1 = ex2f(a1);
+          fadd2(s0, s1, s0, s1, p0, p1);
+          pk[j] = pack_bf16x2(p0, p1);
+        }
+        const uint32_t rowbase = p_addr + ps * (kQB * 128) + static_cast<uint32_t>(r) * 128u;
+        const uint32_t x = static_cast<uint32_t>(r & 7);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(rowbase + ((static_cast<uint32_t>(hh * 4 + j) ^ x) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        mbar_arrive(&p_ready[ps]);
+      }
+      // row sum over both key halves of every block
+      float sum = s0 + s1;
+      xsum[hh * 128 + r] = sum;
+      named_bar_sync(1 + q, 64);
+      sum += xsum[(hh ^ 1) * 128 + r];
+      if (lse_out != nullptr && hh == 0) lse_out[(static_cast<size_t>(b) * H + h) * T + blk * kQB + r] = mx + log2f(sum);
+      // ---- epilogue of this block: O / sum -> bf16 -> merged-head output ----
+      mbar_wait(&o_full[obuf], (blk >> 1) & 1u);
+      tc_fence_after();
+      uint32_t raw16[16];
+      tmem_ld16(tmem_O + obuf * 32 + lane_addr + hh * 16, raw16);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&o_free[obuf]);
+      const float inv = 1.f / sum;
+      uint32_t po[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) po[j] = pack_bf16x2(__uint_as_float(raw16[2 * j]) * inv, __uint_as_float(raw16[2 * j + 1]) * inv);
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + blk * kQB + r) * (kDH * H) + h * kDH + hh * 16);
+      dst[0] = make_uint4(po[0], po[1], po[2], po[3]);
+      dst[1] = make_uint4(po[4], po[5], po[6], po[7]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace
 
 bool attention_tc_applicable(const AttnArgs& a) {
@@ -328,6 +561,22 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
   int rc = make_tmap_2d(&tm, a.qkv, TM_BF16, static_cast<uint64_t>(a.B) * a.T, static_cast<uint64_t>(3) * kDH * a.H,
                         static_cast<uint64_t>(3) * kDH * a.H, kQB, 64);
   if (rc) return rc;
+  static const int tc2 = getenv("ISHARA_ATTN_TC2") ? atoi(getenv("ISHARA_ATTN_TC2")) : 1;
+  if (tc2) {
+    // v4: 64-key streaming, two CTAs per SM
+    const int smem2 = kQKBytes + kVtBytes + kP2Bytes + kMaxT * 4 + 2048 + 128 + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      ISHARA_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      ISHARA_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      attr2 = true;
+    }
+    attn_tc2_kernel<<<dim3(a.H, a.B), kThreadsTc, smem2, stream>>>(tm, a.qkv, a.out, a.key_mask, a.T, a.H, a.scale * 1.4426950408889634f,
+                                                               a.lse_out);
+    ISHARA_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+  }
   const int smem = kQKBytes + kVtBytes + kPBytes + kMaxT * 4 + 2048 + 128 + 1024;
   static bool attr = false;
   if (!attr) {

@@ -39,6 +39,8 @@ VARIANTS = {
     "conv1d_unfused": {"ISHARA_CONV1D_BLOCK": "0"},           # three-kernel Conv1DBlock instead of conv1d_block.cu
     "conv1d_fused": {"ISHARA_CONV1D_FUSED": "1"},
     "attn_mma_sync": {"ISHARA_ATTN_TC": "0"},
+    "attn_tc_v3": {"ISHARA_ATTN_TC2": "0"},                   # one-CTA-per-SM tcgen05 attention instead of the 64-key streaming kernel
+    "gemm_resid_ldg": {"ISHARA_GEMM_RESID_TMA": "0"},         # per-thread residual loads instead of TMA-staged residual boxes
     "ffn_unfused": {"ISHARA_FFN_FUSED": "0"},
     "no_graph": {"ISHARA_GRAPH": "0"},
 }
