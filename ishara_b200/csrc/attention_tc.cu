@@ -326,11 +326,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
 // PV and the epilogue - are never hidden: measured 207 us per launch against a 65 us MUFU floor. Here the key axis is
 // streamed in 64-key blocks through a 2-slot ring (S: 2 x 64 TMEM columns, P: 2 x 16 KB), which brings a CTA down to
 // 109 KB / 256 TMEM columns: two heads are resident per SM and one's exponentials run under the other's latencies.
-// The row maximum is EXACT (first sweep of Q K^T over all key blocks: tcgen05 time is free here), so no score bound, no
-// |k| prologue and no fallback path are needed:
-//   MMA thread, per 128-query block:  QK(kb) for kb < nkb   [sweep 0: maxima]
-//                                      QK(kb), PV(kb-1) interleaved, PV(last)   [sweep 1: P = 2^(s c - max), O += P V]
-//   8 softmax warps (lane == row):    sweep 0: tcgen05.ld -> running max;  sweep 1: tcgen05.ld -> ex2 -> bf16 P tile -> PV
+// The exponent offset is v3's per-row Cauchy-Schwarz bound scale * |q_i| * max_j |k_j| (softmax is invariant to it); when
+// the bound of ANY row of the head is so loose that 2^(s - bound) could underflow (decided once per CTA in the prologue,
+// so the MMA thread knows too), the head runs an extra sweep of Q K^T over all key blocks that yields the exact maxima:
+//   MMA thread, per 128-query block:  [QK(kb) for kb < nkb   - sweep 0, exact maxima, only for such heads]
+//                                      QK(kb), PV(kb-1) interleaved, PV(last)   [sweep 1: P = 2^(s c - offset), O += P V]
+//   8 softmax warps (lane == row):    [sweep 0: tcgen05.ld -> running max]  sweep 1: tcgen05.ld -> ex2 -> bf16 P tile -> PV
+// S ring: three 64-column slots (the MMA thread runs two key blocks ahead), P ring: two 16 KB slots.
 //   epilogue per block: O / rowsum -> bf16 -> global (merged heads); O is double buffered across query blocks.
 constexpr int kP2Bytes = 2 * kQB * 128;  // two [128 x 64-key] P tiles
 __global__ void __launch_bounds__(kThreadsTc, 2)
@@ -351,7 +353,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   uint64_t* pv_done = bars + 7;    // [2] PV MMAs of that P slot retired
   uint64_t* o_full = bars + 9;     // [2] O buffer complete
   uint64_t* o_free = bars + 11;    // [2] epilogue read the O buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* s_full3 = bars + 13;   // third S slot
+  uint64_t* s_free3 = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint32_t* kmax_bits = tmem_slot + 1;  // max_j |k_j|^2 and max_i |q_i|^2 as float bits (non-negative floats order like unsigned ints)
+  uint32_t* qmax_bits = tmem_slot + 2;
+  auto sfull = [&](uint32_t slot) { return slot == 2u ? s_full3 : &s_full[slot]; };
+  auto sfree = [&](uint32_t slot) { return slot == 2u ? s_free3 : &s_free[slot]; };
 
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -361,6 +369,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   if (tid == 0) {
     tma_prefetch_desc(&tmQK);
     mbar_init(qk_full, 1);
+    mbar_init(s_full3, 1);
+    mbar_init(s_free3, 256);
+    *kmax_bits = 0u;
+    *qmax_bits = 0u;
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 256);
@@ -405,8 +417,29 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // largest |k_j| and |q_i| of this head: the score bound, and whether it is tight enough for every row
+  mbar_wait(qk_full, 0);
+  {
+    float km = 0.f, qm = 0.f;
+    for (int t = tid; t < T; t += kThreadsTc) {
+      km = fmaxf(km, row_half_norm2(qk, t, 4));
+      qm = fmaxf(qm, row_half_norm2(qk, t, 0));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      km = fmaxf(km, __shfl_xor_sync(0xffffffffu, km, o));
+      qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, o));
+    }
+    if (lane == 0) {
+      atomicMax(kmax_bits, __float_as_uint(km));
+      atomicMax(qmax_bits, __float_as_uint(qm));
+    }
+  }
+  __syncthreads();
+  const float kmax = sqrtf(__uint_as_float(*kmax_bits));
+  const bool exact = scale_log2 * sqrtf(__uint_as_float(*qmax_bits)) * kmax > 100.f;  // loose bound: 2^(s - bound) could underflow
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 128;     // two 32-column O buffers behind the two 64-column S slots
+  const uint32_t tmem_O = tmem_base + 192;     // two 32-column O buffers behind the three 64-column S slots
   constexpr uint32_t IDESC_S = umma_idesc(128, 64, 1);
   constexpr uint32_t IDESC_O = umma_idesc(128, 32, 1);
   const uint32_t qk_addr = smem_base;
@@ -431,16 +464,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
           umma_commit(&pv_done[ps]);
           ++pc;
         };
-        for (int sweep = 0; sweep < 2; ++sweep) {
+        for (int sweep = exact ? 0 : 1; sweep < 2; ++sweep) {
           for (int kb = 0; kb < nkb; ++kb) {
-            const uint32_t slot = g & 1u;
-            if (g >= 2) mbar_wait(&s_free[slot], ((g >> 1) - 1u) & 1u);
+            const uint32_t slot = g % 3u;
+            if (g >= 3) mbar_wait(sfree(slot), ((g / 3u) - 1u) & 1u);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 2; ++k)
               umma_bf16(tmem_base + slot * 64, umma_desc_sw128(qk_addr + blk * kQB * 128 + k * 32),
                         umma_desc_sw128(qk_addr + kb * 64 * 128 + 64 + k * 32), IDESC_S, k);
-            umma_commit(&s_full[slot]);
+            umma_commit(sfull(slot));
             ++g;
             if (sweep == 1 && kb >= 1) issue_pv(kb - 1);
           }
@@ -461,17 +494,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
     uint32_t g = 0, pc = 0;
     for (int blk = 0; blk < nqb; ++blk) {
       const uint32_t obuf = blk & 1;
-      // ---- sweep 0: exact row maximum of s * scale_log2 (+ mask bias) ----
-      float mx = -INFINITY;
+      // ---- exponent offset: the Cauchy-Schwarz bound of this row, or (sweep 0) the exact maximum of s * scale_log2 + mask bias ----
+      float mx = scale_log2 * sqrtf(row_half_norm2(qk, blk * kQB + r, 0)) * kmax;
+      if (exact) {
+      mx = -INFINITY;
       for (int kb = 0; kb < nkb; ++kb, ++g) {
-        const uint32_t slot = g & 1u;
-        mbar_wait(&s_full[slot], (g >> 1) & 1u);
+        const uint32_t slot = g % 3u;
+        mbar_wait(sfull(slot), (g / 3u) & 1u);
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld32(tmem_base + slot * 64 + hh * 32 + lane_addr, raw);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_free[slot]);
+        mbar_arrive(sfree(slot));
         const int key0 = kb * 64 + hh * 32;
         if (masked) {
 #pragma unroll
@@ -486,19 +521,20 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       xmax[hh * 128 + r] = mx;
       named_bar_sync(1 + q, 64);
       mx = fmaxf(mx, xmax[(hh ^ 1) * 128 + r]);
+      }
       const float nb = -mx;
       // ---- sweep 1: P = 2^(s c - max) as bf16 into the P ring, row sums in fp32 ----
       float s0 = 0.f, s1 = 0.f;
       for (int kb = 0; kb < nkb; ++kb, ++g, ++pc) {
-        const uint32_t slot = g & 1u, ps = pc & 1u;
-        mbar_wait(&s_full[slot], (g >> 1) & 1u);
+        const uint32_t slot = g % 3u, ps = pc & 1u;
+        mbar_wait(sfull(slot), (g / 3u) & 1u);
         if (pc >= 2) mbar_wait(&pv_done[ps], ((pc >> 1) - 1u) & 1u);  // the PV MMAs that last read this P slot have retired
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld32(tmem_base + slot * 64 + hh * 32 + lane_addr, raw);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_free[slot]);
+        mbar_arrive(sfree(slot));
         const int key0 = kb * 64 + hh * 32;
         uint32_t pk[16];
 #pragma unroll
@@ -564,7 +600,7 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
   static const int tc2 = getenv("ISHARA_ATTN_TC2") ? atoi(getenv("ISHARA_ATTN_TC2")) : 1;
   if (tc2) {
     // v4: 64-key streaming, two CTAs per SM
-    const int smem2 = kQKBytes + kVtBytes + kP2Bytes + kMaxT * 4 + 2048 + 128 + 1024;
+    const int smem2 = kQKBytes + kVtBytes + kP2Bytes + kMaxT * 4 + 2048 + 256 + 1024;
     static bool attr2 = false;
     if (!attr2) {
       ISHARA_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
