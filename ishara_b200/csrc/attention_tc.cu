@@ -335,7 +335,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
 // S ring: three 64-column slots (the MMA thread runs two key blocks ahead), P ring: two 16 KB slots.
 //   epilogue per block: O / rowsum -> bf16 -> global (merged heads); O is double buffered across query blocks.
 constexpr int kP2Bytes = 2 * kQB * 128;  // two [128 x 64-key] P tiles
-__global__ void __launch_bounds__(kThreadsTc, 2)
+constexpr int kThreadsTc2 = 320;         // warp 0: TMA + QK issue + TMEM alloc; warps 1-8: softmax / epilogue; warp 9: PV issue
+__global__ void __launch_bounds__(kThreadsTc2, 2)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict__ qkv, bf16* __restrict__ out,
                 const uint8_t* __restrict__ key_mask, int T, int H, float scale_log2, float* __restrict__ lse_out) {
   extern __shared__ uint8_t smem_raw[];
@@ -370,16 +371,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
     tma_prefetch_desc(&tmQK);
     mbar_init(qk_full, 1);
     mbar_init(s_full3, 1);
-    mbar_init(s_free3, 256);
+    mbar_init(s_free3, 8);      // one arrive per softmax warp
     *kmax_bits = 0u;
     *qmax_bits = 0u;
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 256);
-      mbar_init(&p_ready[i], 256);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_ready[i], 8);
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_free[i], 256);
+      mbar_init(&o_free[i], 8);
     }
     mbar_fence_init();
     mbar_arrive_expect_tx(qk_full, static_cast<uint32_t>(T) * 128u);
@@ -390,7 +391,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   // ---- V^T into the canonical K-major, 128B-swizzled B-operand layout: element (d, key) ----
   {
     const bf16* vbase = qkv + static_cast<size_t>(b) * T * ld + h * 3 * kDH + 2 * kDH;
-    for (int key = tid; key < T; key += kThreadsTc) {
+    for (int key = tid; key < T; key += kThreadsTc2) {
       const uint4* vp = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(key) * ld);
       uint4 vv[4];
 #pragma unroll
@@ -421,7 +422,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   mbar_wait(qk_full, 0);
   {
     float km = 0.f, qm = 0.f;
-    for (int t = tid; t < T; t += kThreadsTc) {
+    for (int t = tid; t < T; t += kThreadsTc2) {
       km = fmaxf(km, row_half_norm2(qk, t, 4));
       qm = fmaxf(qm, row_half_norm2(qk, t, 0));
     }
@@ -447,12 +448,31 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   const uint32_t p_addr = vt_addr + kVtBytes;
 
   if (warp == 0) {
+    // ===================== QK issuer: runs up to three key blocks ahead of the softmax warps =====================
     if (lane == 0) {
-      mbar_wait(qk_full, 0);
-      uint32_t g = 0, pc = 0;  // running use counters of the S slots / P slots
+      uint32_t g = 0;  // running use counter of the S slots
+      for (int blk = 0; blk < nqb; ++blk) {
+        for (int sweep = exact ? 0 : 1; sweep < 2; ++sweep) {
+          for (int kb = 0; kb < nkb; ++kb, ++g) {
+            const uint32_t slot = g % 3u;
+            if (g >= 3) mbar_wait(sfree(slot), ((g / 3u) - 1u) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(tmem_base + slot * 64, umma_desc_sw128(qk_addr + blk * kQB * 128 + k * 32),
+                        umma_desc_sw128(qk_addr + kb * 64 * 128 + 64 + k * 32), IDESC_S, k);
+            umma_commit(sfull(slot));
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== PV issuer: O += P V as soon as a P slot is written =====================
+    if (lane == 0) {
+      uint32_t pc = 0;  // running use counter of the P slots
       for (int blk = 0; blk < nqb; ++blk) {
         const uint32_t obuf = blk & 1;
-        auto issue_pv = [&](int kb) {
+        for (int kb = 0; kb < nkb; ++kb, ++pc) {
           const uint32_t ps = pc & 1u;
           mbar_wait(&p_ready[ps], (pc >> 1) & 1u);
           if (kb == 0 && blk >= 2) mbar_wait(&o_free[obuf], static_cast<uint32_t>(((blk >> 1) - 1) & 1));  // block blk-2's epilogue read this O buffer
@@ -462,23 +482,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
             umma_bf16(tmem_O + obuf * 32, umma_desc_sw128(p_addr + ps * (kQB * 128) + k * 32), umma_desc_sw128(vt_addr + kb * 4096 + k * 32),
                       IDESC_O, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&pv_done[ps]);
-          ++pc;
-        };
-        for (int sweep = exact ? 0 : 1; sweep < 2; ++sweep) {
-          for (int kb = 0; kb < nkb; ++kb) {
-            const uint32_t slot = g % 3u;
-            if (g >= 3) mbar_wait(sfree(slot), ((g / 3u) - 1u) & 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              umma_bf16(tmem_base + slot * 64, umma_desc_sw128(qk_addr + blk * kQB * 128 + k * 32),
-                        umma_desc_sw128(qk_addr + kb * 64 * 128 + 64 + k * 32), IDESC_S, k);
-            umma_commit(sfull(slot));
-            ++g;
-            if (sweep == 1 && kb >= 1) issue_pv(kb - 1);
-          }
         }
-        issue_pv(nkb - 1);
         umma_commit(&o_full[obuf]);
       }
     }
@@ -506,7 +510,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
         tmem_ld32(tmem_base + slot * 64 + hh * 32 + lane_addr, raw);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(sfree(slot));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfree(slot));
         const int key0 = kb * 64 + hh * 32;
         if (masked) {
 #pragma unroll
@@ -534,7 +539,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
         tmem_ld32(tmem_base + slot * 64 + hh * 32 + lane_addr, raw);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(sfree(slot));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfree(slot));
         const int key0 = kb * 64 + hh * 32;
         uint32_t pk[16];
 #pragma unroll
@@ -556,7 +562,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
         for (int j = 0; j < 4; ++j)
           st_shared_v4(rowbase + ((static_cast<uint32_t>(hh * 4 + j) ^ x) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async_smem();
-        mbar_arrive(&p_ready[ps]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[ps]);
       }
       // row sum over both key halves of every block
       float sum = s0 + s1;
@@ -571,7 +578,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       tmem_ld16(tmem_O + obuf * 32 + lane_addr + hh * 16, raw16);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&o_free[obuf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[obuf]);
       const float inv = 1.f / sum;
       uint32_t po[8];
 #pragma unroll
@@ -607,7 +615,7 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
       ISHARA_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       attr2 = true;
     }
-    attn_tc2_kernel<<<dim3(a.H, a.B), kThreadsTc, smem2, stream>>>(tm, a.qkv, a.out, a.key_mask, a.T, a.H, a.scale * 1.4426950408889634f,
+    attn_tc2_kernel<<<dim3(a.H, a.B), kThreadsTc2, smem2, stream>>>(tm, a.qkv, a.out, a.key_mask, a.T, a.H, a.scale * 1.4426950408889634f,
                                                                a.lse_out);
     ISHARA_CUDA_OK(cudaGetLastError());
     note_launch();
