@@ -13,6 +13,7 @@
 //     K-major layout; the epilogue scales by 1/rowsum and writes bf16 straight to the merged-head output.
 // The [H,T,T] score tensor never leaves the SM. The softmax exponentials (T^2 per head) bound this kernel on the MUFU
 // pipe; the legacy mma.sync kernel (attention.cu) stays for other head sizes / longer sequences / relative positions.
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -334,6 +335,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict_
 //   8 softmax warps (lane == row):    [sweep 0: tcgen05.ld -> running max]  sweep 1: tcgen05.ld -> ex2 -> bf16 P tile -> PV
 // S ring: three 64-column slots (the MMA thread runs two key blocks ahead), P ring: two 16 KB slots.
 //   epilogue per block: O / rowsum -> bf16 -> global (merged heads); O is double buffered across query blocks.
+// timeline tracing of one CTA (profiling build only, make TRACE=1)
+#ifdef ISHARA_TRACE_BUILD
+__device__ long long* g_attn_trace = nullptr;
+#define ATT_TRACE(ev_) do { if (g_attn_trace != nullptr && blockIdx.y == gridDim.y / 2 && blockIdx.x == 3) g_attn_trace[(ev_)] = clock64(); } while (0)
+#else
+#define ATT_TRACE(ev_) do { } while (0)
+#endif
 constexpr int kP2Bytes = 2 * kQB * 128;  // two [128 x 64-key] P tiles
 constexpr int kThreadsTc2 = 320;         // warp 0: TMA + QK issue + TMEM alloc; warps 1-8: softmax / epilogue; warp 9: PV issue
 __global__ void __launch_bounds__(kThreadsTc2, 2)
@@ -386,6 +394,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
     mbar_arrive_expect_tx(qk_full, static_cast<uint32_t>(T) * 128u);
     for (int r = 0; r < nqb; ++r) tma_load_2d(qk + r * kQB * 128, &tmQK, qk_full, h * 3 * kDH, b * T + r * kQB);
   }
+  if (tid == 0) ATT_TRACE(0);
   if (warp == 0) tmem_alloc(tmem_slot, 256);
 
   // ---- V^T into the canonical K-major, 128B-swizzled B-operand layout: element (d, key) ----
@@ -418,8 +427,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 32) ATT_TRACE(1);
   // largest |k_j| and |q_i| of this head: the score bound, and whether it is tight enough for every row
   mbar_wait(qk_full, 0);
+  if (tid == 32) ATT_TRACE(2);
   {
     float km = 0.f, qm = 0.f;
     for (int t = tid; t < T; t += kThreadsTc2) {
@@ -437,6 +448,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
     }
   }
   __syncthreads();
+  if (tid == 32) ATT_TRACE(3);
   const float kmax = sqrtf(__uint_as_float(*kmax_bits));
   const bool exact = scale_log2 * sqrtf(__uint_as_float(*qmax_bits)) * kmax > 100.f;  // loose bound: 2^(s - bound) could underflow
   const uint32_t tmem_base = *tmem_slot;
@@ -462,6 +474,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
               umma_bf16(tmem_base + slot * 64, umma_desc_sw128(qk_addr + blk * kQB * 128 + k * 32),
                         umma_desc_sw128(qk_addr + kb * 64 * 128 + 64 + k * 32), IDESC_S, k);
             umma_commit(sfull(slot));
+            if (g < 8) ATT_TRACE(40 + g);
           }
         }
       }
@@ -482,8 +495,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
             umma_bf16(tmem_O + obuf * 32, umma_desc_sw128(p_addr + ps * (kQB * 128) + k * 32), umma_desc_sw128(vt_addr + kb * 4096 + k * 32),
                       IDESC_O, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&pv_done[ps]);
+          if (pc < 8) ATT_TRACE(50 + pc);
         }
         umma_commit(&o_full[obuf]);
+        ATT_TRACE(60 + blk);
       }
     }
   } else {
@@ -533,6 +548,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       for (int kb = 0; kb < nkb; ++kb, ++g, ++pc) {
         const uint32_t slot = g % 3u, ps = pc & 1u;
         mbar_wait(sfull(slot), (g / 3u) & 1u);
+        if (tid == 32 && pc < 18) ATT_TRACE(4 + 2 * pc);
         if (pc >= 2) mbar_wait(&pv_done[ps], ((pc >> 1) - 1u) & 1u);  // the PV MMAs that last read this P slot have retired
         tc_fence_after();
         uint32_t raw[32];
@@ -564,6 +580,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[ps]);
+        if (tid == 32 && pc < 18) ATT_TRACE(5 + 2 * pc);
       }
       // row sum over both key halves of every block
       float sum = s0 + s1;
@@ -574,6 +591,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       // ---- epilogue of this block: O / sum -> bf16 -> merged-head output ----
       mbar_wait(&o_full[obuf], (blk >> 1) & 1u);
       tc_fence_after();
+      if (tid == 32) ATT_TRACE(64 + blk);
       uint32_t raw16[16];
       tmem_ld16(tmem_O + obuf * 32 + lane_addr + hh * 16, raw16);
       tmem_ld_wait();
@@ -587,10 +605,12 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + blk * kQB + r) * (kDH * H) + h * kDH + hh * 16);
       dst[0] = make_uint4(po[0], po[1], po[2], po[3]);
       dst[1] = make_uint4(po[4], po[5], po[6], po[7]);
+      if (tid == 32) ATT_TRACE(68 + blk);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) ATT_TRACE(72);
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
@@ -615,10 +635,32 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
       ISHARA_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       attr2 = true;
     }
+#ifdef ISHARA_TRACE_BUILD
+    static long long* tbuf = nullptr;
+    static int printed = 0;
+    const bool tracing = printed < 2 && a.B >= 8;
+    if (tracing) {
+      if (tbuf == nullptr) ISHARA_CUDA_OK(cudaMalloc(&tbuf, 128 * sizeof(long long)));
+      ISHARA_CUDA_OK(cudaMemsetAsync(tbuf, 0, 128 * sizeof(long long), stream));
+      ISHARA_CUDA_OK(cudaMemcpyToSymbolAsync(g_attn_trace, &tbuf, sizeof(tbuf), 0, cudaMemcpyHostToDevice, stream));
+    }
+#endif
     attn_tc2_kernel<<<dim3(a.H, a.B), kThreadsTc2, smem2, stream>>>(tm, a.qkv, a.out, a.key_mask, a.T, a.H, a.scale * 1.4426950408889634f,
                                                                a.lse_out);
     ISHARA_CUDA_OK(cudaGetLastError());
     note_launch();
+#ifdef ISHARA_TRACE_BUILD
+    if (tracing) {
+      ISHARA_CUDA_OK(cudaStreamSynchronize(stream));
+      long long hbuf[128];
+      ISHARA_CUDA_OK(cudaMemcpy(hbuf, tbuf, sizeof(hbuf), cudaMemcpyDeviceToHost));
+      ++printed;
+      fprintf(stderr, "attn trace B=%d T=%d (cycles since CTA start): 1 V^T done | 2 qk landed | 3 norms | 4+2i / 5+2i softmax block i: scores seen / P written | "
+                      "40+ QK issue | 50+ PV issue | 60+ o_full commit | 64+ o_full seen | 68+ epilogue done | 72 end\n ", a.B, a.T);
+      for (int e = 1; e < 80; ++e) if (hbuf[e]) fprintf(stderr, " %d:%lld", e, hbuf[e] - hbuf[0]);
+      fprintf(stderr, "\n");
+    }
+#endif
     return 0;
   }
   const int smem = kQKBytes + kVtBytes + kPBytes + kMaxT * 4 + 2048 + 128 + 1024;

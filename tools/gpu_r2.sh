@@ -30,6 +30,10 @@ case "${1:-quick}" in
     ISHARA_B200_LIB=$PWD/ishara_b200/lib/libishara_b200_trace.so ISHARA_C1B_TRACE_N=3 timeout 200 python tools/fwd_once.py 256 1 > gpurun_out/${TAG}_trace.log 2>&1
     grep "rank\|K=" gpurun_out/${TAG}_trace.log | sed 's/(cycles.*//' | cut -c1-420
     ;;
+  attn_trace)
+    ISHARA_B200_LIB=$PWD/ishara_b200/lib/libishara_b200_trace.so ISHARA_C1B_TRACE_N=0 timeout 200 python tools/fwd_once.py 256 1 > gpurun_out/${TAG}_atrace.log 2>&1
+    grep -A1 "attn trace" gpurun_out/${TAG}_atrace.log | cut -c1-1500
+    ;;
   c1b_prof)  # timeline trace (profiling build) + ncu --set full of the fused Conv1DBlock kernel
     ISHARA_B200_LIB=$PWD/ishara_b200/lib/libishara_b200_trace.so timeout 200 python tools/fwd_once.py 256 2 > gpurun_out/${TAG}_trace.log 2>&1
     grep -A4 "c1b trace" gpurun_out/${TAG}_trace.log | head -40
