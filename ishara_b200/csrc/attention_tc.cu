@@ -346,7 +346,21 @@ constexpr int kP2Bytes = 2 * kQB * 128;  // two [128 x 64-key] P tiles
 constexpr int kThreadsTc2 = 320;         // warp 0: TMA + QK issue + TMEM alloc; warps 1-8: softmax / epilogue; warp 9: PV issue
 __global__ void __launch_bounds__(kThreadsTc2, 2)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                const uint8_t* __restrict__ key_mask, int T, int H, float scale_log2, float* __restrict__ lse_out) {
+                const uint8_t* __restrict__ key_mask, int T, int H, float scale_log2, float* __restrict__ lse_out, int stagger_cycles) {
+  // The two CTAs that share an SM start in lockstep in the first wave, so their prologues and epilogues (no MUFU work)
+  // coincide instead of hiding under each other's exponentials: the second resident CTA of every SM waits half a period.
+  if (stagger_cycles > 0) {
+    const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+    unsigned nsm;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    if (lin >= nsm && lin < 2 * nsm) {
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < stagger_cycles) { }
+      }
+      __syncthreads();
+    }
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -645,8 +659,9 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
       ISHARA_CUDA_OK(cudaMemcpyToSymbolAsync(g_attn_trace, &tbuf, sizeof(tbuf), 0, cudaMemcpyHostToDevice, stream));
     }
 #endif
+    static const int stagger = getenv("ISHARA_ATTN_STAGGER") ? atoi(getenv("ISHARA_ATTN_STAGGER")) : 0;
     attn_tc2_kernel<<<dim3(a.H, a.B), kThreadsTc2, smem2, stream>>>(tm, a.qkv, a.out, a.key_mask, a.T, a.H, a.scale * 1.4426950408889634f,
-                                                               a.lse_out);
+                                                               a.lse_out, stagger);
     ISHARA_CUDA_OK(cudaGetLastError());
     note_launch();
 #ifdef ISHARA_TRACE_BUILD
