@@ -626,11 +626,60 @@ struct Builder {
   }
 };
 
+// Lanes: a large batch is cut into `lanes` independent sub-batches, each with its own slice of every workspace tensor and
+// its own op list, launched on parallel streams (one forked CUDA graph). Every kernel of the path is per-sequence, so
+// the results do not change; what changes is that the partial last wave of one lane's kernel (768 row tiles over 148 SMs
+// = 5.2 waves, 256 clusters over ~47 cluster slots = 5.4 waves) and its launch ramp are filled by the other lane's work.
+int lane_count(const ishara_model* m, int batch) {
+  static const int want = getenv("ISHARA_LANES") ? std::max(1, std::min(kMaxLanes, atoi(getenv("ISHARA_LANES")))) : 2;
+  static const int min_batch = getenv("ISHARA_LANES_MIN_BATCH") ? atoi(getenv("ISHARA_LANES_MIN_BATCH")) : 96;
+  if (m->profile || m->debug_taps || batch < min_batch) return 1;  // per-op events and taps need one serial stream
+  return std::min(want, batch);
+}
+void lane_range(int batch, int lanes, int l, int* b0, int* bl) {
+  const int lo = static_cast<int>(static_cast<int64_t>(batch) * l / lanes), hi = static_cast<int>(static_cast<int64_t>(batch) * (l + 1) / lanes);
+  *b0 = lo;
+  *bl = hi - lo;
+}
+
+int build_lane(ishara_model* m, int batch, float* logits, int lane);
+
 int build_program(ishara_model* m, int batch, float* logits) {
   const ishara_config_t& c = m->cfg;
   m->program.clear();
   m->tap_names.clear();
   m->taps.clear();
+  const int lanes = lane_count(m, batch);
+  if (lanes == 1) return build_lane(m, batch, logits, 0);
+  // point the handle's workspace pointers at this lane's slice while its ops are built, then restore them
+  const size_t T = c.frames, D = c.dim, E = static_cast<size_t>(c.expansion_factor) * c.dim;
+  const size_t W1 = std::max<size_t>(std::max<size_t>(2 * D, E), 3 * D), W2 = std::max<size_t>(2 * D, E);
+  bf16 *const XIN = m->XIN, *const S = m->S, *const XN = m->XN, *const H1 = m->H1, *const H2 = m->H2, *const O = m->O, *const HEAD = m->HEAD;
+  float *const colsum = m->colsum, *const gate = m->gate;
+  uint8_t* const mask = m->mask_dev;
+  uint16_t* const wbits = m->wbits_dev;
+  int32_t* const valid = m->valid_dev;
+  int rc = 0;
+  for (int l = 0; l < lanes && rc == 0; ++l) {
+    int b0, bl;
+    lane_range(batch, lanes, l, &b0, &bl);
+    const size_t r0 = static_cast<size_t>(b0) * T;
+    m->XIN = XIN + r0 * m->fpad(); m->S = S + r0 * D; m->XN = XN + r0 * D; m->H1 = H1 + r0 * W1; m->H2 = H2 + r0 * W2;
+    m->O = O + r0 * D; m->HEAD = HEAD + r0 * 2 * D; m->colsum = colsum + static_cast<size_t>(b0) * E; m->gate = gate + static_cast<size_t>(b0) * D;
+    m->mask_dev = mask + r0; m->wbits_dev = wbits + r0; m->valid_dev = valid + b0;
+    rc = build_lane(m, bl, logits + r0 * c.num_classes, l);
+  }
+  m->XIN = XIN; m->S = S; m->XN = XN; m->H1 = H1; m->H2 = H2; m->O = O; m->HEAD = HEAD; m->colsum = colsum; m->gate = gate;
+  m->mask_dev = mask; m->wbits_dev = wbits; m->valid_dev = valid;
+  if (rc) { m->program.clear(); return rc; }
+  m->program_batch = batch;
+  m->program_logits = logits;
+  return 0;
+}
+
+int build_lane(ishara_model* m, int batch, float* logits, int lane) {
+  const ishara_config_t& c = m->cfg;
+  const size_t first_op = m->program.size();
   Builder b{m, batch, batch * c.frames, c.dim, c.expansion_factor * c.dim, c.frames, m->program, Packed{m}};
   const int D = c.dim, E = b.E, tk = c.transformer_kernel_size;
 
@@ -722,6 +771,7 @@ int build_program(ishara_model* m, int batch, float* logits) {
     m->program.clear();
     return b.rc;
   }
+  for (size_t i = first_op; i < m->program.size(); ++i) m->program[i].lane = lane;
   m->program_batch = batch;
   m->program_logits = logits;
   return 0;
@@ -766,6 +816,10 @@ int model_destroy(ishara_model* m) {
   for (auto& kv : m->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (m->labels_dev) cudaFree(m->labels_dev);
   if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->lane_fork) {
+    cudaEventDestroy(m->lane_fork);
+    for (int l = 0; l < kMaxLanes - 1; ++l) { cudaStreamDestroy(m->lane_stream[l]); cudaEventDestroy(m->lane_join[l]); }
+  }
   for (auto& sl : m->pipe) {
     if (sl.x) cudaFree(sl.x);
     if (sl.labels) cudaFree(sl.labels);
@@ -790,6 +844,13 @@ int model_finalize(ishara_model* m) {
   if (major != 10) { set_last_error("ishara_b200 needs a Blackwell (sm_100a) device; no fallback exists"); return ISHARA_ERR_CUDA; }
   m->num_sms = sms;
   if (m->stream == nullptr) ISHARA_CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  if (m->lane_fork == nullptr) {
+    ISHARA_CUDA_OK(cudaEventCreateWithFlags(&m->lane_fork, cudaEventDisableTiming));
+    for (int l = 0; l < kMaxLanes - 1; ++l) {
+      ISHARA_CUDA_OK(cudaStreamCreateWithFlags(&m->lane_stream[l], cudaStreamNonBlocking));
+      ISHARA_CUDA_OK(cudaEventCreateWithFlags(&m->lane_join[l], cudaEventDisableTiming));
+    }
+  }
   if (m->copy_stream == nullptr) {
     ISHARA_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     for (auto& e : m->copy_done) ISHARA_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -922,8 +983,9 @@ int model_forward_masked(ishara_model* m, const float* x_dev, const uint8_t* mas
 
 int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t stream, bool prof) {
   const ishara_config_t& c = m->cfg;
-  const int64_t M = static_cast<int64_t>(batch) * c.frames;
   int rc;
+  int lanes = 1;
+  for (const Op& op : m->program) lanes = std::max(lanes, op.lane + 1);
   if (prof) {
     while (m->events.size() < m->program.size() + 2) {
       cudaEvent_t e;
@@ -932,39 +994,76 @@ int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t 
     }
     ISHARA_CUDA_OK(cudaEventRecord(m->events[0], stream));
   }
-  if (m->mask_mode == 1 &&
-      (rc = mask_prep_launch(x_dev, m->user_mask_dev, m->use_user_mask_dev, batch, c.frames, c.features, m->mask_dev, m->wbits_dev,
-                             m->valid_dev, stream)))
-    return rc;
-  if ((rc = cast_pad_launch(x_dev, m->XIN, M, c.features, m->fpad(), stream))) return rc;
-  if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[1], stream));
-  size_t op_index = 0;
-  for (const Op& op : m->program) {
-    switch (op.kind) {
-      case OP_GEMM: rc = gemm_launch(op.gemm, m->num_sms, stream); break;
-      case OP_DW: rc = dwconv_launch(op.dw, stream); break;
-      case OP_ATTN: rc = attention_launch(op.at, stream); break;
-      case OP_SEGATE: rc = se_gate_launch(op.se, stream); break;
-      case OP_FFN: rc = ffn_launch(op.ffn, m->num_sms, stream); break;
-      case OP_C1F: rc = conv1d_front_launch(op.c1f, stream); break;
-      case OP_C1B: rc = conv1d_block_launch(op.c1b, stream); break;
-      case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, M, c.dim, stream); break;
-      case OP_TAP:
-        rc = cudaMemcpyAsync(m->taps[op.tap], m->S, M * c.dim * sizeof(bf16), cudaMemcpyDeviceToDevice, stream) == cudaSuccess ? 0 : 3;
-        break;
+  // lane 0 runs on the caller's stream; the others fork from it here and join it at the end (inside a capture this
+  // becomes one graph with parallel branches)
+  cudaStream_t ls[kMaxLanes] = {stream, nullptr, nullptr, nullptr};
+  if (lanes > 1) {
+    ISHARA_CUDA_OK(cudaEventRecord(m->lane_fork, stream));
+    for (int l = 1; l < lanes; ++l) {
+      ls[l] = m->lane_stream[l - 1];
+      ISHARA_CUDA_OK(cudaStreamWaitEvent(ls[l], m->lane_fork, 0));
     }
-    if (rc) {
-      set_last_error(std::string("forward: op '") + op.label + "' failed: " + get_last_error());
+  }
+  for (int l = 0; l < lanes; ++l) {
+    int b0, bl;
+    lane_range(batch, lanes, l, &b0, &bl);
+    const size_t r0 = static_cast<size_t>(b0) * c.frames;
+    const float* xl = x_dev + r0 * c.features;
+    if (m->mask_mode == 1 &&
+        (rc = mask_prep_launch(xl, m->user_mask_dev + r0, m->use_user_mask_dev, bl, c.frames, c.features, m->mask_dev + r0, m->wbits_dev + r0,
+                               m->valid_dev + b0, ls[l])))
       return rc;
+    if ((rc = cast_pad_launch(xl, m->XIN + r0 * m->fpad(), static_cast<int64_t>(bl) * c.frames, c.features, m->fpad(), ls[l]))) return rc;
+  }
+  if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[1], stream));
+  const int64_t M = static_cast<int64_t>(batch) * c.frames;  // OP_LN / OP_TAP only exist in one-lane programs
+  size_t op_index = 0;
+  // interleave the lanes' launches so that neither stream runs far ahead of the other on the host side
+  std::vector<size_t> next(lanes, 0);
+  std::vector<std::vector<size_t>> by_lane(lanes);
+  for (size_t i = 0; i < m->program.size(); ++i) by_lane[m->program[i].lane].push_back(i);
+  for (size_t round = 0, left = m->program.size(); left > 0; ++round) {
+    for (int l = 0; l < lanes; ++l) {
+      if (round >= by_lane[l].size()) continue;
+      const Op& op = m->program[by_lane[l][round]];
+      cudaStream_t st = ls[l];
+      --left;
+      switch (op.kind) {
+        case OP_GEMM: rc = gemm_launch(op.gemm, m->num_sms, st); break;
+        case OP_DW: rc = dwconv_launch(op.dw, st); break;
+        case OP_ATTN: rc = attention_launch(op.at, st); break;
+        case OP_SEGATE: rc = se_gate_launch(op.se, st); break;
+        case OP_FFN: rc = ffn_launch(op.ffn, m->num_sms, st); break;
+        case OP_C1F: rc = conv1d_front_launch(op.c1f, st); break;
+        case OP_C1B: rc = conv1d_block_launch(op.c1b, st); break;
+        case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, M, c.dim, st); break;
+        case OP_TAP:
+          rc = cudaMemcpyAsync(m->taps[op.tap], m->S, M * c.dim * sizeof(bf16), cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : 3;
+          break;
+      }
+      if (rc) {
+        set_last_error(std::string("forward: op '") + op.label + "' failed: " + get_last_error());
+        return rc;
+      }
+      if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[2 + op_index], st));
+      ++op_index;
     }
-    if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[2 + op_index], stream));
-    ++op_index;
+  }
+  for (int l = 1; l < lanes; ++l) {
+    ISHARA_CUDA_OK(cudaEventRecord(m->lane_join[l - 1], ls[l]));
+    ISHARA_CUDA_OK(cudaStreamWaitEvent(stream, m->lane_join[l - 1], 0));
   }
   return ISHARA_OK;
 }
 
 int model_set_profile(ishara_model* m, int on) {
-  m->profile = on != 0;
+  if (m->profile != (on != 0)) {  // profiled programs are built with one lane (per-op events need a serial stream)
+    m->profile = on != 0;
+    m->program.clear();
+    m->program_cache.clear();
+    drop_graphs(m);
+    m->program_batch = 0;
+  }
   return 0;
 }
 int model_profile_count(const ishara_model* m) { return m->program.empty() ? 0 : static_cast<int>(m->program.size()) + 1; }

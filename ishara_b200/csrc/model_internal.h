@@ -45,6 +45,7 @@ struct Op {
   bf16* ln_out = nullptr;
   LnRef ln;
   int tap = -1;
+  int lane = 0;  // sub-batch this op belongs to (model.cu: lanes)
   const char* label = "";
   // algorithmic cost of one launch: useful flops and compulsory HBM bytes (operands read once,
   // results written once; weights counted once per launch)
@@ -63,6 +64,7 @@ inline uint16_t f2bf(float f) {
 
 namespace ishara { struct TrainState; }
 using ishara::bf16;
+constexpr int kMaxLanes = 4;
 
 struct GraphKey {
   int batch;
@@ -122,6 +124,8 @@ struct ishara_model {
   std::map<GraphKey, GraphEntry> graphs;  // captured forwards; dropped whenever programs are rebuilt
   bool graphs_broken = false;
   cudaStream_t stream = nullptr;
+  cudaStream_t lane_stream[kMaxLanes - 1] = {nullptr};  // lanes 1.. of a forward (lane 0 runs on the caller's stream)
+  cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes - 1] = {nullptr};
   cudaStream_t copy_stream = nullptr;     // H2D of the chunked host path
   cudaEvent_t copy_done[8] = {nullptr};
   // pipelined host inference (model_infer_submit / _collect): two input slots so the H2D copy of batch i+1 runs under

@@ -39,6 +39,17 @@ case "${1:-quick}" in
     grep -A4 "c1b trace" gpurun_out/${TAG}_trace.log | head -40
     CMD="python tools/fwd_once.py 256 2" timeout 600 bash tools/ncu_capture.sh ${TAG}_prof_c1b:conv1d_block:3:3
     ;;
+  lanes)   # sub-batch lanes sweep: parity once (default), then a short bench per lane count
+    timeout 400 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -5
+    for L in 1 2 3 4; do
+      ISHARA_LANES=$L timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-train > gpurun_out/${TAG}_lanes$L.json 2> gpurun_out/${TAG}_lanes$L.err
+      python - gpurun_out/${TAG}_lanes$L.json $L <<'PY'
+import json, sys
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
+print("lanes", sys.argv[2], "value", round(d["value"]), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "cfg5", d.get("cfg5", {}).get("value"), "cfg1", d.get("cfg1", {}).get("ms_per_step"))
+PY
+    done
+    ;;
   bench)
     timeout 500 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
     tail -3 gpurun_out/${TAG}_bench.err
