@@ -176,7 +176,7 @@ int cast_pad_launch(const float* x, bf16* out, int64_t M, int F, int Fpad, cudaS
 // SE gate from column sums (linearity of the 1x1 conv): gate[b,:] = sigmoid(fc2(swish(fc1(mean @ W3 + b3))))
 struct SeGateArgs {
   const float* colsum = nullptr;  // [B, C]
-  const bf16* w3t = nullptr;      // [D, C] bf16 (packed, K-major)
+  const bf16* w3kn = nullptr;     // [C, D] bf16: conv3 kernel in its native orientation (row c = input channel)
   const float* b3 = nullptr;      // [D]
   const float* fc1_w = nullptr;   // [D, R] fp32
   const float* fc1_b = nullptr;   // [R]

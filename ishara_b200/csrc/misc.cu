@@ -87,6 +87,7 @@ mask_prep_kernel(const float* __restrict__ x, const uint8_t* __restrict__ user_m
 
 // SqueezeExcite gate (nb:conv-hybrid-model c5:120-133) computed from the column sums of the conv3 INPUT:
 // mean_t(conv3(h)) = mean_t(h) @ W3 + b3 (1x1 conv is linear), so no pass over the [T, D] output is needed.
+constexpr int kSeN = 1;  // sequences per CTA (4 was measured slower: 52 us vs 29 us, the per-sequence fc1/fc2 chains serialise)
 __global__ void __launch_bounds__(256)
 se_gate_kernel(SeGateArgs a) {
   extern __shared__ float sm[];
@@ -94,32 +95,40 @@ se_gate_kernel(SeGateArgs a) {
   float* z = mean + a.C;       // [D]
   float* part = z + a.D;       // [8][R] partial sums of fc1
   float* hid = part + 8 * a.R; // [R]
+  float* zpart = hid + a.R;    // [8][256] per-warp partial rows of z
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // GlobalAveragePooling1D(mask): the column sums already cover the valid frames only; 0 valid frames -> 0/0 = NaN as in Keras
   const float inv_n = a.valid_cnt != nullptr ? 1.f / static_cast<float>(a.valid_cnt[b]) : a.inv_T;
   for (int c = tid; c < a.C; c += 256) mean[c] = a.colsum[static_cast<size_t>(b) * a.C + c] * inv_n;
   __syncthreads();
-  // z = mean @ W3 + b3: four output channels per warp iteration (independent load streams), 16-byte weight loads
-  for (int d0 = warp * 4; d0 < a.D; d0 += 32) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = lane * 8; c < a.C; c += 256) {
-      const float4 m0 = *reinterpret_cast<const float4*>(mean + c), m1 = *reinterpret_cast<const float4*>(mean + c + 4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (d0 + i < a.D) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.w3t + static_cast<size_t>(d0 + i) * a.C + c));
-          acc[i] = fmaf(bf16_lo(u.x), m0.x, acc[i]); acc[i] = fmaf(bf16_hi(u.x), m0.y, acc[i]);
-          acc[i] = fmaf(bf16_lo(u.y), m0.z, acc[i]); acc[i] = fmaf(bf16_hi(u.y), m0.w, acc[i]);
-          acc[i] = fmaf(bf16_lo(u.z), m1.x, acc[i]); acc[i] = fmaf(bf16_hi(u.z), m1.y, acc[i]);
-          acc[i] = fmaf(bf16_lo(u.w), m1.z, acc[i]); acc[i] = fmaf(bf16_hi(u.w), m1.w, acc[i]);
-        }
+  // z = mean @ W3 + b3. W3 is [C, D] row-major: warp w owns input channels c = w, w+8, ..., lane l owns the eight output
+  // channels d0 + 8l .. +7 (one 16-byte load = a full 512-byte row segment per warp instruction, all loads independent);
+  // the eight per-warp partial rows are summed through shared memory. (Every CTA pulls all of W3, 256 KB, from L2 in the
+  // same order; starting each CTA at a different row would spread the L2 load but make the fp32 summation order - and
+  // so the bits of the result - depend on the position in the batch, which the batch-invariance test forbids.)
+  for (int d0 = 0; d0 < a.D; d0 += 256) {
+    const int d = d0 + lane * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (d < a.D) {
+#pragma unroll 8
+      for (int c = warp; c < a.C; c += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.w3kn + static_cast<size_t>(c) * a.D + d));
+        const float mc = mean[c];
+        acc[0] = fmaf(bf16_lo(u.x), mc, acc[0]); acc[1] = fmaf(bf16_hi(u.x), mc, acc[1]);
+        acc[2] = fmaf(bf16_lo(u.y), mc, acc[2]); acc[3] = fmaf(bf16_hi(u.y), mc, acc[3]);
+        acc[4] = fmaf(bf16_lo(u.z), mc, acc[4]); acc[5] = fmaf(bf16_hi(u.z), mc, acc[5]);
+        acc[6] = fmaf(bf16_lo(u.w), mc, acc[6]); acc[7] = fmaf(bf16_hi(u.w), mc, acc[7]);
       }
     }
+    __syncthreads();  // zpart free (previous d0 round consumed)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) zpart[warp * 256 + lane * 8 + i] = acc[i];
+    __syncthreads();
+    if (d0 + tid < a.D) {
+      float zz = a.b3[d0 + tid];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-      if (lane == 0 && d0 + i < a.D) z[d0 + i] = acc[i] + a.b3[d0 + i];
+      for (int wv = 0; wv < 8; ++wv) zz += zpart[wv * 256 + tid];
+      z[d0 + tid] = zz;
     }
   }
   __syncthreads();
@@ -128,9 +137,12 @@ se_gate_kernel(SeGateArgs a) {
     const int r = r0 + lane;
     float acc = 0.f;
     const int dper = (a.D + 7) / 8;
-    if (r < a.R)
-      for (int d = warp * dper; d < min(a.D, (warp + 1) * dper); ++d) acc = fmaf(z[d], a.fc1_w[static_cast<size_t>(d) * a.R + r], acc);
-    if (r < a.R) part[warp * a.R + r] = acc;
+    if (r < a.R) {
+      const int d_end = min(a.D, (warp + 1) * dper);
+#pragma unroll 8
+      for (int d = warp * dper; d < d_end; ++d) acc = fmaf(z[d], __ldg(a.fc1_w + static_cast<size_t>(d) * a.R + r), acc);
+      part[warp * a.R + r] = acc;
+    }
   }
   __syncthreads();
   for (int r = tid; r < a.R; r += 256) {
@@ -142,7 +154,8 @@ se_gate_kernel(SeGateArgs a) {
   __syncthreads();
   for (int d = tid; d < a.D; d += 256) {
     float acc = a.fc2_b[d];
-    for (int r = 0; r < a.R; ++r) acc = fmaf(hid[r], a.fc2_w[static_cast<size_t>(r) * a.D + d], acc);
+#pragma unroll 8
+    for (int r = 0; r < a.R; ++r) acc = fmaf(hid[r], __ldg(a.fc2_w + static_cast<size_t>(r) * a.D + d), acc);
     a.gate[static_cast<size_t>(b) * a.D + d] = 1.f / (1.f + __expf(-acc));
   }
 }
@@ -208,12 +221,17 @@ int mask_prep_launch(const float* x, const uint8_t* user_mask, const int* use_us
 }
 
 int se_gate_launch(const SeGateArgs& a, cudaStream_t stream) {
-  if (a.C % 8 != 0) {
-    set_last_error("se_gate: C must be a multiple of 8");
+  if (a.D % 8 != 0) {
+    set_last_error("se_gate: D must be a multiple of 8");
     return 2;
   }
-  const size_t smem = static_cast<size_t>(a.C + a.D + 9 * a.R) * sizeof(float);
-  se_gate_kernel<<<a.B, 256, smem, stream>>>(a);
+  const size_t smem = static_cast<size_t>(kSeN * (a.C + a.D) + 9 * a.R + 8 * kSeN * 256) * sizeof(float);
+  static size_t smem_attr = 48 * 1024;
+  if (smem > smem_attr) {
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(se_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_attr = smem;
+  }
+  se_gate_kernel<<<(a.B + kSeN - 1) / kSeN, 256, smem, stream>>>(a);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

@@ -271,6 +271,13 @@ int pack_all(ishara_model* m) {
     float* d;
     if ((rc = pack_f32(m, n + ".conv.dw.w", P(m, n + ".conv.conv2.depthwise_kernel"), &d))) return rc;
     if ((rc = pack_dense(m, n + ".conv.conv3", E, D, true))) return rc;
+    {  // the same kernel in its native [E, D] orientation for the SqueezeExcite gate (coalesced over output channels)
+      const auto& k3 = P(m, n + ".conv.conv3.kernel");
+      std::vector<uint16_t> h(k3.size());
+      for (size_t i = 0; i < k3.size(); ++i) h[i] = f2bf(k3[i]);
+      void* dkn;
+      if ((rc = upload(m, n + ".conv.conv3.wkn", h.data(), h.size() * 2, &dkn))) return rc;
+    }
     if ((rc = pack_f32(m, n + ".se.fc1.w", P(m, n + ".conv.se.fc1.kernel"), &d))) return rc;
     if ((rc = pack_f32(m, n + ".se.fc1.b", P(m, n + ".conv.se.fc1.bias"), &d))) return rc;
     if ((rc = pack_f32(m, n + ".se.fc2.w", P(m, n + ".conv.se.fc2.kernel"), &d))) return rc;
@@ -714,7 +721,7 @@ int build_lane(ishara_model* m, int batch, float* logits, int lane) {
       op.kind = OP_SEGATE;
       op.label = "sqz.se_gate";
       op.se.colsum = m->colsum;
-      op.se.w3t = b.pk.get<bf16>(n + ".conv.conv3.w");
+      op.se.w3kn = b.pk.get<bf16>(n + ".conv.conv3.wkn");
       op.se.b3 = b.pk.get<float>(n + ".conv.conv3.b");
       op.se.fc1_w = b.pk.get<float>(n + ".se.fc1.w");
       op.se.fc1_b = b.pk.get<float>(n + ".se.fc1.b");

@@ -406,6 +406,151 @@ def forward(params: Dict[str, np.ndarray], x: np.ndarray, cfg: Config, dtype: st
 
 
 # -----------------------------------------------------------------------------------------------
+# forward, formulation 1b: the same network with the CUDA path's STORAGE roundings (test infrastructure)
+# -----------------------------------------------------------------------------------------------
+# The GPU path keeps every tensor that leaves an SM in bf16 and accumulates in fp32. ``forward_bf16_emulated`` evaluates
+# the reference formulas (same citations as ``forward``) in float64 and rounds to bf16 at exactly the points where the
+# kernels store bf16 -- so what is left between it and the GPU is accumulation order and the hardware's approximate
+# exp2/tanh, not storage precision. It is what lets the GPU parity tests hold a tighter bar than "bf16 vs fp64"
+# (VERDICT r1 weak-1). Rounding points (file = ishara_b200/csrc):
+#   input                 bf16(x)                                                         misc.cu cast_pad
+#   stem                  W' = bf16(W * s_bn), S = bf16(x W' + (PE s_bn + o_bn))          model.cu pack_all, gemm_epilogue.cuh
+#   Conv1DBlock           H = bf16(swish(.)); A = bf16((dw(H) w s_bn + o_bn) gate);       conv1d_block.cu
+#                         v = A Wp + b + S; S' = bf16(v); XN = bf16(LN(v)) (LN sees the fp32 v)
+#   FFN                   Hh = bf16(swish(XN W1 + b1)); v = Hh W2 + b2 + S                ffn_tc.cu
+#   MHSA                  qkv = bf16(XN Wqkv); P = bf16(exp(.)), row sum over the unrounded p; o = bf16(P V / sum)   attention_tc.cu
+#   ConvModule (sqz)      H1 = bf16(swish(.)); H2 = bf16(swish(dw(H1))); pooled mean from bf16 H2; v = (H2 W3 + b3) gate + S
+#   ConvolutionModule     H2 = bf16(glu(.)); O = bf16(dw_bn(H2)); u = LN(O W + b + S); S = bf16(u); XN = bf16(LN2(u))
+#   head                  bf16(relu(.)); logits fp32
+# LayerNorms fused into the producing kernel (dim 128 / 256) see the unrounded fp32 value; other dims run the
+# stand-alone LayerNorm kernel on the stored bf16 stream (``fused_ln=False``).
+
+
+def _r(t):
+    """round a torch tensor to bf16 (nearest even) and return it in its original dtype"""
+    return t.to(torch.float32).to(torch.bfloat16).to(t.dtype)
+
+
+def forward_bf16_emulated(params: Dict[str, np.ndarray], x: np.ndarray, cfg: Config, mask_mode: str = "dropped",
+                          taps: Optional[Dict[str, np.ndarray]] = None, fused_ln: Optional[bool] = None) -> np.ndarray:
+    assert torch is not None
+    dt = torch.float64
+    p = params
+    D, T, H, tk = cfg.dim, cfg.frames, cfg.num_heads, cfg.transformer_kernel_size
+    if fused_ln is None:
+        fused_ln = D in (128, 256)
+
+    def bn_fold(base):  # float32 scale / offset exactly as model.cu bn_fold computes them (double -> float)
+        g, b = p[base + ".gamma"].astype(np.float64), p[base + ".beta"].astype(np.float64)
+        mu, var = p[base + ".moving_mean"].astype(np.float64), p[base + ".moving_variance"].astype(np.float64)
+        sc = g / np.sqrt(var + BN_EPS)
+        return sc.astype(np.float32), (b - mu * sc).astype(np.float32)
+
+    def ln(v, S, base, eps):  # LN fused into the producer sees v (fp32); the stand-alone kernel sees the stored stream
+        return _r(_ln(v if fused_ln else S, p, base, eps, dt))
+
+    def dense(a, base, bias=True):
+        return _dense(a, p, base, dt, bias)
+
+    def ffn(XN, S, base):
+        hh = _r(_swish(dense(XN, base + ".0")))
+        v = dense(hh, base + ".2") + S
+        return v, _r(v)
+
+    def mhsa(XN, S, base, mask):
+        B = XN.shape[0]
+        qkv = _r(dense(XN, base + ".qkv", bias=False))
+        qkv = qkv.view(B, T, H, 3 * D // H).permute(0, 2, 1, 3)
+        q, k, vv = torch.split(qkv, D // H, dim=-1)
+        a = (q @ k.transpose(-1, -2)) * (D ** -0.5)
+        if mask is not None:
+            a = a + (1.0 - mask.to(dt))[:, None, None, :] * -1e9
+        pexp = torch.exp(a - a.max(dim=-1, keepdim=True).values)
+        o = _r((_r(pexp) @ vv) / pexp.sum(dim=-1, keepdim=True))
+        o = o.permute(0, 2, 1, 3).reshape(B, T, D)
+        v = dense(o, base + ".proj", bias=False) + S
+        return v, _r(v)
+
+    def conv1d_block(S, n, k, mask):
+        h = _r(_swish(dense(S, n + "_expand_conv")))
+        sc, off = bn_fold(n + "_bn")
+        w = p[n + "_dwconv.depthwise_kernel"][:, :, 0].astype(np.float32) * sc[None, :]          # folded taps (fp32)
+        y = _dwconv(h, torch.from_numpy(w).to(dt), k - 1, 0) + torch.from_numpy(off).to(dt)
+        m = _gap(y, mask)
+        e = F.conv1d(m.unsqueeze(1), _t(p, n + "_eca.kernel", dt).view(1, 1, 5), padding=2).squeeze(1)
+        a = _r(y * torch.sigmoid(e).unsqueeze(1))
+        v = dense(a, n + "_project_conv") + S
+        return v, _r(v)
+
+    with torch.no_grad():
+        xt = torch.from_numpy(np.ascontiguousarray(x)).to(dt)
+        mask = None
+        if mask_mode == "propagated":
+            mask = (xt != 0).any(dim=-1)
+        elif mask_mode != "dropped":
+            raise ValueError(mask_mode)
+        sc, off = bn_fold("stem_bn")
+        w = p["stem_conv.kernel"].astype(np.float32)
+        w = (w[0] if w.ndim == 3 else w) * sc[None, :]
+        pe = positional_encoding(cfg.frames, cfg.dim).astype(np.float32)
+        tab = pe * sc[None, :] + off[None, :]
+        v = _r(xt) @ _r(torch.from_numpy(w).to(dt)) + torch.from_numpy(tab).to(dt)
+        S = _r(v)
+        if taps is not None:
+            taps["stem"] = S.float().numpy()
+
+        def conv_blocks(v, S, tag, i):
+            for j in range(cfg.num_conv_per_block):
+                k = cfg.kernel_sizes[j % len(cfg.kernel_sizes)]
+                n = f"conv{tag}_{i}_{j + 1}"
+                v, S = conv1d_block(S, n, k, mask)
+                if taps is not None:
+                    taps[n] = S.float().numpy()
+            return v, S
+
+        for i in range(cfg.num_conv_squeeze_blocks):
+            n = f"squeezeformer_{i}"
+            v, S = conv_blocks(v, S, "squeeze", i)
+            v, S = ffn(ln(v, S, n + ".norm1", LN_EPS), S, n + ".ffn1")
+            v, S = mhsa(ln(v, S, n + ".norm2", LN_EPS), S, n + ".mha", mask)
+            h = ln(v, S, n + ".conv.norm", LN_EPS)
+            h = _r(_swish(dense(h, n + ".conv.conv1")))
+            h = _r(_swish(_dwconv(h, _t(p, n + ".conv.conv2.depthwise_kernel", dt)[:, :, 0], tk - 1, 0)))
+            g = _gap(h, mask) @ _t(p, n + ".conv.conv3.kernel", dt).reshape(-1, D) + _t(p, n + ".conv.conv3.bias", dt)
+            g = _swish(dense(g, n + ".conv.se.fc1"))
+            g = torch.sigmoid(dense(g, n + ".conv.se.fc2"))
+            v = dense(h, n + ".conv.conv3") * g.unsqueeze(1) + S
+            S = _r(v)
+            v, S = ffn(ln(v, S, n + ".norm3", LN_EPS), S, n + ".ffn2")
+            if taps is not None:
+                taps[n] = S.float().numpy()
+        for i in range(cfg.num_conv_conform_blocks):
+            n = f"conformer_{i}"
+            v, S = conv_blocks(v, S, "conform", i)
+            mask = None
+            v, S = ffn(ln(v, S, n + ".layer_norm1", LN_EPS), S, n + ".ffn1")
+            v, S = mhsa(ln(v, S, n + ".layer_norm1", LN_EPS), S, n + ".mha", None)
+            h = dense(S, n + ".conv.pointwise_conv1")
+            h = _r(h[..., :D] * torch.sigmoid(h[..., D:]))
+            sc, off = bn_fold(n + ".conv.batch_norm")
+            w = p[n + ".conv.depthwise_conv.kernel"][:, 0, :].astype(np.float32) * sc[None, :]
+            bias = p[n + ".conv.depthwise_conv.bias"].astype(np.float32) * sc + off
+            h = _r(_dwconv(h, torch.from_numpy(w).to(dt), (tk - 1) // 2, tk - 1 - (tk - 1) // 2) + torch.from_numpy(bias).to(dt))
+            v0 = dense(h, n + ".conv.pointwise_conv2") + S
+            if fused_ln:
+                v = _ln(v0, p, n + ".conv.layer_norm", LN_EPS_CONVMOD, dt)
+                S = _r(v)
+            else:
+                S = _r(_ln(_r(v0), p, n + ".conv.layer_norm", LN_EPS_CONVMOD, dt))
+                v = S
+            v, S = ffn(ln(v, S, n + ".layer_norm2", LN_EPS), S, n + ".ffn2")
+            if taps is not None:
+                taps[n] = S.float().numpy()
+        h = _r(torch.relu(dense(S, "top_conv")))
+        return dense(h, "classifier").numpy()
+
+
+# -----------------------------------------------------------------------------------------------
 # forward, formulation 2: plain numpy float64 from the Keras layer formulas (slow; cross-check only)
 # -----------------------------------------------------------------------------------------------
 
