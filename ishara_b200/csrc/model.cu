@@ -486,6 +486,7 @@ struct Builder {
     op.kind = OP_LN;
     op.label = "layernorm";
     op.ln_in = in; op.ln_out = out; op.ln = ln;
+    op.ln_rows = M;
     op.flops = 8.0 * M * D;
     op.bytes = 4.0 * M * D;
     ops.push_back(op);
@@ -1023,7 +1024,7 @@ int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t 
     if ((rc = cast_pad_launch(xl, m->XIN + r0 * m->fpad(), static_cast<int64_t>(bl) * c.frames, c.features, m->fpad(), ls[l]))) return rc;
   }
   if (prof) ISHARA_CUDA_OK(cudaEventRecord(m->events[1], stream));
-  const int64_t M = static_cast<int64_t>(batch) * c.frames;  // OP_LN / OP_TAP only exist in one-lane programs
+  const int64_t M = static_cast<int64_t>(batch) * c.frames;  // OP_TAP only exists in one-lane (debug) programs
   size_t op_index = 0;
   // interleave the lanes' launches so that neither stream runs far ahead of the other on the host side
   std::vector<size_t> next(lanes, 0);
@@ -1043,7 +1044,7 @@ int launch_program(ishara_model* m, const float* x_dev, int batch, cudaStream_t 
         case OP_FFN: rc = ffn_launch(op.ffn, m->num_sms, st); break;
         case OP_C1F: rc = conv1d_front_launch(op.c1f, st); break;
         case OP_C1B: rc = conv1d_block_launch(op.c1b, st); break;
-        case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, M, c.dim, st); break;
+        case OP_LN: rc = layernorm_launch(op.ln_in, op.ln_out, op.ln.g, op.ln.b, op.ln.eps, op.ln_rows, c.dim, st); break;
         case OP_TAP:
           rc = cudaMemcpyAsync(m->taps[op.tap], m->S, M * c.dim * sizeof(bf16), cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : 3;
           break;

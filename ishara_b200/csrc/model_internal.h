@@ -44,6 +44,7 @@ struct Op {
   const bf16* ln_in = nullptr;
   bf16* ln_out = nullptr;
   LnRef ln;
+  int64_t ln_rows = 0;  // rows of this op's (lane's) stream
   int tap = -1;
   int lane = 0;  // sub-batch this op belongs to (model.cu: lanes)
   const char* label = "";

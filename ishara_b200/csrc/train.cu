@@ -75,8 +75,39 @@ struct TrainState {
   // the range of the flat gradient buffer that is final - and reduced - right after that module's backward
   std::vector<int64_t> mod_hi, bucket_lo, bucket_up;
   float* loss_pinned = nullptr;
+  // weight gradients run on a side stream next to the data-gradient GEMM that follows them (both read the same dY and
+  // neither fills the 148 SMs alone at 192 row tiles); the main stream rejoins right after that next step
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
+  bool side_pending = false, last_was_side = false;
   std::shared_ptr<void> builder;  // closures may refer to builder members: it lives as long as the program
 };
+
+// run `fn` on the side stream, ordered after everything enqueued on `s` so far (see TrainState::side)
+template <typename F>
+int side_run(TrainState* ts, cudaStream_t s, F&& fn) {
+  static const int enabled = getenv("ISHARA_WGRAD_SIDE") ? atoi(getenv("ISHARA_WGRAD_SIDE")) : 1;
+  if (!enabled) return fn(s);
+  if (ts->side == nullptr) {
+    ISHARA_CUDA_OK(cudaStreamCreateWithFlags(&ts->side, cudaStreamNonBlocking));
+    ISHARA_CUDA_OK(cudaEventCreateWithFlags(&ts->ev_fork, cudaEventDisableTiming));
+    ISHARA_CUDA_OK(cudaEventCreateWithFlags(&ts->ev_side, cudaEventDisableTiming));
+  }
+  ISHARA_CUDA_OK(cudaEventRecord(ts->ev_fork, s));
+  ISHARA_CUDA_OK(cudaStreamWaitEvent(ts->side, ts->ev_fork, 0));
+  const int rc = fn(ts->side);
+  ISHARA_CUDA_OK(cudaEventRecord(ts->ev_side, ts->side));
+  ts->side_pending = true;
+  ts->last_was_side = true;
+  return rc;
+}
+inline int side_join(TrainState* ts, cudaStream_t s) {
+  if (ts->side_pending) {
+    ISHARA_CUDA_OK(cudaStreamWaitEvent(s, ts->ev_side, 0));
+    ts->side_pending = false;
+  }
+  return 0;
+}
 
 namespace {
 
@@ -229,9 +260,15 @@ struct TB {
       // tcgen05 path: MN-major operands via TMA; the bias gradient rides along (idle epilogue warps sum the G tiles)
       auto plan = std::make_shared<WgradTcPlan>();
       if (!rc) rc = wgrad_tc_plan_init(plan.get(), X, I, Gy, O, MM, I, O, sms);
-      return [=](cudaStream_t s) { return wgrad_tc_launch(plan.get(), dW, Ovalid, db, Ivalid, Ovalid, s); };
+      TrainState* t = ts;
+      return [=](cudaStream_t s) {
+        return side_run(t, s, [&](cudaStream_t q) { return wgrad_tc_launch(plan.get(), dW, Ovalid, db, Ivalid, Ovalid, q); });
+      };
     }
-    return [=](cudaStream_t s) { return wgrad_launch(X, I, Gy, O, dW, Ovalid, db, MM, I, O, Ivalid, Ovalid, sms, s); };
+    TrainState* t = ts;
+    return [=](cudaStream_t s) {
+      return side_run(t, s, [&](cudaStream_t q) { return wgrad_launch(X, I, Gy, O, dW, Ovalid, db, MM, I, O, Ivalid, Ovalid, sms, q); });
+    };
   }
   Step ln_fwd(const bf16* x, bf16* out, const std::string& base, float eps) {
     const float *g = W(base + ".gamma"), *b = W(base + ".beta");
@@ -299,12 +336,17 @@ struct TB {
     // steps were appended in execution order for this module's backward; the global list runs modules in reverse
     if (ts->debug && !in_name.empty()) snap(steps, in_name, din(), D);
     auto packed = std::make_shared<std::vector<Step>>(std::move(steps));
-    ts->bwd.push_back([packed](cudaStream_t s) {
+    TrainState* t = ts;
+    ts->bwd.push_back([packed, t](cudaStream_t s) {
       for (auto& st : *packed) {
-        const int r = st(s);
+        t->last_was_side = false;
+        int r = st(s);
+        // a weight gradient went to the side stream: the step after it (the data gradient of the same dY) runs beside
+        // it, then the main stream waits - nothing later may overwrite the dY the side stream is still reading
+        if (!r && !t->last_was_side) r = side_join(t, s);
         if (r) return r;
       }
-      return 0;
+      return side_join(t, s);  // module boundary: gradients final for the bucket exchange, scratch buffers reusable
     });
     ts->mod_hi.push_back(touch_hi);
     touch_hi = 0;
@@ -926,6 +968,7 @@ void train_destroy(ishara_model* m) {
   if (ts->slow) cudaFree(ts->slow);
   if (ts->repack_dev) cudaFree(ts->repack_dev);
   if (ts->loss_pinned) cudaFreeHost(ts->loss_pinned);
+  if (ts->side) { cudaStreamSynchronize(ts->side); cudaStreamDestroy(ts->side); cudaEventDestroy(ts->ev_fork); cudaEventDestroy(ts->ev_side); }
   delete ts;
   m->train = nullptr;
 }

@@ -43,6 +43,7 @@ VARIANTS = {
     "gemm_resid_ldg": {"ISHARA_GEMM_RESID_TMA": "0"},         # per-thread residual loads instead of TMA-staged residual boxes
     "ffn_unfused": {"ISHARA_FFN_FUSED": "0"},
     "no_graph": {"ISHARA_GRAPH": "0"},
+    "lanes_3": {"ISHARA_LANES": "3", "ISHARA_LANES_MIN_BATCH": "2"},   # 40 sequences as 13 + 13 + 14 on three parallel graph branches
 }
 
 
@@ -72,6 +73,42 @@ def test_opt_in_variants_match_oracle_and_default(tmp_path):
     assert np.array_equal(outs["no_graph"], base)
     assert np.array_equal(outs["gemm_resident"], base)
     assert np.array_equal(outs["gemm_pair"], base)
+    assert np.array_equal(outs["lanes_3"], base)      # lanes only re-partition the batch: every kernel is per-sequence
+
+
+LANES_SNIPPET = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+import ishara_b200 as ib
+from oracle import ishara_oracle as O
+# dim 192 / head dim 48: the general kernels (three-kernel Conv1DBlock, two-GEMM FFN, stand-alone LayerNorm, mma.sync attention)
+cfg = O.Config(dim=192, num_heads=4, frames=128, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
+params = O.init_params(cfg, seed=4)
+m = ib.get_model(dim=192, num_heads=4, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, input_shape=(128, 20)).load_weights(params)
+x = O.make_inputs(cfg, 7, seed=9)
+got = m(x)
+assert np.array_equal(got, m(x))
+ref = O.forward(params, x[:2], cfg, "float64")
+assert np.abs(got[:2] - ref).max() / np.abs(ref).max() < 3e-2
+np.save(sys.argv[1], got)
+""" % ROOT
+
+
+def test_lanes_on_the_general_kernel_path(tmp_path):
+    """Sub-batch lanes with the kernels that dim != 256 selects (incl. the stand-alone LayerNorm, which takes its row count
+    from the lane): 7 sequences as 3 + 4 on two graph branches == one lane, bit for bit."""
+    import numpy as np
+
+    outs = {}
+    for name, env_extra in (("one", {"ISHARA_LANES": "1"}), ("two", {"ISHARA_LANES": "2", "ISHARA_LANES_MIN_BATCH": "2"})):
+        out = tmp_path / f"lanes_{name}.npy"
+        env = {k: v for k, v in os.environ.items() if not k.startswith("ISHARA_")}
+        env.update(env_extra)
+        r = subprocess.run([sys.executable, "-c", LANES_SNIPPET, str(out)], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, f"{name}: {r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+        outs[name] = np.load(out)
+    assert np.array_equal(outs["one"], outs["two"])
 
 
 TRAIN_SNIPPET = r"""

@@ -187,3 +187,22 @@ def test_keras_layer_table_covers_every_parameter_once():
     assert table["squeezeformer_0"][0][0] == "squeezeformer_0.norm1.gamma" and table["squeezeformer_0"][0][-1] == "squeezeformer_0.ffn2.2.bias"
     assert table["conformer_0"][0][-4:] == ["conformer_0.layer_norm1.gamma", "conformer_0.layer_norm1.beta",
                                             "conformer_0.layer_norm2.gamma", "conformer_0.layer_norm2.beta"]
+
+
+def test_bf16_emulated_forward_is_the_same_function_up_to_storage_rounding():
+    """forward_bf16_emulated = forward + bf16 roundings at the CUDA path's storage points: it must stay within bf16-level
+    distance of the fp64 forward (both mask modes) and be exactly reproducible."""
+    import numpy as np
+    from oracle import ishara_oracle as O
+    cfg = O.Config(dim=128, num_heads=4, frames=64, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
+    p = O.init_params(cfg, seed=3)
+    for mode, ragged in (("dropped", False), ("propagated", True)):
+        x = O.make_inputs(cfg, 2, seed=5, ragged=ragged)
+        ref = O.forward(p, x, cfg, "float64", mask_mode=mode)
+        emu = O.forward_bf16_emulated(p, x, cfg, mask_mode=mode)
+        assert np.array_equal(emu, O.forward_bf16_emulated(p, x, cfg, mask_mode=mode))
+        rel = np.abs(emu - ref).max() / np.abs(ref).max()
+        assert 1e-5 < rel < 3e-2, rel          # not identical (roundings are really applied), not a different function
+    # the rounding helper: nearest-even to 8 significant bits
+    t = O.torch.tensor([1.0, 1.00390625, 1.005859375, 1.01171875, -3.1415926], dtype=O.torch.float64)
+    assert O._r(t).tolist() == [1.0, 1.0, 1.0078125, 1.015625, -3.140625]
