@@ -39,10 +39,17 @@ struct FfnBars {
   uint32_t tmem_slot;
 };
 
-__global__ void __launch_bounds__(384, 1)
+// EW = epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter). With 8 the epilogue warps were the
+// critical resource - 4 x swish quarter + the full-row residual / LayerNorm pass took ~2/3 of the 31k-cycle tile period
+// against 8k cycles of MMA; 16 warps halve every pass and give each scheduler four warps to hide tcgen05.ld latency.
+//   EW = 16: warp (q4, c) owns rows [32 q4, +32) and, of a 128-column hidden quarter, the 32 columns [32c, +32); in the
+//   final epilogue the 64-column box c of the 256-wide output, staged through a 2 KB half box (the H bytes).
+template <int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO0,
-              const __grid_constant__ CUtensorMap tmO1, const GemmEpi ep, const float* __restrict__ bias1, int M, int E,
+              const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO0h,
+              const __grid_constant__ CUtensorMap tmO1h, const GemmEpi ep, const float* __restrict__ bias1, int M, int E,
               int num_m_tiles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -72,12 +79,12 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->acc1_full[i], 1);
-      mbar_init(&bars->acc1_empty[i], 8);
+      mbar_init(&bars->acc1_empty[i], EW);
     }
-    mbar_init(&bars->h_full, 8);
+    mbar_init(&bars->h_full, EW);
     mbar_init(&bars->h_empty, 1);
     mbar_init(&bars->acc2_full, 1);
-    mbar_init(&bars->acc2_empty, 8);
+    mbar_init(&bars->acc2_empty, EW);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_slot, 512);
@@ -184,8 +191,89 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       }
     }
+  } else if (warp >= 4 && EW == 16) {
+    // ===================== 16 epilogue warps =====================
+    const int q4 = warp & 3;         // TMEM lane quarter
+    const int c = (warp - 4) >> 2;   // 32-column slice of a hidden quarter / 64-column box of the output tile
+    float2* xch2 = reinterpret_cast<float2*>(xch);
+    float* cvec = reinterpret_cast<float*>(xch) + 2048;   // [5][256]: b2 | ln0 g | ln0 b | ln1 g | ln1 b
+    float* b1s = cvec + 5 * 256;                          // [E] first-layer bias (E <= 768, ffn_applicable)
+    {
+      const int t16 = static_cast<int>(threadIdx.x) - 128;
+      for (int i = t16; i < 5 * 256; i += 512) {
+        const int which = i >> 8, col = i & 255;
+        const float* src = which == 0 ? ep.bias : which == 1 ? ep.ln0_g : which == 2 ? ep.ln0_b : which == 3 ? ep.ln1_g : ep.ln1_b;
+        cvec[i] = src != nullptr ? __ldg(src + col) : 0.f;
+      }
+      for (int i = t16; i < E; i += 512) b1s[i] = __ldg(bias1 + i);
+      named_bar_sync(5, 512);
+    }
+    WarpStore st;
+    st.single = true;
+    st.base = smem_u32(h_ptr) + static_cast<uint32_t>(warp - 4) * (kWarpStgBytes / 2);  // 2 KB half box inside the H bytes
+    st.iter = 0;
+    st.lane = lane;
+    Row16State rst;
+    // this warp's slice of an H quarter: k-block c / 2 of H, rows [32 q4, +32), 64-byte half c % 2 of every 128-byte row
+    const uint32_t hbox = smem_u32(h_ptr) + static_cast<uint32_t>((c >> 1) * 4 + q4) * kWarpStgBytes;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    uint32_t n_q = 0;  // running count of processed quarters
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * kBM + q4 * 32;
+      EpiThread th;
+      th.row = row0 + lane;
+      th.valid = th.row < M;
+      th.seq = th.valid ? th.row / ep.rows_per_seq : 0;
+      th.t = th.valid ? th.row - th.seq * ep.rows_per_seq : 0;
+      th.taddr = tmem_acc2 + lane_addr;
+      for (int q = 0; q < nq; ++q, ++n_q) {
+        const uint32_t buf = n_q & 1;
+        mbar_wait(&bars->acc1_full[buf], (n_q >> 1) & 1);
+        tc_fence_after();
+        if (n_q > 0) mbar_wait(&bars->h_empty, (n_q - 1) & 1);
+        if (q == 0 && it > 0) {
+          // the previous tile's output stores staged through the H bytes - any warp's half box may overlap the bytes this
+          // warp is about to write, so every warp's stores must have been read before anyone continues
+          if (lane == 0) tma_store_wait_read<0>();
+          named_bar_sync(6, 512);
+        }
+        {
+          uint32_t raw[32];
+          float v[32];
+          const int tc = c * 32;
+          tmem_ld32(tmem_base + buf * kFQ + lane_addr + tc, raw);
+          tmem_ld_wait();
+          to_float(v, raw);
+          const float* bq = b1s + q * kFQ + tc;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = *reinterpret_cast<const float4*>(bq + 4 * j);
+            fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], bb.x, bb.y);
+            fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], bb.z, bb.w);
+          }
+          epi_swish(v);
+          stage_write<false>(hbox, lane, c & 1, v);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->acc1_empty[buf]);
+          mbar_arrive(&bars->h_full);
+        }
+      }
+      // ---- final epilogue of the tile: acc2 -> +b2 -> +residual -> [LN] -> S (and LN'(S)) ----
+      mbar_wait(&bars->acc2_full, it & 1);  // every GEMM2 of the tile has retired: the H bytes are free for staging
+      tc_fence_after();
+      epilogue_row16<true>(ep, th, row0, q4, c, lane, st, &tmO0h, &tmO1h, xch2, cvec, rst, nullptr, 0u);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc2_empty);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
   } else if (warp >= 4) {
-    // ===================== epilogue warps =====================
+    // ===================== 8 epilogue warps =====================
     const int q4 = warp & 3;         // TMEM lane quarter
     const int h = (warp - 4) >> 2;   // which 64-column box of a 128-column quarter / alternate boxes of the final tile
     WarpStore st;
@@ -266,7 +354,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 bool ffn_applicable(int D, int E, int M, int num_sms) {
   (void)num_sms;
-  return D == kFD && E % kFQ == 0 && E >= 2 * kFQ && M >= 1;
+  return D == kFD && E % kFQ == 0 && E >= 2 * kFQ && E <= 768 && M >= 1;  // E <= 768: the first-layer bias is kept in shared memory
 }
 
 // plan->tmA: XN [M, 256]; tmW1: W1^T [E, 256] box [128 x 64]; tmW2: W2^T [256, E] box [256 x 64]; tmO0 / tmO1: S / LN'(S)
@@ -281,6 +369,12 @@ int ffn_plan_init(FfnPlan* p, const bf16* xn, const bf16* w1t, const bf16* w2t, 
   } else {
     p->tmO1 = p->tmO0;
   }
+  if ((rc = make_tmap_2d(&p->tmO0h, out0, TM_BF16, p->M, kFD, kFD, 32, 32))) return rc;
+  if (out1 != nullptr) {
+    if ((rc = make_tmap_2d(&p->tmO1h, out1, TM_BF16, p->M, kFD, kFD, 32, 32))) return rc;
+  } else {
+    p->tmO1h = p->tmO0h;
+  }
   return 0;
 }
 
@@ -288,12 +382,17 @@ int ffn_launch(const FfnPlan& p, int num_sms, cudaStream_t stream) {
   const int smem = kFA1Bytes + kFHBytes + kFStages * kFSlot + kXchBytes + 256 + 1024;
   static bool attr = false;
   if (!attr) {
-    ISHARA_CUDA_OK(cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(ffn_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(ffn_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
+  static const int ew16 = getenv("ISHARA_FFN_EW16") ? atoi(getenv("ISHARA_FFN_EW16")) : 1;
   const int mt = (p.M + kBM - 1) / kBM;
   const int grid = mt < num_sms ? mt : num_sms;
-  ffn_tc_kernel<<<grid, 384, smem, stream>>>(p.tmA, p.tmW1, p.tmW2, p.tmO0, p.tmO1, p.epi, p.bias1, p.M, p.E, mt);
+  if (ew16)
+    ffn_tc_kernel<16><<<grid, 640, smem, stream>>>(p.tmA, p.tmW1, p.tmW2, p.tmO0, p.tmO1, p.tmO0h, p.tmO1h, p.epi, p.bias1, p.M, p.E, mt);
+  else
+    ffn_tc_kernel<8><<<grid, 384, smem, stream>>>(p.tmA, p.tmW1, p.tmW2, p.tmO0, p.tmO1, p.tmO0h, p.tmO1h, p.epi, p.bias1, p.M, p.E, mt);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

@@ -433,6 +433,205 @@ __device__ __forceinline__ void epilogue_box16(const GemmEpi& ep, const EpiThrea
   st.release(tmO0, buf, n_tile * cols_out + c * 64, row0);
 }
 
+// 16-epilogue-warp FULL-ROW variant (BN = 256 = the whole model dimension): warp (q, c) owns rows [32q, +32) and the ONE
+// 64-column box c, lane == row. Same dataflow as epilogue_tile's row mode - (bias, gate, rowtab, residual) -> [LN0] -> out0
+// -> [LN1 -> out1], values parked in TMEM between passes - but each pass is half as long per warp and four warps per
+// scheduler hide the tcgen05.ld / shared-memory latencies that two could not (the 8-warp epilogue paced these GEMMs at
+// 15-24k cycles per tile against 2-4k cycles of MMA). One staging box per warp: the residual box lands in it by TMA, is
+// read into registers, and the same bytes then stage out0 and, after that store has been read, out1.
+//   cvec: [5][256] floats in shared memory: bias | ln0 gamma | ln0 beta | ln1 gamma | ln1 beta (zeros where absent)
+//   xch:  [2 slots][4 q][4 c][32] float2 row-statistics exchange; slots alternate per exchange, so a slot is rewritten
+//         only after a later named barrier that every reader of its previous contents has already passed
+struct Row16State {
+  uint32_t xc = 0;  // exchanges done so far by this warp (selects the slot)
+};
+__device__ __forceinline__ void row16_exchange(RowStats& rs, float2* xch, Row16State& rst, int q, int c, int lane, float eps,
+                                               float* mean, float* rstd) {
+  float2* slot = xch + (rst.xc & 1u) * 512;
+  ++rst.xc;
+  slot[(q * 4 + c) * 32 + lane] = make_float2(rs.s0 + rs.s1, rs.q0 + rs.q1);
+  named_bar_sync(1 + q, 128);
+  float s = 0.f, qq = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const float2 o = slot[(q * 4 + cc) * 32 + lane];
+    s += o.x;
+    qq += o.y;
+  }
+  const float m = s * (1.f / 256.f);
+  const float var = fmaxf(qq * (1.f / 256.f) - m * m, 0.f);
+  *mean = m;
+  *rstd = rsqrtf(var + eps);
+}
+__device__ __forceinline__ void row16_layernorm(float (&v)[32], const float* g_s, const float* b_s, float mean, float rstd) {
+  const float nm = -mean * rstd;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 gg = *reinterpret_cast<const float4*>(g_s + 4 * j);
+    const float4 bb = *reinterpret_cast<const float4*>(b_s + 4 * j);
+    float x0, x1, x2, x3;
+    ffma2(x0, x1, v[4 * j + 0], v[4 * j + 1], rstd, rstd, nm, nm);
+    ffma2(x2, x3, v[4 * j + 2], v[4 * j + 3], rstd, rstd, nm, nm);
+    ffma2(v[4 * j + 0], v[4 * j + 1], x0, x1, gg.x, gg.y, bb.x, bb.y);
+    ffma2(v[4 * j + 2], v[4 * j + 3], x2, x3, gg.z, gg.w, bb.z, bb.w);
+  }
+}
+// 32 values of this thread's row into a HALF staging box (32 rows x 64 bytes, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk
+// index XOR-ed with (row / 2) % 4)
+__device__ __forceinline__ void stage_write_half(uint32_t stg, int r, const float (&v)[32]) {
+  const uint32_t rowbase = stg + static_cast<uint32_t>(r) * 64u;
+  const uint32_t x = static_cast<uint32_t>(r >> 1) & 3u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(rowbase + ((static_cast<uint32_t>(j) ^ x) << 4), pack_bf16x2(v[8 * j + 0], v[8 * j + 1]),
+                 pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                 pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+}
+// resid_bar != nullptr: the residual box of this warp was requested by TMA into its staging box (phase = tile parity)
+// HALF: the warp's staging box is 2 KB (32 rows x 32 columns; tmO0 / tmO1 are the matching [32 x 32] maps): every
+// 32-column chunk is staged and stored on its own (ffn_tc.cu, where 16 full boxes do not fit beside the weight ring)
+template <bool HALF = false>
+__device__ __forceinline__ void epilogue_row16(const GemmEpi& ep, const EpiThread& th, int row0, int q, int c, int lane,
+                                               WarpStore& st, const CUtensorMap* tmO0, const CUtensorMap* tmO1, float2* xch,
+                                               const float* cvec, Row16State& rst, uint64_t* resid_bar, uint32_t resid_phase) {
+  const bool ln0 = ep.ln0_g != nullptr, ln1 = ep.ln1_g != nullptr;
+  const uint32_t stg = st.base;
+  uint4 rq[8];
+  if (resid_bar != nullptr) {
+    mbar_wait(resid_bar, resid_phase);
+    const uint32_t rb = stg + static_cast<uint32_t>(lane) * 128u, xr = static_cast<uint32_t>(lane & 7);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(rq[j].x), "=r"(rq[j].y), "=r"(rq[j].z), "=r"(rq[j].w)
+                   : "r"(rb + ((static_cast<uint32_t>(j) ^ xr) << 4))
+                   : "memory");
+  } else if (ep.resid != nullptr && th.valid) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(ep.resid + static_cast<size_t>(th.row) * ep.ld_resid + c * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rq[j] = __ldg(r4 + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rq[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  RowStats rs;
+  if (!HALF && !ln0 && resid_bar == nullptr) st.acquire();  // the box was last read by the previous tile's out1 / out0 store
+  // ---- pass A ----
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub) {
+    const int col = c * 64 + sub * 32;
+    uint32_t raw[32];
+    float v[32];
+    tmem_ld32(th.taddr + col, raw);
+    tmem_ld_wait();
+    to_float(v, raw);
+    if (ep.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(cvec + col + 4 * j);
+        fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], bb.x, bb.y);
+        fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], bb.z, bb.w);
+      }
+    }
+    if (ep.gate != nullptr && th.valid) {
+      const float4* g4 = reinterpret_cast<const float4*>(ep.gate + static_cast<size_t>(th.seq) * 256 + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 g = __ldg(g4 + j);
+        fmul2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], g.x, g.y);
+        fmul2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], g.z, g.w);
+      }
+    }
+    if (ep.rowtab != nullptr && th.valid) {
+      const float4* t4 = reinterpret_cast<const float4*>(ep.rowtab + static_cast<size_t>(th.t) * 256 + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 g = __ldg(t4 + j);
+        fadd2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], g.x, g.y);
+        fadd2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], g.z, g.w);
+      }
+    }
+    if (ep.act == ACT_SWISH) epi_swish(v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 r4 = rq[4 * sub + j];
+      fadd2(v[8 * j + 0], v[8 * j + 1], v[8 * j + 0], v[8 * j + 1], bf16_lo(r4.x), bf16_hi(r4.x));
+      fadd2(v[8 * j + 2], v[8 * j + 3], v[8 * j + 2], v[8 * j + 3], bf16_lo(r4.y), bf16_hi(r4.y));
+      fadd2(v[8 * j + 4], v[8 * j + 5], v[8 * j + 4], v[8 * j + 5], bf16_lo(r4.z), bf16_hi(r4.z));
+      fadd2(v[8 * j + 6], v[8 * j + 7], v[8 * j + 6], v[8 * j + 7], bf16_lo(r4.w), bf16_hi(r4.w));
+    }
+    if (ln0 || ln1) {
+      rs.add(v);
+      to_raw(raw, v);
+      tmem_st32(th.taddr + col, raw);
+    }
+    if (!ln0) {
+      if constexpr (HALF) {
+        st.acquire();
+        stage_write_half(stg, lane, v);
+        st.release(tmO0, stg, col, row0);
+      } else {
+        stage_write<false>(stg, lane, sub, v);
+      }
+    }
+  }
+  if (!HALF && !ln0) st.release(tmO0, stg, c * 64, row0);
+  if (ln0 || ln1) tmem_st_wait();
+  if (ln0) {
+    float mean, rstd;
+    row16_exchange(rs, xch, rst, q, c, lane, ep.ln0_eps, &mean, &rstd);
+    rs = RowStats();
+    if (!HALF && resid_bar == nullptr) st.acquire();
+#pragma unroll 1
+    for (int sub = 0; sub < 2; ++sub) {
+      const int col = c * 64 + sub * 32;
+      uint32_t raw[32];
+      float v[32];
+      tmem_ld32(th.taddr + col, raw);
+      tmem_ld_wait();
+      to_float(v, raw);
+      row16_layernorm(v, cvec + 256 + col, cvec + 512 + col, mean, rstd);
+      if (ln1) {
+        rs.add(v);
+        to_raw(raw, v);
+        tmem_st32(th.taddr + col, raw);
+      }
+      if constexpr (HALF) {
+        st.acquire();
+        stage_write_half(stg, lane, v);
+        st.release(tmO0, stg, col, row0);
+      } else {
+        stage_write<false>(stg, lane, sub, v);
+      }
+    }
+    if (!HALF) st.release(tmO0, stg, c * 64, row0);
+    if (ln1) tmem_st_wait();
+  }
+  if (ln1) {
+    float mean, rstd;
+    row16_exchange(rs, xch, rst, q, c, lane, ep.ln1_eps, &mean, &rstd);
+    if (!HALF) st.acquire();  // the out0 store has finished reading the box
+#pragma unroll 1
+    for (int sub = 0; sub < 2; ++sub) {
+      const int col = c * 64 + sub * 32;
+      uint32_t raw[32];
+      float v[32];
+      tmem_ld32(th.taddr + col, raw);
+      tmem_ld_wait();
+      to_float(v, raw);
+      row16_layernorm(v, cvec + 768 + col, cvec + 1024 + col, mean, rstd);
+      if constexpr (HALF) {
+        st.acquire();
+        stage_write_half(stg, lane, v);
+        st.release(tmO1, stg, col, row0);
+      } else {
+        stage_write<false>(stg, lane, sub, v);
+      }
+    }
+    if (!HALF) st.release(tmO1, stg, c * 64, row0);
+  }
+}
+
 // first residual column a warp needs for a tile (matches the first chunk epilogue_tile processes)
 template <int BN, bool ROW, bool OUT_F32>
 __device__ __forceinline__ int epilogue_first_col(const GemmEpi& ep, int n_tile, int h) {

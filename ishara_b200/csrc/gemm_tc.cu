@@ -71,7 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint64_t* bfull = bars + 2 * STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
-  uint64_t* rbar = bars + 2 * STAGES + 6;  // [8] per epilogue warp: residual boxes landed (row mode, resid_tma)
+  uint64_t* rbar = bars + 2 * STAGES + 6;  // [EW] per epilogue warp: residual boxes landed (row mode, resid_tma)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(&tempty[0], EW);  // one arrive per epilogue warp
     mbar_init(&tempty[1], EW);
     mbar_init(bfull, 1);
-    if (ROW && EW == 8) for (int w = 0; w < 8; ++w) mbar_init(&rbar[w], 1);
+    if (ROW) for (int w = 0; w < EW; ++w) mbar_init(&rbar[w], 1);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -179,6 +179,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     st.skip_store = (ep.dbg & 1) != 0;
     st.skip_fence = (ep.dbg & 16) != 0;
 
+    // 16-warp full-row epilogue: per-column vectors live in shared memory (the xch region: 8 KB exchange + 5 KB vectors)
+    float2* xch2 = reinterpret_cast<float2*>(xch);
+    float* cvec = reinterpret_cast<float*>(xch) + 2048;
+    Row16State rst;
+    if constexpr (ROW && EW == 16) {
+      const int t16 = static_cast<int>(threadIdx.x) - 128;
+      for (int i = t16; i < 5 * 256; i += 512) {
+        const int which = i >> 8, col = i & 255;
+        const float* src = which == 0 ? ep.bias : which == 1 ? ep.ln0_g : which == 2 ? ep.ln0_b : which == 3 ? ep.ln1_g : ep.ln1_b;
+        cvec[i] = src != nullptr ? __ldg(src + col) : 0.f;
+      }
+      named_bar_sync(5, 512);
+    }
+
     int it = 0;
     for (int tile = tile_begin; tile < num_tiles; tile += tile_step, ++it) {
       const uint32_t buf = it & 1;
@@ -209,6 +223,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
         }
       }
+      bool r16_tma = false;
+      if constexpr (ROW && EW == 16) {
+        if (resid_tma && ep.resid != nullptr) {
+          // this warp's residual box: TMA into its staging box once the previous tile's last store has read it
+          r16_tma = true;
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            mbar_arrive_expect_tx(&rbar[warp - 4], kWarpStgBytes);
+            tma_load_2d(stg_ptr + static_cast<uint32_t>(warp - 4) * kWarpStgBytes, &tmR, &rbar[warp - 4], h * 64, row0);
+          }
+          __syncwarp();
+        }
+      }
       if constexpr (EW != 16) {
         if (rsm == 0u) resid_load(rr, ep, th, epilogue_first_col<BN, ROW, OUT_F32>(ep, n_tile, h));  // in flight while the MMAs finish
       }
@@ -217,8 +244,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
       if (!(ep.dbg & 2)) {
-        if constexpr (EW == 16) epilogue_box16<BN>(ep, th, n_tile, N, row0, h, lane, st, &tmO0);
-        else {
+        if constexpr (EW == 16 && ROW) {
+          epilogue_row16(ep, th, row0, q, h, lane, st, &tmO0, &tmO1, xch2, cvec, rst, r16_tma ? &rbar[warp - 4] : nullptr,
+                         static_cast<uint32_t>(it & 1));
+        } else if constexpr (EW == 16) {
+          epilogue_box16<BN>(ep, th, n_tile, N, row0, h, lane, st, &tmO0);
+        } else {
           if constexpr (ROW && EW == 8) {
             if (rsm != 0u) mbar_wait(&rbar[warp - 4], static_cast<uint32_t>(it & 1));
           }
@@ -279,7 +310,7 @@ int launch_inst(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   if (grid > num_sms) grid = num_sms;
   if (RESB) grid = grid / nt * nt;  // every CTA owns exactly one n-tile
   static const int rtma_env = getenv("ISHARA_GEMM_RESID_TMA") ? atoi(getenv("ISHARA_GEMM_RESID_TMA")) : 1;
-  const int rtma = (ROW && EW == 8 && !RESB && p.resid_tma && rtma_env) ? 1 : 0;
+  const int rtma = (ROW && !RESB && p.resid_tma && rtma_env) ? 1 : 0;
   kern<<<grid, 128 + 32 * EW, smem, stream>>>(p.tmA, p.tmB, p.tmO0, p.tmO1, p.tmR, p.epi, p.M, p.N, p.K, mt, nt, stages, rtma);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
@@ -422,8 +453,13 @@ int gemm_launch(const GemmPlan& p_in, int num_sms, cudaStream_t stream) {
 int gemm_launch_inner(const GemmPlan& p, int num_sms, cudaStream_t stream) {
   const bool res = !p.no_resident && resident_fits(p.block_n, p.K) && (p.M + kBM - 1) / kBM * (p.N / p.block_n) >= num_sms;
   if (p.row_mode) {
-    if (p.block_n == 256 && !p.out_f32)
-      return res ? launch_inst<256, true, false, true>(p, num_sms, stream) : launch_inst<256, true, false, false>(p, num_sms, stream);
+    if (p.block_n == 256 && !p.out_f32) {
+      static const int row16 = getenv("ISHARA_GEMM_ROW16") ? atoi(getenv("ISHARA_GEMM_ROW16")) : 1;  // 16-warp full-row epilogue
+      if (res) return launch_inst<256, true, false, true>(p, num_sms, stream);
+      // (the stem's per-row positional table is read per thread: measured 55 us with 16 warps vs 49 us with 8)
+      return row16 && p.epi.rowtab == nullptr ? launch_inst<256, true, false, false, 16>(p, num_sms, stream)
+                                              : launch_inst<256, true, false, false>(p, num_sms, stream);
+    }
     if (p.block_n == 128 && !p.out_f32) return launch_inst<128, true, false, false>(p, num_sms, stream);
   } else {
     if (p.block_n == 256 && !p.out_f32) {

@@ -84,6 +84,7 @@ int gemm_launch(const GemmPlan& p, int num_sms, cudaStream_t stream);
 // ---- fused feed-forward module (ffn_tc.cu): S = [LN0](S + swish(XN @ W1 + b1) @ W2 + b2) [, XN' = LN1(S)] ------
 struct FfnPlan {
   CUtensorMap tmA, tmW1, tmW2, tmO0, tmO1;
+  CUtensorMap tmO0h, tmO1h;    // the same outputs as [32 x 32] boxes (16-warp epilogue: half staging boxes)
   GemmEpi epi;                 // epilogue of the second GEMM: bias = b2, resid, ln0 / ln1
   const float* bias1 = nullptr;  // [E]
   int M = 0, E = 0;

@@ -41,6 +41,8 @@ VARIANTS = {
     "attn_mma_sync": {"ISHARA_ATTN_TC": "0"},
     "attn_tc_v3": {"ISHARA_ATTN_TC2": "0"},                   # one-CTA-per-SM tcgen05 attention instead of the 64-key streaming kernel
     "gemm_resid_ldg": {"ISHARA_GEMM_RESID_TMA": "0"},         # per-thread residual loads instead of TMA-staged residual boxes
+    "gemm_row8": {"ISHARA_GEMM_ROW16": "0"},                   # 8-warp full-row epilogue instead of the 16-warp one
+    "ffn_ew8": {"ISHARA_FFN_EW16": "0"},                       # fused FFN with 8 epilogue warps instead of 16
     "ffn_unfused": {"ISHARA_FFN_FUSED": "0"},
     "no_graph": {"ISHARA_GRAPH": "0"},
     "lanes_3": {"ISHARA_LANES": "3", "ISHARA_LANES_MIN_BATCH": "2"},   # 40 sequences as 13 + 13 + 14 on three parallel graph branches
