@@ -39,6 +39,14 @@ struct FfnBars {
   uint32_t tmem_slot;
 };
 
+// Timeline tracing (profiling builds only: make TRACE=1): clock64 of CTA 60 for its first three tiles, 32 events per tile
+#ifdef ISHARA_TRACE_BUILD
+__device__ long long* g_ffn_trace = nullptr;
+#define FFN_TRACE(it_, ev_) do { if (g_ffn_trace != nullptr && blockIdx.x == 60 && (it_) < 3) g_ffn_trace[(it_) * 32 + (ev_)] = clock64(); } while (0)
+#else
+#define FFN_TRACE(it_, ev_) do { } while (0)
+#endif
+
 // EW = epilogue warps: 8 (two per TMEM lane quarter) or 16 (four per quarter). With 8 the epilogue warps were the
 // critical resource - 4 x swish quarter + the full-row residual / LayerNorm pass took ~2/3 of the 31k-cycle tile period
 // against 8k cycles of MMA; 16 warps halve every pass and give each scheduler four warps to hide tcgen05.ld latency.
@@ -124,6 +132,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int it = 0;
       for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&bars->a1_empty, (it & 1) ^ 1u);
+        FFN_TRACE(it, 0);
         mbar_arrive_expect_tx(&bars->a1_full, kFA1Bytes);
         for (int kb = 0; kb < kFD / kBK; ++kb) tma_load_2d(a1_ptr + kb * kAStageBytes, &tmA, &bars->a1_full, kb * kBK, tile * kBM);
         load_g1(0);
@@ -132,6 +141,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           load_g2(q);
           if (q + 2 < nq) load_g1(q + 2);
         }
+        FFN_TRACE(it, 1);
       }
     }
   } else if (warp == 1) {
@@ -165,13 +175,18 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&bars->a1_full, it & 1);
         tc_fence_after();
+        FFN_TRACE(it, 2);
         issue_g1(0);
+        FFN_TRACE(it, 3);
         if (nq > 1) issue_g1(1);
+        FFN_TRACE(it, 4);
         for (int q = 0; q < nq; ++q) {
           // G2(q): needs H(q) written by the epilogue warps; the first one of a tile also needs acc2 drained
           if (q == 0) mbar_wait(&bars->acc2_empty, (it & 1) ^ 1u);
+          if (q == 0) FFN_TRACE(it, 5);
           mbar_wait(&bars->h_full, n_g2 & 1);
           tc_fence_after();
+          if (q < 4) FFN_TRACE(it, 6 + q);   // H(q) seen
           for (int j = 0; j < 2; ++j) {
             mbar_wait(&bars->w_full[ws], wphase);
             tc_fence_after();
@@ -185,6 +200,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           umma_commit(&bars->h_empty);  // H may be overwritten once these MMAs retire
           ++n_g2;
+          if (q < 4) FFN_TRACE(it, 10 + q);  // G2(q) issued
           if (q == nq - 1) umma_commit(&bars->acc2_full);
           if (q + 2 < nq) issue_g1(q + 2);
           if (q + 2 == nq - 1 || (nq <= 2 && q == 0)) umma_commit(&bars->a1_empty);  // last GEMM1 of the tile issued
@@ -231,7 +247,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t buf = n_q & 1;
         mbar_wait(&bars->acc1_full[buf], (n_q >> 1) & 1);
         tc_fence_after();
+        if (warp == 4 && lane == 0 && q < 4) FFN_TRACE(it, 14 + q);  // acc1(q) seen
         if (n_q > 0) mbar_wait(&bars->h_empty, (n_q - 1) & 1);
+        if (warp == 4 && lane == 0 && q < 4) FFN_TRACE(it, 18 + q);  // H free
         if (q == 0 && it > 0) {
           // the previous tile's output stores staged through the H bytes - any warp's half box may overlap the bytes this
           // warp is about to write, so every warp's stores must have been read before anyone continues
@@ -262,14 +280,17 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           mbar_arrive(&bars->acc1_empty[buf]);
           mbar_arrive(&bars->h_full);
         }
+        if (warp == 4 && lane == 0 && q < 4) FFN_TRACE(it, 22 + q);  // epi1(q) done
       }
       // ---- final epilogue of the tile: acc2 -> +b2 -> +residual -> [LN] -> S (and LN'(S)) ----
       mbar_wait(&bars->acc2_full, it & 1);  // every GEMM2 of the tile has retired: the H bytes are free for staging
       tc_fence_after();
+      if (warp == 4 && lane == 0) FFN_TRACE(it, 26);
       epilogue_row16<true>(ep, th, row0, q4, c, lane, st, &tmO0h, &tmO1h, xch2, cvec, rst, nullptr, 0u);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc2_empty);
+      if (warp == 4 && lane == 0) FFN_TRACE(it, 27);
     }
     if (lane == 0) tma_store_wait_all<0>();
   } else if (warp >= 4) {
@@ -389,12 +410,39 @@ int ffn_launch(const FfnPlan& p, int num_sms, cudaStream_t stream) {
   static const int ew16 = getenv("ISHARA_FFN_EW16") ? atoi(getenv("ISHARA_FFN_EW16")) : 1;
   const int mt = (p.M + kBM - 1) / kBM;
   const int grid = mt < num_sms ? mt : num_sms;
+#ifdef ISHARA_TRACE_BUILD
+  static long long* tbuf = nullptr;
+  static int printed = 0;
+  const bool tracing = printed < 2 && grid > 60;
+  if (tracing) {
+    if (tbuf == nullptr) ISHARA_CUDA_OK(cudaMalloc(&tbuf, 96 * sizeof(long long)));
+    ISHARA_CUDA_OK(cudaMemsetAsync(tbuf, 0, 96 * sizeof(long long), stream));
+    ISHARA_CUDA_OK(cudaMemcpyToSymbolAsync(g_ffn_trace, &tbuf, sizeof(tbuf), 0, cudaMemcpyHostToDevice, stream));
+  }
+#endif
   if (ew16)
     ffn_tc_kernel<16><<<grid, 640, smem, stream>>>(p.tmA, p.tmW1, p.tmW2, p.tmO0, p.tmO1, p.tmO0h, p.tmO1h, p.epi, p.bias1, p.M, p.E, mt);
   else
     ffn_tc_kernel<8><<<grid, 384, smem, stream>>>(p.tmA, p.tmW1, p.tmW2, p.tmO0, p.tmO1, p.tmO0h, p.tmO1h, p.epi, p.bias1, p.M, p.E, mt);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
+#ifdef ISHARA_TRACE_BUILD
+  if (tracing) {
+    ISHARA_CUDA_OK(cudaStreamSynchronize(stream));
+    long long h[96];
+    ISHARA_CUDA_OK(cudaMemcpy(h, tbuf, sizeof(h), cudaMemcpyDeviceToHost));
+    ++printed;
+    fprintf(stderr, "ffn trace M=%d (CTA 60, cycles since its first event): P0 a1_empty ok, P1 loads issued | M2 a1 landed, M3 G1(0) issued, M4 G1(1) issued, "
+                    "M5 acc2 free, M6-9 H(q) seen, M10-13 G2(q) issued | E14-17 acc1(q) seen, E18-21 H free, E22-25 epi1(q) done, E26 acc2 seen, E27 epi2 done\n", p.M);
+    long long t0 = 0;
+    for (int i = 0; i < 32; ++i) if (h[i] != 0 && (t0 == 0 || h[i] < t0)) t0 = h[i];
+    for (int t = 0; t < 3; ++t) {
+      fprintf(stderr, "  tile %d:", t);
+      for (int e = 0; e < 28; ++e) fprintf(stderr, " %d:%lld", e, h[t * 32 + e] ? h[t * 32 + e] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   return 0;
 }
 

@@ -50,6 +50,18 @@ print("lanes", sys.argv[2], "value", round(d["value"]), "ms/step", round(d["ms_p
 PY
     done
     ;;
+  launches)  # ncu launch list of the bench command (after the same command ran clean without ncu)
+    timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu --no-train > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${TAG}_launches_raw.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu --no-train > gpurun_out/${TAG}_ncu.log 2>&1
+    python tools/summarise_launches.py gpurun_out/${TAG}_launches_raw.csv > gpurun_out/${TAG}_launches_step_summary.csv 2>&1
+    head -30 gpurun_out/${TAG}_launches_step_summary.csv
+    ;;
+  fullprof)  # ncu --set full of the three largest kernels, one launch = 256 sequences (one lane) like the profiled pass of the bench
+    export ISHARA_LANES=1
+    CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-train" timeout 1400 bash tools/ncu_capture.sh \
+      ${TAG}_prof_c1b:conv1d_block:12:3 ${TAG}_prof_attn:attn_tc2:4:2 ${TAG}_prof_ffn:ffn_tc:8:2 ${TAG}_prof_rowgemm:gemm_tc_kernel.*16:20:3
+    ;;
   bench)
     timeout 500 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
     tail -3 gpurun_out/${TAG}_bench.err

@@ -10,7 +10,8 @@ def main(path, step=3):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
-    starts = [i for i, n in enumerate(names) if "cast_pad" in n]
+    # a step starts at the input cast; with sub-batch lanes there is one cast per lane, back to back
+    starts = [i for i, n in enumerate(names) if "cast_pad" in n and (i == 0 or "cast_pad" not in names[i - 1])]
     s, e = starts[step], starts[step + 1]
     agg = collections.OrderedDict()
     tot = 0.0
