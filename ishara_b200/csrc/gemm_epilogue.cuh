@@ -487,17 +487,32 @@ __device__ __forceinline__ void stage_write_half(uint32_t stg, int r, const floa
                  pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
                  pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
 }
+// this thread's residual row segment (64 columns of box c) straight from global memory, to be issued well before use
+__device__ __forceinline__ void row16_resid_ldg(const GemmEpi& ep, const EpiThread& th, int c, uint4 (&rq)[8]) {
+  if (ep.resid != nullptr && th.valid) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(ep.resid + static_cast<size_t>(th.row) * ep.ld_resid + c * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rq[j] = __ldg(r4 + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rq[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
 // resid_bar != nullptr: the residual box of this warp was requested by TMA into its staging box (phase = tile parity)
 // HALF: the warp's staging box is 2 KB (32 rows x 32 columns; tmO0 / tmO1 are the matching [32 x 32] maps): every
 // 32-column chunk is staged and stored on its own (ffn_tc.cu, where 16 full boxes do not fit beside the weight ring)
 template <bool HALF = false>
 __device__ __forceinline__ void epilogue_row16(const GemmEpi& ep, const EpiThread& th, int row0, int q, int c, int lane,
                                                WarpStore& st, const CUtensorMap* tmO0, const CUtensorMap* tmO1, float2* xch,
-                                               const float* cvec, Row16State& rst, uint64_t* resid_bar, uint32_t resid_phase) {
+                                               const float* cvec, Row16State& rst, uint64_t* resid_bar, uint32_t resid_phase,
+                                               const uint4* rq_pre = nullptr) {
   const bool ln0 = ep.ln0_g != nullptr, ln1 = ep.ln1_g != nullptr;
   const uint32_t stg = st.base;
   uint4 rq[8];
-  if (resid_bar != nullptr) {
+  if (rq_pre != nullptr) {  // the caller requested the residual row segment earlier (row16_resid_ldg)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rq[j] = rq_pre[j];
+  } else if (resid_bar != nullptr) {
     mbar_wait(resid_bar, resid_phase);
     const uint32_t rb = stg + static_cast<uint32_t>(lane) * 128u, xr = static_cast<uint32_t>(lane & 7);
 #pragma unroll

@@ -85,6 +85,7 @@ int gemm_launch(const GemmPlan& p, int num_sms, cudaStream_t stream);
 struct FfnPlan {
   CUtensorMap tmA, tmW1, tmW2, tmO0, tmO1;
   CUtensorMap tmO0h, tmO1h;    // the same outputs as [32 x 32] boxes (16-warp epilogue: half staging boxes)
+  CUtensorMap tmW1e;           // W1^T as [64 x 64] boxes (ffn_tc_v2_kernel walks the hidden dimension in eighths)
   GemmEpi epi;                 // epilogue of the second GEMM: bias = b2, resid, ln0 / ln1
   const float* bias1 = nullptr;  // [E]
   int M = 0, E = 0;

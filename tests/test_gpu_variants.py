@@ -42,6 +42,7 @@ VARIANTS = {
     "attn_tc_v3": {"ISHARA_ATTN_TC2": "0"},                   # one-CTA-per-SM tcgen05 attention instead of the 64-key streaming kernel
     "gemm_resid_ldg": {"ISHARA_GEMM_RESID_TMA": "0"},         # per-thread residual loads instead of TMA-staged residual boxes
     "gemm_row8": {"ISHARA_GEMM_ROW16": "0"},                   # 8-warp full-row epilogue instead of the 16-warp one
+    "ffn_v2": {"ISHARA_FFN_V2": "1"},                          # hidden dimension in eighths with two H buffers (measured slower, opt-in)
     "ffn_ew8": {"ISHARA_FFN_EW16": "0"},                       # fused FFN with 8 epilogue warps instead of 16
     "ffn_unfused": {"ISHARA_FFN_FUSED": "0"},
     "no_graph": {"ISHARA_GRAPH": "0"},
@@ -75,6 +76,7 @@ def test_opt_in_variants_match_oracle_and_default(tmp_path):
     assert np.array_equal(outs["no_graph"], base)
     assert np.array_equal(outs["gemm_resident"], base)
     assert np.array_equal(outs["gemm_pair"], base)
+    assert np.array_equal(outs["ffn_v2"], base)       # same roundings, different pipelining
     assert np.array_equal(outs["lanes_3"], base)      # lanes only re-partition the batch: every kernel is per-sequence
 
 
