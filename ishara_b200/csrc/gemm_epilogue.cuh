@@ -7,6 +7,13 @@
 namespace ishara {
 namespace {
 
+// Timing-bisect bits (GemmEpi::dbg, ISHARA_GEMM_DBG) and timeline tracing exist only in the profiling build
+// (make TRACE=1 -> libishara_b200_trace.so); the shipped kernels contain neither the branches nor the clock reads.
+#ifdef ISHARA_TRACE_BUILD
+#define ISHARA_DBG_BIT(ep_, bit_) (((ep_).dbg & (bit_)) != 0)
+#else
+#define ISHARA_DBG_BIT(ep_, bit_) false
+#endif
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kAStageBytes = kBM * kBK * 2;
@@ -248,7 +255,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread
         const int tc = b * CH + sub * 32;
         uint32_t raw[32];
         float v[32];
-        if (!(ep.dbg & 32)) tmem_ld32(th.taddr + tc, raw);
+        if (!ISHARA_DBG_BIT(ep, 32)) tmem_ld32(th.taddr + tc, raw);
         ResidRegs rn;
         {  // next chunk of this warp (if any)
           int nb = b, nsub = sub + 1;
@@ -279,7 +286,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, const EpiThread
         }
         if (ep.resid != nullptr) resid_add(v, rr);
         rr = rn;
-        if (!(ep.dbg & 8)) stage_write<OUT_F32>(buf, lane, sub, v);
+        if (!ISHARA_DBG_BIT(ep, 8)) stage_write<OUT_F32>(buf, lane, sub, v);
       }
       st.release(tmO0, buf, n_tile * cols_out + b * CH, row0);
     }

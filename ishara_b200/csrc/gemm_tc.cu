@@ -25,7 +25,11 @@ namespace ishara {
 
 namespace {
 
+#ifdef ISHARA_TRACE_BUILD
 #define ISHARA_TRACE(it_, ev_) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[(it_) * 8 + (ev_)] = clock64(); } while (0)
+#else
+#define ISHARA_TRACE(it_, ev_) do { } while (0)
+#endif
 
 constexpr int kNumStg = 4;            // 2 per epilogue group
 
@@ -156,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sb = RESB ? smem_base + kb * B_KB_BYTES : sa + kAStageBytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            if (ep.dbg & 4) break;
+            if (ISHARA_DBG_BIT(ep, 4)) break;
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
             umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), IDESC,
                       (kb | k) != 0 ? 1u : 0u);
@@ -176,8 +180,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     st.base = smem_u32(stg_ptr) + static_cast<uint32_t>((warp - 4) * (st.single ? 1 : 2)) * kWarpStgBytes;
     st.iter = 0;
     st.lane = lane;
-    st.skip_store = (ep.dbg & 1) != 0;
-    st.skip_fence = (ep.dbg & 16) != 0;
+    st.skip_store = ISHARA_DBG_BIT(ep, 1);
+    st.skip_fence = ISHARA_DBG_BIT(ep, 16);
 
     // 16-warp full-row epilogue: per-column vectors live in shared memory (the xch region: 8 KB exchange + 5 KB vectors)
     float2* xch2 = reinterpret_cast<float2*>(xch);
@@ -243,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
       if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
-      if (!(ep.dbg & 2)) {
+      if (!ISHARA_DBG_BIT(ep, 2)) {
         if constexpr (EW == 16 && ROW) {
           epilogue_row16(ep, th, row0, q, h, lane, st, &tmO0, &tmO1, xch2, cvec, rst, r16_tma ? &rbar[warp - 4] : nullptr,
                          static_cast<uint32_t>(it & 1));
@@ -398,13 +402,21 @@ int gemm_plan_init(GemmPlan* p, const bf16* A, int lda, const bf16* Wt, void* ou
 }
 
 int gemm_launch(const GemmPlan& p_in, int num_sms, cudaStream_t stream) {
+#ifdef ISHARA_TRACE_BUILD
   static const int dbg = getenv("ISHARA_GEMM_DBG") ? atoi(getenv("ISHARA_GEMM_DBG")) : 0;
+#else
+  static const int dbg = 0;  // bisect bits and tracing are compiled out of the shipped library
+#endif
   static const int force = getenv("ISHARA_GEMM_RESIDENT") ? atoi(getenv("ISHARA_GEMM_RESIDENT")) : 0;  // measured: no gain, off by default
   static const int pair = getenv("ISHARA_GEMM_PAIR") ? atoi(getenv("ISHARA_GEMM_PAIR")) : 0;  // CTA-pair variant: opt-in (measured slower)
   GemmPlan p = p_in;
   p.epi.dbg = dbg;
   if (force == 0) p.no_resident = true;
+#ifdef ISHARA_TRACE_BUILD
   static const int trace = getenv("ISHARA_GEMM_TRACE") ? atoi(getenv("ISHARA_GEMM_TRACE")) : 0;
+#else
+  static const int trace = 0;
+#endif
   if (trace > 0) {
     // debugging aid: timeline of CTA 0 (clock64 at 8 events per tile), printed to stderr after a blocking launch
     static long long* dbuf = nullptr;

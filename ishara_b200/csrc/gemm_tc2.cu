@@ -25,7 +25,11 @@
 namespace ishara {
 namespace {
 
+#ifdef ISHARA_TRACE_BUILD
 #define ISHARA_TRACE(it_, ev_) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[(it_) * 8 + (ev_)] = clock64(); } while (0)
+#else
+#define ISHARA_TRACE(it_, ev_) do { } while (0)
+#endif
 
 constexpr int kBN2 = 256;
 constexpr int kBHalfKbBytes = (kBN2 / 2) * kBK * 2;  // one k-block of this CTA's half of the weight tile: 16 KB
@@ -160,8 +164,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     st.base = smem_u32(stg_ptr) + static_cast<uint32_t>((warp - 4) * (st.single ? 1 : 2)) * kWarpStgBytes;
     st.iter = 0;
     st.lane = lane;
-    st.skip_store = (ep.dbg & 1) != 0;
-    st.skip_fence = (ep.dbg & 16) != 0;
+    st.skip_store = ISHARA_DBG_BIT(ep, 1);
+    st.skip_fence = ISHARA_DBG_BIT(ep, 16);
 
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -180,7 +184,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tfull[buf], (it >> 1) & 1);
       tc_fence_after();
       if (q == 0 && h == 0 && lane == 0) ISHARA_TRACE(it, 6);
-      if (!(ep.dbg & 2)) epilogue_tile<BN, ROW, false>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
+      if (!ISHARA_DBG_BIT(ep, 2)) epilogue_tile<BN, ROW, false>(ep, th, n_tile, N, row0, q, h, lane, st, &tmO0, &tmO1, xch, it & 1, rr);
       // this warp is done with its CTA's half of accumulator buffer `buf`: one arrive on the LEADER's barrier
       tc_fence_before();
       __syncwarp();

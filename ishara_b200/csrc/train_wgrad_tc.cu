@@ -14,6 +14,12 @@
 #include "ptx.cuh"
 #include "train_kernels.h"
 
+#ifdef ISHARA_TRACE_BUILD
+#define ISHARA_WGRAD_SKIP(dbg_) (((dbg_) & 1) != 0)
+#else
+#define ISHARA_WGRAD_SKIP(dbg_) false
+#endif
+
 namespace ishara {
 namespace {
 
@@ -146,7 +152,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
           const int i = i0 + q * 32 + rr;
-          if (i < Ivalid && !(dbg & 1)) atomicAdd(dW + static_cast<size_t>(i) * ldw + o, buf[rr * 33 + lane]);
+          if (i < Ivalid && !ISHARA_WGRAD_SKIP(dbg)) atomicAdd(dW + static_cast<size_t>(i) * ldw + o, buf[rr * 33 + lane]);
         }
       }
       __syncwarp();
@@ -190,7 +196,11 @@ int wgrad_tc_plan_init(WgradTcPlan* p, const bf16* X, int ldx, const bf16* G, in
 int wgrad_tc_launch(const WgradTcPlan* p, float* dW, int ldw, float* dbias, int Ivalid, int Ovalid, cudaStream_t s) {
   const WgradTcPlanImpl* q = reinterpret_cast<const WgradTcPlanImpl*>(p);
   const size_t smem = static_cast<size_t>(kTcStages) * kTcStageBytes + 128 + 4 * kTcEpiFloats * sizeof(float) + 1024;
+#ifdef ISHARA_TRACE_BUILD
   static const int dbg = getenv("ISHARA_WGRAD_DBG") ? atoi(getenv("ISHARA_WGRAD_DBG")) : 0;  // bit 0: skip the atomics (timing bisect only)
+#else
+  static const int dbg = 0;
+#endif
   static bool attr_done = false;
   if (!attr_done) {
     ISHARA_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
