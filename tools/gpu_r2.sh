@@ -62,6 +62,15 @@ PY
     CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-train" timeout 1400 bash tools/ncu_capture.sh \
       ${TAG}_prof_c1b:conv1d_block:12:3 ${TAG}_prof_attn:attn_tc2:4:2 ${TAG}_prof_ffn:ffn_tc:8:2 ${TAG}_prof_rowgemm:gemm_tc_kernel.*16:20:3
     ;;
+  dp)   # data-parallel training step at N ranks under a few exchange settings (short inner timeouts)
+    N="${3:-2}"
+    run() { env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551 tools/train_dp_bench.py --steps 20 2>gpurun_out/${TAG}_dp.err | tail -1 | cut -c1-300; }
+    timeout 100 python tools/train_dp_bench.py --steps 20 2>/dev/null | tail -1 | cut -c1-200
+    run A=1
+    run NCCL_MAX_NCHANNELS=2
+    run NCCL_MAX_NCHANNELS=4 ISHARA_COMM_BUCKET=4194304
+    run ISHARA_COMM_BUCKET=100000000
+    ;;
   bench)
     timeout 500 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
     tail -3 gpurun_out/${TAG}_bench.err
