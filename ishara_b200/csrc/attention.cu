@@ -38,7 +38,9 @@ __device__ __forceinline__ float ex2(float x) {
 template <int DH>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const uint8_t* __restrict__ key_mask, int T, int H,
-            int Tp, float scale_log2, uint32_t drop_thr16, float drop_inv_keep, uint64_t drop_key, float* __restrict__ lse_out) {
+            int Tp, float scale_log2, uint32_t drop_thr16, float drop_inv_keep, uint64_t drop_key_val,
+            const uint64_t* __restrict__ drop_key_ptr, float* __restrict__ lse_out) {
+  const uint64_t drop_key = drop_key_ptr != nullptr ? *drop_key_ptr : drop_key_val;
   constexpr int KS = DH + 8;  // K row stride (elements): conflict-free fragment reads
   extern __shared__ __align__(16) uint8_t smem_at[];
   bf16* Ks = reinterpret_cast<bf16*>(smem_at);                 // [Tp][KS]
@@ -448,7 +450,7 @@ int launch_inst(const AttnArgs& a, cudaStream_t stream) {
     smem_attr = smem;
   }
   kern<<<dim3(a.H, a.B), kAttnThreads, smem, stream>>>(a.qkv, a.out, a.key_mask, a.T, a.H, Tp,
-                                                      a.scale * 1.4426950408889634f, a.drop_thr16, a.drop_inv_keep, a.drop_key, a.lse_out);
+                                                      a.scale * 1.4426950408889634f, a.drop_thr16, a.drop_inv_keep, a.drop_key, a.drop_key_ptr, a.lse_out);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

@@ -169,6 +169,7 @@ struct AttnArgs {
   uint32_t drop_thr16 = 0;
   float drop_inv_keep = 1.f;
   uint64_t drop_key = 0;
+  const uint64_t* drop_key_ptr = nullptr;  // when set, the key is read from device memory at run time
 };
 int attention_launch(const AttnArgs& a, cudaStream_t stream);
 

@@ -77,11 +77,19 @@ struct TrainState {
   float* loss_pinned = nullptr;
   // weight gradients run on a side stream next to the data-gradient GEMM that follows them (both read the same dY and
   // neither fills the 148 SMs alone at 192 row tiles); the main stream rejoins right after that next step
+  uint64_t* keys_dev = nullptr;          // [kMaxDropSites] dropout key of every site for the CURRENT step (device)
+  // CUDA-graph replay of forward + CTC + backward (single-GPU, non-debug): captured on the second step of a program
+  cudaGraphExec_t step_graph = nullptr;
+  int step_graph_launches = 0;
+  int steps_since_build = 0;
+  bool step_graph_broken = false;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
   bool side_pending = false, last_was_side = false;
   std::shared_ptr<void> builder;  // closures may refer to builder members: it lives as long as the program
 };
+
+constexpr int kMaxDropSites = 256;
 
 // run `fn` on the side stream, ordered after everything enqueued on `s` so far (see TrainState::side)
 template <typename F>
@@ -143,6 +151,9 @@ void free_program(TrainState* ts) {
   ts->batch = 0;
   ts->stats = nullptr;
   ts->stats_count = 0;
+  if (ts->step_graph != nullptr) { cudaGraphExecDestroy(ts->step_graph); ts->step_graph = nullptr; }
+  ts->steps_since_build = 0;
+  ts->step_graph_broken = false;
 }
 
 struct TB {
@@ -305,8 +316,8 @@ struct TB {
     const bf16* src = tD;
     const int64_t MM = M;
     const int DD = D, TT = T;
-    const uint64_t* seedp = &ts->seed;
-    ts->fwd.push_back([=](cudaStream_t s) { return dropout_launch(src, resid, S_out, MM, DD, TT, p, *seedp, site, per_sample ? 1 : 0, s); });
+    const uint64_t* keyp = ts->keys_dev + site;
+    ts->fwd.push_back([=](cudaStream_t s) { return dropout_keyed_launch(src, resid, S_out, MM, DD, TT, p, keyp, per_sample ? 1 : 0, s); });
     return site;
   }
   // backward: returns the pointer holding dY = drop'(dOut) and appends the step producing it (if any)
@@ -315,8 +326,8 @@ struct TB {
     bf16* dst = tD;
     const int64_t MM = M;
     const int DD = D, TT = T;
-    const uint64_t* seedp = &ts->seed;
-    steps.push_back([=](cudaStream_t s) { return dropout_launch(dOut, nullptr, dst, MM, DD, TT, p, *seedp, site, per_sample ? 1 : 0, s); });
+    const uint64_t* keyp = ts->keys_dev + site;
+    steps.push_back([=](cudaStream_t s) { return dropout_keyed_launch(dOut, nullptr, dst, MM, DD, TT, p, keyp, per_sample ? 1 : 0, s); });
     return dst;
   }
   // in-place elementwise dropout of a wide tensor (same mask in forward and backward)
@@ -325,8 +336,8 @@ struct TB {
     const uint32_t site = site_in ? site_in : ++site_counter;
     const int64_t MM = M;
     const int TT = T;
-    const uint64_t* seedp = &ts->seed;
-    steps.push_back([=](cudaStream_t s) { return dropout_launch(x, nullptr, x, MM, cols, TT, p, *seedp, site, 0, s); });
+    const uint64_t* keyp = ts->keys_dev + site;
+    steps.push_back([=](cudaStream_t s) { return dropout_keyed_launch(x, nullptr, x, MM, cols, TT, p, keyp, 0, s); });
     return site;
   }
 
@@ -543,7 +554,7 @@ struct TB {
     const uint32_t site_a = p_attn > 0.f ? ++site_counter : 0;
     const uint32_t thr_a = p_attn > 0.f ? dropout_thr16(p_attn) : 0;
     const float inv_a = p_attn > 0.f ? 1.f / (1.f - p_attn) : 1.f;
-    const uint64_t* seedp = &ts->seed;
+    const uint64_t* keyp_a = ts->keys_dev + site_a;
     ts->fwd.push_back(ln_fwd(S_in, XN, ln, 1e-6f));
     ts->fwd.push_back(linear(XN, D, base + ".qkv", false, 3 * D, QKV));
     {
@@ -553,7 +564,7 @@ struct TB {
       a.lse_out = lse_save;
       ts->fwd.push_back([=](cudaStream_t s) {
         AttnArgs aa = a;
-        if (site_a) aa.drop_key = dropout_key(*seedp, site_a);
+        if (site_a) aa.drop_key_ptr = keyp_a;
         return attention_launch(aa, s);
       });
     }
@@ -572,7 +583,7 @@ struct TB {
       a.drop_thr16 = thr_a; a.drop_inv_keep = inv_a;
       bw.push_back([=](cudaStream_t s) {
         AttnBwdArgs aa = a;
-        if (site_a) aa.drop_key = dropout_key(*seedp, site_a);
+        if (site_a) aa.drop_key_ptr = keyp_a;
         return attention_bwd_launch(aa, s);
       });
     }
@@ -857,6 +868,7 @@ int init_storage(ishara_model* m, TrainState* ts) {
 
 int build_train_program(ishara_model* m, TrainState* ts, int batch, int labels_len) {
   free_program(ts);
+  if (ts->keys_dev == nullptr) ISHARA_CUDA_OK(cudaMalloc(&ts->keys_dev, kMaxDropSites * sizeof(uint64_t)));
   const ishara_config_t& c = m->cfg;
   auto bp = std::make_shared<TB>();
   ts->builder = bp;
@@ -968,6 +980,7 @@ void train_destroy(ishara_model* m) {
   if (ts->slow) cudaFree(ts->slow);
   if (ts->repack_dev) cudaFree(ts->repack_dev);
   if (ts->loss_pinned) cudaFreeHost(ts->loss_pinned);
+  if (ts->keys_dev) cudaFree(ts->keys_dev);
   if (ts->side) { cudaStreamSynchronize(ts->side); cudaStreamDestroy(ts->side); cudaEventDestroy(ts->ev_fork); cudaEventDestroy(ts->ev_side); }
   delete ts;
   m->train = nullptr;
@@ -1038,27 +1051,71 @@ int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* l
   ++ts->fb_count;
   ISHARA_CUDA_OK(cudaMemcpyAsync(ts->x_dev, x_dev, M * c.features * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   ISHARA_CUDA_OK(cudaMemcpyAsync(ts->labels_dev, labels_dev, static_cast<size_t>(batch) * labels_len * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-  ISHARA_CUDA_OK(cudaMemsetAsync(ts->grad, 0, static_cast<size_t>(ts->n_total) * sizeof(float), stream));
-  ISHARA_CUDA_OK(cudaMemsetAsync(ts->stats, 0, ts->stats_count * sizeof(double), stream));
-  for (auto& st : ts->fwd)
-    if ((rc = st(stream))) { set_last_error(std::string("train forward: ") + get_last_error()); return rc; }
-  if ((rc = ctc_loss_launch(ts->logits, ts->labels_dev, batch, c.frames, c.num_classes, labels_len, c.num_classes - 1, ts->nll, ts->dlogits, ts->ctc_ws, ts->ctc_ws_bytes, stream)))
-    return rc;
-  mean_kernel<<<1, 32, 0, stream>>>(ts->nll, batch, ts->loss_dev);
-  ISHARA_CUDA_OK(cudaGetLastError());
-  note_launch();
+  // this step's dropout keys (one per site) go to the device table the kernels read: the launches below carry no
+  // per-step host values and can be replayed from a graph
+  if ((rc = dropout_keys_launch(ts->seed, ts->keys_dev, kMaxDropSites, stream))) return rc;
   const bool dp = m->comm != nullptr && m->comm_world > 1;
-  // the loss joins the exchange first (one float): nothing is read back to the host before the gradients are on their way
-  if (dp && (rc = comm_allreduce_after(m, ts->loss_dev, 1, stream))) return rc;
-  for (int k = static_cast<int>(ts->bwd.size()) - 1; k >= 0; --k) {
-    if ((rc = ts->bwd[k](stream))) { set_last_error(std::string("train backward: ") + get_last_error()); return rc; }
-    // everything in [bucket_lo[k], bucket_up[k]) is final now: sum it over the ranks on the communication stream while
-    // the backward of the earlier modules keeps the SMs busy
-    if (dp && ts->bucket_up[k] > ts->bucket_lo[k] &&
-        (rc = comm_allreduce_after(m, ts->grad + ts->bucket_lo[k], ts->bucket_up[k] - ts->bucket_lo[k], stream)))
-      return rc;
+  // zero the accumulators, forward, CTC, mean loss, backward (with the gradient exchange when data-parallel)
+  auto body = [&](cudaStream_t st) -> int {
+    int r;
+    ISHARA_CUDA_OK(cudaMemsetAsync(ts->grad, 0, static_cast<size_t>(ts->n_total) * sizeof(float), st));
+    ISHARA_CUDA_OK(cudaMemsetAsync(ts->stats, 0, ts->stats_count * sizeof(double), st));
+    for (auto& step : ts->fwd)
+      if ((r = step(st))) { set_last_error(std::string("train forward: ") + get_last_error()); return r; }
+    if ((r = ctc_loss_launch(ts->logits, ts->labels_dev, batch, c.frames, c.num_classes, labels_len, c.num_classes - 1, ts->nll, ts->dlogits, ts->ctc_ws, ts->ctc_ws_bytes, st)))
+      return r;
+    mean_kernel<<<1, 32, 0, st>>>(ts->nll, batch, ts->loss_dev);
+    ISHARA_CUDA_OK(cudaGetLastError());
+    note_launch();
+    // the loss joins the exchange first (one float): nothing is read back to the host before the gradients are on their way
+    if (dp && (r = comm_allreduce_after(m, ts->loss_dev, 1, st))) return r;
+    for (int k = static_cast<int>(ts->bwd.size()) - 1; k >= 0; --k) {
+      if ((r = ts->bwd[k](st))) { set_last_error(std::string("train backward: ") + get_last_error()); return r; }
+      // everything in [bucket_lo[k], bucket_up[k]) is final now: sum it over the ranks on the communication stream while
+      // the backward of the earlier modules keeps the SMs busy
+      if (dp && ts->bucket_up[k] > ts->bucket_lo[k] &&
+          (r = comm_allreduce_after(m, ts->grad + ts->bucket_lo[k], ts->bucket_up[k] - ts->bucket_lo[k], st)))
+        return r;
+    }
+    if (dp && (r = comm_join(m, st))) return r;  // `st` continues only after every bucket has been reduced
+    return 0;
+  };
+  // CUDA-graph replay: the ~490 launches of a step are captured on the second step of a program (every kernel has run
+  // once: attributes set, lazy state built) and replayed afterwards. Not with the NCCL exchange (its launches stay
+  // direct) and not in debug mode (snapshots).
+  static const int use_graph = getenv("ISHARA_TRAIN_GRAPH") ? atoi(getenv("ISHARA_TRAIN_GRAPH")) : 1;
+  const bool graphable = use_graph && !dp && !ts->debug && !ts->step_graph_broken && m->stream != nullptr;
+  bool done = false;
+  if (graphable && ts->step_graph != nullptr) {
+    ISHARA_CUDA_OK(cudaGraphLaunch(ts->step_graph, stream));
+    note_launches(ts->step_graph_launches);
+    done = true;
+  } else if (graphable && ts->steps_since_build >= 1) {
+    cudaGraph_t graph = nullptr;
+    const uint64_t before = launch_count();
+    if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int rcap = body(m->stream);
+      const cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+      cudaGraphExec_t exec = nullptr;
+      if (rcap == 0 && ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        ts->step_graph = exec;
+        ts->step_graph_launches = static_cast<int>(launch_count() - before);
+        cudaGraphDestroy(graph);
+        ISHARA_CUDA_OK(cudaGraphLaunch(exec, stream));
+        done = true;
+      } else {
+        if (graph != nullptr) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ts->step_graph_broken = true;  // capture is an optimisation: direct launches from now on
+        ts->side_pending = false;
+      }
+    } else {
+      cudaGetLastError();
+      ts->step_graph_broken = true;
+    }
   }
-  if (dp && (rc = comm_join(m, stream))) return rc;  // `stream` continues only after every bucket has been reduced
+  if (!done && (rc = body(stream))) return rc;
+  ++ts->steps_since_build;
   m->host_params_stale = true;  // BatchNorm moving statistics moved
   if (loss_host != nullptr) return train_forward_backward_loss(m, loss_host, stream);
   return 0;

@@ -110,7 +110,8 @@ template <int DH>
 __global__ void __launch_bounds__(kAbThreads)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
                    float* __restrict__ lse_out, float* __restrict__ dsum_out, int T, int H, int Tp, float scale, uint32_t drop_thr16,
-                   float drop_inv_keep, uint64_t drop_key, int have_lse) {
+                   float drop_inv_keep, uint64_t drop_key_val, const uint64_t* __restrict__ drop_key_ptr, int have_lse) {
+  const uint64_t drop_key = drop_key_ptr != nullptr ? *drop_key_ptr : drop_key_val;
   constexpr int KS = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_ab[];
   const int VS = Tp + 8;
@@ -237,7 +238,8 @@ template <int DH>
 __global__ void __launch_bounds__(kAbThreads)
 attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dO, bf16* __restrict__ dqkv, const float* __restrict__ lse_in,
                     const float* __restrict__ dsum_in, int T, int H, int Tp, float scale, uint32_t drop_thr16, float drop_inv_keep,
-                    uint64_t drop_key) {
+                    uint64_t drop_key_val, const uint64_t* __restrict__ drop_key_ptr) {
+  const uint64_t drop_key = drop_key_ptr != nullptr ? *drop_key_ptr : drop_key_val;
   constexpr int KS = DH + 8;
   extern __shared__ __align__(16) uint8_t smem_ab[];
   const int VS = Tp + 8;
@@ -336,11 +338,11 @@ int launch_dh(const AttnBwdArgs& a, cudaStream_t s) {
   }
   const dim3 grid(a.H, a.B);
   attn_bwd_dq_kernel<DH><<<grid, kAbThreads, smem1, s>>>(a.qkv, a.o, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale, a.drop_thr16,
-                                                           a.drop_inv_keep, a.drop_key, a.have_lse);
+                                                           a.drop_inv_keep, a.drop_key, a.drop_key_ptr, a.have_lse);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   attn_bwd_dkv_kernel<DH><<<grid, kAbThreads, smem2, s>>>(a.qkv, a.dO, a.dqkv, a.lse2, a.dsum, a.T, a.H, Tp, a.scale, a.drop_thr16, a.drop_inv_keep,
-                                                            a.drop_key);
+                                                            a.drop_key, a.drop_key_ptr);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

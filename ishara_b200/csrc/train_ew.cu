@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(kEwThreads) scale_cast_pad_kernel(const float*
 
 // ---- dropout ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) dropout_kernel(const bf16* __restrict__ x, const bf16* __restrict__ resid, bf16* __restrict__ y, int64_t M,
-                                                               int C, int T, uint32_t thr16, float inv_keep, uint64_t key, int per_sample) {
+                                                               int C, int T, uint32_t thr16, float inv_keep, uint64_t key_val,
+                                                               const uint64_t* __restrict__ key_ptr, int per_sample) {
+  const uint64_t key = key_ptr != nullptr ? *key_ptr : key_val;  // key table on the device: the launch is graph-replayable
   const int c8 = C / 8;
   EW_LOOP(v, M * c8) {
     const int64_t row = v / c8;
@@ -663,8 +665,24 @@ int dropout_launch(const bf16* x, const bf16* resid, bf16* y, int64_t M, int C, 
   REQUIRE(C % 8 == 0 && p >= 0.f && p < 1.f, "dropout: bad arguments");
   const uint32_t thr = dropout_thr16(p);
   const uint64_t key = dropout_key(seed, site);
-  dropout_kernel<<<ew_grid(M * C / 8), kEwThreads, 0, s>>>(x, resid, y, M, C, T, thr, 1.f / (1.f - p), key, per_sample);
+  dropout_kernel<<<ew_grid(M * C / 8), kEwThreads, 0, s>>>(x, resid, y, M, C, T, thr, 1.f / (1.f - p), key, nullptr, per_sample);
   return check("dropout");
+}
+// same with the site's key read from device memory at run time (dropout_keys_launch fills the table every step)
+int dropout_keyed_launch(const bf16* x, const bf16* resid, bf16* y, int64_t M, int C, int T, float p, const uint64_t* key_dev,
+                         int per_sample, cudaStream_t s) {
+  REQUIRE(C % 8 == 0 && p >= 0.f && p < 1.f && key_dev != nullptr, "dropout: bad arguments");
+  dropout_kernel<<<ew_grid(M * C / 8), kEwThreads, 0, s>>>(x, resid, y, M, C, T, dropout_thr16(p), 1.f / (1.f - p), 0ull, key_dev, per_sample);
+  return check("dropout");
+}
+__global__ void dropout_keys_kernel(uint64_t seed, uint64_t* __restrict__ keys, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = dropout_key(seed, static_cast<uint32_t>(i));
+}
+// keys[site] = dropout_key(seed, site) for site < n: one tiny launch per step in front of the (replayed) program
+int dropout_keys_launch(uint64_t seed, uint64_t* keys_dev, int n, cudaStream_t s) {
+  dropout_keys_kernel<<<(n + 127) / 128, 128, 0, s>>>(seed, keys_dev, n);
+  return check("dropout_keys");
 }
 int colstats_launch(const bf16* x, float* seqsum, double* sum, double* sumsq, int B, int T, int C, cudaStream_t s) {
   REQUIRE(C % 64 == 0, "colstats: C % 64 != 0");

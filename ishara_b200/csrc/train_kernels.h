@@ -31,6 +31,9 @@ int scale_cast_pad_launch(const float* in, bf16* out, int64_t M, int V, int Vpad
 // per_sample != 0: one decision per sequence (noise_shape=(None,1,1), c5:83), i = row / T.
 int dropout_launch(const bf16* x, const bf16* resid, bf16* y, int64_t M, int C, int T, float p, uint64_t seed,
                    uint32_t site, int per_sample, cudaStream_t s);
+int dropout_keyed_launch(const bf16* x, const bf16* resid, bf16* y, int64_t M, int C, int T, float p, const uint64_t* key_dev,
+                         int per_sample, cudaStream_t s);
+int dropout_keys_launch(uint64_t seed, uint64_t* keys_dev, int n, cudaStream_t s);
 
 // ---- reductions (train_ew.cu) ---------------------------------------------------------------------
 // per-sequence column sums seqsum[B,C] (fp32, overwritten) and, when sum/sumsq != null, whole-batch sum / sum of
@@ -122,6 +125,7 @@ struct AttnBwdArgs {
   uint32_t drop_thr16 = 0;  // same dropout mask as the forward (AttnArgs)
   float drop_inv_keep = 1.f;
   uint64_t drop_key = 0;
+  const uint64_t* drop_key_ptr = nullptr;  // when set, the key is read from device memory at run time
 };
 int attention_bwd_launch(const AttnBwdArgs& a, cudaStream_t s);
 

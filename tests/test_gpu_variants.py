@@ -150,3 +150,45 @@ def test_weight_gradient_kernels_agree(tmp_path):
     assert abs(a[-1] - b[-1]) <= 1e-5 * abs(b[-1])                       # same forward => same loss
     rel = np.linalg.norm(a[:-1] - b[:-1]) / np.linalg.norm(b[:-1])
     assert rel < 2e-3, rel                                              # fp32 accumulation order only
+
+
+STEP_SNIPPET = r"""
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+import ishara_b200
+from oracle import ishara_oracle as O
+cfg = O.Config(dim=128, num_heads=4, frames=128, features=20, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1)
+p = O.init_params(cfg)
+x = O.make_inputs(cfg, 4); y = O.make_labels(cfg, 4, max_len=24, min_len=6)
+m = ishara_b200.get_model(dim=128, num_heads=4, num_conv_squeeze_blocks=1, num_conv_conform_blocks=1, dropout_rate=0.2,
+                          input_shape=(128, 20)).load_weights(p)
+m.train_config(0.2, seed=11)
+m.compile(lr=1e-3, weight_decay=0.01)
+losses = [m.train_step(x, y) for _ in range(6)]          # steps 0-1 direct launches, 2+ graph replay (when enabled)
+w = m.get_weights()
+flat = np.concatenate([np.asarray(losses, np.float64)] + [w[k].ravel().astype(np.float64) for k in sorted(w)])
+np.save(sys.argv[1], flat)
+""" % ROOT
+
+
+def test_training_step_graph_replay_matches_direct_launches(tmp_path):
+    """Six optimiser steps with dropout: CUDA-graph replay of forward + CTC + backward (default) vs direct launches
+    (ISHARA_TRAIN_GRAPH=0). Same kernels, same per-step dropout keys (read from the device table) => the same loss curve and
+    weights up to the order of the fp32 gradient atomics."""
+    import numpy as np
+
+    outs = {}
+    for name, env_extra in (("graph", {}), ("direct", {"ISHARA_TRAIN_GRAPH": "0"})):
+        out = tmp_path / f"steps_{name}.npy"
+        env = {k: v for k, v in os.environ.items() if not k.startswith("ISHARA_")}
+        env.update(env_extra)
+        r = subprocess.run([sys.executable, "-c", STEP_SNIPPET, str(out)], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, f"{name}: {r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+        outs[name] = np.load(out)
+    a, b = outs["graph"], outs["direct"]
+    print("losses graph ", a[:6], "\nlosses direct", b[:6])
+    assert np.all(np.diff(a[:6]) != 0)                                  # the weights really move
+    np.testing.assert_allclose(a[:6], b[:6], rtol=2e-3)
+    rel = np.linalg.norm(a[6:] - b[6:]) / np.linalg.norm(b[6:])
+    assert rel < 2e-3, rel
