@@ -21,6 +21,8 @@
 
 namespace ishara {
 
+void train_drop_graph(ishara_model* m);  // train.cu
+
 namespace {
 
 struct NcclApi {
@@ -114,6 +116,7 @@ int model_comm_init(ishara_model* m, const void* id128, int rank, int world) {
   ISHARA_CUDA_OK(cudaSetDevice(m->device));
   ncclUniqueId id;
   std::memcpy(&id, id128, sizeof(id));
+  train_drop_graph(m);  // a step captured without the exchange is no longer the step to replay
   ncclComm_t comm = nullptr;
   ISHARA_NCCL_OK(api->CommInitRank(&comm, world, id, rank));
   m->comm = comm;
@@ -131,6 +134,7 @@ int model_comm_destroy(ishara_model* m) {
   if (m->comm != nullptr) {
     cudaSetDevice(m->device);
     if (m->comm_stream) cudaStreamSynchronize(m->comm_stream);
+    train_drop_graph(m);  // graphs that captured NCCL collectives must go before the communicator does
     nccl_api()->CommDestroy(static_cast<ncclComm_t>(m->comm));
     m->comm = nullptr;
   }

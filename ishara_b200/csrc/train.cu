@@ -986,6 +986,20 @@ void train_destroy(ishara_model* m) {
   m->train = nullptr;
 }
 
+// the captured step refers to the communicator's kernels (or to their absence): drop it whenever the exchange is set up or
+// torn down - NCCL requires graphs that captured its collectives to be destroyed before the communicator
+void train_drop_graph(ishara_model* m) {
+  TrainState* ts = m->train;
+  if (ts == nullptr) return;
+  if (ts->step_graph != nullptr) {
+    cudaDeviceSynchronize();
+    cudaGraphExecDestroy(ts->step_graph);
+    ts->step_graph = nullptr;
+  }
+  ts->steps_since_build = 0;
+  ts->step_graph_broken = false;
+}
+
 // set_param after training started: the next train call re-uploads everything
 void train_invalidate(ishara_model* m) {
   if (m->train != nullptr) train_destroy(m);
@@ -1081,10 +1095,12 @@ int train_forward_backward(ishara_model* m, const float* x_dev, const int32_t* l
     return 0;
   };
   // CUDA-graph replay: the ~490 launches of a step are captured on the second step of a program (every kernel has run
-  // once: attributes set, lazy state built) and replayed afterwards. Not with the NCCL exchange (its launches stay
-  // direct) and not in debug mode (snapshots).
+  // once: attributes set, lazy state built) and replayed afterwards - including, when data-parallel, the bucketed NCCL
+  // all-reduces on the communication stream (forked / joined through events, so they become branches of the same graph).
+  // Not in debug mode (snapshots).
   static const int use_graph = getenv("ISHARA_TRAIN_GRAPH") ? atoi(getenv("ISHARA_TRAIN_GRAPH")) : 1;
-  const bool graphable = use_graph && !dp && !ts->debug && !ts->step_graph_broken && m->stream != nullptr;
+  static const int use_graph_dp = getenv("ISHARA_TRAIN_GRAPH_DP") ? atoi(getenv("ISHARA_TRAIN_GRAPH_DP")) : 1;  // NCCL all-reduces are captured with the step
+  const bool graphable = use_graph && (!dp || use_graph_dp) && !ts->debug && !ts->step_graph_broken && m->stream != nullptr;
   bool done = false;
   if (graphable && ts->step_graph != nullptr) {
     ISHARA_CUDA_OK(cudaGraphLaunch(ts->step_graph, stream));
