@@ -22,6 +22,8 @@ namespace {
 __device__ __forceinline__ int ctc_label(const int32_t* lab, int i, int V) { return min(max(lab[i], 0), V - 1); }
 
 constexpr float kLogZero = -1.0e30f;
+constexpr unsigned kCtcRedoMark = 0x7fc0deadu;  // NaN payload written to nll[b]: "redo this sequence in the log domain"
+constexpr float kCtcLinearMaxRange = 100.f;     // largest per-frame (max - min logit) * log2 e the linear sweep accepts
 constexpr int kCtcBlk = 32;  // frames staged per shared-memory block
 
 // All recursions run in the log2 domain with raw MUFU ex2/lg2 (no range fix-ups, no branches): the sweep is a serial
@@ -69,10 +71,13 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int SPL>
 __global__ void __launch_bounds__(32)
 ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
-           float* __restrict__ nll, float* __restrict__ grad, float* __restrict__ alpha_ws, float* __restrict__ beta_ws) {
+           float* __restrict__ nll, float* __restrict__ grad, float* __restrict__ alpha_ws, float* __restrict__ beta_ws,
+           int only_flagged) {
   extern __shared__ __align__(16) float smem_ctc[];
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x;
+  // second pass behind ctc_alpha_linear_kernel: only the sequences it marked as outside its dynamic range
+  if (only_flagged && __float_as_uint(nll[b]) != kCtcRedoMark) return;
   const int Vpad = (V + 31) & ~31;
   float* lse = smem_ctc;
   float* occ = lse + ((T + 3) & ~3);
@@ -246,6 +251,135 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
   }
 }
 
+// Loss-only forward sweep in the LINEAR domain (no gradient requested: inference step, validation). The log-domain
+// recursion above pays 3 x ex2 + lg2 per state per step ON the serial chain (~720 cycles per frame, 144 us for T = 384);
+// here a step is alpha_t(s) = (alpha_{t-1}(s) + alpha_{t-1}(s-1) + [skip] alpha_{t-1}(s-2)) * y_t(ext(s)) - two adds and a
+// multiply behind the neighbour shuffle - and the emission probabilities y_t = 2^((logit - lse_t) log2 e) are off the chain.
+// Range: block floating point PER LANE. Lane l keeps its SPL states as a_l * 2^K_l; every step it folds the exponent of its
+// own largest value of the previous step into y (one step late, so off the chain) and adds it to K_l; values arriving
+// from lane l-1 are converted with 2^(K_{l-1} - K_l), and a lane that holds no mass yet adopts its neighbour's exponent so
+// that the first mass to arrive is representable. (One exponent for the whole warp is NOT enough: the states a likely
+// path passes through can sit more than 2^-126 below the currently largest state - measured: a 33-label sequence lost
+// 18 nats that way.) log2 p(l|x) = lse2 over the last two states of log2(a) + K; no mass there <=> infeasible labelling.
+template <int SPL>
+__global__ void __launch_bounds__(32)
+ctc_alpha_linear_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
+                        float* __restrict__ nll) {
+  extern __shared__ __align__(16) float smem_ctc[];
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  float* blk = smem_ctc;  // [2][kCtcBlk * V]
+  const int blk_floats = kCtcBlk * V;
+  const float* lg = logits + static_cast<size_t>(b) * T * V;
+  const int32_t* lab = labels + static_cast<size_t>(b) * L;
+  const int nblk = (T + kCtcBlk - 1) / kCtcBlk;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) && (V % 4 == 0);
+  auto stage = [&](int tb) {
+    float* dst = blk + (tb & 1) * blk_floats;
+    const float* src = lg + static_cast<size_t>(tb) * kCtcBlk * V;
+    const int n = min(kCtcBlk, T - tb * kCtcBlk) * V;
+    if (vec_ok) {
+      for (int i = lane * 4; i < n; i += 128) cp_async_16(dst + i, src + i);
+    } else {
+      for (int i = lane; i < n; i += 32) cp_async_4(dst + i, src + i);
+    }
+    cp_async_commit();
+  };
+  stage(0);
+  int cnt = 0;
+  for (int i = lane; i < L; i += 32) cnt += (ctc_label(lab, i, V) != blank) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const int S = 2 * cnt + 1;
+  // everything the serial loop touches is branch-free arithmetic: ONE warp runs it alone on its scheduler, so a step costs
+  // (instructions per step) x (dependent-issue latency) - the first version of this loop compiled to 270 instructions
+  // with five divergent regions per step and was slower (197 us) than the log-domain kernel
+  int extoff[SPL];            // byte offset of the state's class inside a staged logits row
+  float skipf[SPL], livef[SPL];
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    int e = blank;
+    if (s < S && (s & 1)) e = ctc_label(lab, s >> 1, V);
+    extoff[i] = e * 4;
+    livef[i] = s < S ? 1.f : 0.f;
+    skipf[i] = ((s < S) && (s & 1) && (s >= 3) && (ctc_label(lab, s >> 1, V) != ctc_label(lab, (s >> 1) - 1, V))) ? 1.f : 0.f;
+  }
+  // virtual step -1: alpha(0) = 1 makes the recurrence itself produce alpha_0(0) = y_0(blank), alpha_0(1) = y_0(l_1)
+  float a[SPL];
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) a[i] = (lane == 0 && i == 0) ? 1.f : 0.f;
+  bool unsafe = false;  // some frame's logit spread is outside what the linear sweep can represent
+  int K = 0;            // this lane's states are a[] * 2^K
+  int kpend = 0;        // exponent of this lane's largest value after the previous step: folded into this step's y
+  bool empty = lane != 0;  // no mass in this lane yet
+  for (int tb = 0; tb < nblk; ++tb) {
+    if (tb + 1 < nblk) { stage(tb + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncwarp();
+    const float* cur = blk + (tb & 1) * blk_floats;
+    const int nf = min(kCtcBlk, T - tb * kCtcBlk);
+    // log2-domain log-sum-exp of frame (tb*32 + lane); lanes walk the classes in rotated order (bank spread)
+    float lse_l = 0.f;
+    if (lane < nf) {
+      const float* row = cur + lane * V;
+      float m = -INFINITY, mn = INFINITY;
+      int v = lane % V;
+      for (int k = 0; k < V; ++k) { m = fmaxf(m, row[v]); mn = fminf(mn, row[v]); v = (v + 1 == V) ? 0 : v + 1; }
+      float z = 0.f;
+      for (int k = 0; k < V; ++k) { z += ex2a((row[v] - m) * kLog2e); v = (v + 1 == V) ? 0 : v + 1; }
+      lse_l = m * kLog2e + lg2a(z);
+      // a single emission probability below ~2^-106 cannot be held next to this lane's other states in fp32 (the exponent
+      // is folded in one step late): such frames - logit spreads beyond ~69 nats, NaN / inf - go to the log-domain kernel
+      if (!((m - mn) * kLog2e <= kCtcLinearMaxRange)) unsafe = true;
+    }
+    const char* rowb = reinterpret_cast<const char*>(cur);
+#pragma unroll 1
+    for (int tt = 0; tt < nf; ++tt, rowb += V * 4) {
+      const float lt2 = __shfl_sync(0xffffffffu, lse_l, tt) + static_cast<float>(kpend);
+      float y[SPL];
+#pragma unroll
+      for (int i = 0; i < SPL; ++i)
+        y[i] = ex2a(fmaf(*reinterpret_cast<const float*>(rowb + extoff[i]), kLog2e, -lt2)) * livef[i];
+      const int Kup = __shfl_up_sync(0xffffffffu, K, 1);
+      float up1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+      float up2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
+      K = empty ? Kup : K;                                     // nothing here yet: take over the neighbour's scale
+      const int d = max(-126, min(126, Kup - K));
+      const float f = lane == 0 ? 0.f : __uint_as_float(static_cast<unsigned>(d + 127) << 23);  // 2^(Kup - K)
+      up1 *= f;
+      up2 *= f;
+      float na[SPL];
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) {
+        const float q1 = (i == 0) ? up1 : a[i - 1];
+        const float q2 = (i == 0) ? up2 : (i == 1 ? up1 : a[i - 2]);
+        na[i] = fmaf(skipf[i], q2, a[i] + q1) * y[i];
+      }
+      K += kpend;  // the exponent folded into y has been applied
+      float mx = na[0];
+#pragma unroll
+      for (int i = 0; i < SPL; ++i) { a[i] = na[i]; mx = fmaxf(mx, na[i]); }
+      // exponent for the NEXT step from this step's largest value of this lane (off the chain); 0 (no mass / denormal) and
+      // >= 254 (inf / NaN) leave the scale alone
+      const unsigned ebits = __float_as_uint(mx) >> 23;
+      kpend = (ebits - 1u) < 253u ? static_cast<int>(ebits) - 127 : 0;
+      empty = mx == 0.f;
+    }
+    __syncwarp();
+  }
+  // log2 p(l|x) = lse2 over states S-1 and S-2 of log2(a) + K (they may live in neighbouring lanes)
+  float fin = kLogZero;
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int s = lane * SPL + i;
+    if ((s == S - 1 || (s == S - 2 && S >= 2)) && a[i] > 0.f) fin = lse2(fin, lg2a(a[i]) + static_cast<float>(K));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fin = lse2(fin, __shfl_xor_sync(0xffffffffu, fin, o));
+  const bool redo = __any_sync(0xffffffffu, unsafe);
+  if (lane == 0) nll[b] = redo ? __uint_as_float(kCtcRedoMark) : (fin > 0.5f * kLogZero ? -fin * kLn2 : INFINITY);
+}
+
 // d nll_b / d logits[b,t,:] = softmax(logits[b,t,:]) - occupancy_t, occupancy_t(v) = sum_{s: ext(s)=v} alpha_t(s) beta_t(s) / y_t(v)
 // normalised per frame (in exact arithmetic the sum over s is p(l|x) at every t; normalising by the per-frame sum keeps
 // fp32 drift out of the gradient: each row sums to zero to rounding). One warp per frame, alphas/betas from the sweep's
@@ -324,38 +458,69 @@ ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ la
 // ------------------------------------------------------------------------------------------------
 // greedy decode: one warp per sequence
 // ------------------------------------------------------------------------------------------------
-constexpr int kDecWarps = 4;
-__global__ void __launch_bounds__(kDecWarps * 32)
+// One CTA per sequence. Frames are staged 384 at a time in shared memory with coalesced loads (row pitch V + 1 floats;
+// thread = frame then walks its row without bank conflicts); the first version let every lane read its own 240-byte row
+// from global memory - 32 lines per load instruction - and took 45 us for 23.6 MB.
+constexpr int kDecThreads = 384;  // frames per staged chunk = threads per CTA (T = 384: one pass)
+__global__ void __launch_bounds__(kDecThreads)
 greedy_decode_kernel(const float* __restrict__ logits, int B, int T, int V, int blank, int32_t* __restrict__ ids_out,
                      int32_t* __restrict__ lens) {
   extern __shared__ int32_t smem_dec[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kDecWarps + warp;
-  if (b >= B) return;
-  int32_t* ids = smem_dec + warp * (T + 1);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.x;
+  int32_t* ids = smem_dec;                                              // [T + 1]
+  float* rows = reinterpret_cast<float*>(smem_dec + ((T + 1 + 3) & ~3));  // [kDecThreads][V + 1]
+  const int pitch = V + 1;
   const float* lg = logits + static_cast<size_t>(b) * T * V;
-  for (int t = lane; t < T; t += 32) {
-    const float* row = lg + static_cast<size_t>(t) * V;
-    float best = row[0];
-    int bi = 0;
-    if ((V & 3) == 0) {
-      const float4* r4 = reinterpret_cast<const float4*>(row);
-      for (int v4 = 0; v4 < V / 4; ++v4) {
-        const float4 x = __ldg(r4 + v4);
-        if (x.x > best) { best = x.x; bi = 4 * v4; }
-        if (x.y > best) { best = x.y; bi = 4 * v4 + 1; }
-        if (x.z > best) { best = x.z; bi = 4 * v4 + 2; }
-        if (x.w > best) { best = x.w; bi = 4 * v4 + 3; }
+  for (int t0 = 0; t0 < T; t0 += kDecThreads) {
+    const int nf = min(kDecThreads, T - t0);
+    const float* src = lg + static_cast<size_t>(t0) * V;
+    const int n = nf * V;
+    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (V % 4 == 0)) {
+      // 16-byte loads, eight in flight per thread before anything is stored (one load per loop trip left every trip
+      // exposed to a full memory round trip: 28 us)
+      const float4* src4 = reinterpret_cast<const float4*>(src);
+      const int n4 = n / 4;
+      for (int base = 0; base < n4; base += kDecThreads * 8) {
+        float4 buf[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = base + j * kDecThreads + tid;
+          if (idx < n4) buf[j] = __ldg(src4 + idx);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = base + j * kDecThreads + tid;
+          if (idx < n4) {
+            const int e = idx * 4, r = e / V, c = e - r * V;  // V % 4 == 0: the four values stay inside one row
+            float* d = rows + r * pitch + c;
+            d[0] = buf[j].x; d[1] = buf[j].y; d[2] = buf[j].z; d[3] = buf[j].w;
+          }
+        }
       }
     } else {
-      for (int v = 1; v < V; ++v) {
-        const float x = __ldg(row + v);
-        if (x > best) { best = x; bi = v; }
+      const int dr = kDecThreads / V, dc = kDecThreads % V;
+      int r = tid / V, c = tid - r * V;
+      for (int i = tid; i < n; i += kDecThreads) {
+        rows[r * pitch + c] = __ldg(src + i);
+        r += dr; c += dc;
+        if (c >= V) { c -= V; ++r; }
       }
     }
-    ids[t] = bi;
+    __syncthreads();
+    if (tid < nf) {
+      const float* row = rows + tid * pitch;
+      float best = row[0];
+      int bi = 0;
+      for (int v = 1; v < V; ++v) {
+        const float x = row[v];
+        if (x > best) { best = x; bi = v; }  // first index on ties
+      }
+      ids[t0 + tid] = bi;
+    }
+    __syncthreads();
   }
-  __syncwarp();
+  if (tid >= 32) return;
   int32_t* dst = ids_out + static_cast<size_t>(b) * T;
   int total = 0;
   for (int t0 = 0; t0 < T; t0 += 32) {
@@ -403,6 +568,30 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
     set_last_error("ctc_loss: label length above 143 is not supported");
     return 2;
   }
+  static const int linear_fwd = getenv("ISHARA_CTC_LINEAR") ? atoi(getenv("ISHARA_CTC_LINEAR")) : 1;
+  if (grad == nullptr && linear_fwd) {
+    // loss only: linear-domain sweep, then the log-domain kernel for the sequences the sweep marked as out of range (it
+    // returns at once for all others); the log-domain kernel is also the gradient pass and the cross-check
+    const size_t smem_lin = static_cast<size_t>(2 * kCtcBlk * V) * sizeof(float);
+    if (SPL == 5) {
+      if (smem_lin > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_alpha_linear_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_lin)));
+      ctc_alpha_linear_kernel<5><<<B, 32, smem_lin, stream>>>(logits, labels, B, T, V, L, blank, nll);
+      ISHARA_CUDA_OK(cudaGetLastError());
+      note_launch();
+      if (smem > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      ctc_kernel<5><<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, nullptr, nullptr, nullptr, 1);  // marked sequences only
+    } else {
+      if (smem_lin > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_alpha_linear_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_lin)));
+      ctc_alpha_linear_kernel<9><<<B, 32, smem_lin, stream>>>(logits, labels, B, T, V, L, blank, nll);
+      ISHARA_CUDA_OK(cudaGetLastError());
+      note_launch();
+      if (smem > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      ctc_kernel<9><<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, nullptr, nullptr, nullptr, 1);
+    }
+    ISHARA_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+  }
   float* ws = nullptr;
   if (grad != nullptr) {
     const size_t need = ctc_workspace_bytes(B, T, L);  // alphas | betas
@@ -417,7 +606,7 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
     if (smem > 48 * 1024)
       ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     float* bws = ws != nullptr ? ws + static_cast<size_t>(B) * T * 32 * SPL : nullptr;
-    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws);
+    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws, 0);
     if (grad != nullptr) {
       ISHARA_CUDA_OK(cudaGetLastError());
       note_launch();
@@ -430,7 +619,7 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
     if (smem > 48 * 1024)
       ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     float* bws = ws != nullptr ? ws + static_cast<size_t>(B) * T * 32 * SPL : nullptr;
-    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws);
+    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws, 0);
     if (grad != nullptr) {
       ISHARA_CUDA_OK(cudaGetLastError());
       note_launch();
@@ -450,12 +639,17 @@ int greedy_decode_launch(const float* logits, int B, int T, int V, int blank, in
     set_last_error("greedy_decode: bad shape");
     return 2;
   }
-  const size_t smem = static_cast<size_t>(kDecWarps) * (T + 1) * sizeof(int32_t);
-  const int grid = (B + kDecWarps - 1) / kDecWarps;
-  if (smem > 48 * 1024)
-    ISHARA_CUDA_OK(cudaFuncSetAttribute(greedy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-  greedy_decode_kernel<<<grid, kDecWarps * 32, smem, stream>>>(logits, B, T, V, blank, ids_out, lens);
+  const size_t smem = (static_cast<size_t>((T + 1 + 3) & ~3) + static_cast<size_t>(kDecThreads) * (V + 1)) * sizeof(int32_t);
+  if (smem > 200 * 1024) {
+    set_last_error("greedy_decode: T / num_classes too large for the shared-memory staging");
+    return 2;
+  }
+  static size_t smem_attr = 48 * 1024;
+  if (smem > smem_attr) {
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(greedy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_attr = smem;
+  }
+  greedy_decode_kernel<<<B, kDecThreads, smem, stream>>>(logits, B, T, V, blank, ids_out, lens);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

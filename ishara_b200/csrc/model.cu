@@ -645,6 +645,13 @@ int lane_count(const ishara_model* m, int batch) {
   return std::min(want, batch);
 }
 void lane_range(int batch, int lanes, int l, int* b0, int* bl) {
+  static const int frac0 = getenv("ISHARA_LANE0_PCT") ? atoi(getenv("ISHARA_LANE0_PCT")) : 50;  // two lanes: share of lane 0 (tuning)
+  if (lanes == 2 && frac0 > 0 && frac0 < 100) {
+    const int cut = std::max(1, std::min(batch - 1, static_cast<int>(static_cast<int64_t>(batch) * frac0 / 100)));
+    *b0 = l == 0 ? 0 : cut;
+    *bl = l == 0 ? cut : batch - cut;
+    return;
+  }
   const int lo = static_cast<int>(static_cast<int64_t>(batch) * l / lanes), hi = static_cast<int>(static_cast<int64_t>(batch) * (l + 1) / lanes);
   *b0 = lo;
   *bl = hi - lo;

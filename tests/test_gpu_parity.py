@@ -238,6 +238,30 @@ def test_ctc_loss_and_gradient(T, V, L, lens):
     assert abs(mean - ref_nll.mean()) <= 1e-3 * abs(ref_nll.mean())
 
 
+@pytest.mark.parametrize("scale,T,L,lens", [
+    (2.0, 384, 64, [64, 0, 1, 33, 8, 64]),
+    (25.0, 384, 64, [64, 5, 40]),        # peaky frames: per-step probabilities down to ~e^-100, the power-of-two rescaling works hard
+    (0.01, 176, 64, [64, 1]),            # flat distribution
+    (8.0, 384, 100, [100, 77]),          # 9 states per lane
+])
+def test_ctc_loss_only_linear_domain_sweep(scale, T, L, lens):
+    """The loss-only path runs its forward sweep in the LINEAR domain with per-step power-of-two rescaling (ctc.cu:
+    ctc_alpha_linear_kernel); the gradient path keeps the log-domain kernel. Both must agree with the fp64 oracle and with
+    each other over the whole dynamic range."""
+    V = 60
+    rng = np.random.default_rng(int(scale * 100) + T + L)
+    logits = (rng.standard_normal((len(lens), T, V)) * scale).astype(np.float32)
+    labels = np.full((len(lens), L), V - 1, np.int32)
+    for b, n in enumerate(lens):
+        labels[b, :n] = rng.integers(0, V - 1, n)
+    ref = O.ctc_loss(labels, logits, blank=V - 1)
+    lin = ib.CTCLoss(labels, logits, blank=V - 1, reduction="none")                       # linear-domain kernel
+    logd, _ = ib.CTCLoss(labels, logits, blank=V - 1, reduction="none", return_grad=True)   # log-domain kernel
+    print("nll oracle", ref, "linear", lin, "log-domain", logd)
+    assert np.allclose(lin, ref, rtol=1e-3, atol=1e-3)
+    assert np.allclose(lin, logd, rtol=2e-4, atol=2e-3)
+
+
 def test_ctc_infeasible_is_inf_like_the_reference():
     logits = np.zeros((2, 3, 5), np.float32)
     labels = np.array([[0, 0, 1, 4], [1, 4, 4, 4]], np.int32)   # row 0 needs >= 4 frames
