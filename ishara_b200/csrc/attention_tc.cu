@@ -1,4 +1,5 @@
-// ishara_b200 — tcgen05/TMEM multi-head self-attention core for the get_model shape (dh = 32, T <= 384, T % 128 == 0).
+// ishara_b200 — tcgen05/TMEM multi-head self-attention core for the get_model shape (dh = 32, T <= 384; v4 takes any T,
+// v3 whole 128-row blocks).
 //
 // Reference: MultiHeadSelfAttention.call (nb:conv-hybrid-model c5:102-118): softmax(q k^T * dim^-0.5) v
 // on the per-head-interleaved qkv tensor [B*T, H*3*dh] (head h owns columns [96h, 96h+96) = q|k|v). One CTA per
@@ -386,7 +387,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
 
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nqb = T / kQB, nkb = T / 64;
+  // T need not be a multiple of the block sizes (the notebook's INPUT_SHAPE has T = 176): the last query block / key block
+  // is partial. Rows past T inside the loaded tile are the next sequence's (or TMA zero fill at the end of the tensor):
+  // finite garbage that is never stored as a query and is masked out as a key.
+  const int nqb = (T + kQB - 1) / kQB, nkb = (T + 63) / 64;
+  const bool ragged = (T & 63) != 0;
   const int ld = 3 * kDH * H;
 
   if (tid == 0) {
@@ -405,7 +410,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       mbar_init(&o_free[i], 8);
     }
     mbar_fence_init();
-    mbar_arrive_expect_tx(qk_full, static_cast<uint32_t>(T) * 128u);
+    mbar_arrive_expect_tx(qk_full, static_cast<uint32_t>(nqb) * kQB * 128u);
     for (int r = 0; r < nqb; ++r) tma_load_2d(qk + r * kQB * 128, &tmQK, qk_full, h * 3 * kDH, b * T + r * kQB);
   }
   if (tid == 0) ATT_TRACE(0);
@@ -414,11 +419,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   // ---- V^T into the canonical K-major, 128B-swizzled B-operand layout: element (d, key) ----
   {
     const bf16* vbase = qkv + static_cast<size_t>(b) * T * ld + h * 3 * kDH + 2 * kDH;
-    for (int key = tid; key < T; key += kThreadsTc2) {
+    for (int key = tid; key < nkb * 64; key += kThreadsTc2) {
       const uint4* vp = reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(key) * ld);
       uint4 vv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vv[i] = __ldg(vp + i);
+      for (int i = 0; i < 4; ++i) vv[i] = key < T ? __ldg(vp + i) : make_uint4(0u, 0u, 0u, 0u);  // padded keys: V = 0 (their P is 0 too)
       const int kb = key >> 6, kin = key & 63;
       uint8_t* blk = vt + kb * 4096;
 #pragma unroll
@@ -434,7 +439,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
           }
         }
       }
-      if (key_mask != nullptr) mb[key] = key_mask[static_cast<size_t>(b) * T + key] ? 0.f : -1.0e9f * 1.4426950408889634f;
+      if (key_mask != nullptr || ragged) {
+        const bool valid = key < T && (key_mask == nullptr || key_mask[static_cast<size_t>(b) * T + key] != 0);
+        mb[key] = valid ? 0.f : -1.0e9f * 1.4426950408889634f;
+      }
     }
   }
   fence_proxy_async_smem();  // V^T (generic-proxy writes) must be visible to the tensor core's async proxy
@@ -521,7 +529,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
     const int hh = (warp - 1) >> 2;               // which 32 of the 64 keys of a block / which 16 output columns
     const int r = q * 32 + lane;                  // row within the 128-query block
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const bool masked = key_mask != nullptr;
+    const bool masked = key_mask != nullptr || ragged;
     float* xmax = xch;                            // [2][128]
     float* xsum = xch + 256;                      // [2][128]
     uint32_t g = 0, pc = 0;
@@ -601,7 +609,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       xsum[hh * 128 + r] = sum;
       named_bar_sync(1 + q, 64);
       sum += xsum[(hh ^ 1) * 128 + r];
-      if (lse_out != nullptr && hh == 0) lse_out[(static_cast<size_t>(b) * H + h) * T + blk * kQB + r] = mx + log2f(sum);
+      const bool row_ok = blk * kQB + r < T;
+      if (lse_out != nullptr && hh == 0 && row_ok) lse_out[(static_cast<size_t>(b) * H + h) * T + blk * kQB + r] = mx + log2f(sum);
       // ---- epilogue of this block: O / sum -> bf16 -> merged-head output ----
       mbar_wait(&o_full[obuf], (blk >> 1) & 1u);
       tc_fence_after();
@@ -617,8 +626,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) po[j] = pack_bf16x2(__uint_as_float(raw16[2 * j]) * inv, __uint_as_float(raw16[2 * j + 1]) * inv);
       uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + blk * kQB + r) * (kDH * H) + h * kDH + hh * 16);
-      dst[0] = make_uint4(po[0], po[1], po[2], po[3]);
-      dst[1] = make_uint4(po[4], po[5], po[6], po[7]);
+      if (row_ok) {
+        dst[0] = make_uint4(po[0], po[1], po[2], po[3]);
+        dst[1] = make_uint4(po[4], po[5], po[6], po[7]);
+      }
       if (tid == 32) ATT_TRACE(68 + blk);
     }
   }
@@ -631,7 +642,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
 }  // namespace
 
 bool attention_tc_applicable(const AttnArgs& a) {
-  return a.dh == kDH && a.pos == nullptr && a.T <= kMaxT && a.T % kQB == 0;  // T in {128, 256, 384}
+  static const int tc2 = getenv("ISHARA_ATTN_TC2") ? atoi(getenv("ISHARA_ATTN_TC2")) : 1;
+  // v4 (attn_tc2_kernel) takes any T <= 384 (partial last blocks); v3 needs whole 128-row blocks
+  return a.dh == kDH && a.pos == nullptr && a.T <= kMaxT && a.T >= 1 && (tc2 || a.T % kQB == 0);
 }
 
 int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
