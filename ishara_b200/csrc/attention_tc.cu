@@ -368,7 +368,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   uint8_t* qk = smem;                          // [T][128 B] swizzled: cols 0-31 q, 32-63 k
   uint8_t* vt = qk + kQKBytes;                 // [T/64][32][128 B] swizzled V^T
   float* mb = reinterpret_cast<float*>(vt + kVtBytes + kP2Bytes);  // [T] additive key bias (log2 domain), only with a mask
-  float* xch = mb + kMaxT;                     // [2 (max | sum)][2 column halves][128 rows]
+  float* qn = mb + kMaxT;                      // [T] |q_i| of every query row (score bound), written once in the prologue
+  float* xch = qn + kMaxT;                     // [2 (max | sum)][2 column halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 512);
   uint64_t* qk_full = bars;        // TMA landed
   uint64_t* s_full = bars + 1;     // [2] S slot holds Q K_kb^T
@@ -453,11 +454,31 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
   // largest |k_j| and |q_i| of this head: the score bound, and whether it is tight enough for every row
   mbar_wait(qk_full, 0);
   if (tid == 32) ATT_TRACE(2);
+  // the first three score tiles of query block 0 are the same whether or not the exact-maximum sweep is needed: issue
+  // them now, so that the tensor core works while every warp computes the row norms below
+  const int npre = nkb < 3 ? nkb : 3;
+  if (warp == 0 && lane == 0) {
+    const uint32_t tb = *tmem_slot;
+    constexpr uint32_t IDESC_S0 = umma_idesc(128, 64, 1);
+    tc_fence_after();
+    for (int kb = 0; kb < npre; ++kb) {
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2)
+        umma_bf16(tb + kb * 64, umma_desc_sw128(smem_base + k2 * 32), umma_desc_sw128(smem_base + kb * 64 * 128 + 64 + k2 * 32), IDESC_S0, k2);
+      umma_commit(sfull(static_cast<uint32_t>(kb)));
+      if (kb < 8) ATT_TRACE(40 + kb);
+    }
+  }
+  __syncwarp();
   {
     float km = 0.f, qm = 0.f;
-    for (int t = tid; t < T; t += kThreadsTc2) {
-      km = fmaxf(km, row_half_norm2(qk, t, 4));
-      qm = fmaxf(qm, row_half_norm2(qk, t, 0));
+    for (int t = tid; t < nqb * kQB; t += kThreadsTc2) {
+      const float q2 = row_half_norm2(qk, t, 0);
+      qn[t] = sqrtf(q2);
+      if (t < T) {
+        km = fmaxf(km, row_half_norm2(qk, t, 4));
+        qm = fmaxf(qm, q2);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -488,6 +509,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       for (int blk = 0; blk < nqb; ++blk) {
         for (int sweep = exact ? 0 : 1; sweep < 2; ++sweep) {
           for (int kb = 0; kb < nkb; ++kb, ++g) {
+            if (g < static_cast<uint32_t>(npre)) continue;  // issued before the norm pass
             const uint32_t slot = g % 3u;
             if (g >= 3) mbar_wait(sfree(slot), ((g / 3u) - 1u) & 1u);
             tc_fence_after();
@@ -533,10 +555,34 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
     float* xmax = xch;                            // [2][128]
     float* xsum = xch + 256;                      // [2][128]
     uint32_t g = 0, pc = 0;
+    // O / sum -> bf16 -> merged-head output for query block eb. Called one key block INTO the next query block (and after
+    // the last one), so the wait for the block's last P V MMA hides under the next block's first exponentials.
+    auto epilogue = [&](int eb, float esum) {
+      const uint32_t eo = eb & 1;
+      mbar_wait(&o_full[eo], (eb >> 1) & 1u);
+      tc_fence_after();
+      if (tid == 32) ATT_TRACE(64 + eb);
+      uint32_t raw16[16];
+      tmem_ld16(tmem_O + eo * 32 + lane_addr + hh * 16, raw16);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[eo]);
+      const float inv = 1.f / esum;
+      uint32_t po[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) po[j] = pack_bf16x2(__uint_as_float(raw16[2 * j]) * inv, __uint_as_float(raw16[2 * j + 1]) * inv);
+      if (eb * kQB + r < T) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + eb * kQB + r) * (kDH * H) + h * kDH + hh * 16);
+        dst[0] = make_uint4(po[0], po[1], po[2], po[3]);
+        dst[1] = make_uint4(po[4], po[5], po[6], po[7]);
+      }
+      if (tid == 32) ATT_TRACE(68 + eb);
+    };
+    float sum_prev = 1.f;
     for (int blk = 0; blk < nqb; ++blk) {
-      const uint32_t obuf = blk & 1;
       // ---- exponent offset: the Cauchy-Schwarz bound of this row, or (sweep 0) the exact maximum of s * scale_log2 + mask bias ----
-      float mx = scale_log2 * sqrtf(row_half_norm2(qk, blk * kQB + r, 0)) * kmax;
+      float mx = scale_log2 * qn[blk * kQB + r] * kmax;
       if (exact) {
       mx = -INFINITY;
       for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -603,6 +649,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[ps]);
         if (tid == 32 && pc < 18) ATT_TRACE(5 + 2 * pc);
+        if (kb == 0 && blk > 0) epilogue(blk - 1, sum_prev);
       }
       // row sum over both key halves of every block
       float sum = s0 + s1;
@@ -611,27 +658,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQK, const bf16* __restrict
       sum += xsum[(hh ^ 1) * 128 + r];
       const bool row_ok = blk * kQB + r < T;
       if (lse_out != nullptr && hh == 0 && row_ok) lse_out[(static_cast<size_t>(b) * H + h) * T + blk * kQB + r] = mx + log2f(sum);
-      // ---- epilogue of this block: O / sum -> bf16 -> merged-head output ----
-      mbar_wait(&o_full[obuf], (blk >> 1) & 1u);
-      tc_fence_after();
-      if (tid == 32) ATT_TRACE(64 + blk);
-      uint32_t raw16[16];
-      tmem_ld16(tmem_O + obuf * 32 + lane_addr + hh * 16, raw16);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[obuf]);
-      const float inv = 1.f / sum;
-      uint32_t po[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) po[j] = pack_bf16x2(__uint_as_float(raw16[2 * j]) * inv, __uint_as_float(raw16[2 * j + 1]) * inv);
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + blk * kQB + r) * (kDH * H) + h * kDH + hh * 16);
-      if (row_ok) {
-        dst[0] = make_uint4(po[0], po[1], po[2], po[3]);
-        dst[1] = make_uint4(po[4], po[5], po[6], po[7]);
-      }
-      if (tid == 32) ATT_TRACE(68 + blk);
+      sum_prev = sum;
     }
+    epilogue(nqb - 1, sum_prev);
   }
   tc_fence_before();
   __syncthreads();
@@ -655,7 +684,7 @@ int attention_tc_launch(const AttnArgs& a, cudaStream_t stream) {
   static const int tc2 = getenv("ISHARA_ATTN_TC2") ? atoi(getenv("ISHARA_ATTN_TC2")) : 1;
   if (tc2) {
     // v4: 64-key streaming, two CTAs per SM
-    const int smem2 = kQKBytes + kVtBytes + kP2Bytes + kMaxT * 4 + 2048 + 256 + 1024;
+    const int smem2 = kQKBytes + kVtBytes + kP2Bytes + 2 * kMaxT * 4 + 2048 + 256 + 1024;
     static bool attr2 = false;
     if (!attr2) {
       ISHARA_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
