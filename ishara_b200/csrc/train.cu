@@ -516,8 +516,11 @@ struct TB {
     const int64_t nE = static_cast<int64_t>(M) * E;
     ts->fwd.push_back(ln_fwd(S_in, XN, ln, 1e-6f));
     ts->fwd.push_back(linear(XN, D, base + ".0", true, E, U));
-    ts->fwd.push_back([=](cudaStream_t s) { return act_fwd_launch(U, Hh, nE, TACT_SWISH, s); });
-    const uint32_t site_h = drop_inplace(ts->fwd, Hh, E, p);
+    // swish and the inner dropout in one pass over the [M, E] tensor (forward and backward)
+    const uint32_t site_h = p > 0.f ? ++site_counter : 0;
+    const uint64_t* keyp_h = ts->keys_dev + site_h;
+    if (site_h) ts->fwd.push_back([=](cudaStream_t s) { return act_drop_fwd_launch(U, Hh, nE, TACT_SWISH, p, keyp_h, s); });
+    else ts->fwd.push_back([=](cudaStream_t s) { return act_fwd_launch(U, Hh, nE, TACT_SWISH, s); });
     const uint32_t site = branch_fwd(Hh, E, base + ".2", true, S_in, S_out, pb, false);
 
     std::vector<Step> bw;
@@ -526,10 +529,10 @@ struct TB {
     const bf16* dY = branch_bwd(bw, dOut, pb, site, false);
     bw.push_back(wgrad(Hh, E, E, dY, D, D, base + ".2", true));
     bw.push_back(dgrad(dY, D, base + ".2", E, gW1));  // dH
-    if (site_h) drop_inplace(bw, gW1, E, p, site_h);
     {
       bf16* g1 = gW1;
-      bw.push_back([=](cudaStream_t s) { return act_bwd_launch(g1, U, g1, nE, TACT_SWISH, s); });  // dU
+      if (site_h) bw.push_back([=](cudaStream_t s) { return act_bwd_drop_launch(g1, U, g1, nE, TACT_SWISH, p, keyp_h, s); });  // dU
+      else bw.push_back([=](cudaStream_t s) { return act_bwd_launch(g1, U, g1, nE, TACT_SWISH, s); });
     }
     snap(bw, base + ".u", gW1, E);
     bw.push_back(wgrad(XN, D, D, gW1, E, E, base + ".0", true));
@@ -739,10 +742,11 @@ struct TB {
     }
     bw.push_back(wgrad(HH, C, C, dL, Vp, V, "classifier", true));
     bw.push_back(dgrad(dL, Vp, "classifier", C, gW1));  // dHH
-    if (site) drop_inplace(bw, gW1, C, p, site);
     {
       bf16* g1 = gW1;
-      bw.push_back([=](cudaStream_t s) { return act_bwd_launch(g1, HH, g1, nC, TACT_RELU, s); });
+      const uint64_t* keyp = ts->keys_dev + site;
+      if (site) bw.push_back([=](cudaStream_t s) { return act_bwd_drop_launch(g1, HH, g1, nC, TACT_RELU, p, keyp, s); });
+      else bw.push_back([=](cudaStream_t s) { return act_bwd_launch(g1, HH, g1, nC, TACT_RELU, s); });
     }
     snap(bw, "head.h", gW1, C);
     bw.push_back(wgrad(S_in, D, D, gW1, C, C, "top_conv", true));

@@ -49,21 +49,48 @@ inline int ew_grid(int64_t nvec) {
   for (int64_t v = static_cast<int64_t>(blockIdx.x) * kEwThreads + threadIdx.x; v < (nvec); v += static_cast<int64_t>(gridDim.x) * kEwThreads)
 
 // ---- activations ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads) act_fwd_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int64_t nvec, int act) {
+// 8 keep factors (inv_keep or 0) of element vector v: the same bits dropout_kernel draws for a tensor of the same shape
+__device__ __forceinline__ void drop_factors8(uint64_t key, int64_t v, uint32_t thr16, float inv_keep, float (&k)[8]) {
+  const uint64_t r0 = mix64(key + 2ull * static_cast<uint64_t>(v)), r1 = mix64(key + 2ull * static_cast<uint64_t>(v) + 1ull);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t u = static_cast<uint32_t>(((i < 4 ? r0 : r1) >> (16 * (i & 3))) & 0xFFFFu);
+    k[i] = u >= thr16 ? inv_keep : 0.f;
+  }
+}
+// out = drop(act(in)): key_ptr == nullptr -> no dropout (one pass instead of activation + in-place dropout)
+__global__ void __launch_bounds__(kEwThreads) act_fwd_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int64_t nvec, int act,
+                                                               uint32_t thr16, float inv_keep, const uint64_t* __restrict__ key_ptr) {
+  const uint64_t key = key_ptr != nullptr ? *key_ptr : 0ull;
   EW_LOOP(v, nvec) {
     float f[8];
     ld8(in + v * 8, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = act == TACT_SWISH ? swish_f(f[i]) : (act == TACT_RELU ? fmaxf(f[i], 0.f) : f[i]);
+    if (key_ptr != nullptr) {
+      float k[8];
+      drop_factors8(key, v, thr16, inv_keep, k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] *= k[i];
+    }
     st8(out + v * 8, f);
   }
 }
+// dU = act'(ref) * drop'(dH): key_ptr == nullptr -> no dropout
 __global__ void __launch_bounds__(kEwThreads) act_bwd_kernel(const bf16* __restrict__ dH, const bf16* __restrict__ ref, bf16* __restrict__ dU,
-                                                               int64_t nvec, int act) {
+                                                               int64_t nvec, int act, uint32_t thr16, float inv_keep,
+                                                               const uint64_t* __restrict__ key_ptr) {
+  const uint64_t key = key_ptr != nullptr ? *key_ptr : 0ull;
   EW_LOOP(v, nvec) {
     float d[8], r[8];
     ld8(dH + v * 8, d);
     ld8(ref + v * 8, r);
+    if (key_ptr != nullptr) {
+      float k[8];
+      drop_factors8(key, v, thr16, inv_keep, k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] *= k[i];
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = act == TACT_SWISH ? d[i] * swish_d(r[i]) : (act == TACT_RELU ? (r[i] > 0.f ? d[i] : 0.f) : d[i]);
     st8(dU + v * 8, d);
@@ -625,13 +652,23 @@ int check(const char* what) {
 
 int act_fwd_launch(const bf16* in, bf16* out, int64_t n, int act, cudaStream_t s) {
   REQUIRE(n % 8 == 0, "act_fwd: n % 8 != 0");
-  act_fwd_kernel<<<ew_grid(n / 8), kEwThreads, 0, s>>>(in, out, n / 8, act);
+  act_fwd_kernel<<<ew_grid(n / 8), kEwThreads, 0, s>>>(in, out, n / 8, act, 0u, 1.f, nullptr);
   return check("act_fwd");
+}
+int act_drop_fwd_launch(const bf16* in, bf16* out, int64_t n, int act, float p, const uint64_t* key_dev, cudaStream_t s) {
+  REQUIRE(n % 8 == 0 && p >= 0.f && p < 1.f && key_dev != nullptr, "act_drop_fwd: bad arguments");
+  act_fwd_kernel<<<ew_grid(n / 8), kEwThreads, 0, s>>>(in, out, n / 8, act, dropout_thr16(p), 1.f / (1.f - p), key_dev);
+  return check("act_drop_fwd");
 }
 int act_bwd_launch(const bf16* dH, const bf16* ref, bf16* dU, int64_t n, int act, cudaStream_t s) {
   REQUIRE(n % 8 == 0, "act_bwd: n % 8 != 0");
-  act_bwd_kernel<<<ew_grid(n / 8), kEwThreads, 0, s>>>(dH, ref, dU, n / 8, act);
+  act_bwd_kernel<<<ew_grid(n / 8), kEwThreads, 0, s>>>(dH, ref, dU, n / 8, act, 0u, 1.f, nullptr);
   return check("act_bwd");
+}
+int act_bwd_drop_launch(const bf16* dH, const bf16* ref, bf16* dU, int64_t n, int act, float p, const uint64_t* key_dev, cudaStream_t s) {
+  REQUIRE(n % 8 == 0 && p >= 0.f && p < 1.f && key_dev != nullptr, "act_bwd_drop: bad arguments");
+  act_bwd_kernel<<<ew_grid(n / 8), kEwThreads, 0, s>>>(dH, ref, dU, n / 8, act, dropout_thr16(p), 1.f / (1.f - p), key_dev);
+  return check("act_bwd_drop");
 }
 int glu_fwd_launch(const bf16* P, bf16* out, int64_t M, int C, cudaStream_t s) {
   REQUIRE(C % 8 == 0, "glu_fwd: C % 8 != 0");

@@ -34,6 +34,9 @@ int dropout_launch(const bf16* x, const bf16* resid, bf16* y, int64_t M, int C, 
 int dropout_keyed_launch(const bf16* x, const bf16* resid, bf16* y, int64_t M, int C, int T, float p, const uint64_t* key_dev,
                          int per_sample, cudaStream_t s);
 int dropout_keys_launch(uint64_t seed, uint64_t* keys_dev, int n, cudaStream_t s);
+// activation and elementwise dropout of the same [M, C] tensor in one pass (same mask bits as dropout_kernel)
+int act_drop_fwd_launch(const bf16* in, bf16* out, int64_t n, int act, float p, const uint64_t* key_dev, cudaStream_t s);
+int act_bwd_drop_launch(const bf16* dH, const bf16* ref, bf16* dU, int64_t n, int act, float p, const uint64_t* key_dev, cudaStream_t s);
 
 // ---- reductions (train_ew.cu) ---------------------------------------------------------------------
 // per-sequence column sums seqsum[B,C] (fp32, overwritten) and, when sum/sumsq != null, whole-batch sum / sum of
