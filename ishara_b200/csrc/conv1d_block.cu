@@ -112,16 +112,37 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int row_g0 = b * T + rank * kBM;
   const uint32_t w_base = smem_base + kHRegion;
 
+  // Expand operand slots. Loads 0-3 feed accumulator half 0, loads 4-7 half 1; the second half only uses the two slots
+  // that do not overlap boxes 0-3, so the drain of half 0 can run under the MMAs of half 1.
+  //   slot 0 = [0, 48K) (boxes 0-2), slot 1 = [72K, 120K) (boxes 4-6), slot 2 = [120K, 168K) (boxes 6-7 + Wp slot 0)
+  const uint32_t slot_off[3] = {0u, 72u * 1024u, 120u * 1024u};
+  const int slot_of[8] = {0, 1, 2, 0, 1, 2, 1, 2};
+  const int use_of[8] = {0, 0, 0, 1, 1, 1, 2, 2};
+
   if (warp == 0 && lane == 0) {
+    // the TMA thread initialises the barriers its first loads signal and issues those loads BEFORE the CTA-wide
+    // barrier below (timeline: the first expand MMA used to start 2.4k cycles into the CTA, ~1k of it this prologue)
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmWe);
+    for (int s = 0; s < 3; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) mbar_init(&bars->wfull[s], 1);
+    mbar_fence_init();
+    for (int i = 0; i < 3; ++i) {
+      const int s = slot_of[i];
+      mbar_arrive_expect_tx(&bars->full[s], kXSlot);
+      uint8_t* dst = smem + slot_off[s];
+      tma_load_2d(dst, &tmX, &bars->full[s], i * kBK, row_g0);
+      tma_load_2d(dst + kAStageBytes, &tmWe, &bars->full[s], i * kBK, 0);
+    }
     tma_prefetch_desc(&tmWp);
+    // Wp slice 1 lives in [176K, 208K): never touched by the expand slots, prefetch it right away
+    mbar_arrive_expect_tx(&bars->wfull[1], kWSlot);
+    tma_load_2d(smem + kHRegion + kWSlot, &tmWp, &bars->wfull[1], 1 * kBK, 0);
     tma_prefetch_desc(&tmO0);
     if (pr.ln_g != nullptr) tma_prefetch_desc(&tmO1);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 3; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars->accf[s], 1); mbar_init(&bars->wfull[s], 1); mbar_init(&bars->wempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->accf[s], 1); mbar_init(&bars->wempty[s], 1); }
     for (int s = 0; s < 8; ++s) mbar_init(&bars->boxr[s], 8);
     mbar_init(&bars->acc2f, 1);
     mbar_init(&bars->taps_full, 2);
@@ -138,21 +159,12 @@ conv1d_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   constexpr uint32_t IDESC = umma_idesc(kBM, 256, 1);
   if (threadIdx.x == 0) CB_TRACE(0);
 
-  // Expand operand slots. Loads 0-3 feed accumulator half 0, loads 4-7 half 1; the second half only uses the two slots
-  // that do not overlap boxes 0-3, so the drain of half 0 can run under the MMAs of half 1.
-  //   slot 0 = [0, 48K) (boxes 0-2), slot 1 = [72K, 120K) (boxes 4-6), slot 2 = [120K, 168K) (boxes 6-7 + Wp slot 0)
-  const uint32_t slot_off[3] = {0u, 72u * 1024u, 120u * 1024u};
-  const int slot_of[8] = {0, 1, 2, 0, 1, 2, 1, 2};
-  const int use_of[8] = {0, 0, 0, 1, 1, 1, 2, 2};
-
   // ======================================= phase 1: expand GEMM + drain =======================================
   if (warp == 0) {
     if (lane == 0) {
-      // Wp slice 1 lives in [176K, 208K): never touched by the expand slots, prefetch it right away
-      mbar_arrive_expect_tx(&bars->wfull[1], kWSlot);
-      tma_load_2d(smem + kHRegion + kWSlot, &tmWp, &bars->wfull[1], 1 * kBK, 0);
+      // (loads 0-2 and Wp slice 1 were issued in the prologue)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 3; i < 8; ++i) {
         const int s = slot_of[i], u = use_of[i];
         const int nh = i >> 2, kb = i & 3;
         if (u > 0) mbar_wait(&bars->empty[s], static_cast<uint32_t>((u - 1) & 1));

@@ -283,10 +283,12 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (warp == 4 && lane == 0 && q < 4) FFN_TRACE(it, 22 + q);  // epi1(q) done
       }
       // ---- final epilogue of the tile: acc2 -> +b2 -> +residual -> [LN] -> S (and LN'(S)) ----
+      uint4 rq[8];
+      row16_resid_ldg(ep, th, c, rq);       // residual row segment: in flight while the last GEMM2 finishes
       mbar_wait(&bars->acc2_full, it & 1);  // every GEMM2 of the tile has retired: the H bytes are free for staging
       tc_fence_after();
       if (warp == 4 && lane == 0) FFN_TRACE(it, 26);
-      epilogue_row16<true>(ep, th, row0, q4, c, lane, st, &tmO0h, &tmO1h, xch2, cvec, rst, nullptr, 0u);
+      epilogue_row16<true>(ep, th, row0, q4, c, lane, st, &tmO0h, &tmO1h, xch2, cvec, rst, nullptr, 0u, rq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc2_empty);
