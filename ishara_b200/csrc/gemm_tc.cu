@@ -407,11 +407,13 @@ int gemm_launch(const GemmPlan& p_in, int num_sms, cudaStream_t stream) {
 #else
   static const int dbg = 0;  // bisect bits and tracing are compiled out of the shipped library
 #endif
-  static const int force = getenv("ISHARA_GEMM_RESIDENT") ? atoi(getenv("ISHARA_GEMM_RESIDENT")) : 0;  // measured: no gain, off by default
+  static const int force = getenv("ISHARA_GEMM_RESIDENT") ? atoi(getenv("ISHARA_GEMM_RESIDENT")) : 0;  // 1 = wherever it fits, -1 = never, 0 = qkv only
   static const int pair = getenv("ISHARA_GEMM_PAIR") ? atoi(getenv("ISHARA_GEMM_PAIR")) : 0;  // CTA-pair variant: opt-in (measured slower)
   GemmPlan p = p_in;
   p.epi.dbg = dbg;
-  if (force == 0) p.no_resident = true;
+  // weight-stationary only where it measured faster: plain GEMMs with three or more n-tiles (qkv, N = 768: 55 -> 51 us;
+  // the one- and two-tile GEMMs lose more on the 8-warp epilogue the variant is limited to than they gain on the ring)
+  if (force < 0 || (force == 0 && !(!p.row_mode && !p.out_f32 && p.block_n == 256 && p.N >= 3 * 256))) p.no_resident = true;
 #ifdef ISHARA_TRACE_BUILD
   static const int trace = getenv("ISHARA_GEMM_TRACE") ? atoi(getenv("ISHARA_GEMM_TRACE")) : 0;
 #else

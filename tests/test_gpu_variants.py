@@ -36,6 +36,7 @@ VARIANTS = {
     "default": {},
     "gemm_pair": {"ISHARA_GEMM_PAIR": "1"},
     "gemm_resident": {"ISHARA_GEMM_RESIDENT": "1"},
+    "gemm_streaming": {"ISHARA_GEMM_RESIDENT": "-1"},          # no weight-stationary GEMM at all (default: qkv only)
     "conv1d_unfused": {"ISHARA_CONV1D_BLOCK": "0"},           # three-kernel Conv1DBlock instead of conv1d_block.cu
     "conv1d_fused": {"ISHARA_CONV1D_FUSED": "1"},
     "attn_mma_sync": {"ISHARA_ATTN_TC": "0"},
@@ -75,6 +76,7 @@ def test_opt_in_variants_match_oracle_and_default(tmp_path):
     # same kernels, different launch mechanism / operand residency => bit-identical results
     assert np.array_equal(outs["no_graph"], base)
     assert np.array_equal(outs["gemm_resident"], base)
+    assert np.array_equal(outs["gemm_streaming"], base)
     assert np.array_equal(outs["gemm_pair"], base)
     assert np.array_equal(outs["ffn_v2"], base)       # same roundings, different pipelining
     assert np.array_equal(outs["lanes_3"], base)      # lanes only re-partition the batch: every kernel is per-sequence
