@@ -200,6 +200,30 @@ def workload_config(args, extra=None):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def pin_host_threads(torch, local, world):
+    """Multi-GPU runs: bind this rank's host threads (and therefore its pinned staging buffers, first-touch) to its own slice
+    of the CPUs that are local to its GPU's PCIe root (sysfs local_cpulist), instead of all ranks floating over - and
+    allocating on - NUMA node 0. Returns what was done for the JSON line; never fails the run."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        cpus = []
+        for part in open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        # ranks whose GPUs share these CPUs split them evenly (at least two CPUs per rank: Python thread + copy thread)
+        per = max(2, len(allowed) // max(1, min(world, 8)))
+        start = (local * per) % max(1, len(allowed))
+        mine = [allowed[(start + i) % len(allowed)] for i in range(min(per, len(allowed)))]
+        os.sched_setaffinity(0, set(mine))
+        return {"pci": bdf, "cpus": mine, "local_cpus": len(allowed)}
+    except Exception as ex:  # no sysfs / no permission: leave the default affinity
+        return {"error": repr(ex)}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -220,6 +244,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ishara_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    host_affinity = pin_host_threads(torch, local, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -552,6 +577,7 @@ def run_ours(args):
             "whole_step": whole if rank == 0 else None,
             "timed_regions_ms": [round(v, 3) for v in region_ms],
             "cfg1": cfg1, "cfg5": cfg5,
+            "host_affinity": host_affinity,
             "kernels": kernels,
             "train": train,
             "preprocess": prep,
