@@ -11,6 +11,8 @@
 // Decode: decode_phrase (c8:4-12): argmax over classes (first index on ties) -> keep position t only
 // if t < T-1 and ids[t] != ids[t+1] -> drop blanks. NOTE the reference quirk, reproduced on purpose:
 // the last run is never emitted because index T-1 is never selected.
+#include <algorithm>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -464,7 +466,7 @@ ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ la
 constexpr int kDecThreads = 384;  // frames per staged chunk = threads per CTA (T = 384: one pass)
 __global__ void __launch_bounds__(kDecThreads)
 greedy_decode_kernel(const float* __restrict__ logits, int B, int T, int V, int blank, int32_t* __restrict__ ids_out,
-                     int32_t* __restrict__ lens) {
+                     int32_t* __restrict__ lens, int chunk) {
   extern __shared__ int32_t smem_dec[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int b = blockIdx.x;
@@ -472,8 +474,8 @@ greedy_decode_kernel(const float* __restrict__ logits, int B, int T, int V, int 
   float* rows = reinterpret_cast<float*>(smem_dec + ((T + 1 + 3) & ~3));  // [kDecThreads][V + 1]
   const int pitch = V + 1;
   const float* lg = logits + static_cast<size_t>(b) * T * V;
-  for (int t0 = 0; t0 < T; t0 += kDecThreads) {
-    const int nf = min(kDecThreads, T - t0);
+  for (int t0 = 0; t0 < T; t0 += chunk) {  // chunk <= kDecThreads frames fit the shared-memory staging (large vocabularies: fewer)
+    const int nf = min(chunk, T - t0);
     const float* src = lg + static_cast<size_t>(t0) * V;
     const int n = nf * V;
     if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (V % 4 == 0)) {
@@ -639,17 +641,24 @@ int greedy_decode_launch(const float* logits, int B, int T, int V, int blank, in
     set_last_error("greedy_decode: bad shape");
     return 2;
   }
-  const size_t smem = (static_cast<size_t>((T + 1 + 3) & ~3) + static_cast<size_t>(kDecThreads) * (V + 1)) * sizeof(int32_t);
-  if (smem > 200 * 1024) {
+  const size_t ids_words = static_cast<size_t>((T + 1 + 3) & ~3);
+  const size_t budget = 96 * 1024 / sizeof(int32_t);  // two CTAs per SM
+  if (ids_words + static_cast<size_t>(V + 1) > 200 * 1024 / sizeof(int32_t)) {
     set_last_error("greedy_decode: T / num_classes too large for the shared-memory staging");
     return 2;
   }
+  int chunk = kDecThreads;
+  if (ids_words + static_cast<size_t>(chunk) * (V + 1) > budget) {
+    const size_t room = ids_words + static_cast<size_t>(V + 1) > budget ? static_cast<size_t>(V + 1) : budget - ids_words;
+    chunk = static_cast<int>(std::max<size_t>(1, std::min<size_t>(kDecThreads, room / (V + 1))));
+  }
+  const size_t smem = (ids_words + static_cast<size_t>(chunk) * (V + 1)) * sizeof(int32_t);
   static size_t smem_attr = 48 * 1024;
   if (smem > smem_attr) {
     ISHARA_CUDA_OK(cudaFuncSetAttribute(greedy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     smem_attr = smem;
   }
-  greedy_decode_kernel<<<B, kDecThreads, smem, stream>>>(logits, B, T, V, blank, ids_out, lens);
+  greedy_decode_kernel<<<B, kDecThreads, smem, stream>>>(logits, B, T, V, blank, ids_out, lens, chunk);
   ISHARA_CUDA_OK(cudaGetLastError());
   note_launch();
   return 0;

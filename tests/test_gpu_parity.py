@@ -320,6 +320,10 @@ def test_decode_edge_cases_quirk_ties_and_short_sequences():
     lg = rng.standard_normal((3, 50, 13)).astype(np.float32)
     got = ib.decode_ids(lg, blank=12)
     assert [list(g) for g in got] == [list(O.decode_phrase(r, blank=12)) for r in lg]
+    # large vocabulary: the shared-memory staging holds fewer frames per pass
+    lg = rng.standard_normal((2, 700, 1000)).astype(np.float32)
+    got = ib.decode_ids(lg, blank=999)
+    assert [list(g) for g in got] == [list(O.decode_phrase(r, blank=999)) for r in lg]
 
 
 def test_decode_full_size_properties():
@@ -411,6 +415,27 @@ def test_explicit_mask_argument():
     with pytest.raises(ValueError):
         m0(x, mask=mask)                                          # a mask needs mask_mode="propagated"
     m0.close()
+    m.close()
+
+
+def test_lanes_with_propagated_masks_are_batch_invariant():
+    """Batches of 96+ sequences run as two lanes on parallel graph branches, each with its own slice of the mask / window
+    bit / valid count tensors: row b of the big batch must equal the same sequence alone, bit for bit, in both the
+    Masking(0.0) mode and with an explicit mask."""
+    cfg = O.Config()
+    params = O.init_params(cfg, seed=42)
+    m = _masked_model(cfg, params)
+    x = O.make_inputs(cfg, 100, seed=31, ragged=True)
+    got = m(x)
+    got2 = m(x)                                                   # graph replay
+    assert np.array_equal(got, got2)
+    for b in (0, 49, 50, 99):
+        assert np.array_equal(m(x[b:b + 1])[0], got[b]), b
+    mask = (x != 0).any(-1)
+    mask[:, :5] = True                                            # differs from the derived mask on every sequence
+    gm = m(x, mask=mask)
+    for b in (0, 50, 99):
+        assert np.array_equal(m(x[b:b + 1], mask=mask[b:b + 1])[0], gm[b]), b
     m.close()
 
 
