@@ -276,6 +276,11 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path, optimizer):
     assert np.allclose(got, want, rtol=5e-4), (got, want)
     w_got = m2.get_weights()
     for k in w_want:
+        if k.endswith(".conv.depthwise_conv.bias"):
+            # exactly-zero true gradient (BatchNorm follows): what the optimiser sees is fp32 atomics noise, which Adam's
+            # normalisation turns into steps of up to +-lr each - two runs may differ by lr per step on this tensor
+            assert np.abs(w_got[k] - w_want[k]).max() <= 3 * 1e-3 + 1e-6, k
+            continue
         assert np.abs(w_got[k] - w_want[k]).max() <= 2e-3 * (np.abs(w_want[k]).max() + 1e-6), k
     m.close()
     m2.close()
