@@ -263,14 +263,20 @@ ctc_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
 // that the first mass to arrive is representable. (One exponent for the whole warp is NOT enough: the states a likely
 // path passes through can sit more than 2^-126 below the currently largest state - measured: a 33-label sequence lost
 // 18 nats that way.) log2 p(l|x) = lse2 over the last two states of log2(a) + K; no mass there <=> infeasible labelling.
-template <int SPL>
+// GRAD: the training variant. The alpha sweep also parks a_t and K_t of every frame, then a mirrored beta sweep
+// (beta_t(s) = y_t(s) (beta_{t+1}(s) + beta_{t+1}(s+1) + [skip] beta_{t+1}(s+2)), started from a virtual beta_T(S-1) = 1) parks
+// b_t and its exponents; ctc_grad_kernel turns them into log2 alpha + log2 beta per state (mode[b] = 0). Sequences outside
+// the linear range get mode[b] = 1 and are redone by the log-domain kernel into the same workspace.
+template <int SPL, bool GRAD>
 __global__ void __launch_bounds__(32)
 ctc_alpha_linear_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
-                        float* __restrict__ nll) {
+                        float* __restrict__ nll, float* __restrict__ alpha_ws, float* __restrict__ beta_ws, int* __restrict__ ka_ws,
+                        int* __restrict__ kb_ws, int* __restrict__ mode) {
   extern __shared__ __align__(16) float smem_ctc[];
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x;
-  float* blk = smem_ctc;  // [2][kCtcBlk * V]
+  float* lse = smem_ctc;                                   // [T] log2-domain frame log-sum-exp (GRAD only)
+  float* blk = smem_ctc + (GRAD ? ((T + 3) & ~3) : 0);     // [2][kCtcBlk * V]
   const int blk_floats = kCtcBlk * V;
   const float* lg = logits + static_cast<size_t>(b) * T * V;
   const int32_t* lab = labels + static_cast<size_t>(b) * L;
@@ -298,6 +304,7 @@ ctc_alpha_linear_kernel(const float* __restrict__ logits, const int32_t* __restr
   // with five divergent regions per step and was slower (197 us) than the log-domain kernel
   int extoff[SPL];            // byte offset of the state's class inside a staged logits row
   float skipf[SPL], livef[SPL];
+  float skipb[SPL];           // beta: transition to s + 2 allowed (GRAD only)
 #pragma unroll
   for (int i = 0; i < SPL; ++i) {
     const int s = lane * SPL + i;
@@ -306,7 +313,10 @@ ctc_alpha_linear_kernel(const float* __restrict__ logits, const int32_t* __restr
     extoff[i] = e * 4;
     livef[i] = s < S ? 1.f : 0.f;
     skipf[i] = ((s < S) && (s & 1) && (s >= 3) && (ctc_label(lab, s >> 1, V) != ctc_label(lab, (s >> 1) - 1, V))) ? 1.f : 0.f;
+    skipb[i] = (GRAD && (s + 2 < S) && (s & 1) && (ctc_label(lab, (s >> 1) + 1, V) != ctc_label(lab, s >> 1, V))) ? 1.f : 0.f;
   }
+  float* aw = GRAD ? alpha_ws + static_cast<size_t>(b) * T * (32 * SPL) + lane * SPL : nullptr;
+  int* kaw = GRAD ? ka_ws + static_cast<size_t>(b) * T * 32 + lane : nullptr;
   // virtual step -1: alpha(0) = 1 makes the recurrence itself produce alpha_0(0) = y_0(blank), alpha_0(1) = y_0(l_1)
   float a[SPL];
 #pragma unroll
@@ -333,6 +343,7 @@ ctc_alpha_linear_kernel(const float* __restrict__ logits, const int32_t* __restr
       // a single emission probability below ~2^-106 cannot be held next to this lane's other states in fp32 (the exponent
       // is folded in one step late): such frames - logit spreads beyond ~69 nats, NaN / inf - go to the log-domain kernel
       if (!((m - mn) * kLog2e <= kCtcLinearMaxRange)) unsafe = true;
+      if (GRAD) lse[tb * kCtcBlk + lane] = lse_l;
     }
     const char* rowb = reinterpret_cast<const char*>(cur);
 #pragma unroll 1
@@ -366,6 +377,12 @@ ctc_alpha_linear_kernel(const float* __restrict__ logits, const int32_t* __restr
       const unsigned ebits = __float_as_uint(mx) >> 23;
       kpend = (ebits - 1u) < 253u ? static_cast<int>(ebits) - 127 : 0;
       empty = mx == 0.f;
+      if (GRAD) {
+        const size_t t = static_cast<size_t>(tb) * kCtcBlk + tt;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) aw[t * (32 * SPL) + i] = a[i];
+        kaw[t * 32] = K;
+      }
     }
     __syncwarp();
   }
@@ -380,6 +397,64 @@ ctc_alpha_linear_kernel(const float* __restrict__ logits, const int32_t* __restr
   for (int o = 16; o > 0; o >>= 1) fin = lse2(fin, __shfl_xor_sync(0xffffffffu, fin, o));
   const bool redo = __any_sync(0xffffffffu, unsafe);
   if (lane == 0) nll[b] = redo ? __uint_as_float(kCtcRedoMark) : (fin > 0.5f * kLogZero ? -fin * kLn2 : INFINITY);
+  if constexpr (GRAD) {
+    if (lane == 0) mode[b] = redo ? 1 : 0;
+    if (redo || !(fin > 0.5f * kLogZero)) return;  // log-domain redo, or infeasible: the gradient kernel writes NaNs without reading
+    // ---------------- beta sweep (frames in reverse) ----------------
+    float* bw = beta_ws + static_cast<size_t>(b) * T * (32 * SPL) + lane * SPL;
+    int* kbw = kb_ws + static_cast<size_t>(b) * T * 32 + lane;
+    float bt[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) bt[i] = (lane * SPL + i == S - 1) ? 1.f : 0.f;  // virtual step T
+    const float nl31 = lane == 31 ? 0.f : 1.f;
+    K = 0;
+    kpend = 0;
+    empty = (S - 1) / SPL != lane;
+    __syncwarp();
+    stage(nblk - 1);
+    for (int tb = nblk - 1; tb >= 0; --tb) {
+      if (tb > 0) { stage(tb - 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      __syncwarp();
+      const float* cur = blk + (tb & 1) * blk_floats;
+      const int nf = min(kCtcBlk, T - tb * kCtcBlk);
+      const char* rowb = reinterpret_cast<const char*>(cur) + static_cast<size_t>(nf - 1) * V * 4;
+#pragma unroll 1
+      for (int tt = nf - 1; tt >= 0; --tt, rowb -= V * 4) {
+        const size_t t = static_cast<size_t>(tb) * kCtcBlk + tt;
+        const float lt2 = lse[t] + static_cast<float>(kpend);
+        float y[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i)
+          y[i] = ex2a(fmaf(*reinterpret_cast<const float*>(rowb + extoff[i]), kLog2e, -lt2)) * livef[i];
+        const int Kdn = __shfl_down_sync(0xffffffffu, K, 1);
+        float dn1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+        float dn2 = __shfl_down_sync(0xffffffffu, bt[SPL > 1 ? 1 : 0], 1);
+        K = (empty && lane != 31) ? Kdn : K;
+        const int d = max(-126, min(126, Kdn - K));
+        const float f = nl31 * __uint_as_float(static_cast<unsigned>(d + 127) << 23);  // 2^(Kdn - K), nothing beyond lane 31
+        dn1 *= f;
+        dn2 *= f;
+        float nb[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+          const float q1 = (i + 1 < SPL) ? bt[i + 1] : dn1;
+          const float q2 = (i + 2 < SPL) ? bt[i + 2] : (i + 1 < SPL ? dn1 : dn2);
+          nb[i] = fmaf(skipb[i], q2, bt[i] + q1) * y[i];
+        }
+        K += kpend;
+        float mx = nb[0];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) { bt[i] = nb[i]; mx = fmaxf(mx, nb[i]); }
+        const unsigned ebits = __float_as_uint(mx) >> 23;
+        kpend = (ebits - 1u) < 253u ? static_cast<int>(ebits) - 127 : 0;
+        empty = mx == 0.f;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) bw[t * (32 * SPL) + i] = bt[i];
+        kbw[t * 32] = K;
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // d nll_b / d logits[b,t,:] = softmax(logits[b,t,:]) - occupancy_t, occupancy_t(v) = sum_{s: ext(s)=v} alpha_t(s) beta_t(s) / y_t(v)
@@ -390,7 +465,8 @@ constexpr int kGradWarps = 8;
 template <int SPL>
 __global__ void __launch_bounds__(kGradWarps * 32)
 ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int B, int T, int V, int L, int blank,
-                const float* __restrict__ nll, const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws, float* __restrict__ grad) {
+                const float* __restrict__ nll, const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws, float* __restrict__ grad,
+                const int* __restrict__ ka_ws, const int* __restrict__ kb_ws, const int* __restrict__ mode) {
   extern __shared__ __align__(16) float smem_cg[];  // [kGradWarps][Vpad]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Vpad = (V + 31) & ~31;
@@ -422,6 +498,9 @@ ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ la
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     const int S = 2 * cnt + 1;
     const size_t off = (static_cast<size_t>(b) * T + t) * (32 * SPL) + lane * SPL;
+    // workspace of this sequence: log2 alpha / beta (mode 1, log-domain sweep) or scaled linear values + per-lane exponents
+    const bool linear = mode != nullptr && mode[b] == 0;
+    const float kab = linear ? static_cast<float>(ka_ws[(static_cast<size_t>(b) * T + t) * 32 + lane] + kb_ws[(static_cast<size_t>(b) * T + t) * 32 + lane]) : 0.f;
     float e[SPL];
     int ext[SPL];
     float mx = kLogZero;
@@ -432,7 +511,14 @@ ctc_grad_kernel(const float* __restrict__ logits, const int32_t* __restrict__ la
       if (s < S && (s & 1)) ex = ctc_label(lab, s >> 1, V);
       ext[i] = ex;
       const float em = (row[ex] - lt) * kLog2e;
-      e[i] = (s < S) ? alpha_ws[off + i] + beta_ws[off + i] - em : kLogZero;
+      float ab;
+      if (linear) {
+        const float pa = alpha_ws[off + i], pb = beta_ws[off + i];
+        ab = (pa > 0.f && pb > 0.f) ? lg2a(pa) + lg2a(pb) + kab : kLogZero;
+      } else {
+        ab = alpha_ws[off + i] + beta_ws[off + i];
+      }
+      e[i] = (s < S) ? ab - em : kLogZero;
       mx = fmaxf(mx, e[i]);
     }
 #pragma unroll
@@ -542,6 +628,48 @@ greedy_decode_kernel(const float* __restrict__ logits, int B, int T, int V, int 
   if (lane == 0) lens[b] = total;
 }
 
+// One states-per-lane instantiation of the whole CTC call:
+//   linear sweep(s) -> log-domain kernel for the sequences the sweep marked as out of range (returns at once for the
+//   others; with linear == false it does all of them) -> [gradient of every frame, one warp per frame]
+template <int SPL>
+int ctc_launch_spl(const float* logits, const int32_t* labels, int B, int T, int V, int L, int blank, float* nll, float* grad,
+                   float* ws, size_t smem_log, bool linear, cudaStream_t stream) {
+  const int Vpad = (V + 31) & ~31;
+  const size_t per = static_cast<size_t>(B) * T * 32;
+  float* aws = ws;
+  float* bws = ws != nullptr ? ws + per * SPL : nullptr;
+  int* kaw = ws != nullptr ? reinterpret_cast<int*>(ws + 2 * per * SPL) : nullptr;
+  int* kbw = ws != nullptr ? kaw + per : nullptr;
+  int* mode = ws != nullptr ? kbw + per : nullptr;
+  if (smem_log > 48 * 1024)
+    ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_kernel<SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_log)));
+  if (linear) {
+    const size_t smem_lin = (static_cast<size_t>(2 * kCtcBlk * V) + (grad != nullptr ? ((T + 3) & ~3) : 0)) * sizeof(float);
+    if (grad != nullptr) {
+      if (smem_lin > 48 * 1024)
+        ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_alpha_linear_kernel<SPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_lin)));
+      ctc_alpha_linear_kernel<SPL, true><<<B, 32, smem_lin, stream>>>(logits, labels, B, T, V, L, blank, nll, aws, bws, kaw, kbw, mode);
+    } else {
+      if (smem_lin > 48 * 1024)
+        ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_alpha_linear_kernel<SPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_lin)));
+      ctc_alpha_linear_kernel<SPL, false><<<B, 32, smem_lin, stream>>>(logits, labels, B, T, V, L, blank, nll, nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
+    ISHARA_CUDA_OK(cudaGetLastError());
+    note_launch();
+  }
+  ctc_kernel<SPL><<<B, 32, smem_log, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, aws, bws, linear ? 1 : 0);
+  ISHARA_CUDA_OK(cudaGetLastError());
+  note_launch();
+  if (grad != nullptr) {
+    const int64_t frames = static_cast<int64_t>(B) * T;
+    ctc_grad_kernel<SPL><<<static_cast<unsigned>((frames + kGradWarps - 1) / kGradWarps), kGradWarps * 32, kGradWarps * Vpad * sizeof(float), stream>>>(
+        logits, labels, B, T, V, L, blank, nll, aws, bws, grad, kaw, kbw, linear ? mode : nullptr);
+    ISHARA_CUDA_OK(cudaGetLastError());
+    note_launch();
+  }
+  return 0;
+}
+
 }  // namespace
 
 // alphas | betas of the gradient pass: caller-owned (per handle / per call), so two handles, devices or streams never
@@ -549,7 +677,9 @@ greedy_decode_kernel(const float* __restrict__ logits, int B, int T, int V, int 
 size_t ctc_workspace_bytes(int B, int T, int L) {
   const int spl = (2 * L + 1 + 31) / 32;
   const int SPL = spl <= 5 ? 5 : 9;
-  return 2 * static_cast<size_t>(B) * T * 32 * SPL * sizeof(float);
+  // alphas | betas (floats) | per-lane exponents of the linear sweeps (2 x [B, T, 32] ints) | mode [B] ints
+  return 2 * static_cast<size_t>(B) * T * 32 * SPL * sizeof(float) + 2 * static_cast<size_t>(B) * T * 32 * sizeof(int) +
+         static_cast<size_t>(B) * sizeof(int);
 }
 
 int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, int V, int L, int blank, float* nll,
@@ -571,68 +701,17 @@ int ctc_loss_launch(const float* logits, const int32_t* labels, int B, int T, in
     return 2;
   }
   static const int linear_fwd = getenv("ISHARA_CTC_LINEAR") ? atoi(getenv("ISHARA_CTC_LINEAR")) : 1;
-  if (grad == nullptr && linear_fwd) {
-    // loss only: linear-domain sweep, then the log-domain kernel for the sequences the sweep marked as out of range (it
-    // returns at once for all others); the log-domain kernel is also the gradient pass and the cross-check
-    const size_t smem_lin = static_cast<size_t>(2 * kCtcBlk * V) * sizeof(float);
-    if (SPL == 5) {
-      if (smem_lin > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_alpha_linear_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_lin)));
-      ctc_alpha_linear_kernel<5><<<B, 32, smem_lin, stream>>>(logits, labels, B, T, V, L, blank, nll);
-      ISHARA_CUDA_OK(cudaGetLastError());
-      note_launch();
-      if (smem > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      ctc_kernel<5><<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, nullptr, nullptr, nullptr, 1);  // marked sequences only
-    } else {
-      if (smem_lin > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_alpha_linear_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_lin)));
-      ctc_alpha_linear_kernel<9><<<B, 32, smem_lin, stream>>>(logits, labels, B, T, V, L, blank, nll);
-      ISHARA_CUDA_OK(cudaGetLastError());
-      note_launch();
-      if (smem > 48 * 1024) ISHARA_CUDA_OK(cudaFuncSetAttribute(ctc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      ctc_kernel<9><<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, nullptr, nullptr, nullptr, 1);
-    }
-    ISHARA_CUDA_OK(cudaGetLastError());
-    note_launch();
-    return 0;
-  }
   float* ws = nullptr;
   if (grad != nullptr) {
-    const size_t need = ctc_workspace_bytes(B, T, L);  // alphas | betas
+    const size_t need = ctc_workspace_bytes(B, T, L);  // alphas | betas | exponents | mode
     if (workspace == nullptr || workspace_bytes < need) {
       set_last_error("ctc_loss: the gradient pass needs a caller-owned workspace of ctc_workspace_bytes(B, T, L) bytes");
       return 2;
     }
     ws = workspace;
   }
-  if (SPL == 5) {
-    auto kern = ctc_kernel<5>;
-    if (smem > 48 * 1024)
-      ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    float* bws = ws != nullptr ? ws + static_cast<size_t>(B) * T * 32 * SPL : nullptr;
-    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws, 0);
-    if (grad != nullptr) {
-      ISHARA_CUDA_OK(cudaGetLastError());
-      note_launch();
-      const int64_t frames = static_cast<int64_t>(B) * T;
-      ctc_grad_kernel<5><<<static_cast<unsigned>((frames + kGradWarps - 1) / kGradWarps), kGradWarps * 32, kGradWarps * Vpad * sizeof(float), stream>>>(
-          logits, labels, B, T, V, L, blank, nll, ws, bws, grad);
-    }
-  } else {
-    auto kern = ctc_kernel<9>;
-    if (smem > 48 * 1024)
-      ISHARA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    float* bws = ws != nullptr ? ws + static_cast<size_t>(B) * T * 32 * SPL : nullptr;
-    kern<<<B, 32, smem, stream>>>(logits, labels, B, T, V, L, blank, nll, grad, ws, bws, 0);
-    if (grad != nullptr) {
-      ISHARA_CUDA_OK(cudaGetLastError());
-      note_launch();
-      const int64_t frames = static_cast<int64_t>(B) * T;
-      ctc_grad_kernel<9><<<static_cast<unsigned>((frames + kGradWarps - 1) / kGradWarps), kGradWarps * 32, kGradWarps * Vpad * sizeof(float), stream>>>(
-          logits, labels, B, T, V, L, blank, nll, ws, bws, grad);
-    }
-  }
-  ISHARA_CUDA_OK(cudaGetLastError());
-  note_launch();
-  return 0;
+  return SPL == 5 ? ctc_launch_spl<5>(logits, labels, B, T, V, L, blank, nll, grad, ws, smem, linear_fwd != 0, stream)
+                  : ctc_launch_spl<9>(logits, labels, B, T, V, L, blank, nll, grad, ws, smem, linear_fwd != 0, stream);
 }
 
 int greedy_decode_launch(const float* logits, int B, int T, int V, int blank, int32_t* ids_out, int32_t* lens,

@@ -39,3 +39,9 @@ def timeit(fn, n=40):
 ctc = lambda i: _lib.check(lib.ishara_ctc_loss(vp(logits[i % 4]), vp(labels), B, T, V, L, V - 1, vp(nll), None, sp))
 dec = lambda i: _lib.check(lib.ishara_greedy_decode(vp(logits[i % 4]), B, T, V, V - 1, vp(ids), vp(lens), sp))
 print("ctc_loss us/launch", round(timeit(ctc), 1), " greedy_decode us/launch", round(timeit(dec), 1))
+
+# training shape: loss + gradient at B = 64
+Bt = 64
+grad = torch.empty(Bt, T, V, device=dev)
+ctcg = lambda i: _lib.check(lib.ishara_ctc_loss(vp(logits[i % 4][:Bt]), vp(labels[:Bt]), Bt, T, V, L, V - 1, vp(nll[:Bt]), vp(grad), sp))
+print("ctc_loss + gradient (B=64) us/call", round(timeit(ctcg), 1))
