@@ -106,20 +106,47 @@ se_gate_kernel(SeGateArgs a) {
   // the eight per-warp partial rows are summed through shared memory. (Every CTA pulls all of W3, 256 KB, from L2 in the
   // same order; starting each CTA at a different row would spread the L2 load but make the fp32 summation order - and
   // so the bits of the result - depend on the position in the batch, which the batch-invariance test forbids.)
+  // Every CTA needs all of W3 (256 KB from L2) and all CTAs would ask the same L2 slices for the same lines at the same
+  // moment. The rows of a warp are therefore cut into four groups whose partial sums are formed separately (each in its
+  // own fixed order) and added in a fixed order at the end: the CTA may then WALK the groups starting from b % 4 without
+  // changing a single bit of the result (batch invariance), and at any moment only a quarter of the CTAs hit a given line.
   for (int d0 = 0; d0 < a.D; d0 += 256) {
     const int d = d0 + lane * 8;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float part4[4][8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part4[g][i] = 0.f;
     if (d < a.D) {
+      const int rows_w = (a.C - warp + 7) / 8;          // rows c = warp + 8 i of this warp
+      const int per_g = (rows_w + 3) / 4;
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        const int g = (k + b) & 3;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int i_end = min(rows_w, (g + 1) * per_g);
 #pragma unroll 8
-      for (int c = warp; c < a.C; c += 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.w3kn + static_cast<size_t>(c) * a.D + d));
-        const float mc = mean[c];
-        acc[0] = fmaf(bf16_lo(u.x), mc, acc[0]); acc[1] = fmaf(bf16_hi(u.x), mc, acc[1]);
-        acc[2] = fmaf(bf16_lo(u.y), mc, acc[2]); acc[3] = fmaf(bf16_hi(u.y), mc, acc[3]);
-        acc[4] = fmaf(bf16_lo(u.z), mc, acc[4]); acc[5] = fmaf(bf16_hi(u.z), mc, acc[5]);
-        acc[6] = fmaf(bf16_lo(u.w), mc, acc[6]); acc[7] = fmaf(bf16_hi(u.w), mc, acc[7]);
+        for (int i = g * per_g; i < i_end; ++i) {
+          const int c = warp + 8 * i;
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.w3kn + static_cast<size_t>(c) * a.D + d));
+          const float mc = mean[c];
+          acc[0] = fmaf(bf16_lo(u.x), mc, acc[0]); acc[1] = fmaf(bf16_hi(u.x), mc, acc[1]);
+          acc[2] = fmaf(bf16_lo(u.y), mc, acc[2]); acc[3] = fmaf(bf16_hi(u.y), mc, acc[3]);
+          acc[4] = fmaf(bf16_lo(u.z), mc, acc[4]); acc[5] = fmaf(bf16_hi(u.z), mc, acc[5]);
+          acc[6] = fmaf(bf16_lo(u.w), mc, acc[6]); acc[7] = fmaf(bf16_hi(u.w), mc, acc[7]);
+        }
+        // group g's slot (compile-time indices keep part4 in registers)
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg)
+          if (gg == g) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part4[gg][i] = acc[i];
+          }
       }
     }
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (part4[0][i] + part4[1][i]) + (part4[2][i] + part4[3][i]);
     __syncthreads();  // zpart free (previous d0 round consumed)
 #pragma unroll
     for (int i = 0; i < 8; ++i) zpart[warp * 256 + lane * 8 + i] = acc[i];
