@@ -273,7 +273,7 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path, optimizer):
     got = [m2.train_step(x, y) for _ in range(3)]
     # the weight-gradient kernels accumulate with fp32 atomics, so two runs differ in the last bits and the difference grows
     # slowly over the steps; a missing / misplaced optimiser slot or counter shows up at the 1e-2 level
-    assert np.allclose(got, want, rtol=5e-4), (got, want)
+    assert np.allclose(got, want, rtol=1e-3), (got, want)
     w_got = m2.get_weights()
     for k in w_want:
         if k.endswith(".conv.depthwise_conv.bias"):
@@ -281,7 +281,7 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path, optimizer):
             # normalisation turns into steps of up to +-lr each - two runs may differ by lr per step on this tensor
             assert np.abs(w_got[k] - w_want[k]).max() <= 3 * 1e-3 + 1e-6, k
             continue
-        assert np.abs(w_got[k] - w_want[k]).max() <= 2e-3 * (np.abs(w_want[k]).max() + 1e-6), k
+        assert np.abs(w_got[k] - w_want[k]).max() <= 3e-3 * (np.abs(w_want[k]).max() + 1e-6), k
     m.close()
     m2.close()
 
