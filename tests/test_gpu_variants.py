@@ -193,4 +193,5 @@ def test_training_step_graph_replay_matches_direct_launches(tmp_path):
     assert np.all(np.diff(a[:6]) != 0)                                  # the weights really move
     np.testing.assert_allclose(a[:6], b[:6], rtol=2e-3)
     rel = np.linalg.norm(a[6:] - b[6:]) / np.linalg.norm(b[6:])
-    assert rel < 2e-3, rel
+    print("relative L2 distance of the weights after six steps", rel)
+    assert rel < 5e-3, rel   # atomics-order noise (incl. the zero-gradient biases Adam turns into +-lr steps) is ~1e-3; wrong masks give >> 1e-2
